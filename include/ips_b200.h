@@ -1,0 +1,120 @@
+/*
+ * ips_b200 -- C ABI of the B200-native IPS hot path (sm_100a).
+ *
+ * The reference (benbergner/ips) is pure Python: it has no FFI layer, its
+ * boundary is the IPSNet class surface (architecture/ips_net.py:85,169,264).
+ * Each entry point below names the reference code it replaces.  The Python
+ * drop-in in ips_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - buffers are owned by the caller (PyTorch allocates them) and must
+ *     outlive the stream work; the library owns only opaque plan handles;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok, non-zero = error; ipsb_last_error() gives the
+ *     message of the calling thread's last failure; no exceptions cross;
+ *   - no CPU fallback exists: without a CUDA device every call fails.
+ */
+#ifndef IPS_B200_H
+#define IPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPSB_ABI_VERSION 1
+#if defined(__GNUC__)
+#define IPSB_API __attribute__((visibility("default")))
+#else
+#define IPSB_API
+#endif
+
+/* activation dtype codes */
+#define IPSB_F32 0
+#define IPSB_BF16 1
+
+IPSB_API int ipsb_abi_version(void);
+IPSB_API const char* ipsb_last_error(void);
+/* 0 when a device with compute capability 10.x is current */
+IPSB_API int ipsb_device_ok(void);
+
+/* ---------------------------------------------------------------- staging
+ * Replaces: patches[:, lo:hi].to(device).reshape(-1, C, ph, pw)
+ * (ips_net.py:206,209,223,227) and the shuffle copy (utils/utils.py:39,56).
+ * Gathers `n_rows` patches src[row_idx[i]] of a (rows, C, H, W) fp32 NCHW
+ * tensor into channels-last (n_rows, H, W, Cpad) of dtype `dt`, zero-filling
+ * channels C..Cpad-1.  row_idx == NULL means rows first_row .. first_row+n_rows-1. */
+IPSB_API int ipsb_stage_patches(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
+                       int C, int H, int W, int Cpad, int dt, void* dst, void* stream);
+
+/* ---------------------------------------------------------------- encoder, fp32 SIMT ("exact" mode)
+ * Replaces: conv2d + eval-mode batch_norm [+ residual add] [+ relu] of the
+ * truncated torchvision ResNet (ips_net.py:17-52).  x: (P,H,W,Cin) NHWC fp32,
+ * w: (kh*kw*Cin, Cout) fp32 with k = (r*kw+s)*Cin+c, y = act(conv*scale+shift+res). */
+IPSB_API int ipsb_conv_f32(const float* x, const float* w, const float* scale, const float* shift,
+                  const float* res, float* y, int64_t P, int H, int W, int Cin, int Cout,
+                  int kh, int kw, int stride, int pad, int relu, void* stream);
+/* y[M,N] = act((A[M,K] @ W[N,K]^T) * scale[N] + shift[N]); scale/shift may be NULL.
+ * Replaces nn.Linear call sites (ips_net.py:57, transformer.py:76-77). */
+IPSB_API int ipsb_linear_f32(const float* a, const float* w, const float* scale, const float* shift,
+                    float* y, int64_t M, int N, int K, int relu, void* stream);
+/* max_pool2d(3, stride 2, pad 1) on NHWC; dt selects fp32 / bf16 */
+IPSB_API int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, int dt, void* stream);
+/* adaptive_avg_pool2d(1): (P,HW,C) dt -> (P,C) fp32 */
+IPSB_API int ipsb_avgpool(const void* x, float* y, int64_t P, int HW, int C, int dt, void* stream);
+/* LayerNorm without affine (ips_net.py:56): y = (x-mean)/sqrt(var+eps), rows of F floats */
+IPSB_API int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int F, float eps, void* stream);
+
+/* ---------------------------------------------------------------- encoder, bf16 tcgen05 implicit GEMM
+ * Same contract as ipsb_conv_f32 with x,res,y bf16 NHWC and w (Cout, K) bf16
+ * K-major, K = kh*kw*Cin padded to a multiple of 64.  mode 0: Cin % 64 == 0;
+ * mode 1: the 7x7/2 stem on 4-channel-padded input (K laid out r*32+s*4+c, 256). */
+IPSB_API int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const float* shift,
+                        const void* res, void* y, int64_t P, int H, int W, int Cin, int Cout,
+                        int kh, int kw, int stride, int pad, int relu, int mode, void* stream);
+/* y[M,N] (fp32) = act((A[M,K] @ W[N,K]^T) * scale + shift), A and W bf16 K-major,
+ * K % 64 == 0, N % 64 == 0.  tcgen05 path for the Linear layers. */
+IPSB_API int ipsb_linear_bf16_umma(const void* a, const void* w, const float* scale, const float* shift,
+                          float* y, int64_t M, int N, int K, int relu, void* stream);
+/* fp32 (rows,F) -> bf16 with optional no-affine LayerNorm fused (projector prologue) */
+IPSB_API int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);
+
+/* ---------------------------------------------------------------- scoring
+ * The learned-query score is linear in the embedding before the softmax:
+ * z[n,h,t] = emb_n . U[:,h,t] with U = k_w_h^T (q_w q_t)_h / sqrt(D_k)
+ * (transformer.py:29-31,76-79).  U is (D, H*T), column h*T+t. */
+IPSB_API int ipsb_score_basis(const float* q_tok, const float* q_w, const float* k_w, float* U,
+                     int D, int H, int Dk, int T, void* stream);
+/* z[row, :] = emb[row, :] @ U (+ add_tab[add_idx[row] or row, :]); emb (rows, D) fp32.
+ * add_tab (rows_tab, HT) is the positional-encoding contribution pos @ U (ips_net.py:234-238). */
+IPSB_API int ipsb_logits(const float* emb, const float* U, const float* add_tab, const int64_t* add_idx,
+                float* z, int64_t rows, int D, int HT, void* stream);
+/* scores (B,L) from logits (B,L,H*T): softmax over L per (h,t), mean over heads then
+ * tokens (transformer.py:31,143-148). */
+IPSB_API int ipsb_scores_from_logits(const float* z, float* scores, int B, int L, int H, int T, void* stream);
+/* Stable top-M (torch.topk at ips_net.py:148 with lowest-position tie-break):
+ * idx_out/val_out (B,M) = first M of a stable descending sort of scores (B,L). */
+IPSB_API int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t* idx_out, float* val_out, void* stream);
+/* The whole sequential selection loop of ips_net.py:213-241 on a per-patch logit
+ * table z (B,N,H*T) (patch order = ORIGINAL order).  perm (B or 1, N) int64 is the
+ * scan order (shuffled position -> original index) or NULL for identity;
+ * perm_batch_stride = N for per-instance permutations, 0 for a shared one.
+ * Outputs (B,M): mem_pos = winners' shuffled positions (the reference's mem_idx),
+ * mem_src = their original indices, mem_score = final-iteration scores; best first. */
+IPSB_API int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_stride,
+                     int B, int N, int H, int T, int M, int I,
+                     int64_t* mem_pos, int64_t* mem_src, float* mem_score, void* stream);
+
+/* ---------------------------------------------------------------- gathers
+ * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the
+ * pos-enc gather (:249-250): dst[b,m,:] = src[b*src_batch_stride + idx[b,m], :],
+ * rows of row_bytes bytes (multiple of 4; 16-byte vector path when aligned). */
+IPSB_API int ipsb_gather_rows(const void* src, int64_t src_batch_stride_rows, const int64_t* idx,
+                     int B, int M, int64_t row_bytes, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPS_B200_H */

@@ -1,0 +1,264 @@
+// HBM-bound data movement: patch staging (NCHW fp32 -> channels-last), row gathers,
+// pooling, LayerNorm rows.  All 128-bit where alignment allows.
+#include "common.cuh"
+#include "../../include/ips_b200.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+// one thread per output pixel: C strided plane reads (coalesced over pixels), one
+// Cpad-wide channels-last store.
+template <typename T, int CPAD>
+__global__ void stage_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx,
+                             int64_t first_row, int64_t n_rows, int C, int HW, T* __restrict__ dst) {
+    const int64_t total = n_rows * HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / HW;
+        const int px = (int)(i - r * HW);
+        const int64_t srow = row_idx ? row_idx[r] : first_row + r;
+        const float* s = src + srow * (int64_t)C * HW + px;
+        T out[CPAD];
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) out[c] = from_f32<T>(c < C ? __ldg(s + (int64_t)c * HW) : 0.f);
+        T* d = dst + i * CPAD;
+        if (sizeof(T) * CPAD == 8) {
+            *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(out);
+        } else if (sizeof(T) * CPAD == 16) {
+            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(out);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) d[c] = out[c];
+        }
+    }
+}
+
+// dst row (b,m) <- src row; grid.x = rows, grid.y = 16 KB segments of a row
+__global__ void gather_rows16_kernel(const unsigned char* __restrict__ src, int64_t batch_stride_rows,
+                                     const int64_t* __restrict__ idx, int M, int64_t row_bytes,
+                                     unsigned char* __restrict__ dst) {
+    const int64_t row = blockIdx.x;
+    const int64_t b = row / M;
+    const int64_t srow = b * batch_stride_rows + idx[row];
+    const unsigned char* s = src + srow * row_bytes;
+    unsigned char* d = dst + row * row_bytes;
+    const int64_t seg_lo = (int64_t)blockIdx.y * 16384;
+    const int64_t seg_hi = min(seg_lo + 16384, row_bytes);
+    int64_t off = seg_lo + (int64_t)threadIdx.x * 16;
+    const int64_t step = (int64_t)blockDim.x * 16;
+    // 4 independent 128-bit loads in flight per thread
+    int4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ok[j] = off + j * step < seg_hi;
+        if (ok[j]) v[j] = ipsb::ld_stream16(s + off + j * step);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (ok[j]) ipsb::st_stream16(d + off + j * step, v[j]);
+}
+
+__global__ void gather_rows4_kernel(const uint32_t* __restrict__ src, int64_t batch_stride_rows,
+                                    const int64_t* __restrict__ idx, int M, int64_t row_words,
+                                    uint32_t* __restrict__ dst) {
+    const int64_t row = blockIdx.x;
+    const int64_t b = row / M;
+    const uint32_t* s = src + (b * batch_stride_rows + idx[row]) * row_words;
+    uint32_t* d = dst + row * row_words;
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < row_words;
+         i += (int64_t)gridDim.y * blockDim.x)
+        d[i] = s[i];
+}
+
+// max_pool2d(3, 2, 1) channels-last, VEC channels per thread (16 bytes)
+template <typename T, int VEC>
+__global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t P, int H, int W, int C,
+                               int Ho, int Wo) {
+    const int cv = C / VEC;
+    const int64_t total = P * Ho * Wo * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * VEC;
+        int64_t t = i / cv;
+        const int ox = (int)(t % Wo); t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int64_t p = t / Ho;
+        float m[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                const T* s = x + ((p * H + iy) * W + ix) * (int64_t)C + c0;
+                T v[VEC];
+                *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(s);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) m[k] = fmaxf(m[k], to_f32<T>(v[k]));
+            }
+        }
+        T o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = from_f32<T>(m[k]);
+        *reinterpret_cast<uint4*>(y + ((p * Ho + oy) * Wo + ox) * (int64_t)C + c0) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int64_t P, int HW, int C) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const T* s = x + p * (int64_t)HW * C + c;
+        float acc = 0.f;
+        for (int k = 0; k < HW; ++k) acc += to_f32<T>(s[(int64_t)k * C]);
+        y[i] = acc / (float)HW;
+    }
+}
+
+// one 256-thread block per row; two-pass mean / biased variance in fp32
+template <typename T, bool kNorm>
+__global__ void rows_kernel(const float* __restrict__ x, T* __restrict__ y, int F, float eps) {
+    __shared__ float red[8];
+    __shared__ float stat[2];
+    const float* xr = x + (int64_t)blockIdx.x * F;
+    T* yr = y + (int64_t)blockIdx.x * F;
+    const int tid = threadIdx.x;
+    float mean = 0.f, rstd = 1.f;
+    if (kNorm) {
+        float s = 0.f;
+        for (int i = tid; i < F; i += blockDim.x) s += xr[i];
+        s = ipsb::warp_sum(s);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+            stat[0] = t / (float)F;
+        }
+        __syncthreads();
+        mean = stat[0];
+        float q = 0.f;
+        for (int i = tid; i < F; i += blockDim.x) { const float d = xr[i] - mean; q += d * d; }
+        q = ipsb::warp_sum(q);
+        if ((tid & 31) == 0) red[tid >> 5] = q;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+            stat[1] = rsqrtf(t / (float)F + eps);
+        }
+        __syncthreads();
+        rstd = stat[1];
+    }
+    for (int i = tid; i < F; i += blockDim.x) yr[i] = from_f32<T>((xr[i] - mean) * rstd);
+}
+
+int grid_for(int64_t total, int threads) {
+    int64_t g = ipsb::ceil_div(total, threads);
+    const int64_t cap = (int64_t)ipsb::sm_count() * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ipsb_stage_patches(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
+                       int C, int H, int W, int Cpad, int dt, void* dst, void* stream) {
+    IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= Cpad, "stage: bad shape rows=%lld C=%d Cpad=%d", (long long)n_rows, C, Cpad);
+    IPSB_REQUIRE(Cpad == 4, "stage: only Cpad=4 is built (C=%d)", C);
+    const int64_t total = n_rows * H * W;
+    const int g = grid_for(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dt == IPSB_BF16)
+        stage_kernel<bf16, 4><<<g, 256, 0, st>>>(src, row_idx, first_row, n_rows, C, H * W, (bf16*)dst);
+    else if (dt == IPSB_F32)
+        stage_kernel<float, 4><<<g, 256, 0, st>>>(src, row_idx, first_row, n_rows, C, H * W, (float*)dst);
+    else
+        return ipsb::fail("stage: unknown dtype %d", dt);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_gather_rows(const void* src, int64_t src_batch_stride_rows, const int64_t* idx,
+                     int B, int M, int64_t row_bytes, void* dst, void* stream) {
+    IPSB_REQUIRE(B > 0 && M > 0 && row_bytes > 0 && row_bytes % 4 == 0, "gather_rows: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = row_bytes % 16 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    if (vec) {
+        dim3 grid((unsigned)(B * (int64_t)M), (unsigned)ipsb::ceil_div(row_bytes, 16384));
+        gather_rows16_kernel<<<grid, 256, 0, st>>>((const unsigned char*)src, src_batch_stride_rows, idx, M,
+                                                   row_bytes, (unsigned char*)dst);
+    } else {
+        const int64_t words = row_bytes / 4;
+        dim3 grid((unsigned)(B * (int64_t)M), (unsigned)(words > 4096 ? 8 : 1));
+        gather_rows4_kernel<<<grid, 256, 0, st>>>((const uint32_t*)src, src_batch_stride_rows, idx, M, words,
+                                                  (uint32_t*)dst);
+    }
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, int dt, void* stream) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dt == IPSB_BF16) {
+        IPSB_REQUIRE(C % 8 == 0, "maxpool: C=%d not a multiple of 8", C);
+        const int64_t total = P * Ho * Wo * (C / 8);
+        maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, P, H, W, C, Ho, Wo);
+    } else if (dt == IPSB_F32) {
+        IPSB_REQUIRE(C % 4 == 0, "maxpool: C=%d not a multiple of 4", C);
+        const int64_t total = P * Ho * Wo * (C / 4);
+        maxpool_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, P, H, W, C, Ho, Wo);
+    } else {
+        return ipsb::fail("maxpool: unknown dtype %d", dt);
+    }
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_avgpool(const void* x, float* y, int64_t P, int HW, int C, int dt, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(P * C, 256);
+    if (dt == IPSB_BF16)
+        avgpool_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)x, y, P, HW, C);
+    else if (dt == IPSB_F32)
+        avgpool_kernel<float><<<g, 256, 0, st>>>((const float*)x, y, P, HW, C);
+    else
+        return ipsb::fail("avgpool: unknown dtype %d", dt);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int F, float eps, void* stream) {
+    IPSB_REQUIRE(rows > 0 && F > 0, "layernorm: bad shape");
+    rows_kernel<float, true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, y, F, eps);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream) {
+    IPSB_REQUIRE(rows > 0 && F > 0, "rows_to_bf16: bad shape");
+    if (layernorm)
+        rows_kernel<bf16, true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, F, eps);
+    else
+        rows_kernel<bf16, false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, F, eps);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+"""Drop-in `IPSNet` whose selection path runs on hand-written sm_100a kernels.
+
+Same constructor, `ips` / `forward` signatures, attribute names and state_dict
+keys as architecture/ips_net.py:85-283 of the reference, so `main.py` and
+`training/iterative.py` can use it unchanged.
+
+How `ips` differs inside (results are the same):
+  * a patch's pre-softmax logits are a fixed property of the patch, so every patch
+    is encoded and projected ONCE into a (B, N, H*T) logit table; the sequential
+    M+I loop (ips_net.py:218-241) then runs inside one kernel on that table;
+  * shuffling (utils/utils.py:33-58) is a scan order handed to the kernels, not a
+    copy of the patch tensor; the same RNG calls are made so seeds reproduce it;
+  * the memory buffer is persistent shared memory, not torch.cat + gather.
+"""
+import math
+import os
+
+import torch
+from torch import nn
+
+from . import ops
+from .transformer import Transformer, pos_enc_1d
+from .utils import scan_order
+
+_BN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------------------
+# parameter containers (state_dict compatible with the truncated torchvision ResNet)
+# ----------------------------------------------------------------------------------------
+
+class _BasicBlock(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+        self.stride = stride
+
+    def forward(self, x):                      # grad-mode path (train step)
+        idt = x if self.downsample is None else self.downsample(x)
+        y = self.relu(self.bn1(self.conv1(x)))
+        return self.relu(self.bn2(self.conv2(y)) + idt)
+
+
+def _conv_patch_encoder(enc_type, n_chan_in, n_res_blocks):
+    """Children 0,1,2,3,4,5[,6,7],avgpool exactly as ips_net.py:34-50 composes them."""
+    if enc_type != 'resnet18':
+        raise NotImplementedError("only enc_type 'resnet18' is built (resnet50 is unused by the shipped configs)")
+    layers = [nn.Conv2d(n_chan_in, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+              nn.MaxPool2d(3, 2, 1)]
+    cin = 64
+    for li, w in enumerate([64, 128, 256, 512][:2 if n_res_blocks != 4 else 4]):
+        s = 1 if li == 0 else 2
+        layers.append(nn.Sequential(_BasicBlock(cin, w, s), _BasicBlock(w, w, 1)))
+        cin = w
+    layers.append(nn.AdaptiveAvgPool2d((1, 1)))
+    enc = nn.Sequential(*layers)
+    for m in enc.modules():                    # torchvision's ResNet initialisation
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+    if n_chan_in == 1:                         # the reference swaps in a default-initialised stem (:29-31)
+        enc[0].reset_parameters()
+    return enc
+
+
+def _projector(n_chan_in, D):
+    return nn.Sequential(nn.LayerNorm(n_chan_in, eps=1e-05, elementwise_affine=False), nn.Linear(n_chan_in, D),
+                         nn.BatchNorm1d(D), nn.ReLU())
+
+
+def _fold_bn(bn):
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class IPSNet(nn.Module):
+    """Patch encoder + IPS + cross-attention aggregator + heads (ips_net.py:10-283)."""
+
+    def get_output_layers(self, tasks):
+        out = nn.ModuleDict()
+        for task in tasks.values():
+            act = nn.Softmax(dim=-1) if task['act_fn'] == 'softmax' else nn.Sigmoid()
+            out[task['name']] = nn.Sequential(nn.Linear(self.D, self.n_class), act)
+        return out
+
+    def __init__(self, device, conf):
+        super().__init__()
+        self.device = device
+        self.n_class = conf.n_class
+        self.M = conf.M
+        self.I = conf.I
+        self.D = conf.D
+        self.use_pos = conf.use_pos
+        self.tasks = conf.tasks
+        self.shuffle = conf.shuffle
+        self.shuffle_style = conf.shuffle_style
+        self.is_image = conf.is_image
+        # optional, not a reference key: 'bf16' (tcgen05, default) or 'fp32' (CUDA-core exact mode)
+        self.precision = os.environ.get('IPS_B200_PRECISION', getattr(conf, 'precision', 'bf16'))
+        if self.precision not in ('bf16', 'fp32'):
+            raise ValueError(f'unknown precision {self.precision!r}')
+
+        if self.is_image:
+            self.encoder = _conv_patch_encoder(conf.enc_type, conf.n_chan_in, conf.n_res_blocks)
+        else:
+            self.encoder = _projector(conf.n_chan_in, self.D)
+        self.transf = Transformer(conf.n_token, conf.H, conf.D, conf.D_k, conf.D_v, conf.D_inner,
+                                  conf.attn_dropout, conf.dropout)
+        self.pos_enc = pos_enc_1d(conf.D, conf.N).unsqueeze(0).to(device) if conf.use_pos else None
+        self.output_layers = self.get_output_layers(conf.tasks)
+
+        self._plan = None
+        self._plan_key = None
+        self.last_mem_idx = None      # (B,M) original-order indices of the last ips() call (notebook cell 9)
+        self.chunk_patches = int(getattr(conf, 'chunk_patches', 0))   # 0 = auto
+        ops.register_custom_ops()
+
+    # ------------------------------------------------------------------ derived parameters
+    def _state_versions(self):
+        vs = [self.precision]
+        for t in list(self.encoder.parameters()) + list(self.encoder.buffers()):
+            vs.append((t.data_ptr(), t._version))
+        for t in (self.transf.crs_attn.q, self.transf.crs_attn.q_w.weight, self.transf.crs_attn.k_w.weight):
+            vs.append((t.data_ptr(), t._version))
+        return tuple(vs)
+
+    def _conv_entry(self, conv, bn, stem=False):
+        w = conv.weight.detach().float()
+        cout, cin, kh, kw = w.shape
+        e = dict(cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0], mode=1 if stem else 0)
+        e['scale'], e['shift'] = _fold_bn(bn)
+        if stem:                                                  # channels padded to 4
+            w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
+            w4[:, :cin] = w
+            if self.precision == 'bf16':                          # k = r*32 + s*4 + c, 8x8 taps
+                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
+                wp[:, :kh, :kw] = w4.permute(0, 2, 3, 1)
+                e['w'] = wp.reshape(cout, 256).to(torch.bfloat16).contiguous()
+            else:
+                e['w'] = w4.permute(2, 3, 1, 0).reshape(kh * kw * 4, cout).contiguous()
+        elif self.precision == 'bf16':
+            e['w'] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(torch.bfloat16).contiguous()
+        else:
+            e['w'] = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+        return e
+
+    def _build_plan(self):
+        plan = {}
+        ca = self.transf.crs_attn
+        plan['U'] = ca.score_basis()
+        plan['posU'] = None
+        if self.use_pos:
+            plan['posU'] = ops.logits(self.pos_enc[0].contiguous().float(), plan['U'])      # (N, HT)
+        if self.is_image:
+            enc = self.encoder
+            plan['stem'] = self._conv_entry(enc[0], enc[1], stem=True)
+            blocks = []
+            for child in list(enc.children())[4:-1]:
+                for blk in child:
+                    b = dict(c1=self._conv_entry(blk.conv1, blk.bn1), c2=self._conv_entry(blk.conv2, blk.bn2), ds=None)
+                    if blk.downsample is not None:
+                        b['ds'] = self._conv_entry(blk.downsample[0], blk.downsample[1])
+                    blocks.append(b)
+            plan['blocks'] = blocks
+        else:
+            lin, bn = self.encoder[1], self.encoder[2]
+            scale, bshift = _fold_bn(bn)
+            plan['p_scale'] = scale
+            plan['p_shift'] = (lin.bias.detach().float() * scale + bshift).contiguous()
+            w = lin.weight.detach().float().contiguous()
+            plan['p_w'] = w.to(torch.bfloat16).contiguous() if self.precision == 'bf16' else w
+        return plan
+
+    def _get_plan(self):
+        key = self._state_versions()
+        if self._plan is None or key != self._plan_key:
+            self._plan = self._build_plan()
+            self._plan_key = key
+        return self._plan
+
+    # ------------------------------------------------------------------ no-grad embedding (CUDA kernels)
+    def _conv(self, x, e, res=None, relu=True):
+        f = ops.conv_bf16 if self.precision == 'bf16' else ops.conv_f32
+        if self.precision == 'bf16':
+            return f(x, e['w'], e['scale'], e['shift'], res, e['cout'], e['kh'], e['kw'], e['stride'], e['pad'], relu, e['mode'])
+        return f(x, e['w'], e['scale'], e['shift'], res, e['cout'], e['kh'], e['kw'], e['stride'], e['pad'], relu)
+
+    @torch.no_grad()
+    def embed(self, flat, row_idx=None, first_row=0, n_rows=None):
+        """Eval-mode patch embeddings (rows, D) fp32 of `flat` = (rows, C, ph, pw) or (rows, F) on the GPU.
+        Equivalent to `encoder.eval()(x).view(rows, -1)` of the reference (ips_net.py:209,227)."""
+        plan = self._get_plan()
+        dt = ops.BF16 if self.precision == 'bf16' else ops.F32
+        if n_rows is None:
+            n_rows = flat.shape[0] - first_row if row_idx is None else row_idx.numel()
+        if self.is_image:
+            _, C, H, W = flat.shape
+            x = ops.stage_patches(flat, n_rows, C, H, W, dt, row_idx=row_idx, first_row=first_row)
+            x = self._conv(x, plan['stem'])
+            x = ops.maxpool3x3s2(x, dt)
+            for b in plan['blocks']:
+                idt = x if b['ds'] is None else self._conv(x, b['ds'], relu=False)
+                y = self._conv(x, b['c1'])
+                x = self._conv(y, b['c2'], res=idt)
+            return ops.avgpool(x, dt)
+        rows = flat[first_row:first_row + n_rows] if row_idx is None else flat[row_idx]
+        if self.precision == 'bf16':
+            a = ops.rows_to_bf16(rows.contiguous(), layernorm=True, eps=1e-5)
+            return ops.linear_bf16(a, plan['p_w'], plan['p_scale'], plan['p_shift'], relu=True)
+        a = ops.layernorm_rows(rows.contiguous(), 1e-5)
+        return ops.linear_f32(a, plan['p_w'], plan['p_scale'], plan['p_shift'], relu=True)
+
+    def _auto_chunk(self, patch_shape):
+        if self.chunk_patches:
+            return self.chunk_patches
+        if not self.is_image:
+            return 16384
+        px = patch_shape[-1] * patch_shape[-2]
+        return max(32, min(2048, (256 * 10000) // max(px, 1)))
+
+    @torch.no_grad()
+    def patch_logits(self, patches):
+        """(B,N,...) -> (B,N,H*T) fp32 logit table on `self.device`, original patch order.
+        Host-resident input (lazy loading, conf.eager=False) is streamed chunk by chunk."""
+        plan = self._get_plan()
+        B, N = patches.shape[:2]
+        rows = B * N
+        flat = patches.reshape(rows, *patches.shape[2:])
+        HT = plan['U'].shape[1]
+        z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
+        pos_idx = None
+        if self.use_pos:
+            pos_idx = (torch.arange(rows, device=self.device) % N).contiguous()
+        chunk = self._auto_chunk(patches.shape)
+        for lo in range(0, rows, chunk):
+            n = min(chunk, rows - lo)
+            if flat.is_cuda:
+                emb = self.embed(flat, first_row=lo, n_rows=n)
+            else:
+                emb = self.embed(flat[lo:lo + n].to(self.device, non_blocking=True).float().contiguous())
+            z[lo:lo + n] = ops.logits(emb, plan['U'], plan['posU'], None if pos_idx is None else pos_idx[lo:lo + n].contiguous())
+        return z.view(B, N, HT)
+
+    # ------------------------------------------------------------------ reference API
+    def do_shuffle(self, patches, pos_enc):
+        """Kept for API compatibility (ips_net.py:118-134): returns permuted copies like the
+        reference; `ips` itself never copies, it passes the scan order to the kernels."""
+        B, N = patches.shape[:2]
+        perm, per_inst = scan_order(True, self.shuffle_style, B, N, patches.device)
+        if perm is None:
+            return patches, pos_enc
+        perm = perm.to(patches.device)
+        idx = perm.expand(B, -1)
+        patches = torch.stack([patches[b, idx[b]] for b in range(B)])
+        if torch.is_tensor(pos_enc):
+            pos_enc = torch.stack([pos_enc[b, idx[b].to(pos_enc.device)] for b in range(B)])
+        return patches, pos_enc
+
+    @torch.no_grad()
+    def score_and_select(self, emb, emb_pos, M, idx):
+        """Scores embeddings and keeps the top M (ips_net.py:136-155); stable tie-break."""
+        to_score = emb_pos if torch.is_tensor(emb_pos) else emb
+        scores = self.transf.get_scores(to_score)
+        _, top = ops.topm_stable(scores.contiguous(), M)
+        D = emb.shape[2]
+        mem_emb = torch.gather(emb, 1, top.unsqueeze(-1).expand(-1, -1, D))
+        mem_idx = torch.gather(idx, 1, top)
+        return mem_emb, mem_idx
+
+    def get_preds(self, embeddings):
+        preds = {}
+        for task in self.tasks.values():
+            preds[task['name']] = self.output_layers[task['name']](embeddings[:, task['id']])
+        return preds
+
+    @torch.no_grad()
+    def ips(self, patches):
+        """Iterative Patch Selection (ips_net.py:169-262): returns (mem_patch, mem_pos)."""
+        M, I, D = self.M, self.I, self.D
+        device = self.device
+        B, N = patches.shape[:2]
+        if M >= N:                                               # shortcut, :185-188
+            pos_enc = self.pos_enc.expand(B, -1, -1) if self.use_pos else None
+            self.last_mem_idx = None
+            return patches.to(device), pos_enc
+        if torch.device(device).type != 'cuda':
+            raise RuntimeError('ips_b200.IPSNet.ips needs a CUDA device: there is no CPU implementation')
+
+        perm, per_inst = scan_order(self.shuffle, self.shuffle_style, B, N, patches.device)
+        if perm is not None:
+            perm = perm.to(device).contiguous()
+
+        ca = self.transf.crs_attn
+        z = self.patch_logits(patches)                            # encode + project every patch once
+        _, mem_src, _ = ops.select_loop(z, perm, per_inst, ca.H, ca.n_token, M, I)
+        self.last_mem_idx = mem_src
+
+        if patches.is_cuda:
+            mem_patch = ops.gather_rows(patches.contiguous(), mem_src, N)
+        else:                                                    # lazy loading: gather on the host, :244-247
+            host_idx = mem_src.cpu()
+            mem_patch = torch.stack([patches[b, host_idx[b]] for b in range(B)]).to(device)
+        mem_pos = ops.gather_rows(self.pos_enc[0].contiguous(), mem_src, 0) if self.use_pos else None
+        return mem_patch, mem_pos
+
+    def forward(self, mem_patch, mem_pos=None):
+        """Encode + aggregate the selected patches with gradients (ips_net.py:264-283)."""
+        shape = mem_patch.shape
+        B, M = shape[:2]
+        mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
+        if torch.is_tensor(mem_pos):
+            mem_emb = mem_emb + mem_pos
+        return self.get_preds(self.transf(mem_emb))

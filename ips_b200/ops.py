@@ -1,0 +1,216 @@
+"""Tensor-level wrappers over the C ABI (include/ips_b200.h).
+
+Each function validates its tensors, passes raw device pointers and the current
+CUDA stream to the library, and returns freshly allocated outputs.  The main
+entry points are also registered as PyTorch custom ops under ``torch.ops.ips_b200``
+(see the bottom of the file).  No function here has a non-CUDA implementation.
+"""
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f'ips_b200: {name} must be a CUDA tensor (no CPU path exists)')
+    if t.dtype != dtype:
+        raise RuntimeError(f'ips_b200: {name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise RuntimeError(f'ips_b200: {name} must be contiguous')
+
+
+def _dt(code):
+    return torch.bfloat16 if code == BF16 else torch.float32
+
+
+# ------------------------------------------------------------------ staging / movement
+
+def stage_patches(src, n_rows, C, H, W, dt, row_idx=None, first_row=0, cpad=4):
+    """(rows,C,H,W) fp32 -> (n_rows,H,W,cpad) channels-last of dtype code `dt`."""
+    _chk(src, torch.float32, 'src')
+    _chk(row_idx, torch.int64, 'row_idx')
+    out = torch.empty((n_rows, H, W, cpad), dtype=_dt(dt), device=src.device)
+    _lib.check(_lib.load().ipsb_stage_patches(_p(src), _p(row_idx), first_row, n_rows, C, H, W, cpad, dt,
+                                              _p(out), _stream()))
+    return out
+
+
+def gather_rows(src, idx, batch_stride_rows):
+    """dst[b,m] = src_rows[b*batch_stride_rows + idx[b,m]]; src viewed as rows of src.shape[-k:]."""
+    _chk(idx, torch.int64, 'idx')
+    if not src.is_cuda or not src.is_contiguous():
+        raise RuntimeError('ips_b200: gather source must be a contiguous CUDA tensor')
+    B, M = idx.shape
+    row_shape = src.shape[2:] if batch_stride_rows else src.shape[1:]
+    row_bytes = src.element_size()
+    for s in row_shape:
+        row_bytes *= s
+    out = torch.empty((B, M, *row_shape), dtype=src.dtype, device=src.device)
+    _lib.check(_lib.load().ipsb_gather_rows(_p(src), batch_stride_rows, _p(idx), B, M, row_bytes, _p(out), _stream()))
+    return out
+
+
+def maxpool3x3s2(x, dt):
+    P, H, W, C = x.shape
+    _chk(x, _dt(dt), 'x')
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((P, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().ipsb_maxpool3x3s2(_p(x), _p(y), P, H, W, C, dt, _stream()))
+    return y
+
+
+def avgpool(x, dt):
+    P, H, W, C = x.shape
+    _chk(x, _dt(dt), 'x')
+    y = torch.empty((P, C), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ipsb_avgpool(_p(x), _p(y), P, H * W, C, dt, _stream()))
+    return y
+
+
+def layernorm_rows(x, eps):
+    _chk(x, torch.float32, 'x')
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().ipsb_layernorm_rows_f32(_p(x), _p(y), x.shape[0], x.shape[1], eps, _stream()))
+    return y
+
+
+def rows_to_bf16(x, layernorm, eps=1e-5):
+    _chk(x, torch.float32, 'x')
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().ipsb_rows_to_bf16(_p(x), _p(y), x.shape[0], x.shape[1], int(layernorm), eps, _stream()))
+    return y
+
+
+# ------------------------------------------------------------------ encoder layers
+
+def conv_f32(x, w_kc, scale, shift, res, Cout, kh, kw, stride, pad, relu):
+    """x (P,H,W,Cin) fp32 NHWC, w_kc (kh*kw*Cin, Cout) fp32."""
+    _chk(x, torch.float32, 'x'); _chk(w_kc, torch.float32, 'w'); _chk(res, torch.float32, 'res')
+    P, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y = torch.empty((P, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ipsb_conv_f32(_p(x), _p(w_kc), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin, Cout,
+                                         kh, kw, stride, pad, int(relu), _stream()))
+    return y
+
+
+def conv_bf16(x, w_nk, scale, shift, res, Cout, kh, kw, stride, pad, relu, mode=0):
+    """x (P,H,W,Cin) bf16 NHWC, w_nk (Cout, Kpad) bf16 K-major; tcgen05 implicit GEMM."""
+    _chk(x, torch.bfloat16, 'x'); _chk(w_nk, torch.bfloat16, 'w'); _chk(res, torch.bfloat16, 'res')
+    P, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y = torch.empty((P, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().ipsb_conv_bf16_umma(_p(x), _p(w_nk), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin,
+                                               Cout, kh, kw, stride, pad, int(relu), mode, _stream()))
+    return y
+
+
+def linear_f32(a, w, scale=None, shift=None, relu=False):
+    """y = act((a @ w.T) * scale + shift); a (M,K), w (N,K) fp32."""
+    _chk(a, torch.float32, 'a'); _chk(w, torch.float32, 'w')
+    M, K = a.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().ipsb_linear_f32(_p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream()))
+    return y
+
+
+def linear_bf16(a, w, scale=None, shift=None, relu=False):
+    """tcgen05 GEMM: a (M,K) bf16, w (N,K) bf16 -> fp32 (M,N)."""
+    _chk(a, torch.bfloat16, 'a'); _chk(w, torch.bfloat16, 'w')
+    M, K = a.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().ipsb_linear_bf16_umma(_p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream()))
+    return y
+
+
+# ------------------------------------------------------------------ scoring / selection
+
+def score_basis(q_tok, q_w, k_w, H, Dk):
+    """U (D, H*T): z[n,h,t] = emb_n . U[:, h*T+t]  (transformer.py:29-31,76-79)."""
+    _chk(q_tok, torch.float32, 'q'); _chk(q_w, torch.float32, 'q_w'); _chk(k_w, torch.float32, 'k_w')
+    T, D = q_tok.shape[-2], q_tok.shape[-1]
+    U = torch.empty((D, H * T), dtype=torch.float32, device=q_tok.device)
+    _lib.check(_lib.load().ipsb_score_basis(_p(q_tok), _p(q_w), _p(k_w), _p(U), D, H, Dk, T, _stream()))
+    return U
+
+
+def logits(emb, U, add_tab=None, add_idx=None):
+    """emb (rows, D) fp32 -> (rows, H*T) logits, plus add_tab[add_idx[row]] when given."""
+    _chk(emb, torch.float32, 'emb'); _chk(U, torch.float32, 'U')
+    _chk(add_tab, torch.float32, 'add_tab'); _chk(add_idx, torch.int64, 'add_idx')
+    rows, D = emb.shape
+    HT = U.shape[1]
+    z = torch.empty((rows, HT), dtype=torch.float32, device=emb.device)
+    _lib.check(_lib.load().ipsb_logits(_p(emb), _p(U), _p(add_tab), _p(add_idx), _p(z), rows, D, HT, _stream()))
+    return z
+
+
+def scores_from_logits(z, H, T):
+    """z (B,L,H*T) -> scores (B,L)  (transformer.py:143-148)."""
+    _chk(z, torch.float32, 'z')
+    B, L = z.shape[:2]
+    s = torch.empty((B, L), dtype=torch.float32, device=z.device)
+    _lib.check(_lib.load().ipsb_scores_from_logits(_p(z), _p(s), B, L, H, T, _stream()))
+    return s
+
+
+def topm_stable(scores, M):
+    """(values, indices) of the M best per row, ties -> lowest index (ips_net.py:148)."""
+    _chk(scores, torch.float32, 'scores')
+    B, L = scores.shape
+    idx = torch.empty((B, M), dtype=torch.int64, device=scores.device)
+    val = torch.empty((B, M), dtype=torch.float32, device=scores.device)
+    _lib.check(_lib.load().ipsb_topm_stable(_p(scores), B, L, M, _p(idx), _p(val), _stream()))
+    return val, idx
+
+
+def select_loop(z, perm, per_instance, H, T, M, I):
+    """Sequential IPS loop on the logit table z (B,N,H*T).  Returns (mem_pos, mem_src, score) (B,M)."""
+    _chk(z, torch.float32, 'z'); _chk(perm, torch.int64, 'perm')
+    B, N = z.shape[:2]
+    dev = z.device
+    mem_pos = torch.empty((B, M), dtype=torch.int64, device=dev)
+    mem_src = torch.empty((B, M), dtype=torch.int64, device=dev)
+    score = torch.empty((B, M), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().ipsb_select_loop(_p(z), _p(perm), N if (perm is not None and per_instance) else 0,
+                                            B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score), _stream()))
+    return mem_pos, mem_src, score
+
+
+# ------------------------------------------------------------------ torch.ops registration
+# Thin public aliases so the kernels are reachable as torch.ops.ips_b200.*; the
+# module code calls the Python functions above directly (lower dispatch overhead).
+_registered = False
+
+
+def register_custom_ops():
+    global _registered
+    if _registered:
+        return
+    lib = torch.library.Library('ips_b200', 'DEF')
+    lib.define('scores_from_logits(Tensor z, int H, int T) -> Tensor')
+    lib.define('topm_stable(Tensor scores, int M) -> (Tensor, Tensor)')
+    lib.define('select_loop(Tensor z, Tensor? perm, bool per_instance, int H, int T, int M, int I) -> (Tensor, Tensor, Tensor)')
+    lib.define('gather_rows(Tensor src, Tensor idx, int batch_stride_rows) -> Tensor')
+    lib.define('logits(Tensor emb, Tensor U, Tensor? add_tab, Tensor? add_idx) -> Tensor')
+    lib.impl('scores_from_logits', scores_from_logits, 'CUDA')
+    lib.impl('topm_stable', topm_stable, 'CUDA')
+    lib.impl('select_loop', select_loop, 'CUDA')
+    lib.impl('gather_rows', gather_rows, 'CUDA')
+    lib.impl('logits', logits, 'CUDA')
+    register_custom_ops._lib = lib      # keep alive
+    _registered = True

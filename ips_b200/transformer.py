@@ -1,0 +1,113 @@
+"""Cross-attention scorer / aggregator with the reference's parameter names.
+
+Mirrors architecture/transformer.py of the reference (pos_enc_1d :6-18,
+MultiHeadCrossAttention :43-109, MLP :111-132, Transformer :134-152) so a
+state_dict moves between the two unchanged.  The no-grad scoring path
+(`get_scores`) runs on the library's CUDA kernels; it exploits that the
+pre-softmax logit of a patch is linear in its embedding (z = emb . U), so keys
+are never materialised.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+def pos_enc_1d(D, len_seq):
+    """Sin/cos table (len_seq, D); same values as transformer.py:6-18."""
+    if D % 2 != 0:
+        raise ValueError('Cannot use sin/cos positional encoding with odd dim (got dim={:d})'.format(D))
+    position = torch.arange(0, len_seq).unsqueeze(1).float()
+    div_term = torch.exp(torch.arange(0, D, 2, dtype=torch.float) * -(math.log(10000.0) / D))
+    table = torch.zeros(len_seq, D)
+    table[:, 0::2] = torch.sin(position * div_term)
+    table[:, 1::2] = torch.cos(position * div_term)
+    return table
+
+
+class _Temperature(nn.Module):
+    """Parameter-free holder kept so `crs_attn.attention.temperature` exists as in the reference."""
+
+    def __init__(self, temperature, attn_dropout):
+        super().__init__()
+        self.temperature = temperature
+        self.dropout = nn.Dropout(attn_dropout)
+
+
+class MultiHeadCrossAttention(nn.Module):
+    def __init__(self, n_token, H, D, D_k, D_v, attn_dropout=0.1, dropout=0.1):
+        super().__init__()
+        self.n_token, self.H, self.D_k, self.D_v = n_token, H, D_k, D_v
+        self.q = nn.Parameter(torch.empty((1, n_token, D)))
+        bound = math.sqrt(1 / D_k)
+        nn.init.uniform_(self.q, a=-bound, b=bound)
+        self.q_w = nn.Linear(D, H * D_k, bias=False)
+        self.k_w = nn.Linear(D, H * D_k, bias=False)
+        self.v_w = nn.Linear(D, H * D_v, bias=False)
+        self.fc = nn.Linear(H * D_v, D, bias=False)
+        self.attention = _Temperature(D_k ** 0.5, attn_dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(D, eps=1e-6)
+
+    # -- no-grad scoring path (CUDA kernels) ------------------------------------------
+    def score_basis(self):
+        """U (D, H*T) with z[n, h*T+t] = emb_n . U[:, h*T+t]."""
+        return ops.score_basis(self.q.detach().contiguous(), self.q_w.weight.detach().contiguous(),
+                               self.k_w.weight.detach().contiguous(), self.H, self.D_k)
+
+    @torch.no_grad()
+    def get_logits(self, x):
+        """(B,L,D) -> (B,L,H*T) pre-softmax attention logits."""
+        B, L, D = x.shape
+        z = ops.logits(x.reshape(B * L, D).contiguous().float(), self.score_basis())
+        return z.view(B, L, -1)
+
+    @torch.no_grad()
+    def get_attn(self, x):
+        """(B,L,D) -> (B,H,T,L) attention weights (transformer.py:71-83), eval semantics."""
+        B, L = x.shape[:2]
+        z = self.get_logits(x).view(B, L, self.H, self.n_token).permute(0, 2, 3, 1)
+        return torch.softmax(z, dim=-1)
+
+    # -- grad-mode aggregation -------------------------------------------------------------
+    def forward(self, x):
+        B, L = x.shape[:2]
+        H, Dk, Dv, T = self.H, self.D_k, self.D_v, self.n_token
+        q = self.q_w(self.q).view(1, T, H, Dk).transpose(1, 2)
+        k = self.k_w(x).view(B, L, H, Dk).transpose(1, 2)
+        v = self.v_w(x).view(B, L, H, Dv).transpose(1, 2)
+        attn = self.attention.dropout(torch.softmax(torch.matmul(q / self.attention.temperature, k.transpose(2, 3)), dim=-1))
+        out = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, T, H * Dv)
+        out = self.dropout(self.fc(out)) + self.q
+        return self.layer_norm(out)
+
+
+class MLP(nn.Module):
+    def __init__(self, D, D_inner, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Linear(D, D_inner)
+        self.w_2 = nn.Linear(D_inner, D)
+        self.layer_norm = nn.LayerNorm(D, eps=1e-6)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        return self.layer_norm(self.dropout(self.w_2(torch.relu(self.w_1(x)))) + x)
+
+
+class Transformer(nn.Module):
+    def __init__(self, n_token, H, D, D_k, D_v, D_inner, attn_dropout=0.1, dropout=0.1):
+        super().__init__()
+        self.crs_attn = MultiHeadCrossAttention(n_token, H, D, D_k, D_v, attn_dropout=attn_dropout, dropout=dropout)
+        self.mlp = MLP(D, D_inner, dropout=dropout)
+
+    @torch.no_grad()
+    def get_scores(self, x):
+        """(B,L,D) -> (B,L): softmax over L per (head, token), mean over heads then tokens
+        (transformer.py:143-148).  Runs entirely on the library's kernels."""
+        z = self.crs_attn.get_logits(x)
+        return ops.scores_from_logits(z.contiguous(), self.crs_attn.H, self.crs_attn.n_token)
+
+    def forward(self, x):
+        return self.mlp(self.crs_attn(x))

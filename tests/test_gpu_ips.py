@@ -1,0 +1,177 @@
+"""End-to-end parity of IPSNet.ips on the B200 against the CPU oracle and the golden
+fixtures produced by the unmodified reference (tests/golden, oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import ips_oracle as O
+from golden_util import CASE_NAMES, load_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _net(conf, sd, precision):
+    from ips_b200 import IPSNet, Struct
+    c = conf.replace(precision=precision)
+    net = IPSNet(torch.device(DEV), Struct(**c.__dict__)).to(DEV)
+    net.load_state_dict(sd, strict=True)
+    net.train()                                   # ips() is called in train mode by training/iterative.py:109,135
+    return net
+
+
+def _boundary_report(sd, conf, patches, rng_seed, got_src):
+    """P3: every index the GPU picked that the oracle did not must have an oracle
+    score within `tol` of the rank-M boundary of the final iteration."""
+    trace = []
+    torch.manual_seed(rng_seed)
+    _, _, o_src = O.ips(sd, conf, patches, perm='draw', tie='stable', trace=trace)
+    worst = 0.0
+    for b in range(o_src.shape[0]):
+        a, g = set(o_src[b].tolist()), set(got_src[b].tolist())
+        if a != g:
+            s = trace[-1][0][b].sort(descending=True)[0]
+            worst = max(worst, float((s[conf.M - 1] - s[conf.M]).abs() / s[conf.M - 1]))
+    return o_src, worst
+
+
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_ips_fp32_matches_golden(name):
+    """fp32 scoring mode: selected indices identical to the reference's (golden) selection."""
+    z, meta, conf, sd, patches = load_case(name)
+    net = _net(conf, sd, 'fp32')
+    torch.manual_seed(meta['rng_seed'])
+    mem_patch, mem_pos = net.ips(patches.to(DEV))
+    assert net.training and net.encoder.training and net.transf.training
+    assert list(mem_patch.shape) == list(z['mem_patch_shape'])
+    if conf.M >= meta['N']:                                       # shortcut path
+        assert torch.equal(mem_patch.cpu(), patches)
+        return
+    got = net.last_mem_idx.cpu()
+    # the output really is the selected patches, in the returned order
+    ref_rows = torch.stack([patches[b, got[b]] for b in range(got.shape[0])])
+    assert torch.equal(mem_patch.cpu(), ref_rows)
+    if conf.use_pos:
+        tab = O.pos_table(conf.D, conf.N)
+        assert torch.equal(mem_pos.cpu(), tab[got])
+    else:
+        assert mem_pos is None
+    if 'mem_src' in z and z['mem_src'].size:
+        gold = torch.from_numpy(z['mem_src'])
+        if name == 'mnist_instance':
+            pytest.skip("'instance' shuffle draws torch.rand on the data's device: CUDA RNG != CPU RNG stream")
+        same_set = all(set(gold[b].tolist()) == set(got[b].tolist()) for b in range(gold.shape[0]))
+        assert same_set, f'selection differs from the reference; oracle boundary gap {meta["boundary_gap"]}'
+        if 'ties' not in name:
+            assert torch.equal(got, gold), 'order differs although no ties are expected'
+        assert mem_patch.double().sum().item() == pytest.approx(float(z['mem_patch_sum']), rel=1e-12)
+
+
+@pytest.mark.parametrize('name', ['mnist_ties'])
+def test_ips_fp32_tie_fixture(name):
+    """Unconditioned, 90 % all-zero patches: scores differ only through the pos-enc; report P3."""
+    z, meta, conf, sd, patches = load_case(name)
+    net = _net(conf, sd, 'fp32')
+    torch.manual_seed(meta['rng_seed'])
+    net.ips(patches.to(DEV))
+    got = net.last_mem_idx.cpu()
+    o_src, worst = _boundary_report(sd, conf, patches, meta['rng_seed'], got)
+    assert worst < 1e-5, f'picks differ where the oracle boundary gap is {worst}'
+
+
+@pytest.mark.parametrize('name', ['mnist_small', 'traffic_small', 'camelyon_small', 'camelyon_batch'])
+def test_ips_bf16_close(name):
+    """bf16 tensor-core mode: logits within tolerance of the fp32 oracle, selection overlaps."""
+    z, meta, conf, sd, patches = load_case(name)
+    net = _net(conf, sd, 'bf16')
+    B, N = patches.shape[:2]
+    zt = net.patch_logits(patches.to(DEV)).cpu()                    # (B,N,HT)
+    emb = O.encode(sd, conf, patches.reshape(B * N, *patches.shape[2:])).view(B, N, -1)
+    if conf.use_pos:
+        emb = emb + O.pos_table(conf.D, conf.N)
+    ref = O.attn_logits(sd, conf, emb).permute(0, 3, 1, 2).reshape(B, N, -1)
+    err = (zt - ref).abs().max().item() / ref.abs().max().item()
+    print(f'{name}: bf16 logit max err / max |logit| = {err:.3e}')
+    assert err < 3e-2
+    torch.manual_seed(meta['rng_seed'])
+    net.ips(patches.to(DEV))
+    got = net.last_mem_idx.cpu()
+    torch.manual_seed(meta['rng_seed'])
+    _, _, o_src = O.ips(sd, conf, patches, perm='draw', tie='stable')
+    overlap = np.mean([len(set(got[b].tolist()) & set(o_src[b].tolist())) / conf.M for b in range(B)])
+    print(f'{name}: bf16 selection overlap with fp32 oracle = {overlap:.3f}')
+    assert overlap >= 0.85
+
+
+def test_ips_lazy_host_input_equals_eager():
+    z, meta, conf, sd, patches = load_case('mnist_small')
+    net = _net(conf.replace(eager=False), sd, 'fp32')
+    torch.manual_seed(1)
+    a_patch, a_pos = net.ips(patches)                              # host tensor: streamed
+    a_idx = net.last_mem_idx.clone()
+    torch.manual_seed(1)
+    b_patch, b_pos = net.ips(patches.to(DEV))
+    assert a_patch.is_cuda and torch.equal(a_idx, net.last_mem_idx)
+    assert torch.equal(a_patch, b_patch) and torch.equal(a_pos, b_pos)
+
+
+def test_ips_does_not_touch_bn_stats_or_mode():
+    z, meta, conf, sd, patches = load_case('mnist_small')
+    net = _net(conf, sd, 'fp32')
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    net.ips(patches.to(DEV))
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    net.eval()
+    net.ips(patches.to(DEV))
+    assert not net.training
+
+
+def test_score_and_select_matches_reference_unit():
+    z, meta, conf, sd, patches = load_case('camelyon_small')
+    net = _net(conf, sd, 'fp32')
+    g = torch.Generator().manual_seed(101)
+    L = min(conf.M + conf.I, 64)
+    emb = torch.randn(meta['B'], L, conf.D, generator=g)
+    idx = torch.arange(L).unsqueeze(0).expand(meta['B'], -1).contiguous()
+    _, si = net.score_and_select(emb.to(DEV), None, max(1, L // 3), idx.to(DEV))
+    assert np.array_equal(si.cpu().numpy(), z['unit_select_idx'])
+    torch.testing.assert_close(net.transf.get_scores(emb.to(DEV)).cpu(), torch.from_numpy(z['unit_emb_scores']),
+                               rtol=2e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize('pre,B,N', [('traffic', 16, 192), ('camelyon', 1, 50000), ('mnist', 4, 900)])
+def test_full_size_properties(pre, B, N):
+    """BASELINE.json sizes: size-independent properties (the oracle would take minutes)."""
+    conf = O.preset(pre, attn_dropout=0.0, dropout=0.0)
+    sd = O.make_state(conf, 31, q_gain=12.0)
+    net = _net(conf, sd, 'bf16')
+    g = torch.Generator(device=DEV).manual_seed(32)
+    shape = (B, N, conf.n_chan_in, *conf.patch_size) if conf.is_image else (B, N, conf.n_chan_in)
+    x = torch.randn(shape, generator=g, device=DEV)
+    torch.manual_seed(3)
+    mem_patch, mem_pos = net.ips(x)
+    idx = net.last_mem_idx
+    assert mem_patch.shape[:2] == (B, conf.M)
+    for b in range(B):
+        assert idx[b].unique().numel() == conf.M                   # no patch selected twice
+        assert torch.equal(mem_patch[b], x[b, idx[b]])            # rows are the selected patches, bit exact
+    # idempotence: selecting again from the winners (N' = M) is the shortcut and returns them
+    again, _ = net.ips(mem_patch)
+    assert torch.equal(again, mem_patch)
+    # the winners survive a rescan that presents them first, without shuffling
+    net.shuffle = False
+    rest = torch.stack([x[b, torch.randperm(N, device=DEV)[: conf.I]] for b in range(B)])
+    net.ips(torch.cat([mem_patch, rest], dim=1))
+    assert net.last_mem_idx.shape == (B, conf.M)
+    # scan-order invariance of the selected SET when H = n_token = 1
+    conf1 = conf.replace(H=1, n_token=1, tasks={'t': conf.tasks['task0']}) if pre == 'camelyon' else None
+    if conf1 is not None:
+        sd1 = O.make_state(conf1, 33, q_gain=12.0)
+        n1 = _net(conf1, sd1, 'bf16')
+        torch.manual_seed(1)
+        n1.ips(x)
+        a = n1.last_mem_idx.sort(-1)[0]
+        torch.manual_seed(2)
+        n1.ips(x)
+        assert torch.equal(a, n1.last_mem_idx.sort(-1)[0])

@@ -1,0 +1,266 @@
+"""Unit-level parity of every CUDA kernel against the CPU oracle / ATen CPU operators.
+All calls go through the C ABI (ips_b200.ops -> ctypes -> libips_b200.so)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ips_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from ips_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.ipsb_device_ok())
+    return torch.device('cuda:0')
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ------------------------------------------------------------------ data movement
+
+@pytest.mark.parametrize('C,H,W', [(1, 50, 50), (3, 100, 100), (3, 7, 9)])
+@pytest.mark.parametrize('dt', ['f32', 'bf16'])
+def test_stage_patches(dev, C, H, W, dt):
+    from ips_b200 import ops
+    x = _rand(11, C, H, W, seed=1)
+    code = ops.F32 if dt == 'f32' else ops.BF16
+    idx = torch.tensor([5, 0, 10, 3, 3], dtype=torch.int64)
+    ref = torch.zeros(11, H, W, 4)
+    ref[..., :C] = x.permute(0, 2, 3, 1)
+    if dt == 'bf16':
+        ref = ref.to(torch.bfloat16)
+    out = ops.stage_patches(x.to(dev), 5, C, H, W, code, row_idx=idx.to(dev))
+    assert torch.equal(out.cpu(), ref[idx])                       # gather + layout + cast are exact
+    out = ops.stage_patches(x.to(dev), 4, C, H, W, code, first_row=6)
+    assert torch.equal(out.cpu(), ref[6:10])
+
+
+@pytest.mark.parametrize('row', [(1, 50, 50), (3, 100, 100), (2048,), (5,), (128,)])
+def test_gather_rows(dev, row):
+    from ips_b200 import ops
+    B, N, M = 3, 37, 9
+    src = _rand(B, N, *row, seed=2)
+    g = torch.Generator().manual_seed(3)
+    idx = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(B)])
+    out = ops.gather_rows(src.to(dev), idx.to(dev), N)
+    ref = torch.stack([src[b, idx[b]] for b in range(B)])
+    assert torch.equal(out.cpu(), ref)
+    tab = _rand(N, *row, seed=4)                                   # shared table (pos-enc gather)
+    out = ops.gather_rows(tab.to(dev), idx.to(dev), 0)
+    assert torch.equal(out.cpu(), tab[idx])
+
+
+@pytest.mark.parametrize('H,W,C', [(25, 25, 64), (50, 50, 64), (7, 6, 8)])
+def test_pools(dev, H, W, C):
+    from ips_b200 import ops
+    x = _rand(5, C, H, W, seed=5)
+    nhwc = x.permute(0, 2, 3, 1).contiguous()
+    ref = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(ops.maxpool3x3s2(nhwc.to(dev), ops.F32).cpu(), ref)
+    xb = nhwc.to(torch.bfloat16)
+    refb = F.max_pool2d(xb.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(ops.maxpool3x3s2(xb.to(dev), ops.BF16).cpu(), refb)
+    ref = F.adaptive_avg_pool2d(x, 1).flatten(1)
+    torch.testing.assert_close(ops.avgpool(nhwc.to(dev), ops.F32).cpu(), ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ops.avgpool(xb.to(dev), ops.BF16).cpu(),
+                               xb.float().mean(dim=(1, 2)), rtol=1e-5, atol=1e-6)
+
+
+def test_layernorm_rows(dev):
+    from ips_b200 import ops
+    x = _rand(33, 2048, seed=6) * 3 + 0.7
+    ref = F.layer_norm(x, (2048,), eps=1e-5)
+    torch.testing.assert_close(ops.layernorm_rows(x.to(dev), 1e-5).cpu(), ref, rtol=1e-5, atol=1e-5)
+    got = ops.rows_to_bf16(x.to(dev), True, 1e-5).cpu().float()
+    torch.testing.assert_close(got, ref, rtol=8e-3, atol=8e-3)
+    assert torch.equal(ops.rows_to_bf16(x.to(dev), False).cpu(), x.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------ fp32 encoder layers
+
+CONV_CASES = [  # Cin, Cout, k, stride, pad, H, W
+    (4, 64, 7, 2, 3, 50, 50),       # stem on channel-padded input
+    (64, 64, 3, 1, 1, 13, 13),
+    (64, 128, 3, 2, 1, 13, 13),
+    (64, 128, 1, 2, 0, 13, 13),
+    (128, 128, 3, 1, 1, 7, 7),
+    (256, 512, 3, 2, 1, 7, 7),
+]
+
+
+def _conv_ref(x_nhwc, w, scale, shift, res, stride, pad, relu):
+    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), w, stride=stride, padding=pad)
+    y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    y = y.permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_f32(dev, case):
+    from ips_b200 import ops
+    Cin, Cout, k, s, p, H, W = case
+    P = 5
+    x = _rand(P, H, W, Cin, seed=7)
+    w = _rand(Cout, Cin, k, k, seed=8, scale=math.sqrt(2.0 / (Cin * k * k)))
+    scale = torch.rand(Cout) + 0.5
+    shift = _rand(Cout, seed=9, scale=0.1)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = _rand(P, Ho, Wo, Cout, seed=10)
+    w_kc = w.permute(2, 3, 1, 0).reshape(k * k * Cin, Cout).contiguous()
+    for use_res, relu in ((False, True), (True, True), (False, False)):
+        ref = _conv_ref(x, w, scale, shift, res if use_res else None, s, p, relu)
+        got = ops.conv_f32(x.to(dev), w_kc.to(dev), scale.to(dev), shift.to(dev), res.to(dev) if use_res else None,
+                           Cout, k, k, s, p, relu).cpu()
+        torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('M,N,K', [(70, 512, 2048), (5, 10, 128), (300, 64, 512), (129, 130, 132)])
+def test_linear_f32(dev, M, N, K):
+    from ips_b200 import ops
+    a, w = _rand(M, K, seed=11), _rand(N, K, seed=12, scale=1 / math.sqrt(K))
+    scale, shift = torch.rand(N) + 0.5, _rand(N, seed=13)
+    ref = torch.relu((a @ w.t()) * scale + shift)
+    got = ops.linear_f32(a.to(dev), w.to(dev), scale.to(dev), shift.to(dev), relu=True).cpu()
+    torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-5)
+    got = ops.linear_f32(a.to(dev), w.to(dev)).cpu()
+    torch.testing.assert_close(got, a @ w.t(), rtol=2e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------ tcgen05 layers (bf16 in, fp32 accumulate)
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_bf16_umma(dev, case):
+    from ips_b200 import ops
+    Cin, Cout, k, s, p, H, W = case
+    P = 37                                                       # several M tiles + a ragged tail
+    x = _rand(P, H, W, Cin, seed=14).to(torch.bfloat16)
+    w = _rand(Cout, Cin, k, k, seed=15, scale=math.sqrt(2.0 / (Cin * k * k))).to(torch.bfloat16)
+    scale = torch.rand(Cout) + 0.5
+    shift = _rand(Cout, seed=16, scale=0.1)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = _rand(P, Ho, Wo, Cout, seed=17).to(torch.bfloat16)
+    if Cin == 4:
+        wp = torch.zeros(Cout, 8, 8, 4)
+        wp[:, :k, :k] = w.float().permute(0, 2, 3, 1)
+        w_nk, mode = wp.reshape(Cout, 256).to(torch.bfloat16), 1
+    else:
+        w_nk, mode = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous(), 0
+    for use_res, relu in ((False, True), (True, True), (False, False)):
+        ref = _conv_ref(x.float(), w.float(), scale, shift, res.float() if use_res else None, s, p, relu)
+        got = ops.conv_bf16(x.to(dev), w_nk.to(dev), scale.to(dev), shift.to(dev), res.to(dev) if use_res else None,
+                            Cout, k, k, s, p, relu, mode).cpu().float()
+        # exact products, fp32 accumulation; only the bf16 output rounding (2^-8 relative) differs
+        torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2)
+        assert (got - ref).abs().mean() < 4e-3 * ref.abs().mean() + 1e-4
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (70, 512, 2048), (1000, 128, 512), (257, 192, 128)])
+def test_linear_bf16_umma(dev, M, N, K):
+    from ips_b200 import ops
+    a = _rand(M, K, seed=18).to(torch.bfloat16)
+    w = _rand(N, K, seed=19, scale=1 / math.sqrt(K)).to(torch.bfloat16)
+    scale, shift = torch.rand(N) + 0.5, _rand(N, seed=20)
+    ref = torch.relu((a.float() @ w.float().t()) * scale + shift)
+    got = ops.linear_bf16(a.to(dev), w.to(dev), scale.to(dev), shift.to(dev), relu=True).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)    # fp32 output: accumulation order only
+
+
+# ------------------------------------------------------------------ scoring
+
+@pytest.mark.parametrize('pre', ['mnist', 'traffic', 'camelyon'])
+def test_logits_and_scores(dev, pre):
+    """P2: scores vs Transformer.get_scores of the reference (through the oracle)."""
+    from ips_b200 import IPSNet, Struct
+    conf = O.preset(pre, N=64) if pre != 'camelyon' else O.preset(pre)
+    sd = O.make_state(conf, 21, q_gain=12.0)
+    net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+    net.load_state_dict(sd)
+    B, L = 3, 77
+    emb = _rand(B, L, conf.D, seed=22)
+    ref_logits = O.attn_logits(sd, conf, emb)                     # (B,H,T,L)
+    got_logits = net.transf.crs_attn.get_logits(emb.to(dev)).cpu().view(B, L, conf.H, conf.n_token).permute(0, 2, 3, 1)
+    torch.testing.assert_close(got_logits, ref_logits, rtol=1e-4, atol=2e-5)
+    ref = O.attn_scores(sd, conf, emb)
+    got = net.transf.get_scores(emb.to(dev)).cpu()
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=1e-7)
+    torch.testing.assert_close(got.sum(-1), torch.ones(B), rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('H,T,L', [(8, 1, 42), (8, 4, 200), (8, 1, 10000), (3, 2, 130), (1, 1, 33)])
+def test_scores_from_logits(dev, H, T, L):
+    from ips_b200 import ops
+    z = _rand(2, L, H * T, seed=23, scale=2.0)
+    a = torch.softmax(z.view(2, L, H, T).permute(0, 2, 3, 1), dim=-1)      # (B,H,T,L)
+    ref = a.mean(dim=1).transpose(1, 2).mean(-1)
+    got = ops.scores_from_logits(z.to(dev), H, T).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize('L,M', [(42, 10), (200, 100), (10000, 5000), (16384, 5000), (7, 7), (1000, 1)])
+def test_topm_stable(dev, L, M):
+    """P1: exactly the first M of a stable descending sort, including heavy ties."""
+    from ips_b200 import ops
+    g = torch.Generator().manual_seed(24)
+    s = torch.rand(3, L, generator=g)
+    s[1] = (s[1] * 8).floor() / 8                                # 8 distinct values -> many ties
+    s[2] = 0.25                                                  # all tied -> positions 0..M-1
+    val, idx = ops.topm_stable(s.to(dev), M)
+    rv, ri = torch.sort(s, dim=-1, descending=True, stable=True)
+    assert torch.equal(idx.cpu(), ri[:, :M])
+    assert torch.equal(val.cpu(), rv[:, :M])
+
+
+def _loop_reference(z, perm, H, T, M, I):
+    """Python restatement of ips_net.py:213-241 on a logit table, stable tie-break."""
+    B, N, HT = z.shape
+    out_pos, out_src = [], []
+    for b in range(B):
+        order = perm[b] if perm is not None else torch.arange(N)
+        mem = torch.arange(M)
+        for it in range(math.ceil((N - M) / I)):
+            lo = M + it * I
+            hi = min(lo + I, N)
+            cand = torch.cat([mem, torch.arange(lo, hi)])
+            zz = z[b, order[cand]].view(1, -1, H, T).permute(0, 2, 3, 1)
+            sc = torch.softmax(zz, -1).mean(1).transpose(1, 2).mean(-1)[0]
+            top = torch.sort(sc, descending=True, stable=True)[1][:M]
+            mem = cand[top]
+        out_pos.append(mem)
+        out_src.append(order[mem])
+    return torch.stack(out_pos), torch.stack(out_src)
+
+
+@pytest.mark.parametrize('N,M,I,H,T', [(192, 10, 32, 8, 1), (900, 100, 100, 8, 4), (3000, 500, 500, 8, 1),
+                                       (50, 49, 7, 2, 2), (23000, 5000, 5000, 8, 1)])
+@pytest.mark.parametrize('shuffle', ['none', 'batch', 'instance'])
+def test_select_loop(dev, N, M, I, H, T, shuffle):
+    from ips_b200 import ops
+    B = 2
+    z = _rand(B, N, H * T, seed=25, scale=1.5)
+    g = torch.Generator().manual_seed(26)
+    perm, per_inst = None, False
+    if shuffle == 'batch':
+        perm = torch.randperm(N, generator=g).unsqueeze(0)
+    elif shuffle == 'instance':
+        perm, per_inst = torch.stack([torch.randperm(N, generator=g) for _ in range(B)]), True
+    pos, src, score = ops.select_loop(z.to(dev), None if perm is None else perm.to(dev), per_inst, H, T, M, I)
+    ref_pos, ref_src = _loop_reference(z, None if perm is None else perm.expand(B, -1), H, T, M, I)
+    mism = (src.cpu() != ref_src).sum().item()
+    # fp32 softmax on the GPU vs CPU differs in the last ulp: allow order swaps only between
+    # candidates whose final scores are within 1e-6 relative
+    if mism:
+        assert torch.equal(src.cpu().sort(-1)[0], ref_src.sort(-1)[0]), f'{mism} different picks'
+    else:
+        assert torch.equal(pos.cpu(), ref_pos)
+    sc = score.cpu()
+    assert (sc[:, :-1] >= sc[:, 1:]).all()                        # best first

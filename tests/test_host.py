@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the drop-in
+module keeps the reference's surface, and the grad-mode forward reproduces the golden
+train step.  No kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ips_oracle as O
+from golden_util import CASE_NAMES, load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ips_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'ips_b200.h')).read()
+    declared = set(re.findall(r'IPSB_API\s+[\w\s\*]+?\b(ipsb_\w+)\s*\(', header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ipsb_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    from ips_b200 import IPSNet, Struct, ops
+    conf = O.preset('camelyon', M=4, I=4)
+    net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    with pytest.raises(RuntimeError):
+        net.ips(torch.randn(1, 16, 2048))
+    with pytest.raises(RuntimeError):
+        ops.topm_stable(torch.rand(2, 8), 3)
+
+
+@pytest.mark.parametrize('pre', ['mnist', 'traffic', 'camelyon'])
+def test_state_dict_surface(pre):
+    from ips_b200 import IPSNet, Struct
+    conf = O.preset(pre)
+    net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    want = O.param_shapes(conf)
+    got = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    assert got == [(k, tuple(s)) for k, s in want]
+    assert ('pos_enc' not in net.state_dict())
+    assert (net.pos_enc is None) == (not conf.use_pos)
+    for attr in ('M', 'I', 'D', 'encoder', 'transf', 'score_and_select', 'ips', 'output_layers'):
+        assert hasattr(net, attr)
+
+
+def test_camelyon_config_needs_no_image_keys():
+    from ips_b200 import IPSNet, Struct
+    conf = O.preset('camelyon')
+    for k in ('N', 'n_res_blocks', 'patch_size', 'patch_stride'):
+        assert not hasattr(conf, k)
+    IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+
+
+def test_shortcut_when_memory_covers_all_patches():
+    from ips_b200 import IPSNet, Struct
+    z, meta, conf, sd, patches = load_case('camelyon_shortcut')
+    net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    mem_patch, mem_pos = net.ips(patches)
+    assert torch.equal(mem_patch, patches) and mem_pos is None
+
+
+def test_scan_order_consumes_rng_like_reference():
+    from ips_b200.utils import scan_order
+    torch.manual_seed(9)
+    perm, per = scan_order(True, 'batch', 4, 50, torch.device('cpu'))
+    torch.manual_seed(9)
+    assert torch.equal(perm[0], torch.randperm(50)) and not per
+    torch.manual_seed(9)
+    perm, per = scan_order(True, 'instance', 4, 50, torch.device('cpu'))
+    torch.manual_seed(9)
+    assert torch.equal(perm, torch.rand(4, 50).argsort(1)) and per
+    assert scan_order(False, 'batch', 4, 50, torch.device('cpu')) == (None, False)
+
+
+@pytest.mark.parametrize('name', [n for n in CASE_NAMES if 'shortcut' not in n])
+def test_grad_mode_forward_matches_golden(name):
+    """IPSNet.forward + the reference's loss on the golden selection (train-mode BN, dropout 0)."""
+    from ips_b200 import IPSNet, Struct
+    z, meta, conf, sd, patches = load_case(name)
+    net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    net.load_state_dict(sd)
+    net.train()
+    torch.manual_seed(meta['rng_seed'])
+    mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+    preds = net(mem_patch, mem_pos)
+    loss = O.loss_fn(conf, preds, O.make_labels(conf, meta['B'], meta['label_seed']))
+    loss.backward()
+    assert abs(loss.item() - float(z['loss'])) <= 1e-5 * max(1.0, abs(float(z['loss'])))
+    g = net.transf.crs_attn.q.grad.reshape(-1)[:256].numpy()
+    np.testing.assert_allclose(g, z['grad_transf.crs_attn.q'], rtol=1e-3, atol=1e-7)
