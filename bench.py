@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the IPS selection hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload traffic|mnist|mnist5000|camelyon]
+                    [--precision bf16|fp32] [--impl ours|reference]
+
+One "step" = one ``IPSNet.ips`` call over one batch of synthetic patches
+(``conf.B`` images x N patches); metric = patches scanned per second.  For N>1 GPUs
+(launched with torch.distributed.run) every rank scans its own batch (weak scaling, no
+data-path collective); the time is the max over ranks.  Rank 0 prints ONE JSON line.
+
+``--impl reference`` times the reference algorithm on the host CPU (the oracle port:
+the same ATen CPU operators the reference's modules dispatch to) on a bounded sample of
+the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, overrides, B, N)        -- BASELINE.json configs[1], [0], [2], [3]
+    'traffic': ('traffic', {}, 16, 192),
+    'mnist': ('mnist', {}, 16, 900),
+    'mnist5000': ('mnist', {'N': 10000}, 2, 10000),
+    'camelyon': ('camelyon', {}, 1, 50000),
+}
+# algorithmic work per scanned patch, SURVEY.md section 8(d)
+ALG = {
+    'traffic': dict(flop=883.06e6, bytes=120000),
+    'mnist': dict(flop=105.17e6, bytes=10000),
+    'mnist5000': dict(flop=105.17e6, bytes=10000),
+    'camelyon': dict(flop=2.6225e6, bytes=8192),
+}
+
+
+def conf_for(workload, precision):
+    from ips_b200.configs import load_config
+    pre, over, B, N = WORKLOADS[workload]
+    conf = load_config(pre, precision=precision, **over)
+    conf.B = B
+    return conf, B, N
+
+
+def patch_shape(conf, B, N):
+    return (B, N, conf.n_chan_in, *conf.patch_size) if conf.is_image else (B, N, conf.n_chan_in)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {'hw_slowdown': 'nvmlClocksThrottleReasonHwSlowdown',
+                 'hw_thermal_slowdown': 'nvmlClocksThrottleReasonHwThermalSlowdown',
+                 'sw_thermal_slowdown': 'nvmlClocksThrottleReasonSwThermalSlowdown',
+                 'sw_power_cap': 'nvmlClocksThrottleReasonSwPowerCap'}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, attr in names.items():
+                    if mask & getattr(nv, attr, 0):
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return None
+        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle)
+def cpu_reference_rate(workload, sample_images, repeats):
+    """Reference algorithm on the host cores; returns (patches/s, cores, sample description)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ips_oracle as O
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    pre, over, B, N = WORKLOADS[workload]
+    conf = O.preset(pre, **over)
+    if workload in ('mnist5000', 'camelyon'):
+        sample_images = 1
+        N = min(N, 20000 if workload == 'camelyon' else 2000)
+        if conf.use_pos:
+            conf.N = N
+    Bs = min(B, sample_images)
+    sd = O.make_state(conf, 0, q_gain=12.0)
+    x = O.make_patches(conf, Bs, N, 1)
+    times = []
+    O.ips(sd, conf, x[:, :max(conf.M + conf.I, N // 4)], perm='draw')            # warm-up on a slice
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.ips(sd, conf, x, perm='draw')
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return Bs * N / t, cores, f'{Bs} image(s) x {N} patches, {repeats} calls, median; fp32 ATen CPU ops, {cores} threads'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t_start = time.perf_counter()
+    rate, cores, sample = cpu_reference_rate(args.workload, sample_images=2, repeats=max(1, min(args.steps, 3)))
+    conf, B, N = conf_for(args.workload, 'fp32')
+    line = {
+        'impl': 'reference', 'metric': 'ips_selection_patches_per_sec', 'value': rate, 'unit': 'patches/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * B * N / rate, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: IPSNet.ips, B={B} N={N} M={conf.M} I={conf.I}', 'l2': 'n/a (CPU)'},
+        'cpu_baseline': {'value': rate, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': time.perf_counter() - t_start,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ips_b200 import IPSNet, Struct, ops
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    conf, B, N = conf_for(args.workload, args.precision)
+    torch.manual_seed(1234 + rank)
+    net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+    net.train()
+    with torch.no_grad():
+        net.transf.crs_attn.q.mul_(12.0)           # conditioned logits; does not change the work
+    shape = patch_shape(conf, B, N)
+    x = torch.randn(shape, device=dev)             # inputs resident in HBM (eager mode)
+    in_bytes = x.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident throughput ------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        net.ips(x)
+    launches0 = ops.LAUNCHES
+    with ClockSampler(local) as clk:
+        ms = timed(lambda: net.ips(x), args.steps)
+    launches = ops.LAUNCHES - launches0
+    value = world * B * N * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers ---------------------
+    xh = x.cpu().pin_memory()
+    res_h = torch.empty((B, conf.M, *shape[2:]), dtype=torch.float32).pin_memory()
+    idx_h = torch.empty((B, conf.M), dtype=torch.int64).pin_memory()
+    xd = torch.empty_like(x)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)            # H2D of this step's patches (pinned)
+        mem_patch, _ = net.ips(xd)
+        res_h.copy_(mem_patch, non_blocking=True)  # D2H of the step's result
+        idx_h.copy_(net.last_mem_idx, non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    ms_e2e = timed(e2e_step, e2e_steps)
+    e2e_value = world * B * N * e2e_steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family (per-launch CUDA events, same work) ---
+    roof = None
+    if rank == 0:
+        ops.TIMER = {}
+        net.ips(x)
+        net.ips(x)
+        torch.cuda.synchronize()
+        per = {k: sum(a.elapsed_time(b) for a, b, _ in v) / 2 for k, v in ops.TIMER.items()}   # ms per step
+        counts = {k: len(v) // 2 for k, v in ops.TIMER.items()}
+        ops.TIMER = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        dom = max(per, key=per.get)
+        alg = ALG[args.workload]
+        if dom in ('ipsb_conv_bf16_umma', 'ipsb_linear_bf16_umma', 'ipsb_conv_f32', 'ipsb_linear_f32'):
+            peak = peaks.get('bf16_tflops_sustained', 1400.0)
+            enc_flop = alg['flop'] * B * N
+            achieved = enc_flop / (per[dom] / 1e3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': achieved / peak, 'traffic': None,
+                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s',
+                    'launches_per_step': counts[dom], 'kernel_ms_per_step': per[dom],
+                    'algorithmic_flop_per_patch': alg['flop']}
+        else:
+            peak = peaks.get('hbm_gbs', 6650.0)
+            achieved = alg['bytes'] * B * N / (per[dom] / 1e3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': None,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
+                    'launches_per_step': counts[dom], 'kernel_ms_per_step': per[dom]}
+        roof['kernel_ms_all'] = {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+
+    # ---- CPU baseline on rank 0 at N=1 -------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, cores, sample = cpu_reference_rate(args.workload, sample_images=2, repeats=3)
+        cpu = {'value': rate, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        line = {
+            'metric': 'ips_selection_patches_per_sec', 'value': value, 'unit': 'patches/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: IPSNet.ips, B={B} N={N} M={conf.M} I={conf.I} per GPU',
+                       'precision': args.precision, 'parallelism': f'dp{world} (independent batches, no collective)',
+                       'l2': f'input {in_bytes / 2**20:.0f} MiB per step > 126 MB L2, no flush needed'},
+            'clocks': clk.summary(),
+            'e2e': {'value': e2e_value, 'unit': 'patches/s', 'h2d_bytes_per_step': in_bytes,
+                    'd2h_bytes_per_step': res_h.numel() * 4 + idx_h.numel() * 8, 'ms_per_step': ms_e2e / e2e_steps},
+            'gpu_launches': launches,
+            'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='traffic', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -26,7 +26,7 @@ __global__ void stage_kernel(const float* __restrict__ src, const int64_t* __res
         const int px = (int)(i - r * HW);
         const int64_t srow = row_idx ? row_idx[r] : first_row + r;
         const float* s = src + srow * (int64_t)C * HW + px;
-        T out[CPAD];
+        __align__(16) T out[CPAD];
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) out[c] = from_f32<T>(c < C ? __ldg(s + (int64_t)c * HW) : 0.f);
         T* d = dst + i * CPAD;
@@ -102,13 +102,13 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64
                 const int ix = ox * 2 - 1 + dx;
                 if (ix < 0 || ix >= W) continue;
                 const T* s = x + ((p * H + iy) * W + ix) * (int64_t)C + c0;
-                T v[VEC];
+                __align__(16) T v[VEC];
                 *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(s);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) m[k] = fmaxf(m[k], to_f32<T>(v[k]));
             }
         }
-        T o[VEC];
+        __align__(16) T o[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) o[k] = from_f32<T>(m[k]);
         *reinterpret_cast<uint4*>(y + ((p * Ho + oy) * Wo + ox) * (int64_t)C + c0) = *reinterpret_cast<const uint4*>(o);

@@ -41,7 +41,7 @@ template <typename T> struct OutStore;
 template <> struct OutStore<bf16> {
     // 8 consecutive channels
     static __device__ __forceinline__ void store8(void* base, int64_t off, const float (&v)[8]) {
-        __nv_bfloat162 h[4];
+        __align__(16) __nv_bfloat162 h[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off) = *reinterpret_cast<const uint4*>(h);

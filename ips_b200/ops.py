@@ -12,8 +12,28 @@ from . import _lib
 F32, BF16 = 0, 1
 
 
+LAUNCHES = 0          # kernels launched through the C ABI by this process (bench.py reports it)
+TIMER = None          # optional {kernel name: [(start_event, end_event, tag)]} filled when set to a dict
+TAG = None            # free-form tag attached to timed launches (e.g. layer name + algorithmic FLOPs)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    """One C-ABI call = one kernel launch on the current stream."""
+    global LAUNCHES
+    fn = getattr(_lib.load(), name)
+    LAUNCHES += 1
+    if TIMER is None:
+        _lib.check(fn(*args))
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args))
+    e1.record()
+    TIMER.setdefault(name, []).append((e0, e1, TAG))
 
 
 def _p(t):
@@ -42,8 +62,8 @@ def stage_patches(src, n_rows, C, H, W, dt, row_idx=None, first_row=0, cpad=4):
     _chk(src, torch.float32, 'src')
     _chk(row_idx, torch.int64, 'row_idx')
     out = torch.empty((n_rows, H, W, cpad), dtype=_dt(dt), device=src.device)
-    _lib.check(_lib.load().ipsb_stage_patches(_p(src), _p(row_idx), first_row, n_rows, C, H, W, cpad, dt,
-                                              _p(out), _stream()))
+    _call('ipsb_stage_patches', _p(src), _p(row_idx), first_row, n_rows, C, H, W, cpad, dt,
+                                              _p(out), _stream())
     return out
 
 
@@ -58,7 +78,7 @@ def gather_rows(src, idx, batch_stride_rows):
     for s in row_shape:
         row_bytes *= s
     out = torch.empty((B, M, *row_shape), dtype=src.dtype, device=src.device)
-    _lib.check(_lib.load().ipsb_gather_rows(_p(src), batch_stride_rows, _p(idx), B, M, row_bytes, _p(out), _stream()))
+    _call('ipsb_gather_rows', _p(src), batch_stride_rows, _p(idx), B, M, row_bytes, _p(out), _stream())
     return out
 
 
@@ -67,7 +87,7 @@ def maxpool3x3s2(x, dt):
     _chk(x, _dt(dt), 'x')
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((P, Ho, Wo, C), dtype=x.dtype, device=x.device)
-    _lib.check(_lib.load().ipsb_maxpool3x3s2(_p(x), _p(y), P, H, W, C, dt, _stream()))
+    _call('ipsb_maxpool3x3s2', _p(x), _p(y), P, H, W, C, dt, _stream())
     return y
 
 
@@ -75,21 +95,21 @@ def avgpool(x, dt):
     P, H, W, C = x.shape
     _chk(x, _dt(dt), 'x')
     y = torch.empty((P, C), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().ipsb_avgpool(_p(x), _p(y), P, H * W, C, dt, _stream()))
+    _call('ipsb_avgpool', _p(x), _p(y), P, H * W, C, dt, _stream())
     return y
 
 
 def layernorm_rows(x, eps):
     _chk(x, torch.float32, 'x')
     y = torch.empty_like(x)
-    _lib.check(_lib.load().ipsb_layernorm_rows_f32(_p(x), _p(y), x.shape[0], x.shape[1], eps, _stream()))
+    _call('ipsb_layernorm_rows_f32', _p(x), _p(y), x.shape[0], x.shape[1], eps, _stream())
     return y
 
 
 def rows_to_bf16(x, layernorm, eps=1e-5):
     _chk(x, torch.float32, 'x')
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.load().ipsb_rows_to_bf16(_p(x), _p(y), x.shape[0], x.shape[1], int(layernorm), eps, _stream()))
+    _call('ipsb_rows_to_bf16', _p(x), _p(y), x.shape[0], x.shape[1], int(layernorm), eps, _stream())
     return y
 
 
@@ -101,8 +121,8 @@ def conv_f32(x, w_kc, scale, shift, res, Cout, kh, kw, stride, pad, relu):
     P, H, W, Cin = x.shape
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     y = torch.empty((P, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().ipsb_conv_f32(_p(x), _p(w_kc), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin, Cout,
-                                         kh, kw, stride, pad, int(relu), _stream()))
+    _call('ipsb_conv_f32', _p(x), _p(w_kc), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin, Cout,
+                                         kh, kw, stride, pad, int(relu), _stream())
     return y
 
 
@@ -112,8 +132,8 @@ def conv_bf16(x, w_nk, scale, shift, res, Cout, kh, kw, stride, pad, relu, mode=
     P, H, W, Cin = x.shape
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     y = torch.empty((P, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.load().ipsb_conv_bf16_umma(_p(x), _p(w_nk), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin,
-                                               Cout, kh, kw, stride, pad, int(relu), mode, _stream()))
+    _call('ipsb_conv_bf16_umma', _p(x), _p(w_nk), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin,
+                                               Cout, kh, kw, stride, pad, int(relu), mode, _stream())
     return y
 
 
@@ -123,7 +143,7 @@ def linear_f32(a, w, scale=None, shift=None, relu=False):
     M, K = a.shape
     N = w.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    _lib.check(_lib.load().ipsb_linear_f32(_p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream()))
+    _call('ipsb_linear_f32', _p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream())
     return y
 
 
@@ -133,7 +153,7 @@ def linear_bf16(a, w, scale=None, shift=None, relu=False):
     M, K = a.shape
     N = w.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    _lib.check(_lib.load().ipsb_linear_bf16_umma(_p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream()))
+    _call('ipsb_linear_bf16_umma', _p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream())
     return y
 
 
@@ -144,7 +164,7 @@ def score_basis(q_tok, q_w, k_w, H, Dk):
     _chk(q_tok, torch.float32, 'q'); _chk(q_w, torch.float32, 'q_w'); _chk(k_w, torch.float32, 'k_w')
     T, D = q_tok.shape[-2], q_tok.shape[-1]
     U = torch.empty((D, H * T), dtype=torch.float32, device=q_tok.device)
-    _lib.check(_lib.load().ipsb_score_basis(_p(q_tok), _p(q_w), _p(k_w), _p(U), D, H, Dk, T, _stream()))
+    _call('ipsb_score_basis', _p(q_tok), _p(q_w), _p(k_w), _p(U), D, H, Dk, T, _stream())
     return U
 
 
@@ -155,7 +175,7 @@ def logits(emb, U, add_tab=None, add_idx=None):
     rows, D = emb.shape
     HT = U.shape[1]
     z = torch.empty((rows, HT), dtype=torch.float32, device=emb.device)
-    _lib.check(_lib.load().ipsb_logits(_p(emb), _p(U), _p(add_tab), _p(add_idx), _p(z), rows, D, HT, _stream()))
+    _call('ipsb_logits', _p(emb), _p(U), _p(add_tab), _p(add_idx), _p(z), rows, D, HT, _stream())
     return z
 
 
@@ -164,7 +184,7 @@ def scores_from_logits(z, H, T):
     _chk(z, torch.float32, 'z')
     B, L = z.shape[:2]
     s = torch.empty((B, L), dtype=torch.float32, device=z.device)
-    _lib.check(_lib.load().ipsb_scores_from_logits(_p(z), _p(s), B, L, H, T, _stream()))
+    _call('ipsb_scores_from_logits', _p(z), _p(s), B, L, H, T, _stream())
     return s
 
 
@@ -174,7 +194,7 @@ def topm_stable(scores, M):
     B, L = scores.shape
     idx = torch.empty((B, M), dtype=torch.int64, device=scores.device)
     val = torch.empty((B, M), dtype=torch.float32, device=scores.device)
-    _lib.check(_lib.load().ipsb_topm_stable(_p(scores), B, L, M, _p(idx), _p(val), _stream()))
+    _call('ipsb_topm_stable', _p(scores), B, L, M, _p(idx), _p(val), _stream())
     return val, idx
 
 
@@ -186,8 +206,8 @@ def select_loop(z, perm, per_instance, H, T, M, I):
     mem_pos = torch.empty((B, M), dtype=torch.int64, device=dev)
     mem_src = torch.empty((B, M), dtype=torch.int64, device=dev)
     score = torch.empty((B, M), dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().ipsb_select_loop(_p(z), _p(perm), N if (perm is not None and per_instance) else 0,
-                                            B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score), _stream()))
+    _call('ipsb_select_loop', _p(z), _p(perm), N if (perm is not None and per_instance) else 0,
+                                            B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score), _stream())
     return mem_pos, mem_src, score
 
 
