@@ -48,6 +48,10 @@ IPSB_API int ipsb_device_ok(void);
  * channels C..Cpad-1.  row_idx == NULL means rows first_row .. first_row+n_rows-1. */
 IPSB_API int ipsb_stage_patches(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
                        int C, int H, int W, int Cpad, int dt, void* dst, void* stream);
+/* Same gather into a zero-bordered bf16 frame (n_rows, Hp, Wp, 4) with the image at (pad_top, pad_left):
+ * the input format of the TMA-fed stem (mode 3 of ipsb_conv_bf16_umma: pad_top 3, pad_left 4, Hp=H+6, Wp=W+6). */
+IPSB_API int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
+                              int C, int H, int W, int pad_top, int pad_left, int Hp, int Wp, void* dst, void* stream);
 
 /* ---------------------------------------------------------------- encoder, fp32 SIMT ("exact" mode)
  * Replaces: conv2d + eval-mode batch_norm [+ residual add] [+ relu] of the
@@ -69,8 +73,10 @@ IPSB_API int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int
 
 /* ---------------------------------------------------------------- encoder, bf16 tcgen05 implicit GEMM
  * Same contract as ipsb_conv_f32 with x,res,y bf16 NHWC and w (Cout, K) bf16
- * K-major, K = kh*kw*Cin padded to a multiple of 64.  mode 0: Cin % 64 == 0;
- * mode 1: the 7x7/2 stem on 4-channel-padded input (K laid out r*32+s*4+c, 256). */
+ * K-major, K = kh*kw*Cin padded to a multiple of 64.  mode 0: Cin % 64 == 0, TMA-fed
+ * (M tile = box of output pixels); mode 2: same contract through a cp.async gather;
+ * mode 3: the stem on the zero-bordered frame of ipsb_stage_patches_padded (H, W = frame size), TMA-fed;
+ * mode 1: the 7x7/2 stem on 4-channel-padded input (K laid out r*32+(s+1)*4+c, 256). */
 IPSB_API int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const float* shift,
                         const void* res, void* y, int64_t P, int H, int W, int Cin, int Cout,
                         int kh, int kw, int stride, int pad, int relu, int mode, void* stream);
@@ -106,6 +112,40 @@ IPSB_API int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t*
 IPSB_API int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_stride,
                      int B, int N, int H, int T, int M, int I,
                      int64_t* mem_pos, int64_t* mem_src, float* mem_score, void* stream);
+
+/* ---------------------------------------------------------------- native encoder executor
+ * One call = the whole eval-mode patch encoder + logit projection for `n_rows` patches
+ * (everything ips_net.py:209/227 + transformer.py:76-79 do per chunk), chunked internally
+ * so activations stay L2-sized.  Issues every launch on `stream`; no host synchronisation. */
+typedef struct {
+    const void* w;        /* bf16 (Cout,Kpad) K-major, or fp32 (K,Cout) in IPSB_F32 mode */
+    const float* scale;   /* folded BatchNorm */
+    const float* shift;
+    int32_t cin, cout, kh, kw, stride, pad, mode, _pad;
+} ipsb_conv_desc;
+
+typedef struct {
+    ipsb_conv_desc c1, c2, ds;
+    int32_t has_ds, _pad;
+} ipsb_block_desc;
+
+typedef struct {
+    int32_t dt;           /* IPSB_BF16 or IPSB_F32 */
+    int32_t n_blocks;     /* BasicBlocks after the stem + maxpool (4 or 8) */
+    ipsb_conv_desc stem;  /* 7x7/2 on 4-channel-padded input */
+    ipsb_block_desc blocks[8];
+    int32_t D, HT;        /* embedding width, H*T */
+    const float* U;       /* (D, HT) score basis */
+    const float* add_tab; /* (N, HT) positional contribution or NULL */
+} ipsb_resnet_desc;
+
+/* bytes of scratch needed for chunks of `chunk` patches of (C,H,W) */
+IPSB_API int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W);
+/* patches: (rows,C,H,W) fp32 NCHW on the device; row r reads patch first_row + r; add_tab row = (first_row + r) % n_per_image.
+ * emb_out (n_rows, D) fp32 may be NULL; z_out (n_rows, HT) fp32. */
+IPSB_API int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
+                                int C, int H, int W, int64_t n_per_image, int64_t chunk,
+                                void* workspace, int64_t workspace_bytes, float* emb_out, float* z_out, void* stream);
 
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the

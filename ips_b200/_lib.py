@@ -12,12 +12,33 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libips_b200.so')
 
 _i32, _i64, _f32, _ptr = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
+
+
+class ConvDesc(ctypes.Structure):
+    """ipsb_conv_desc"""
+    _fields_ = [('w', _ptr), ('scale', _ptr), ('shift', _ptr),
+                ('cin', ctypes.c_int32), ('cout', ctypes.c_int32), ('kh', ctypes.c_int32), ('kw', ctypes.c_int32),
+                ('stride', ctypes.c_int32), ('pad', ctypes.c_int32), ('mode', ctypes.c_int32), ('_pad', ctypes.c_int32)]
+
+
+class BlockDesc(ctypes.Structure):
+    """ipsb_block_desc"""
+    _fields_ = [('c1', ConvDesc), ('c2', ConvDesc), ('ds', ConvDesc), ('has_ds', ctypes.c_int32), ('_pad', ctypes.c_int32)]
+
+
+class ResnetDesc(ctypes.Structure):
+    """ipsb_resnet_desc"""
+    _fields_ = [('dt', ctypes.c_int32), ('n_blocks', ctypes.c_int32), ('stem', ConvDesc), ('blocks', BlockDesc * 8),
+                ('D', ctypes.c_int32), ('HT', ctypes.c_int32), ('U', _ptr), ('add_tab', _ptr)]
+
+
 # name -> argtypes (restype is int status unless listed in _RESTYPE)
 SIGNATURES = {
     'ipsb_abi_version': [],
     'ipsb_last_error': [],
     'ipsb_device_ok': [],
     'ipsb_stage_patches': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
+    'ipsb_stage_patches_padded': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_conv_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_linear_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_maxpool3x3s2': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr],
@@ -32,8 +53,11 @@ SIGNATURES = {
     'ipsb_topm_stable': [_ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr],
     'ipsb_select_loop': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
+    'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
+    'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64,
+                           _ptr, _ptr, _ptr],
 }
-_RESTYPE = {'ipsb_last_error': ctypes.c_char_p}
+_RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64}
 
 _lib = None
 

@@ -34,6 +34,13 @@ int fail(const char* fmt, ...);
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int sm_count();
 
+// TMA-fed tcgen05 implicit GEMM (umma_conv_tma.cu)
+int conv_tma(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
+             int64_t P, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
+             bool out_f32, cudaStream_t st);
+int conv_stem_tma(const void* x, const void* w, const float* scale, const float* shift, void* y,
+                  int64_t P, int H, int W, int Cout, int relu, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

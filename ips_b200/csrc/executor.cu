@@ -1,0 +1,127 @@
+// Native executor for the eval-mode ResNet patch encoder: issues the whole layer sequence
+// of one chunk (stage -> stem -> maxpool -> BasicBlocks -> avgpool -> logits) from C++, so an
+// ips() call costs one library call instead of ~25 Python round trips per chunk.
+#include "common.cuh"
+#include "../../include/ips_b200.h"
+
+namespace {
+
+struct Geo { int H, W, C; };
+
+inline int out_dim(int x, int k, int s, int p) { return (x + 2 * p - k) / s + 1; }
+inline size_t esize(int dt) { return dt == IPSB_BF16 ? 2 : 4; }
+inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+// largest activation (elements per patch) of each of the three rotating buffers
+int64_t max_act_elems(const ipsb_resnet_desc* net, int H, int W, int64_t* staged_elems) {
+    *staged_elems = (net->stem.mode == 3) ? (int64_t)(H + 6) * (W + 6) * 4 : (int64_t)H * W * 4;
+    int h = out_dim(H, 7, 2, 3), w = out_dim(W, 7, 2, 3);
+    int64_t mx = (int64_t)h * w * net->stem.cout;
+    h = out_dim(h, 3, 2, 1); w = out_dim(w, 3, 2, 1);
+    for (int b = 0; b < net->n_blocks; ++b) {
+        const ipsb_conv_desc& c1 = net->blocks[b].c1;
+        h = out_dim(h, c1.kh, c1.stride, c1.pad); w = out_dim(w, c1.kw, c1.stride, c1.pad);
+        const int64_t e = (int64_t)h * w * c1.cout;
+        if (e > mx) mx = e;
+    }
+    return mx;
+}
+
+int run_conv(const ipsb_resnet_desc* net, const ipsb_conv_desc& c, const void* x, const void* res, void* y,
+             int64_t P, int H, int W, int relu, void* stream) {
+    if (net->dt == IPSB_BF16)
+        return ipsb_conv_bf16_umma(x, c.w, c.scale, c.shift, res, y, P, H, W, c.cin, c.cout, c.kh, c.kw, c.stride,
+                                   c.pad, relu, c.mode, stream);
+    return ipsb_conv_f32((const float*)x, (const float*)c.w, c.scale, c.shift, (const float*)res, (float*)y, P, H, W,
+                         c.cin, c.cout, c.kh, c.kw, c.stride, c.pad, relu, stream);
+}
+
+__global__ void iota_mod_kernel(int64_t* out, int64_t first, int64_t n, int64_t mod) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (first + i) % mod;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W) {
+    (void)C;
+    int64_t staged;
+    const int64_t act = max_act_elems(net, H, W, &staged);
+    const int64_t es = (int64_t)esize(net->dt);
+    return align256(chunk * staged * es) + 4 * align256(chunk * act * es) + align256(chunk * net->D * 4) +
+           align256(chunk * 8) + 1024;
+}
+
+int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
+                       int C, int H, int W, int64_t n_per_image, int64_t chunk,
+                       void* workspace, int64_t workspace_bytes, float* emb_out, float* z_out, void* stream) {
+    IPSB_REQUIRE(net && patches && z_out && workspace, "resnet_logits: null argument");
+    IPSB_REQUIRE(n_rows > 0 && chunk > 0 && net->n_blocks > 0 && net->n_blocks <= 8, "resnet_logits: bad sizes");
+    IPSB_REQUIRE(workspace_bytes >= ipsb_resnet_workspace_bytes(net, chunk, C, H, W), "resnet_logits: workspace too small");
+    const int dt = net->dt;
+    const int64_t es = (int64_t)esize(dt);
+    int64_t staged_elems;
+    const int64_t act = max_act_elems(net, H, W, &staged_elems);
+    char* ws = (char*)workspace;
+    void* staged = ws;                       ws += align256(chunk * staged_elems * es);
+    void* buf[4];
+    for (int i = 0; i < 4; ++i) { buf[i] = ws; ws += align256(chunk * act * es); }
+    float* emb_ws = (float*)ws;               ws += align256(chunk * net->D * 4);
+    int64_t* pos_idx = (int64_t*)ws;
+
+    for (int64_t lo = 0; lo < n_rows; lo += chunk) {
+        const int64_t P = (n_rows - lo < chunk) ? n_rows - lo : chunk;
+        int rc;
+        int h = out_dim(H, 7, 2, 3), w = out_dim(W, 7, 2, 3);
+        if (net->stem.mode == 3) {           // zero-bordered frame for the TMA-fed stem
+            rc = ipsb_stage_patches_padded(patches, nullptr, first_row + lo, P, C, H, W, 3, 4, H + 6, W + 6, staged, stream);
+            if (rc) return rc;
+            rc = run_conv(net, net->stem, staged, nullptr, buf[0], P, H + 6, W + 6, 1, stream);
+        } else {
+            rc = ipsb_stage_patches(patches, nullptr, first_row + lo, P, C, H, W, 4, dt, staged, stream);
+            if (rc) return rc;
+            rc = run_conv(net, net->stem, staged, nullptr, buf[0], P, H, W, 1, stream);
+        }
+        if (rc) return rc;
+        rc = ipsb_maxpool3x3s2(buf[0], buf[1], P, h, w, net->stem.cout, dt, stream);
+        if (rc) return rc;
+        h = out_dim(h, 3, 2, 1); w = out_dim(w, 3, 2, 1);
+        int cur = 1;                          // index of the buffer holding the block input
+        int c_out = net->stem.cout;
+        for (int b = 0; b < net->n_blocks; ++b) {
+            const ipsb_block_desc& blk = net->blocks[b];
+            int free_ids[3], nf = 0;
+            for (int i = 0; i < 4; ++i) if (i != cur) free_ids[nf++] = i;
+            const void* idt = buf[cur];
+            const int ho = out_dim(h, blk.c1.kh, blk.c1.stride, blk.c1.pad), wo = out_dim(w, blk.c1.kw, blk.c1.stride, blk.c1.pad);
+            if (blk.has_ds) {
+                rc = run_conv(net, blk.ds, buf[cur], nullptr, buf[free_ids[0]], P, h, w, 0, stream);
+                if (rc) return rc;
+                idt = buf[free_ids[0]];
+            }
+            rc = run_conv(net, blk.c1, buf[cur], nullptr, buf[free_ids[1]], P, h, w, 1, stream);
+            if (rc) return rc;
+            rc = run_conv(net, blk.c2, buf[free_ids[1]], idt, buf[free_ids[2]], P, ho, wo, 1, stream);
+            if (rc) return rc;
+            cur = free_ids[2];
+            h = ho; w = wo; c_out = blk.c2.cout;
+        }
+        IPSB_REQUIRE(c_out == net->D, "resnet_logits: encoder width %d != D %d", c_out, net->D);
+        float* emb = emb_out ? emb_out + lo * net->D : emb_ws;
+        rc = ipsb_avgpool(buf[cur], emb, P, h * w, c_out, dt, stream);
+        if (rc) return rc;
+        const int64_t* idx = nullptr;
+        if (net->add_tab) {
+            iota_mod_kernel<<<(unsigned)ipsb::ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(pos_idx, first_row + lo, P, n_per_image);
+            IPSB_LAUNCH_CHECK();
+            idx = pos_idx;
+        }
+        rc = ipsb_logits(emb, net->U, net->add_tab, idx, z_out + lo * net->HT, P, net->D, net->HT, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -41,6 +41,31 @@ __global__ void stage_kernel(const float* __restrict__ src, const int64_t* __res
     }
 }
 
+// same, into a zero-bordered (Hp, Wp) frame with the image at (pt, pl): feeds the TMA stem
+template <typename T, int CPAD>
+__global__ void stage_padded_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx,
+                                    int64_t first_row, int64_t n_rows, int C, int H, int W, int Hp, int Wp,
+                                    int pt, int pl, T* __restrict__ dst) {
+    const int64_t total = n_rows * Hp * Wp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / (Hp * Wp);
+        const int rem = (int)(i - r * (Hp * Wp));
+        const int y = rem / Wp - pt, x = rem % Wp - pl;
+        __align__(16) T out[CPAD];
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const int64_t srow = row_idx ? row_idx[r] : first_row + r;
+            const float* s = src + srow * (int64_t)C * H * W + (int64_t)y * W + x;
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) out[c] = from_f32<T>(c < C ? __ldg(s + (int64_t)c * H * W) : 0.f);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) out[c] = from_f32<T>(0.f);
+        }
+        *reinterpret_cast<uint2*>(dst + i * CPAD) = *reinterpret_cast<const uint2*>(out);
+    }
+}
+
 // dst row (b,m) <- src row; grid.x = rows, grid.y = 16 KB segments of a row
 __global__ void gather_rows16_kernel(const unsigned char* __restrict__ src, int64_t batch_stride_rows,
                                      const int64_t* __restrict__ idx, int M, int64_t row_bytes,
@@ -190,6 +215,16 @@ int ipsb_stage_patches(const float* src, const int64_t* row_idx, int64_t first_r
         stage_kernel<float, 4><<<g, 256, 0, st>>>(src, row_idx, first_row, n_rows, C, H * W, (float*)dst);
     else
         return ipsb::fail("stage: unknown dtype %d", dt);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
+                              int C, int H, int W, int pad_top, int pad_left, int Hp, int Wp, void* dst, void* stream) {
+    IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= 4 && Hp >= H + pad_top && Wp >= W + pad_left, "stage_padded: bad shape");
+    const int64_t total = n_rows * Hp * Wp;
+    stage_padded_kernel<bf16, 4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, row_idx, first_row, n_rows, C, H, W, Hp, Wp, pad_top, pad_left, (bf16*)dst);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -83,6 +83,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
+// same for rows of 64 bytes (32 bf16): 8-row atoms of 512 bytes, SWIZZLE_64B (4)
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -126,6 +132,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+// named barrier among a subset of warps (id 1..15)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

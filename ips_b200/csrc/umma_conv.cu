@@ -56,7 +56,8 @@ template <> struct OutStore<float> {
 };
 
 // MODE 0: Cin % 64 == 0, one stage = one filter tap x 64 channels
-// MODE 1: 7x7 stride-2 stem on 4-channel input, one stage = two filter rows x 8 taps x 4 ch
+// MODE 1: 7x7 stride-2 stem on 4-channel input, one stage = two filter rows x 8 taps x 4 ch;
+//         the 8 taps are columns ix0-1 .. ix0+6 (k = r*32 + (s+1)*4 + c) so every 16-byte chunk is aligned
 template <int BN, int STAGES, int MODE, typename OutT>
 __global__ void __launch_bounds__(160)
 conv_umma_kernel(const ConvParams p) {
@@ -94,60 +95,68 @@ conv_umma_kernel(const ConvParams p) {
 
     if (warp < 4) {
         // ------------------------------------------------------------ producer
-        const int64_t m = m0 + tid;
-        const bool valid = m < p.M;
-        int oy = 0, ox = 0;
-        int64_t pimg = 0;
-        if (valid) {
-            const int hw = p.Ho * p.Wo;
-            pimg = m / hw;
-            const int rem = (int)(m - pimg * hw);
-            oy = rem / p.Wo;
-            ox = rem - oy * p.Wo;
+        // Lane l owns the 16-byte chunk j = l & 7 of eight tile rows (warp*32 + i*4 + (l >> 3)):
+        // eight consecutive lanes fetch one full 128-byte line, four lines per instruction.
+        const uint32_t j = (uint32_t)(lane & 7);
+        const int rsub = lane >> 3;
+        const int cin8 = p.Cin >> 3;                       // 16-byte chunks per input pixel (mode 0)
+        uint32_t img_chunk[8];                             // chunk offset of the row's patch image
+        int iy0[8], ix0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t mr = m0 + warp * 32 + i * 4 + rsub;
+            if (mr < p.M) {
+                const int hw = p.Ho * p.Wo;
+                const int64_t pimg = mr / hw;
+                const int rem = (int)(mr - pimg * hw);
+                const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+                iy0[i] = oy * p.stride - p.pad;
+                ix0[i] = ox * p.stride - p.pad - (MODE == 1 ? 1 : 0);   // stem: taps shifted by one, 8th tap first
+                img_chunk[i] = (uint32_t)(pimg * (int64_t)p.H * p.W * (MODE == 0 ? cin8 : 1) / (MODE == 0 ? 1 : 2));
+            } else {
+                iy0[i] = -(1 << 28);                       // never in bounds -> zero fill
+                ix0[i] = 0;
+                img_chunk[i] = 0;
+            }
         }
-        const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-        const bf16* ximg = p.x + pimg * (int64_t)p.H * p.W * p.Cin;
-        const uint32_t sw = (uint32_t)(tid & 7);
         const int cblocks = (MODE == 0) ? p.Cin / BK : 1;
+        const uint4* xq = reinterpret_cast<const uint4*>(p.x);
+        const uint4* wq = reinterpret_cast<const uint4*>(p.w);
+        const uint32_t kp8 = (uint32_t)(p.Kp >> 3);
 
         for (int ks = 0; ks < KS; ++ks) {
             const int stage = ks % STAGES, use = ks / STAGES;
             umma::mbar_wait(empty_bar(stage), (use & 1) ^ 1);
-            const uint32_t a_row = smem0 + stage * STAGE_BYTES + (uint32_t)tid * 128u;
+            const uint32_t a_base = smem0 + stage * STAGE_BYTES;
+            int r, s_or_q, cb = 0;
             if (MODE == 0) {
-                const int tap = ks / cblocks, cb = ks - tap * cblocks;
-                const int r = tap / p.kw, s = tap - r * p.kw;
-                const int iy = iy0 + r, ix = ix0 + s;
-                const bool ok = valid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                const bf16* src = ok ? ximg + ((int64_t)iy * p.W + ix) * p.Cin + cb * BK : p.x;
-                const uint32_t nbytes = ok ? 16u : 0u;
-#pragma unroll
-                for (uint32_t j = 0; j < 8; ++j) umma::cp_async16(a_row + ((j ^ sw) << 4), src + j * 8, nbytes);
+                const int tap = ks / cblocks;
+                cb = ks - tap * cblocks;
+                r = tap / p.kw;
+                s_or_q = tap - r * p.kw;
             } else {
+                r = 2 * ks + (int)(j >> 2);                // two filter rows per stage
+                s_or_q = 2 * (int)(j & 3);                 // pixel pair within the 8 (shifted) taps
+            }
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int r = 2 * ks + rr;
-                    const int iy = iy0 + r;
-                    const bool rok = valid && r < p.kh && iy >= 0 && iy < p.H;
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const int ix = ix0 + s;
-                        const bool ok = rok && s < p.kw && ix >= 0 && ix < p.W;
-                        const bf16* src = ok ? ximg + ((int64_t)iy * p.W + ix) * 4 : p.x;
-                        const uint32_t j = (uint32_t)(rr * 4 + (s >> 1));
-                        umma::cp_async8(a_row + ((j ^ sw) << 4) + (uint32_t)(s & 1) * 8u, src, ok ? 8u : 0u);
-                    }
+            for (int i = 0; i < 8; ++i) {
+                const int row = warp * 32 + i * 4 + rsub;
+                const int iy = iy0[i] + r, ix = ix0[i] + s_or_q;
+                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && (MODE == 0 || r < p.kh);
+                uint32_t off = 0;
+                if (ok) {
+                    off = (MODE == 0) ? img_chunk[i] + (uint32_t)(iy * p.W + ix) * (uint32_t)cin8 + (uint32_t)cb * 8u + j
+                                      : img_chunk[i] + (uint32_t)((iy * p.W + ix) >> 1);
                 }
+                umma::cp_async16(a_base + (uint32_t)row * 128u + ((j ^ (uint32_t)(row & 7)) << 4), xq + off, ok ? 16u : 0u);
             }
             // weight rows n0 .. n0+BN of this K slab
-            const uint32_t b_base = smem0 + stage * STAGE_BYTES + A_STAGE_BYTES;
+            const uint32_t b_base = a_base + A_STAGE_BYTES;
 #pragma unroll
-            for (int n = tid; n < BN; n += 128) {
-                const bf16* src = p.w + (int64_t)(n0 + n) * p.Kp + ks * BK;
-                const uint32_t b_row = b_base + (uint32_t)n * 128u;
-                const uint32_t swb = (uint32_t)(n & 7);
-#pragma unroll
-                for (uint32_t j = 0; j < 8; ++j) umma::cp_async16(b_row + ((j ^ swb) << 4), src + j * 8, 16u);
+            for (int i = 0; i < BN / 16; ++i) {
+                const int n = warp * (BN / 4) + i * 4 + rsub;
+                const uint32_t off = (uint32_t)(n0 + n) * kp8 + (uint32_t)ks * 8u + j;
+                umma::cp_async16(b_base + (uint32_t)n * 128u + ((j ^ (uint32_t)(n & 7)) << 4), wq + off, 16u);
             }
             umma::cp_async_commit();
             if (ks >= LAG) {
@@ -159,6 +168,10 @@ conv_umma_kernel(const ConvParams p) {
         umma::cp_async_wait<0>();
         umma::fence_proxy_async();
         for (int ks = (KS > LAG ? KS - LAG : 0); ks < KS; ++ks) umma::mbar_arrive(full_bar(ks % STAGES));
+
+        // this thread's output row in the epilogue
+        const int64_t m = m0 + tid;
+        const bool valid = m < p.M;
 
         // ------------------------------------------------------------ epilogue
         umma::mbar_wait(accum_bar, 0);
@@ -253,13 +266,21 @@ int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const 
     p.Wo = (W + 2 * pad - kw) / stride + 1;
     p.M = P * p.Ho * p.Wo;
     IPSB_REQUIRE(P > 0 && p.Ho > 0 && p.Wo > 0, "conv_umma: bad geometry");
-    if (mode == 0) {
-        IPSB_REQUIRE(Cin % 64 == 0, "conv_umma mode 0: Cin=%d must be a multiple of 64", Cin);
+    if (mode == 0)      // TMA-fed path: the M tile is a box of output pixels
+        return ipsb::conv_tma(x, w, scale, shift, res, y, P, H, W, Cin, Cout, kh, kw, stride, pad, relu, false,
+                              (cudaStream_t)stream);
+    if (mode == 3) {    // TMA-fed stem: x is the zero-bordered (P, H, W, 4) frame, image = (H-6) x (W-6)
+        IPSB_REQUIRE(Cin == 4 && kh == 7 && kw == 7 && stride == 2, "conv_umma mode 3 is the 7x7/2 stem");
+        return ipsb::conv_stem_tma(x, w, scale, shift, y, P, H - 6, W - 6, Cout, relu, (cudaStream_t)stream);
+    }
+    if (mode == 2) {    // cp.async gather path (any geometry with Cin % 64 == 0); kept as a cross-check
+        IPSB_REQUIRE(Cin % 64 == 0, "conv_umma mode 2: Cin=%d must be a multiple of 64", Cin);
         p.Kp = kh * kw * Cin;
         return dispatch_bn<0, bf16>(p, (cudaStream_t)stream);
     }
     if (mode == 1) {
-        IPSB_REQUIRE(Cin == 4 && kh == 7 && kw == 7, "conv_umma mode 1 is the 7x7 stem on 4-channel input");
+        IPSB_REQUIRE(Cin == 4 && kh == 7 && kw == 7 && stride == 2 && pad == 3 && W % 2 == 0,
+                     "conv_umma mode 1 is the 7x7/2 pad-3 stem on 4-channel input of even width");
         p.Kp = 256;
         return dispatch_bn<1, bf16>(p, (cudaStream_t)stream);
     }
@@ -269,11 +290,7 @@ int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const 
 int ipsb_linear_bf16_umma(const void* a, const void* w, const float* scale, const float* shift,
                           float* y, int64_t M, int N, int K, int relu, void* stream) {
     IPSB_REQUIRE(M > 0 && K % 64 == 0 && N % 64 == 0, "linear_umma: K=%d, N=%d must be multiples of 64", K, N);
-    ConvParams p;
-    p.x = (const bf16*)a; p.w = (const bf16*)w; p.scale = scale; p.shift = shift; p.res = nullptr; p.y = y;
-    p.H = 1; p.W = 1; p.Cin = K; p.Cout = N; p.kh = 1; p.kw = 1; p.stride = 1; p.pad = 0; p.relu = relu;
-    p.Ho = 1; p.Wo = 1; p.M = M; p.Kp = K;
-    return dispatch_bn<0, float>(p, (cudaStream_t)stream);
+    return ipsb::conv_tma(a, w, scale, shift, nullptr, y, M, 1, 1, K, N, 1, 1, 1, 0, relu, true, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -120,6 +120,12 @@ class IPSNet(nn.Module):
         self._plan_key = None
         self.last_mem_idx = None      # (B,M) original-order indices of the last ips() call (notebook cell 9)
         self.chunk_patches = int(getattr(conf, 'chunk_patches', 0))   # 0 = auto
+        # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
+        self.executor = os.environ.get('IPS_B200_EXECUTOR', 'native')
+        self._ws_cache = {}
+        # bf16 stem: 3 = TMA-fed (zero-bordered staged frame, even patch sizes), 1 = cp.async gather
+        ps = getattr(conf, 'patch_size', [0, 0])
+        self.stem_tma = self.is_image and ps[0] % 2 == 0 and ps[1] % 2 == 0 and os.environ.get('IPS_B200_STEM', 'tma') == 'tma'
         ops.register_custom_ops()
 
     # ------------------------------------------------------------------ derived parameters
@@ -134,14 +140,15 @@ class IPSNet(nn.Module):
     def _conv_entry(self, conv, bn, stem=False):
         w = conv.weight.detach().float()
         cout, cin, kh, kw = w.shape
-        e = dict(cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0], mode=1 if stem else 0)
+        e = dict(cin=4 if stem else cin, cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0],
+                 mode=(3 if self.precision == 'bf16' and self.stem_tma else 1) if stem else 0)
         e['scale'], e['shift'] = _fold_bn(bn)
         if stem:                                                  # channels padded to 4
             w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
             w4[:, :cin] = w
-            if self.precision == 'bf16':                          # k = r*32 + s*4 + c, 8x8 taps
+            if self.precision == 'bf16':                          # k = r*32 + (s+1)*4 + c, 8x8 taps
                 wp = torch.zeros((cout, 8, 8, 4), device=w.device)
-                wp[:, :kh, :kw] = w4.permute(0, 2, 3, 1)
+                wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
                 e['w'] = wp.reshape(cout, 256).to(torch.bfloat16).contiguous()
             else:
                 e['w'] = w4.permute(2, 3, 1, 0).reshape(kh * kw * 4, cout).contiguous()
@@ -202,7 +209,10 @@ class IPSNet(nn.Module):
             n_rows = flat.shape[0] - first_row if row_idx is None else row_idx.numel()
         if self.is_image:
             _, C, H, W = flat.shape
-            x = ops.stage_patches(flat, n_rows, C, H, W, dt, row_idx=row_idx, first_row=first_row)
+            if plan['stem']['mode'] == 3:
+                x = ops.stage_patches_padded(flat, n_rows, C, H, W, row_idx=row_idx, first_row=first_row)
+            else:
+                x = ops.stage_patches(flat, n_rows, C, H, W, dt, row_idx=row_idx, first_row=first_row)
             x = self._conv(x, plan['stem'])
             x = ops.maxpool3x3s2(x, dt)
             for b in plan['blocks']:
@@ -223,7 +233,7 @@ class IPSNet(nn.Module):
         if not self.is_image:
             return 16384
         px = patch_shape[-1] * patch_shape[-2]
-        return max(32, min(2048, (256 * 10000) // max(px, 1)))
+        return max(32, min(4096, (1024 * 10000) // max(px, 1)))      # ~1024 patches of 100x100: fills 148 SMs in every layer
 
     @torch.no_grad()
     def patch_logits(self, patches):
@@ -234,11 +244,16 @@ class IPSNet(nn.Module):
         rows = B * N
         flat = patches.reshape(rows, *patches.shape[2:])
         HT = plan['U'].shape[1]
+        chunk = self._auto_chunk(patches.shape)
+        if self.is_image and flat.is_cuda and self.executor == 'native':
+            if 'desc' not in plan:
+                plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
+            z, _ = ops.resnet_logits(plan['desc'], flat.contiguous(), N, chunk, self._ws_cache)
+            return z.view(B, N, HT)
         z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
         pos_idx = None
         if self.use_pos:
             pos_idx = (torch.arange(rows, device=self.device) % N).contiguous()
-        chunk = self._auto_chunk(patches.shape)
         for lo in range(0, rows, chunk):
             n = min(chunk, rows - lo)
             if flat.is_cuda:

@@ -67,6 +67,16 @@ def stage_patches(src, n_rows, C, H, W, dt, row_idx=None, first_row=0, cpad=4):
     return out
 
 
+def stage_patches_padded(src, n_rows, C, H, W, row_idx=None, first_row=0):
+    """(rows,C,H,W) fp32 -> zero-bordered (n_rows,H+6,W+6,4) bf16 frame for the TMA stem (image at row 3, col 4)."""
+    _chk(src, torch.float32, 'src')
+    _chk(row_idx, torch.int64, 'row_idx')
+    out = torch.empty((n_rows, H + 6, W + 6, 4), dtype=torch.bfloat16, device=src.device)
+    _call('ipsb_stage_patches_padded', _p(src), _p(row_idx), first_row, n_rows, C, H, W, 3, 4, H + 6, W + 6,
+          _p(out), _stream())
+    return out
+
+
 def gather_rows(src, idx, batch_stride_rows):
     """dst[b,m] = src_rows[b*batch_stride_rows + idx[b,m]]; src viewed as rows of src.shape[-k:]."""
     _chk(idx, torch.int64, 'idx')
@@ -130,7 +140,10 @@ def conv_bf16(x, w_nk, scale, shift, res, Cout, kh, kw, stride, pad, relu, mode=
     """x (P,H,W,Cin) bf16 NHWC, w_nk (Cout, Kpad) bf16 K-major; tcgen05 implicit GEMM."""
     _chk(x, torch.bfloat16, 'x'); _chk(w_nk, torch.bfloat16, 'w'); _chk(res, torch.bfloat16, 'res')
     P, H, W, Cin = x.shape
-    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    if mode == 3:                                    # zero-bordered frame: the padding is in the data
+        Ho, Wo = (H - kh) // stride + 1, (W - kw) // stride + 1
+    else:
+        Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     y = torch.empty((P, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
     _call('ipsb_conv_bf16_umma', _p(x), _p(w_nk), _p(scale), _p(shift), _p(res), _p(y), P, H, W, Cin,
                                                Cout, kh, kw, stride, pad, int(relu), mode, _stream())
@@ -155,6 +168,43 @@ def linear_bf16(a, w, scale=None, shift=None, relu=False):
     y = torch.empty((M, N), dtype=torch.float32, device=a.device)
     _call('ipsb_linear_bf16_umma', _p(a), _p(w), _p(scale), _p(shift), _p(y), M, N, K, int(relu), _stream())
     return y
+
+
+def make_resnet_desc(plan, dt, D, HT):
+    """Pack the folded-parameter plan of IPSNet into the ipsb_resnet_desc the native executor reads."""
+    def conv(e):
+        return _lib.ConvDesc(_p(e['w']), _p(e['scale']), _p(e['shift']), e['cin'], e['cout'], e['kh'], e['kw'],
+                             e['stride'], e['pad'], e['mode'], 0)
+    d = _lib.ResnetDesc()
+    d.dt, d.n_blocks, d.stem = dt, len(plan['blocks']), conv(plan['stem'])
+    for i, b in enumerate(plan['blocks']):
+        d.blocks[i].c1, d.blocks[i].c2 = conv(b['c1']), conv(b['c2'])
+        d.blocks[i].has_ds = int(b['ds'] is not None)
+        if b['ds'] is not None:
+            d.blocks[i].ds = conv(b['ds'])
+    d.D, d.HT, d.U, d.add_tab = D, HT, _p(plan['U']), _p(plan['posU'])
+    return d
+
+
+def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False):
+    """Whole eval-mode encoder + logit projection of (rows,C,H,W) fp32 patches in ONE library call."""
+    global LAUNCHES
+    _chk(patches, torch.float32, 'patches')
+    rows, C, H, W = patches.shape
+    lib = _lib.load()
+    need = lib.ipsb_resnet_workspace_bytes(desc, chunk, C, H, W)
+    ws = workspace_cache.get('ws')
+    if ws is None or ws.numel() < need or ws.device != patches.device:
+        ws = torch.empty(need, dtype=torch.uint8, device=patches.device)
+        workspace_cache['ws'] = ws
+    z = torch.empty((rows, desc.HT), dtype=torch.float32, device=patches.device)
+    emb = torch.empty((rows, desc.D), dtype=torch.float32, device=patches.device) if want_emb else None
+    n_chunks = -(-rows // chunk)
+    LAUNCHES += n_chunks * (4 + 2 * desc.n_blocks + sum(int(desc.blocks[i].has_ds) for i in range(desc.n_blocks))
+                            + (1 if desc.add_tab else 0))
+    _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), 0, rows, C, H, W, n_per_image, chunk, _p(ws), ws.numel(),
+                                      _p(emb), _p(z), _stream()))
+    return z, emb
 
 
 # ------------------------------------------------------------------ scoring / selection

@@ -175,3 +175,16 @@ def test_full_size_properties(pre, B, N):
         torch.manual_seed(2)
         n1.ips(x)
         assert torch.equal(a, n1.last_mem_idx.sort(-1)[0])
+
+
+@pytest.mark.parametrize('name,precision', [('mnist_small', 'fp32'), ('traffic_small', 'bf16'), ('mnist_small', 'bf16')])
+def test_native_executor_equals_per_layer_calls(name, precision):
+    """The C++ executor issues the same kernels as the per-layer Python path: identical logits."""
+    z, meta, conf, sd, patches = load_case(name)
+    net = _net(conf.replace(chunk_patches=5), sd, precision)       # several ragged chunks
+    x = patches.to(DEV)
+    net.executor = 'native'
+    a = net.patch_logits(x)
+    net.executor = 'python'
+    b = net.patch_logits(x)
+    assert torch.equal(a, b)

@@ -43,6 +43,37 @@ def test_stage_patches(dev, C, H, W, dt):
     assert torch.equal(out.cpu(), ref[6:10])
 
 
+@pytest.mark.parametrize('C,H,W', [(1, 50, 50), (3, 100, 100), (3, 8, 10)])
+def test_stage_patches_padded(dev, C, H, W):
+    from ips_b200 import ops
+    x = _rand(7, C, H, W, seed=1)
+    idx = torch.tensor([5, 0, 6, 3], dtype=torch.int64)
+    ref = torch.zeros(7, H + 6, W + 6, 4)
+    ref[:, 3:3 + H, 4:4 + W, :C] = x.permute(0, 2, 3, 1)
+    ref = ref.to(torch.bfloat16)
+    assert torch.equal(ops.stage_patches_padded(x.to(dev), 4, C, H, W, row_idx=idx.to(dev)).cpu(), ref[idx])
+    assert torch.equal(ops.stage_patches_padded(x.to(dev), 3, C, H, W, first_row=2).cpu(), ref[2:5])
+
+
+@pytest.mark.parametrize('H,W,P', [(50, 50, 37), (100, 100, 9), (20, 36, 5)])
+def test_stem_tma(dev, H, W, P):
+    """7x7/2 stem through the 5-D overlapping-window tensor map, against conv2d on the same bf16 data."""
+    from ips_b200 import ops
+    x = _rand(P, 3, H, W, seed=30)
+    w = _rand(64, 3, 7, 7, seed=31, scale=math.sqrt(2.0 / 147)).to(torch.bfloat16)
+    scale, shift = torch.rand(64) + 0.5, _rand(64, seed=32, scale=0.1)
+    frame = ops.stage_patches_padded(x.to(dev), P, 3, H, W)
+    wp = torch.zeros(64, 8, 8, 4)
+    wp[:, :7, 1:8, :3] = w.float().permute(0, 2, 3, 1)
+    got = ops.conv_bf16(frame, wp.reshape(64, 256).to(torch.bfloat16).to(dev), scale.to(dev), shift.to(dev), None,
+                        64, 7, 7, 2, 3, True, 3).cpu().float()
+    xb = x.to(torch.bfloat16).float()
+    ref = torch.relu(F.conv2d(xb, w.float(), stride=2, padding=3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    ref = ref.permute(0, 2, 3, 1)
+    assert got.shape == ref.shape
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2)
+
+
 @pytest.mark.parametrize('row', [(1, 50, 50), (3, 100, 100), (2048,), (5,), (128,)])
 def test_gather_rows(dev, row):
     from ips_b200 import ops
@@ -138,10 +169,14 @@ def test_linear_f32(dev, M, N, K):
 
 # ------------------------------------------------------------------ tcgen05 layers (bf16 in, fp32 accumulate)
 
-@pytest.mark.parametrize('case', CONV_CASES)
-def test_conv_bf16_umma(dev, case):
+@pytest.mark.parametrize('case', CONV_CASES + [(64, 64, 3, 1, 1, 25, 25), (512, 512, 3, 1, 1, 4, 4), (128, 256, 3, 2, 1, 13, 13),
+                                               (64, 64, 3, 1, 1, 9, 14)])
+@pytest.mark.parametrize('path', ['tma', 'gather'])
+def test_conv_bf16_umma(dev, case, path):
     from ips_b200 import ops
     Cin, Cout, k, s, p, H, W = case
+    if Cin == 4 and path == 'gather':
+        pytest.skip('the stem has a single path')
     P = 37                                                       # several M tiles + a ragged tail
     x = _rand(P, H, W, Cin, seed=14).to(torch.bfloat16)
     w = _rand(Cout, Cin, k, k, seed=15, scale=math.sqrt(2.0 / (Cin * k * k))).to(torch.bfloat16)
@@ -151,10 +186,10 @@ def test_conv_bf16_umma(dev, case):
     res = _rand(P, Ho, Wo, Cout, seed=17).to(torch.bfloat16)
     if Cin == 4:
         wp = torch.zeros(Cout, 8, 8, 4)
-        wp[:, :k, :k] = w.float().permute(0, 2, 3, 1)
+        wp[:, :k, 1:k + 1] = w.float().permute(0, 2, 3, 1)       # taps shifted by one column
         w_nk, mode = wp.reshape(Cout, 256).to(torch.bfloat16), 1
     else:
-        w_nk, mode = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous(), 0
+        w_nk, mode = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous(), (0 if path == 'tma' else 2)
     for use_res, relu in ((False, True), (True, True), (False, False)):
         ref = _conv_ref(x.float(), w.float(), scale, shift, res.float() if use_res else None, s, p, relu)
         got = ops.conv_bf16(x.to(dev), w_nk.to(dev), scale.to(dev), shift.to(dev), res.to(dev) if use_res else None,

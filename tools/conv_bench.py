@@ -1,0 +1,46 @@
+"""Per-layer timing of the tcgen05 conv kernel on the traffic / mnist encoder shapes."""
+import sys, os, math
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ips_b200 import ops
+
+dev = torch.device('cuda:0')
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+only = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'all' else None
+MODE0 = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+# name, Cin, Cout, k, stride, pad, H
+LAYERS = [
+    ('stem', 4, 64, 7, 2, 3, 100),
+    ('l1', 64, 64, 3, 1, 1, 25),
+    ('l2s', 64, 128, 3, 2, 1, 25),
+    ('l2d', 64, 128, 1, 2, 0, 25),
+    ('l2', 128, 128, 3, 1, 1, 13),
+    ('l3s', 128, 256, 3, 2, 1, 13),
+    ('l3', 256, 256, 3, 1, 1, 7),
+    ('l4s', 256, 512, 3, 2, 1, 7),
+    ('l4', 512, 512, 3, 1, 1, 4),
+]
+tot_ms = 0
+for name, Cin, Cout, k, s, p, H in LAYERS:
+    if only and name != only:
+        continue
+    stem3 = (Cin == 4 and MODE0 == 0)
+    Hx = H + 6 if stem3 else H
+    x = torch.randn(P, Hx, Hx, Cin, device=dev).to(torch.bfloat16)
+    Kp = 256 if Cin == 4 else k * k * Cin
+    w = (torch.randn(Cout, Kp, device=dev) / math.sqrt(Kp)).to(torch.bfloat16)
+    scale = torch.ones(Cout, device=dev); shift = torch.zeros(Cout, device=dev)
+    mode = (3 if stem3 else 1) if Cin == 4 else MODE0
+    f = lambda: ops.conv_bf16(x, w, scale, shift, None, Cout, k, k, s, p, True, mode)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n): f()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    Ho = (H + 2 * p - k) // s + 1
+    kreal = (147 if Cin == 4 else k * k * Cin)
+    fl = 2.0 * P * Ho * Ho * Cout * kreal
+    print(f'{name:5s} M={P*Ho*Ho:7d} N={Cout:3d} K={Kp:4d}  {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (algorithmic)  tiles={-(-P*Ho*Ho//128)}x{Cout//(128 if Cout%128==0 else 64)}')
