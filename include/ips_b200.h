@@ -80,6 +80,16 @@ IPSB_API int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int
 IPSB_API int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const float* shift,
                         const void* res, void* y, int64_t P, int H, int W, int Cin, int Cout,
                         int kh, int kw, int stride, int pad, int relu, int mode, void* stream);
+/* Padded-flat (PF) activations: P patches of HxW pixels stored as rows of C channels with one zero pixel after
+ * every image row and one zero row after every patch, row(p,y,x) = (W+2) + p*(H+1)*(W+1) + y*(W+1) + x
+ * (ips_b200/csrc/pf.cuh).  A stride-1 3x3 convolution on PF input/output runs as a shifted-window implicit
+ * GEMM that reads its input once; other geometries read/write PF through TMA boxes.  res is PF iff out_pf. */
+IPSB_API int64_t ipsb_pf_rows(int64_t P, int H, int W);    /* rows to allocate (zero-initialised once) */
+IPSB_API int ipsb_conv_bf16_pf(const void* x, const void* w, const float* scale, const float* shift, const void* res,
+                      void* y, int64_t P, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                      int relu, int in_pf, int out_pf, void* stream);
+IPSB_API int ipsb_maxpool3x3s2_pf(const void* x, void* y, int64_t P, int H, int W, int C, void* stream);  /* dense bf16 -> PF */
+IPSB_API int ipsb_avgpool_pf(const void* x, float* y, int64_t P, int H, int W, int C, void* stream);      /* PF bf16 -> (P,C) fp32 */
 /* y[M,N] (fp32) = act((A[M,K] @ W[N,K]^T) * scale + shift), A and W bf16 K-major,
  * K % 64 == 0, N % 64 == 0.  tcgen05 path for the Linear layers. */
 IPSB_API int ipsb_linear_bf16_umma(const void* a, const void* w, const float* scale, const float* shift,

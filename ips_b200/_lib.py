@@ -45,6 +45,10 @@ SIGNATURES = {
     'ipsb_avgpool': [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_layernorm_rows_f32': [_ptr, _ptr, _i64, _i32, _f32, _ptr],
     'ipsb_conv_bf16_umma': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
+    'ipsb_pf_rows': [_i64, _i32, _i32],
+    'ipsb_conv_bf16_pf': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
+    'ipsb_maxpool3x3s2_pf': [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
+    'ipsb_avgpool_pf': [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_linear_bf16_umma': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_rows_to_bf16': [_ptr, _ptr, _i64, _i32, _i32, _f32, _ptr],
     'ipsb_score_basis': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
@@ -57,7 +61,8 @@ SIGNATURES = {
     'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64,
                            _ptr, _ptr, _ptr],
 }
-_RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64}
+_RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64,
+            'ipsb_pf_rows': ctypes.c_int64}
 
 _lib = None
 

@@ -37,7 +37,10 @@ int sm_count();
 // TMA-fed tcgen05 implicit GEMM (umma_conv_tma.cu)
 int conv_tma(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
              int64_t P, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
-             bool out_f32, cudaStream_t st);
+             bool out_f32, cudaStream_t st, bool in_pf = false, bool out_pf = false);
+// stride-1 3x3 convolution on padded-flat activations (umma_conv_halo.cu)
+int conv3x3_halo(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
+                 int64_t P, int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
 int conv_stem_tma(const void* x, const void* w, const float* scale, const float* shift, void* y,
                   int64_t P, int H, int W, int Cout, int relu, cudaStream_t st);
 

@@ -1,0 +1,145 @@
+// Shared epilogue of the tcgen05 convolution kernels.
+//
+// One warpgroup (128 threads, thread = accumulator row) drains one TMEM accumulator in slabs
+// of 128 bytes per row (64 bf16 / 32 fp32 channels): tcgen05.ld -> folded BatchNorm from shared
+// memory, residual, ReLU -> 128B-swizzled staging tile in shared memory -> ONE TMA tensor store
+// per slab.  Stores therefore leave the SM as full 128-byte lines issued by the TMA unit
+// (a warp's direct 16-byte stores to 32 different rows were measured at < 2 TB/s chip-wide and
+// bound the 64-channel layers).  The TMA unit clips rows outside the tensor, so ragged tiles
+// need no masking.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "umma.cuh"
+
+namespace epi {
+
+using bf16 = __nv_bfloat16;
+constexpr int STAGE_BYTES = 128 * 128;        // 128 rows x 128 bytes
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <typename T> struct Slab;
+template <> struct Slab<bf16> { static constexpr int COLS = 64; };
+template <> struct Slab<float> { static constexpr int COLS = 32; };
+
+// 32 accumulator columns of one row -> staging row (swizzled 16-byte chunks)
+template <typename OutT>
+__device__ __forceinline__ void stage32(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
+                                        const bf16* res32, int relu, uint32_t row_smem, int row, int chunk0);
+
+template <>
+__device__ __forceinline__ void stage32<bf16>(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
+                                              const bf16* res32, int relu, uint32_t row_smem, int row, int chunk0) {
+    const float4* sc4 = reinterpret_cast<const float4*>(sc);
+    const float4* sh4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {                 // 8 channels = one 16-byte chunk
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (pixel) {
+            const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
+            float o[8];
+            o[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, h0.x);
+            o[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, h0.y);
+            o[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, h0.z);
+            o[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, h0.w);
+            o[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, h1.x);
+            o[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, h1.y);
+            o[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, h1.z);
+            o[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, h1.w);
+            if (res32 != nullptr) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res32 + g * 8);
+                const bf16* rb = reinterpret_cast<const bf16*>(&rv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rb[i]);
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+        const uint32_t chunk = (uint32_t)(chunk0 + g);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(row_smem + ((chunk ^ (uint32_t)(row & 7)) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    }
+}
+
+template <>
+__device__ __forceinline__ void stage32<float>(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
+                                               const bf16* res32, int relu, uint32_t row_smem, int row, int chunk0) {
+    (void)res32;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {                 // 4 channels = one 16-byte chunk
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pixel) {
+            const float4 s = reinterpret_cast<const float4*>(sc)[g], h = reinterpret_cast<const float4*>(sh)[g];
+            o[0] = fmaf(__uint_as_float(v[g * 4 + 0]), s.x, h.x);
+            o[1] = fmaf(__uint_as_float(v[g * 4 + 1]), s.y, h.y);
+            o[2] = fmaf(__uint_as_float(v[g * 4 + 2]), s.z, h.z);
+            o[3] = fmaf(__uint_as_float(v[g * 4 + 3]), s.w, h.w);
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], 0.f);
+            }
+        }
+        const uint32_t chunk = (uint32_t)(chunk0 + g);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(row_smem + ((chunk ^ (uint32_t)(row & 7)) << 4)), "r"(__float_as_uint(o[0])), "r"(__float_as_uint(o[1])),
+                       "r"(__float_as_uint(o[2])), "r"(__float_as_uint(o[3])) : "memory");
+    }
+}
+
+// Drain one accumulator (BN fp32 columns of this thread's row) through the staging tile.
+//   t_row      TMEM address of this thread's lane + the accumulator's first column
+//   sc / sh    shared-memory scale / shift for the BN columns of this tile
+//   pixel      row carries a real output (else zeros are staged)
+//   res_row    residual row (bf16, BN channels) or null
+//   stage      this warpgroup's 16 KB staging tile (1024-byte aligned), bar_id: its named barrier
+//   issue(slab_col0, stage) is called by ONE thread per slab and must issue the TMA store.
+template <int BN, typename OutT, class Issue>
+__device__ __forceinline__ void drain_tile(uint32_t t_row, uint32_t tempty_bar, const float* sc, const float* sh, bool pixel,
+                                           const bf16* res_row, int relu, uint32_t stage, int row, uint32_t bar_id,
+                                           bool issuer, const Issue& issue) {
+    constexpr int COLS = Slab<OutT>::COLS;
+    const uint32_t row_smem = stage + (uint32_t)row * 128u;
+#pragma unroll 1
+    for (int s0 = 0; s0 < BN; s0 += COLS) {
+        if (issuer) bulk_wait_read0();                 // previous store has finished reading the staging tile
+        umma::named_bar_sync(bar_id, 128);
+#pragma unroll
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+            uint32_t v[32];
+            umma::tmem_ld32(t_row + (uint32_t)(s0 + c0), v);
+            umma::tmem_ld_wait();
+            if (s0 + c0 + 32 >= BN) {                  // accumulator fully read: hand it back to the MMA warp
+                umma::tc_fence_before();
+                umma::mbar_arrive(tempty_bar);
+            }
+            stage32<OutT>(v, sc + s0 + c0, sh + s0 + c0, pixel, res_row ? res_row + s0 + c0 : nullptr, relu, row_smem, row,
+                          c0 * (int)sizeof(OutT) / 16);
+        }
+        umma::fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA unit
+        umma::named_bar_sync(bar_id, 128);
+        if (issuer) {
+            issue(s0, stage);
+            bulk_commit();
+        }
+    }
+}
+
+}  // namespace epi

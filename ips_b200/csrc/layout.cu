@@ -1,6 +1,7 @@
 // HBM-bound data movement: patch staging (NCHW fp32 -> channels-last), row gathers,
 // pooling, LayerNorm rows.  All 128-bit where alignment allows.
 #include "common.cuh"
+#include "pf.cuh"
 #include "../../include/ips_b200.h"
 
 namespace {
@@ -107,7 +108,7 @@ __global__ void gather_rows4_kernel(const uint32_t* __restrict__ src, int64_t ba
 // max_pool2d(3, 2, 1) channels-last, VEC channels per thread (16 bytes)
 template <typename T, int VEC>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t P, int H, int W, int C,
-                               int Ho, int Wo) {
+                               int Ho, int Wo, int oG0, int oWp, int oSp) {
     const int cv = C / VEC;
     const int64_t total = P * Ho * Wo * cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -136,7 +137,7 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64
         __align__(16) T o[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) o[k] = from_f32<T>(m[k]);
-        *reinterpret_cast<uint4*>(y + ((p * Ho + oy) * Wo + ox) * (int64_t)C + c0) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(y + (oG0 + p * oSp + (int64_t)oy * oWp + ox) * (int64_t)C + c0) = *reinterpret_cast<const uint4*>(o);
     }
 }
 
@@ -150,6 +151,19 @@ __global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, i
         const T* s = x + p * (int64_t)HW * C + c;
         float acc = 0.f;
         for (int k = 0; k < HW; ++k) acc += to_f32<T>(s[(int64_t)k * C]);
+        y[i] = acc / (float)HW;
+    }
+}
+
+__global__ void avgpool_pf_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t P, int Sp, int HW, int C) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const bf16* s = x + p * (int64_t)Sp * C + c;
+        float acc = 0.f;
+        for (int k = 0; k < Sp; ++k) acc += __bfloat162float(s[(int64_t)k * C]);
         y[i] = acc / (float)HW;
     }
 }
@@ -254,17 +268,38 @@ int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, in
     if (dt == IPSB_BF16) {
         IPSB_REQUIRE(C % 8 == 0, "maxpool: C=%d not a multiple of 8", C);
         const int64_t total = P * Ho * Wo * (C / 8);
-        maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, P, H, W, C, Ho, Wo);
+        maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, P, H, W, C, Ho, Wo, 0, Wo, Ho * Wo);
     } else if (dt == IPSB_F32) {
         IPSB_REQUIRE(C % 4 == 0, "maxpool: C=%d not a multiple of 4", C);
         const int64_t total = P * Ho * Wo * (C / 4);
-        maxpool_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, P, H, W, C, Ho, Wo);
+        maxpool_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, P, H, W, C, Ho, Wo, 0, Wo, Ho * Wo);
     } else {
         return ipsb::fail("maxpool: unknown dtype %d", dt);
     }
     IPSB_LAUNCH_CHECK();
     return 0;
 }
+
+int ipsb_maxpool3x3s2_pf(const void* x, void* y, int64_t P, int H, int W, int C, void* stream) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    IPSB_REQUIRE(C % 8 == 0, "maxpool_pf: C=%d not a multiple of 8", C);
+    const pf::Geo g = pf::make(P, Ho, Wo);
+    const int64_t total = P * Ho * Wo * (C / 8);
+    maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, P, H, W, C,
+                                                                                   Ho, Wo, g.G0, g.Wp, g.Sp);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_avgpool_pf(const void* x, float* y, int64_t P, int H, int W, int C, void* stream) {
+    // pad rows are zero: the mean over the patch's Sp rows divided by H*W pixels
+    const pf::Geo g = pf::make(P, H, W);
+    avgpool_pf_kernel<<<grid_for(P * C, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x + (int64_t)g.G0 * C, y, P, g.Sp, H * W, C);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t ipsb_pf_rows(int64_t P, int H, int W) { return pf::make(P, H, W).rows; }
 
 int ipsb_avgpool(const void* x, float* y, int64_t P, int HW, int C, int dt, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -287,6 +287,15 @@ int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const 
     return ipsb::fail("conv_umma: unknown mode %d", mode);
 }
 
+int ipsb_conv_bf16_pf(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
+                      int64_t P, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
+                      int in_pf, int out_pf, void* stream) {
+    if (in_pf && out_pf && kh == 3 && kw == 3 && stride == 1 && pad == 1 && (Cout == 64 || Cout == 128))
+        return ipsb::conv3x3_halo(x, w, scale, shift, res, y, P, H, W, Cin, Cout, relu, (cudaStream_t)stream);
+    return ipsb::conv_tma(x, w, scale, shift, res, y, P, H, W, Cin, Cout, kh, kw, stride, pad, relu, false,
+                          (cudaStream_t)stream, in_pf != 0, out_pf != 0);
+}
+
 int ipsb_linear_bf16_umma(const void* a, const void* w, const float* scale, const float* shift,
                           float* y, int64_t M, int N, int K, int relu, void* stream) {
     IPSB_REQUIRE(M > 0 && K % 64 == 0 && N % 64 == 0, "linear_umma: K=%d, N=%d must be multiples of 64", K, N);

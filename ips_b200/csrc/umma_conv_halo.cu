@@ -1,0 +1,295 @@
+// Stride-1 3x3 convolution on padded-flat (PF) activations: shifted-window implicit GEMM.
+//
+// An M tile is 128 CONSECUTIVE PF rows g0 .. g0+127 (pixels and pad rows alike).  The block
+// of input rows [g0 - Wp - 1, g0 + 128 + Wp + 1) is fetched ONCE per 64-channel slab with a
+// single 2-D TMA box; the im2col operand of filter tap (r, s) is that block viewed from row
+// offset r*Wp + s, which for a 128B-swizzled K-major operand is nothing but a different
+// descriptor start address (see pf.cuh).  Activations are therefore read from L2/HBM once
+// per layer instead of nine times, and the main loop is MMA-bound.
+//
+//   warp 0   TMA producer: A blocks (ring) + weight slabs (ring, or resident when they fit)
+//   warp 1   tcgen05.mma issuer, two TMEM accumulators
+//   warps 2-9 epilogue (two warpgroups alternating tiles): TMEM -> folded BN, residual, ReLU -> PF rows
+//            (pad rows written as zero)
+//
+// Replaces conv2d(3x3, stride 1) + batch_norm(eval) + add + relu of the reference's BasicBlocks
+// (architecture/ips_net.py:17-52).
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "umma.cuh"
+#include "pf.cuh"
+#include "epilogue.cuh"
+#include "../../include/ips_b200.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int TILE_M = 128;
+constexpr int BK = 64;
+
+struct HaloParams {
+    const float* scale;
+    const float* shift;
+    const bf16* res;      // PF, same geometry as the output, or null
+    bf16* y;              // PF output
+    int P, H, W, Wp, Sp, G0, Cout, relu;
+    int dbg;              // IPSB_DEBUG bits: 1 skip stores, 2 skip MMAs, 4 load A only for the first tile of a CTA
+    int cblocks;          // Cin / 64
+    int total_tiles;
+    int a_rows;           // rows per A block = 130 + 2*Wp
+    uint32_t a_slot_bytes;
+    int64_t pix_rows;     // P * Sp: rows [G0, G0 + pix_rows) hold pixels / pads of real patches
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <int BN, int SA, int SB, bool RESB>
+__global__ void __launch_bounds__(320, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const HaloParams p) {
+    constexpr int B_SLAB_BYTES = BN * 128;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b0 = smem0 + SA * p.a_slot_bytes;                                   // weight ring or resident slabs
+    const uint32_t out_stage0 = b0 + (RESB ? (uint32_t)(9 * p.cblocks) : (uint32_t)SB) * B_SLAB_BYTES;   // 2 x 16 KB epilogue staging
+    const uint32_t bar0 = out_stage0 + 2u * epi::STAGE_BYTES;
+    auto a_full = [&](int s) { return bar0 + 8u * s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (SA + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (2 * SA + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (2 * SA + SB + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + 2 + a); };
+    const uint32_t resb_bar = bar0 + 8u * (2 * SA + 2 * SB + 4);
+    const uint32_t tmem_slot = resb_bar + 8u;
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - umma::smem_u32(smem_raw)));
+    const uint32_t sc_addr = (tmem_slot + 4u + 15u) & ~15u;
+    float* sc_smem = reinterpret_cast<float*>(smem_raw + (sc_addr - umma::smem_u32(smem_raw)));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < SA; ++s) { umma::mbar_init(a_full(s), 1); umma::mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < SB; ++s) { umma::mbar_init(b_full(s), 1); umma::mbar_init(b_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), 128); }
+        umma::mbar_init(resb_bar, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * BN);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int n_slabs = 9 * p.cblocks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            if (RESB) {
+                umma::mbar_expect_tx(resb_bar, (uint32_t)n_slabs * B_SLAB_BYTES);
+                for (int ks = 0; ks < n_slabs; ++ks) tma_load_2d(b0 + ks * B_SLAB_BYTES, &tmB, resb_bar, ks * BK, 0);
+            }
+            uint32_t ia = 0, ib = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
+                    const int sa = ia % SA;
+                    umma::mbar_wait(a_empty(sa), ((ia / SA) & 1) ^ 1);
+                    if ((p.dbg & 4) && ia >= (uint32_t)SA) { umma::mbar_arrive(a_full(sa)); }
+                    else {
+                    umma::mbar_expect_tx(a_full(sa), (uint32_t)p.a_rows * 128u);
+                    tma_load_2d(smem0 + sa * p.a_slot_bytes, &tmA, a_full(sa), cb * BK, tile * TILE_M);
+                    }
+                    if (!RESB) {
+                        for (int tap = 0; tap < 9; ++tap, ++ib) {
+                            const int sb = ib % SB;
+                            umma::mbar_wait(b_empty(sb), ((ib / SB) & 1) ^ 1);
+                            umma::mbar_expect_tx(b_full(sb), B_SLAB_BYTES);
+                            tma_load_2d(b0 + sb * B_SLAB_BYTES, &tmB, b_full(sb), (tap * p.cblocks + cb) * BK, 0);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::idesc_bf16_f32(TILE_M, BN);
+            if (RESB) umma::mbar_wait(resb_bar, 0);
+            uint32_t ia = 0, ib = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                umma::mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1);
+                umma::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
+                    const int sa = ia % SA;
+                    umma::mbar_wait(a_full(sa), (ia / SA) & 1);
+                    umma::tc_fence_after();
+                    const uint32_t a_base = smem0 + sa * p.a_slot_bytes;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int r = tap / 3, s = tap - 3 * r;
+                        uint32_t b_addr;
+                        int sb = 0;
+                        if (RESB) {
+                            b_addr = b0 + (tap * p.cblocks + cb) * B_SLAB_BYTES;
+                        } else {
+                            sb = ib % SB;
+                            umma::mbar_wait(b_full(sb), (ib / SB) & 1);
+                            umma::tc_fence_after();
+                            b_addr = b0 + sb * B_SLAB_BYTES;
+                        }
+                        const uint64_t adesc = umma::smem_desc_sw128(a_base + (uint32_t)(r * p.Wp + s) * 128u);
+                        const uint64_t bdesc = umma::smem_desc_sw128(b_addr);
+                        if (!(p.dbg & 2)) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma::mma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (cb | tap | k) != 0);
+                        }
+                        if (!RESB) { umma::mma_commit(b_empty(sb)); ++ib; }
+                    }
+                    umma::mma_commit(a_empty(sa));
+                }
+                umma::mma_commit(tfull_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue
+        // two warpgroups (warps 2-5 and 6-9) alternate tiles; each owns one TMEM accumulator
+        const int wg = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        for (int i = tid - 64; i < p.Cout; i += 256) {
+            sc_smem[i] = p.scale ? p.scale[i] : 1.f;
+            sc_smem[p.Cout + i] = p.shift ? p.shift[i] : 0.f;
+        }
+        umma::named_bar_sync(1, 256);
+        uint32_t tcount = wg;
+        const uint32_t stage = out_stage0 + (uint32_t)wg * epi::STAGE_BYTES;
+        const bool issuer = (row == 0);
+        for (int tile = blockIdx.x + wg * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tcount += 2) {
+            const int rel = tile * TILE_M + row;                     // row index relative to G0 (fits int32: checked on the host)
+            const bool in_range = rel < (int)p.pix_rows;             // rows of real patches (pixels or their pads)
+            const int rem = rel % p.Sp;
+            const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
+            const bool pixel = in_range && yy < p.H && xx < p.W;     // pad rows are stored as zeros
+            const int64_t g = (int64_t)p.G0 + rel;
+            umma::mbar_wait(tfull_bar(wg), (tcount >> 1) & 1);
+            umma::tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+            const int g0 = p.G0 + tile * TILE_M;
+            epi::drain_tile<BN, bf16>(t_row, tempty_bar(wg), sc_smem, sc_smem + p.Cout, pixel,
+                                      (p.res && pixel) ? p.res + g * p.Cout : nullptr, p.relu, stage, row, 2u + (uint32_t)wg, issuer,
+                                      [&](int s0, uint32_t src) { if (!(p.dbg & 1)) epi::tma_store_2d(&tmC, src, s0, g0); });
+        }
+        if (issuer) epi::bulk_wait0();
+    }
+
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+template <int BN, int SA, int SB, bool RESB>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? 9 * p.cblocks : SB) * BN * 128 + 2 * epi::STAGE_BYTES + 1024 +
+                        8 * (2 * SA + 2 * SB + 5) + 32 + 8 * (size_t)p.Cout;
+    IPSB_REQUIRE(smem <= 227 * 1024, "conv_halo: %zu bytes of shared memory", smem);
+    auto kern = conv_halo_kernel<BN, SA, SB, RESB>;
+    static size_t configured = 0;
+    if (configured < smem) {
+        IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
+    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+namespace ipsb {
+
+// x, res, y: PF(H, W) tensors with Cin / Cout / Cout channels; w: (Cout, 9*Cin) bf16, k = (r*3+s)*Cin + c.
+int conv3x3_halo(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
+                 int64_t P, int H, int W, int Cin, int Cout, int relu, cudaStream_t st) {
+    IPSB_REQUIRE(Cin % 64 == 0 && (Cout == 64 || Cout == 128), "conv3x3_halo: Cin=%d Cout=%d not supported", Cin, Cout);
+    EncodeTiledFn enc = encode_fn();
+    IPSB_REQUIRE(enc != nullptr, "conv3x3_halo: cuTensorMapEncodeTiled not available from the driver");
+    const pf::Geo g = pf::make(P, H, W);
+    HaloParams p;
+    p.scale = scale; p.shift = shift; p.res = (const bf16*)res; p.y = (bf16*)y;
+    p.P = (int)P; p.H = H; p.W = W; p.Wp = g.Wp; p.Sp = g.Sp; p.G0 = g.G0; p.Cout = Cout; p.relu = relu;
+    p.cblocks = Cin / BK;
+    { const char* e = getenv("IPSB_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    p.pix_rows = P * (int64_t)g.Sp;
+    IPSB_REQUIRE(p.pix_rows + TILE_M < (1ll << 31), "conv3x3_halo: too many rows");
+    p.total_tiles = (int)((p.pix_rows + TILE_M - 1) / TILE_M);
+    p.a_rows = TILE_M + 2 * g.Wp + 2;
+    IPSB_REQUIRE(p.a_rows <= 256, "conv3x3_halo: width %d too large for one TMA box", W);
+    p.a_slot_bytes = (uint32_t)((p.a_rows * 128 + 1023) / 1024 * 1024);
+
+    alignas(64) CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)g.rows};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p.a_rows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPSB_REQUIRE(r == CUDA_SUCCESS, "conv3x3_halo: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        const int K = 9 * Cin;
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)Cout};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPSB_REQUIRE(r == CUDA_SUCCESS, "conv3x3_halo: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    alignas(64) CUtensorMap tmC;
+    {   // output rows [G0 + pix_rows) as a 2-D tensor; rows past the last patch are clipped by the TMA unit
+        cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)(g.G0 + p.pix_rows)};
+        cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)TILE_M};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPSB_REQUIRE(r == CUDA_SUCCESS, "conv3x3_halo: cuTensorMapEncodeTiled(output) failed with %d", (int)r);
+    }
+    if (Cout == 64) {
+        if ((size_t)9 * p.cblocks * 64 * 128 <= 80 * 1024) return launch<64, 4, 1, true>(tmA, tmB, tmC, p, st);
+        return launch<64, 4, 6, false>(tmA, tmB, tmC, p, st);
+    }
+    return launch<128, 4, 5, false>(tmA, tmB, tmC, p, st);
+}
+
+}  // namespace ipsb

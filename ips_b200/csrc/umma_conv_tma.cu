@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "umma.cuh"
+#include "pf.cuh"
+#include "epilogue.cuh"
 #include "../../include/ips_b200.h"
 
 namespace {
@@ -42,6 +44,7 @@ struct TmaConvParams {
     int n_tiles_n, total_tiles;
     int KS, cblocks;                    // K stages per tile, 64-channel slabs per tap
     int b_slabs;                        // resident 64-wide weight slabs (RESB)
+    int out_G0, out_Wp, out_Sp;         // output row = G0 + p*Sp + oy*Wp + ox (dense: 0, Wo, Ho*Wo; or padded-flat)
     uint32_t a_bytes;                   // bytes one A box deposits
 };
 
@@ -67,23 +70,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-template <typename T> struct Store8;
-template <> struct Store8<bf16> {
-    static __device__ __forceinline__ void run(void* base, int64_t off, const float (&v)[8]) {
-        __align__(16) __nv_bfloat162 h[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off) = *reinterpret_cast<const uint4*>(h);
-    }
-};
-template <> struct Store8<float> {
-    static __device__ __forceinline__ void run(void* base, int64_t off, const float (&v)[8]) {
-        float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
-        d[0] = make_float4(v[0], v[1], v[2], v[3]);
-        d[1] = make_float4(v[4], v[5], v[6], v[7]);
-    }
-};
-
 struct TileCoord { int p0, oy0, ox0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const TmaConvParams& p, int tile, int BN) {
     const int nt = tile % p.n_tiles_n;                 // n fastest: neighbouring CTAs share the A box in L2
@@ -96,8 +82,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TmaConvParams& p, int til
 // STEM: A through the 5-D overlapping-window map (KS = 7, one stage = one filter row = 32 k)
 // RESB: all weight K-slabs resident in shared memory (single N tile)
 template <int BN, int STAGES, bool STEM, bool RESB, typename OutT>
-__global__ void __launch_bounds__(192, 1)
-conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TmaConvParams p) {
+__global__ void __launch_bounds__(320, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const TmaConvParams p) {
     constexpr int B_SLAB_BYTES = BN * 128;
     constexpr int A_BYTES = STEM ? TILE_M * 64 : A_STAGE_BYTES;             // stem: 64-byte rows (one filter row)
     constexpr int STAGE_BYTES = A_BYTES + (RESB ? 0 : B_SLAB_BYTES);
@@ -105,7 +92,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem0 = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t resb0 = smem0 + STAGES * STAGE_BYTES;                     // resident weights (RESB)
-    const uint32_t bar0 = resb0 + (RESB ? (uint32_t)p.b_slabs * B_SLAB_BYTES : 0u);
+    const uint32_t out_stage0 = resb0 + (RESB ? (uint32_t)p.b_slabs * B_SLAB_BYTES : 0u);      // 2 x 16 KB epilogue staging
+    const uint32_t bar0 = out_stage0 + 2u * epi::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
@@ -201,72 +189,36 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue
+        // two warpgroups (warps 2-5 and 6-9) alternate tiles; each owns one TMEM accumulator
+        const int wg = (warp - 2) >> 2;               // accumulator / tile parity of this warpgroup
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         const int per_patch = p.bw * p.bh;
         const int pi = row / per_patch, rem = row - pi * per_patch;
         const int yi = rem / p.bw, xi = rem - yi * p.bw;
-        // folded BatchNorm parameters -> shared memory once (broadcast reads in the tile loop)
-        for (int i = tid - 64; i < p.Cout; i += 128) {
+        for (int i = tid - 64; i < p.Cout; i += 256) {   // folded BatchNorm parameters -> shared memory, once
             sc_smem[i] = p.scale ? p.scale[i] : 1.f;
             sc_smem[p.Cout + i] = p.shift ? p.shift[i] : 0.f;
         }
-        umma::named_bar_sync(1, 128);
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        umma::named_bar_sync(1, 256);
+        uint32_t tcount = wg;
+        const uint32_t stage = out_stage0 + (uint32_t)wg * epi::STAGE_BYTES;
+        const bool issuer = (row == 0);
+        for (int tile = blockIdx.x + wg * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tcount += 2) {
             const TileCoord tc = decode_tile(p, tile, BN);
             const int pp = tc.p0 + pi, oy = tc.oy0 + yi, ox = tc.ox0 + xi;
             const bool valid = pi < p.bp && pp < p.P && oy < p.Ho && ox < p.Wo;
-            const int64_t m = ((int64_t)pp * p.Ho + oy) * p.Wo + ox;
-            const uint32_t acc = tcount & 1;
-            umma::mbar_wait(tfull_bar(acc), (tcount >> 1) & 1);
+            const int64_t m = p.out_G0 + (int64_t)pp * p.out_Sp + oy * p.out_Wp + ox;
+            umma::mbar_wait(tfull_bar(wg), (tcount >> 1) & 1);
             umma::tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int nb = tc.n0 + c0;
-                uint4 rv[4];
-                if (p.res && valid) {                 // residual loads in flight while TMEM is read
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) rv[g] = *reinterpret_cast<const uint4*>(p.res + m * p.Cout + nb + g * 8);
-                }
-                uint32_t v[32];
-                umma::tmem_ld32(t_row + (uint32_t)c0, v);
-                umma::tmem_ld_wait();
-                if (c0 + 32 >= BN) {                  // accumulator fully read: hand it back to the MMA warp
-                    umma::tc_fence_before();
-                    umma::mbar_arrive(tempty_bar(acc));
-                }
-                if (valid) {
-                    const float4* sc4 = reinterpret_cast<const float4*>(sc_smem + nb);
-                    const float4* sh4 = reinterpret_cast<const float4*>(sc_smem + p.Cout + nb);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
-                        float o[8];
-                        o[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, h0.x);
-                        o[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, h0.y);
-                        o[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, h0.z);
-                        o[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, h0.w);
-                        o[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, h1.x);
-                        o[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, h1.y);
-                        o[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, h1.z);
-                        o[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, h1.w);
-                        if (p.res) {
-                            const bf16* rb = reinterpret_cast<const bf16*>(&rv[g]);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rb[i]);
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-                        }
-                        Store8<OutT>::run(p.y, m * p.Cout + nb + g * 8, o);
-                    }
-                }
-            }
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+            epi::drain_tile<BN, OutT>(t_row, tempty_bar(wg), sc_smem + tc.n0, sc_smem + p.Cout + tc.n0, valid,
+                                      (p.res && valid) ? p.res + m * p.Cout + tc.n0 : nullptr, p.relu, stage, row,
+                                      2u + (uint32_t)wg, issuer,
+                                      [&](int s0, uint32_t src) { epi::tma_store_4d(&tmC, src, tc.n0 + s0, tc.ox0, tc.oy0, tc.p0); });
         }
+        if (issuer) epi::bulk_wait0();
     }
 
     umma::tc_fence_before();
@@ -293,9 +245,10 @@ EncodeTiledFn encode_fn() {
 }
 
 template <int BN, int STAGES, bool STEM, bool RESB, typename OutT>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmaConvParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TmaConvParams& p, cudaStream_t st) {
     const size_t smem = (size_t)STAGES * ((STEM ? TILE_M * 64 : A_STAGE_BYTES) + (RESB ? 0 : BN * 128)) +
-                        (RESB ? (size_t)p.b_slabs * BN * 128 : 0) + 1024 + 8 * (2 * STAGES + 5) + 32 + 8 * (size_t)p.Cout;
+                        (RESB ? (size_t)p.b_slabs * BN * 128 : 0) + 2 * epi::STAGE_BYTES + 1024 + 8 * (2 * STAGES + 5) + 32 +
+                        8 * (size_t)p.Cout;
     IPSB_REQUIRE(smem <= 227 * 1024, "conv_tma: %zu bytes of shared memory", smem);
     auto kern = conv_tma_kernel<BN, STAGES, STEM, RESB, OutT>;
     static size_t configured = 0;
@@ -304,18 +257,19 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmaConvParams& 
         configured = smem;
     }
     const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
-    kern<<<grid, 192, smem, st>>>(tmA, tmB, p);
+    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
 
 template <bool STEM, typename OutT>
-int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmaConvParams& p, int BN, bool resb, cudaStream_t st) {
-    if (!STEM && BN == 256) return launch<256, 4, false, false, OutT>(tmA, tmB, p, st);
-    if (!STEM && BN == 128) return launch<128, 6, false, false, OutT>(tmA, tmB, p, st);
-    if (STEM) return launch<64, 8, true, true, OutT>(tmA, tmB, p, st);
-    if (resb) return launch<64, 6, false, true, OutT>(tmA, tmB, p, st);
-    return launch<64, 8, false, false, OutT>(tmA, tmB, p, st);
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TmaConvParams& p, int BN, bool resb,
+             cudaStream_t st) {
+    if (!STEM && BN == 256) return launch<256, 3, false, false, OutT>(tmA, tmB, tmC, p, st);
+    if (!STEM && BN == 128) return launch<128, 5, false, false, OutT>(tmA, tmB, tmC, p, st);
+    if (STEM) return launch<64, 8, true, true, OutT>(tmA, tmB, tmC, p, st);
+    if (resb) return launch<64, 6, false, true, OutT>(tmA, tmB, tmC, p, st);
+    return launch<64, 6, false, false, OutT>(tmA, tmB, tmC, p, st);
 }
 
 // choose the pixel box (bw x bh x bp <= 128) with the most useful accumulator rows
@@ -350,6 +304,27 @@ int encode_weights(EncodeTiledFn enc, CUtensorMap* tm, const void* w, int K, int
     return 0;
 }
 
+// output tensor (dense or padded-flat view) as {C, W', H', P}; the store box is the M-tile box
+template <typename OutT>
+int encode_output(EncodeTiledFn enc, CUtensorMap* tm, void* y, const TmaConvParams& p, bool out_pf) {
+    const size_t es = sizeof(OutT);
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.P};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cout * es, (cuuint64_t)p.Wo * p.Cout * es, (cuuint64_t)p.Ho * p.Wo * p.Cout * es};
+    char* base = (char*)y;
+    if (out_pf) {
+        base += (size_t)p.out_G0 * p.Cout * es;
+        dims[1] = (cuuint64_t)p.out_Wp; dims[2] = (cuuint64_t)(p.Ho + 1);
+        strides[1] = (cuuint64_t)p.out_Wp * p.Cout * es; strides[2] = (cuuint64_t)p.out_Sp * p.Cout * es;
+    }
+    cuuint32_t box[4] = {(cuuint32_t)epi::Slab<OutT>::COLS, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bp};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled(output) failed with %d", (int)r);
+    return 0;
+}
+
 }  // namespace
 
 namespace ipsb {
@@ -357,7 +332,7 @@ namespace ipsb {
 // x: (P,H,W,Cin) bf16 channels-last, w: (Cout, kh*kw*Cin) bf16.  out_f32 selects the output type.
 int conv_tma(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
              int64_t P, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
-             bool out_f32, cudaStream_t st) {
+             bool out_f32, cudaStream_t st, bool in_pf, bool out_pf) {
     IPSB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tma: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     IPSB_REQUIRE(Ho > 0 && Wo > 0, "conv_tma: bad geometry");
@@ -369,6 +344,8 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
     p.scale = scale; p.shift = shift; p.res = (const bf16*)res; p.y = y;
     p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.kw = kw; p.stride = stride; p.pad = pad; p.relu = relu;
     choose_box(P, Ho, Wo, p);
+    p.out_G0 = 0; p.out_Wp = Wo; p.out_Sp = Ho * Wo;
+    if (out_pf) { const pf::Geo go = pf::make(P, Ho, Wo); p.out_G0 = go.G0; p.out_Wp = go.Wp; p.out_Sp = go.Sp; }
     p.cblocks = Cin / BK; p.KS = kh * kw * p.cblocks;
     p.a_bytes = (uint32_t)(p.bw * p.bh * p.bp) * 128u;
     const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
@@ -381,6 +358,12 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)P};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        if (in_pf) {       // padded-flat input: a (P, H+1, W+1, C) tensor starting G0 rows in; the pads hold zeros
+            const pf::Geo gi = pf::make(P, H, W);
+            x = (const char*)x + (size_t)gi.G0 * Cin * 2;
+            dims[1] = (cuuint64_t)gi.Wp; dims[2] = (cuuint64_t)(H + 1);
+            strides[1] = (cuuint64_t)gi.Wp * Cin * 2; strides[2] = (cuuint64_t)gi.Sp * Cin * 2;
+        }
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)p.bp};
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         IPSB_REQUIRE(box[1] <= 256 && box[2] <= 256 && box[3] <= 256, "conv_tma: box too large");
@@ -390,7 +373,13 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     if (int rc = encode_weights(enc, &tmB, w, kh * kw * Cin, Cout, BN)) return rc;
-    return out_f32 ? dispatch<false, float>(tmA, tmB, p, BN, resb, st) : dispatch<false, bf16>(tmA, tmB, p, BN, resb, st);
+    alignas(64) CUtensorMap tmC;
+    if (out_f32) {
+        if (int rc = encode_output<float>(enc, &tmC, y, p, out_pf)) return rc;
+        return dispatch<false, float>(tmA, tmB, tmC, p, BN, resb, st);
+    }
+    if (int rc = encode_output<bf16>(enc, &tmC, y, p, out_pf)) return rc;
+    return dispatch<false, bf16>(tmA, tmB, tmC, p, BN, resb, st);
 }
 
 // 7x7 stride-2 pad-3 stem.  x: (P, H+6, W+6, 4) bf16 with a zero border (3 rows above, 4 columns left);
@@ -406,6 +395,7 @@ int conv_stem_tma(const void* x, const void* w, const float* scale, const float*
     p.scale = scale; p.shift = shift; p.res = nullptr; p.y = y;
     p.P = (int)P; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.kw = 8; p.stride = 2; p.pad = 0; p.relu = relu;
     choose_box(P, Ho, Wo, p);
+    p.out_G0 = 0; p.out_Wp = Wo; p.out_Sp = Ho * Wo;
     p.cblocks = 1; p.KS = 7; p.b_slabs = 4;          // one filter row (32 k) per stage; weights resident
     p.a_bytes = (uint32_t)(p.bw * p.bh * p.bp) * 64u;
     p.n_tiles_n = 1;
@@ -424,7 +414,9 @@ int conv_stem_tma(const void* x, const void* w, const float* scale, const float*
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_stem_tma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     if (int rc = encode_weights(enc, &tmB, w, 256, Cout, 64)) return rc;
-    return dispatch<true, bf16>(tmA, tmB, p, 64, true, st);
+    alignas(64) CUtensorMap tmC;
+    if (int rc = encode_output<bf16>(enc, &tmC, y, p, false)) return rc;
+    return dispatch<true, bf16>(tmA, tmB, tmC, p, 64, true, st);
 }
 
 }  // namespace ipsb

@@ -150,6 +150,66 @@ def conv_bf16(x, w_nk, scale, shift, res, Cout, kh, kw, stride, pad, relu, mode=
     return y
 
 
+# ---- padded-flat (PF) activations: see ips_b200/csrc/pf.cuh ------------------------------------
+
+def pf_geo(P, H, W):
+    """(rows, G0, Wp, Sp) of the PF layout of P patches of HxW pixels."""
+    Wp, Sp, G0 = W + 1, (H + 1) * (W + 1), W + 2
+    return (G0 + P * Sp + Wp + 2 + 7) // 8 * 8, G0, Wp, Sp
+
+
+def to_pf(x):
+    """dense (P,H,W,C) -> PF (rows, C) with zero pads (torch ops; test / debugging helper)."""
+    P, H, W, C = x.shape
+    rows, G0, Wp, Sp = pf_geo(P, H, W)
+    out = torch.zeros((rows, C), dtype=x.dtype, device=x.device)
+    body = out[G0:G0 + P * Sp].view(P, H + 1, Wp, C)
+    body[:, :H, :W] = x
+    return out
+
+
+def from_pf(x, P, H, W):
+    """PF (rows, C) -> dense (P,H,W,C) view copy (test / debugging helper)."""
+    rows, G0, Wp, Sp = pf_geo(P, H, W)
+    return x[G0:G0 + P * Sp].view(P, H + 1, Wp, -1)[:, :H, :W].contiguous()
+
+
+def conv_bf16_pf(x, w_nk, scale, shift, res, P, H, W, Cout, kh, kw, stride, pad, relu, in_pf, out_pf, out=None):
+    """bf16 tcgen05 convolution reading / writing padded-flat tensors.  x: PF (rows,Cin) if in_pf else dense
+    (P,H,W,Cin).  Returns PF (rows,Cout) if out_pf else dense (P,Ho,Wo,Cout).  3x3/1 PF->PF with
+    Cout in {64,128} runs the shifted-window kernel.  `out` (PF) must have zero pad rows."""
+    _chk(x, torch.bfloat16, 'x'); _chk(w_nk, torch.bfloat16, 'w'); _chk(res, torch.bfloat16, 'res')
+    Cin = x.shape[-1]
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        if out_pf:
+            out = torch.zeros((pf_geo(P, Ho, Wo)[0], Cout), dtype=torch.bfloat16, device=x.device)
+        else:
+            out = torch.empty((P, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    _call('ipsb_conv_bf16_pf', _p(x), _p(w_nk), _p(scale), _p(shift), _p(res), _p(out), P, H, W, Cin, Cout, kh, kw,
+          stride, pad, int(relu), int(in_pf), int(out_pf), _stream())
+    return out
+
+
+def maxpool3x3s2_pf(x, out=None):
+    """dense bf16 (P,H,W,C) -> PF (rows,C) of the pooled (Ho,Wo) map."""
+    _chk(x, torch.bfloat16, 'x')
+    P, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.zeros((pf_geo(P, Ho, Wo)[0], C), dtype=torch.bfloat16, device=x.device)
+    _call('ipsb_maxpool3x3s2_pf', _p(x), _p(out), P, H, W, C, _stream())
+    return out
+
+
+def avgpool_pf(x, P, H, W):
+    _chk(x, torch.bfloat16, 'x')
+    C = x.shape[-1]
+    y = torch.empty((P, C), dtype=torch.float32, device=x.device)
+    _call('ipsb_avgpool_pf', _p(x), _p(y), P, H, W, C, _stream())
+    return y
+
+
 def linear_f32(a, w, scale=None, shift=None, relu=False):
     """y = act((a @ w.T) * scale + shift); a (M,K), w (N,K) fp32."""
     _chk(a, torch.float32, 'a'); _chk(w, torch.float32, 'w')

@@ -199,6 +199,65 @@ def test_conv_bf16_umma(dev, case, path):
         assert (got - ref).abs().mean() < 4e-3 * ref.abs().mean() + 1e-4
 
 
+PF_CASES = [  # Cin, Cout, k, stride, pad, H, W, in_pf, out_pf
+    (64, 64, 3, 1, 1, 25, 25, True, True),       # shifted-window kernel, resident weights
+    (64, 64, 3, 1, 1, 13, 13, True, True),
+    (128, 128, 3, 1, 1, 13, 13, True, True),     # shifted-window kernel, streamed weights
+    (128, 128, 3, 1, 1, 7, 7, True, True),
+    (64, 64, 3, 1, 1, 6, 11, True, True),
+    (64, 128, 3, 2, 1, 25, 25, True, True),      # TMA box kernel reading / writing PF
+    (64, 128, 1, 2, 0, 25, 25, True, True),
+    (128, 256, 3, 2, 1, 13, 13, True, True),
+    (256, 256, 3, 1, 1, 7, 7, True, True),
+    (512, 512, 3, 1, 1, 4, 4, True, False),
+    (64, 64, 3, 1, 1, 13, 13, False, True),
+]
+
+
+@pytest.mark.parametrize('case', PF_CASES)
+def test_conv_bf16_pf(dev, case):
+    """Padded-flat activations: shifted-window 3x3 kernel and the PF in/out modes of the box kernel."""
+    from ips_b200 import ops
+    Cin, Cout, k, s, p, H, W, in_pf, out_pf = case
+    P = 41
+    x = _rand(P, H, W, Cin, seed=40).to(torch.bfloat16)
+    w = _rand(Cout, Cin, k, k, seed=41, scale=math.sqrt(2.0 / (Cin * k * k))).to(torch.bfloat16)
+    scale, shift = torch.rand(Cout) + 0.5, _rand(Cout, seed=42, scale=0.1)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = _rand(P, Ho, Wo, Cout, seed=43).to(torch.bfloat16)
+    w_nk = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous().to(dev)
+    xd = x.to(dev)
+    xin = ops.to_pf(xd) if in_pf else xd
+    for use_res, relu in ((False, True), (True, True), (False, False)):
+        ref = _conv_ref(x.float(), w.float(), scale, shift, res.float() if use_res else None, s, p, relu)
+        r = None
+        if use_res:
+            r = ops.to_pf(res.to(dev)) if out_pf else res.to(dev)
+        y = ops.conv_bf16_pf(xin, w_nk, scale.to(dev), shift.to(dev), r, P, H, W, Cout, k, k, s, p, relu, in_pf, out_pf)
+        if out_pf:
+            got = ops.from_pf(y, P, Ho, Wo).cpu().float()
+            # pad rows must still be zero: the next layer relies on it
+            chk = y.clone()
+            rows, G0, Wp, Sp = ops.pf_geo(P, Ho, Wo)
+            chk[G0:G0 + P * Sp].view(P, Ho + 1, Wp, Cout)[:, :Ho, :Wo] = 0
+            assert float(chk.abs().max()) == 0.0
+        else:
+            got = y.cpu().float()
+        torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2)
+
+
+def test_pools_pf(dev):
+    from ips_b200 import ops
+    x = _rand(9, 64, 50, 50, seed=44).to(torch.bfloat16)
+    nhwc = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    y = ops.maxpool3x3s2_pf(nhwc)
+    ref = F.max_pool2d(x.float(), 3, 2, 1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(ops.from_pf(y, 9, 25, 25).cpu(), ref)
+    assert torch.equal(ops.to_pf(ref.to(dev)), y)                  # pads zero, same layout as the helper
+    a = ops.avgpool_pf(y, 9, 25, 25).cpu()
+    torch.testing.assert_close(a, ref.float().mean(dim=(1, 2)), rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize('M,N,K', [(128, 64, 64), (70, 512, 2048), (1000, 128, 512), (257, 192, 128)])
 def test_linear_bf16_umma(dev, M, N, K):
     from ips_b200 import ops

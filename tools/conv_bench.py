@@ -44,3 +44,23 @@ for name, Cin, Cout, k, s, p, H in LAYERS:
     kreal = (147 if Cin == 4 else k * k * Cin)
     fl = 2.0 * P * Ho * Ho * Cout * kreal
     print(f'{name:5s} M={P*Ho*Ho:7d} N={Cout:3d} K={Kp:4d}  {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (algorithmic)  tiles={-(-P*Ho*Ho//128)}x{Cout//(128 if Cout%128==0 else 64)}')
+
+# ---- padded-flat shifted-window kernel
+print('--- PF shifted-window 3x3 (halo) kernel')
+for name, Cin, Cout, H in [('l1', 64, 64, 25), ('l2', 128, 128, 13), ('m_l1', 64, 64, 13), ('m_l2', 128, 128, 7)]:
+    if only and name != only:
+        continue
+    x = ops.to_pf(torch.randn(P, H, H, Cin, device=dev).to(torch.bfloat16))
+    w = (torch.randn(Cout, 9 * Cin, device=dev) / math.sqrt(9 * Cin)).to(torch.bfloat16)
+    scale = torch.ones(Cout, device=dev); shift = torch.zeros(Cout, device=dev)
+    out = torch.zeros((ops.pf_geo(P, H, H)[0], Cout), dtype=torch.bfloat16, device=dev)
+    f = lambda: ops.conv_bf16_pf(x, w, scale, shift, None, P, H, H, Cout, 3, 3, 1, 1, True, True, True, out=out)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): f()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    fl = 2.0 * P * H * H * Cout * 9 * Cin
+    print(f'{name:5s} P={P} {H}x{H} {Cin}->{Cout}  {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (algorithmic)')
