@@ -152,10 +152,12 @@ typedef struct {
 /* bytes of scratch needed for chunks of `chunk` patches of (C,H,W) */
 IPSB_API int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W);
 /* patches: (rows,C,H,W) fp32 NCHW on the device; row r reads patch first_row + r; add_tab row = (first_row + r) % n_per_image.
- * emb_out (n_rows, D) fp32 may be NULL; z_out (n_rows, HT) fp32. */
+ * emb_out (n_rows, D) fp32 may be NULL; z_out (n_rows, HT) fp32.  zero_init != 0 on the first use of a workspace
+ * (the padded-flat activation buffers rely on zero pad rows, which the kernels then preserve). */
 IPSB_API int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
                                 int C, int H, int W, int64_t n_per_image, int64_t chunk,
-                                void* workspace, int64_t workspace_bytes, float* emb_out, float* z_out, void* stream);
+                                void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out,
+                                void* stream);
 
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the

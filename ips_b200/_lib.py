@@ -58,7 +58,7 @@ SIGNATURES = {
     'ipsb_select_loop': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
-    'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64,
+    'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64, _i32,
                            _ptr, _ptr, _ptr],
 }
 _RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64,

@@ -2,6 +2,7 @@
 // of one chunk (stage -> stem -> maxpool -> BasicBlocks -> avgpool -> logits) from C++, so an
 // ips() call costs one library call instead of ~25 Python round trips per chunk.
 #include "common.cuh"
+#include "pf.cuh"
 #include "../../include/ips_b200.h"
 
 namespace {
@@ -41,25 +42,140 @@ __global__ void iota_mod_kernel(int64_t* out, int64_t first, int64_t n, int64_t 
     if (i < n) out[i] = (first + i) % mod;
 }
 
+// ---- bf16 path: padded-flat activations after the max-pool (see pf.cuh) -------------------------
+struct PfPlan {
+    int n_groups;                 // resolution groups = layers of two BasicBlocks
+    int H[4], W[4], C[4];         // geometry of each group's activations
+    int64_t rows[4];              // PF rows per buffer for `chunk` patches
+    int64_t staged_bytes, stem_bytes, group_bytes[4], total;
+};
+
+PfPlan make_pf_plan(const ipsb_resnet_desc* net, int64_t chunk, int H, int W) {
+    PfPlan pl;
+    pl.staged_bytes = align256(chunk * (int64_t)(H + 6) * (W + 6) * 4 * 2);
+    int h = out_dim(H, 7, 2, 3), w = out_dim(W, 7, 2, 3);
+    pl.stem_bytes = align256(chunk * (int64_t)h * w * net->stem.cout * 2);
+    h = out_dim(h, 3, 2, 1); w = out_dim(w, 3, 2, 1);
+    pl.n_groups = net->n_blocks / 2;
+    pl.total = pl.staged_bytes + pl.stem_bytes;
+    for (int g = 0; g < pl.n_groups; ++g) {
+        const ipsb_conv_desc& c1 = net->blocks[2 * g].c1;
+        h = out_dim(h, c1.kh, c1.stride, c1.pad); w = out_dim(w, c1.kw, c1.stride, c1.pad);
+        pl.H[g] = h; pl.W[g] = w; pl.C[g] = c1.cout;
+        pl.rows[g] = ipsb_pf_rows(chunk, h, w);
+        pl.group_bytes[g] = align256(pl.rows[g] * c1.cout * 2);
+        pl.total += 4 * pl.group_bytes[g];
+    }
+    return pl;
+}
+
+int run_conv_pf(const ipsb_conv_desc& c, const void* x, const void* res, void* y, int64_t P, int H, int W, int relu,
+                void* stream) {
+    return ipsb_conv_bf16_pf(x, c.w, c.scale, c.shift, res, y, P, H, W, c.cin, c.cout, c.kh, c.kw, c.stride, c.pad, relu,
+                             1, 1, stream);
+}
+
 }  // namespace
 
 extern "C" {
 
 int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W) {
     (void)C;
+    const int64_t tail = align256(chunk * net->D * 4) + align256(chunk * 8) + 1024;
+    if (net->dt == IPSB_BF16 && net->stem.mode == 3) return make_pf_plan(net, chunk, H, W).total + tail;
     int64_t staged;
     const int64_t act = max_act_elems(net, H, W, &staged);
     const int64_t es = (int64_t)esize(net->dt);
-    return align256(chunk * staged * es) + 4 * align256(chunk * act * es) + align256(chunk * net->D * 4) +
-           align256(chunk * 8) + 1024;
+    return align256(chunk * staged * es) + 4 * align256(chunk * act * es) + tail;
+}
+
+static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
+                            int C, int H, int W, int64_t n_per_image, int64_t chunk, void* workspace, int zero_init,
+                            float* emb_out, float* z_out, void* stream) {
+    const PfPlan pl = make_pf_plan(net, chunk, H, W);
+    char* ws = (char*)workspace;
+    void* staged = ws;               ws += pl.staged_bytes;
+    void* stem_out = ws;             ws += pl.stem_bytes;
+    void* gb[4][4];
+    char* pf_begin = ws;
+    for (int g = 0; g < pl.n_groups; ++g)
+        for (int i = 0; i < 4; ++i) { gb[g][i] = ws; ws += pl.group_bytes[g]; }
+    if (zero_init)   // pad rows of the padded-flat buffers must be zero; kernels keep them zero afterwards
+        IPSB_CUDA(cudaMemsetAsync(pf_begin, 0, (size_t)(ws - pf_begin), (cudaStream_t)stream));
+    float* emb_ws = (float*)ws;      ws += align256(chunk * net->D * 4);
+    int64_t* pos_idx = (int64_t*)ws;
+
+    for (int64_t lo = 0; lo < n_rows; lo += chunk) {
+        const int64_t P = (n_rows - lo < chunk) ? n_rows - lo : chunk;
+        // stage -> stem -> max-pool in sub-chunks whose stem output (the largest activation) stays in L2
+        int rc = 0;
+        const ipsb_conv_desc& st = net->stem;
+        const int hs = out_dim(H, 7, 2, 3), wsz = out_dim(W, 7, 2, 3);
+        const int hq = out_dim(hs, 3, 2, 1), wq = out_dim(wsz, 3, 2, 1);
+        const int64_t per_patch = (int64_t)hs * wsz * st.cout * 2;
+        int64_t sub = P;                      // (sub-chunking to keep the stem output in L2 measured slower: smaller grids)
+        (void)per_patch;
+        const pf::Geo gq = pf::make(P, hq, wq);
+        for (int64_t s0 = 0; s0 < P; s0 += sub) {
+            const int64_t Ps = (P - s0 < sub) ? P - s0 : sub;
+            rc = ipsb_stage_patches_padded(patches, nullptr, first_row + lo + s0, Ps, C, H, W, 3, 4, H + 6, W + 6, staged, stream);
+            if (rc) return rc;
+            rc = ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H + 6, W + 6, 4, st.cout, 7, 7, 2, 3,
+                                     1, 3, stream);
+            if (rc) return rc;
+            // patch s0 of the chunk starts s0*Sp rows into the padded-flat buffer (same lead-in G0)
+            rc = ipsb_maxpool3x3s2_pf(stem_out, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, hs, wsz, st.cout, stream);
+            if (rc) return rc;
+        }
+        int h = out_dim(hs, 3, 2, 1), w = out_dim(wsz, 3, 2, 1);   // geometry of the current activation
+        const void* cur = gb[0][0];
+        int cur_slot = 0;
+        for (int b = 0; b < net->n_blocks; ++b) {
+            const ipsb_block_desc& blk = net->blocks[b];
+            const int g = b / 2;
+            int free_ids[3], nf = 0;
+            if (b % 2 == 0 && g > 0) { free_ids[0] = 0; free_ids[1] = 1; free_ids[2] = 2; nf = 3; }   // input lives in the previous group
+            else for (int i = 0; i < 4; ++i) if (i != cur_slot) free_ids[nf++] = i;
+            const void* idt = cur;
+            if (blk.has_ds) {
+                rc = run_conv_pf(blk.ds, cur, nullptr, gb[g][free_ids[0]], P, h, w, 0, stream);
+                if (rc) return rc;
+                idt = gb[g][free_ids[0]];
+            }
+            rc = run_conv_pf(blk.c1, cur, nullptr, gb[g][free_ids[1]], P, h, w, 1, stream);
+            if (rc) return rc;
+            rc = run_conv_pf(blk.c2, gb[g][free_ids[1]], idt, gb[g][free_ids[2]], P, pl.H[g], pl.W[g], 1, stream);
+            if (rc) return rc;
+            cur = gb[g][free_ids[2]];
+            cur_slot = free_ids[2];
+            h = pl.H[g]; w = pl.W[g];
+        }
+        const int gl = pl.n_groups - 1;
+        IPSB_REQUIRE(pl.C[gl] == net->D, "resnet_logits: encoder width %d != D %d", pl.C[gl], net->D);
+        float* emb = emb_out ? emb_out + lo * net->D : emb_ws;
+        rc = ipsb_avgpool_pf(cur, emb, P, h, w, pl.C[gl], stream);
+        if (rc) return rc;
+        const int64_t* idx = nullptr;
+        if (net->add_tab) {
+            iota_mod_kernel<<<(unsigned)ipsb::ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(pos_idx, first_row + lo, P, n_per_image);
+            IPSB_LAUNCH_CHECK();
+            idx = pos_idx;
+        }
+        rc = ipsb_logits(emb, net->U, net->add_tab, idx, z_out + lo * net->HT, P, net->D, net->HT, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
                        int C, int H, int W, int64_t n_per_image, int64_t chunk,
-                       void* workspace, int64_t workspace_bytes, float* emb_out, float* z_out, void* stream) {
+                       void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out, void* stream) {
     IPSB_REQUIRE(net && patches && z_out && workspace, "resnet_logits: null argument");
-    IPSB_REQUIRE(n_rows > 0 && chunk > 0 && net->n_blocks > 0 && net->n_blocks <= 8, "resnet_logits: bad sizes");
+    IPSB_REQUIRE(n_rows > 0 && chunk > 0 && net->n_blocks > 0 && net->n_blocks <= 8 && net->n_blocks % 2 == 0, "resnet_logits: bad sizes");
     IPSB_REQUIRE(workspace_bytes >= ipsb_resnet_workspace_bytes(net, chunk, C, H, W), "resnet_logits: workspace too small");
+    if (net->dt == IPSB_BF16 && net->stem.mode == 3)
+        return resnet_logits_pf(net, patches, first_row, n_rows, C, H, W, n_per_image, chunk, workspace, zero_init, emb_out,
+                                z_out, stream);
     const int dt = net->dt;
     const int64_t es = (int64_t)esize(dt);
     int64_t staged_elems;

@@ -148,6 +148,8 @@ __device__ __forceinline__ int next_pow2(int v) {
     return p;
 }
 
+int host_next_pow2(int v);
+
 struct LoopParams {
     const float* z;
     const int64_t* perm;
@@ -200,16 +202,275 @@ __global__ void __launch_bounds__(1024, 1) select_loop_kernel(LoopParams p) {
                 p.out_src[(int64_t)b * M + r] = src;
                 if (p.out_score) p.out_score[(int64_t)b * M + r] = order_bits_inv((uint32_t)(k >> 32));
             }
-            keys[r] = ((unsigned long long)(uint32_t)pos << 32) | (uint32_t)src;
+            keys[r] = ~(((unsigned long long)(uint32_t)pos << 32) | (uint32_t)src);
         }
+        // the memory buffer is kept in SCAN ORDER (ascending position), so "lowest buffer position"
+        // always means "scanned first": re-sort the winners by position (descending on the complement)
+        const int Mpad = next_pow2(M);
+        for (int r = M + tid; r < Mpad; r += nthreads) keys[r] = 0ull;
         __syncthreads();
+        bitonic_desc(keys, Mpad);
         for (int r = tid; r < M; r += nthreads) {
-            const unsigned long long k = keys[r];
+            const unsigned long long k = ~keys[r];
             mem_pos[r] = (int)(k >> 32);
             mem_src[r] = (int)(k & 0xffffffffull);
         }
         __syncthreads();
     }
+}
+
+
+// ---- register-resident variant for long buffers -------------------------------------------------
+// Each of 1024 threads owns E consecutive buffer positions.  The memory buffer is kept in scan
+// order, so an iteration only needs the SET of survivors: a 4-pass radix select finds the score of
+// rank M, a stable compaction keeps everything above it plus the first-scanned equals (the
+// library's tie-break contract), and the winners are sorted once, after the last iteration.
+template <int HT, int E>
+__global__ void __launch_bounds__(1024, 1) select_loop_reg_kernel(LoopParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = 1024;
+    constexpr int CAP = NT * E;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.M;
+    uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);            // [CAP] order bits of the scores
+    int* cand = reinterpret_cast<int*>(keyA + CAP);                    // [CAP] table row of each buffer position
+    uint32_t* fin_key = reinterpret_cast<uint32_t*>(cand + CAP);       // [M] score bits of the survivors
+    int* mem_pos = reinterpret_cast<int*>(fin_key + M);                // [2][M] scan positions (double buffered)
+    int* mem_src = mem_pos + M;                                        // interleaved halves: pos0 src0 pos1 src1
+    int* hist = mem_pos + 4 * M;                                       // [256]
+    int* sel = hist + 256;                                             // [2]
+    int* wsum = sel + 2;                                               // [64]
+    float* red = reinterpret_cast<float*>(wsum + 64);                  // [32][HT] partials, [HT] result, [HT] maxima
+
+    const float* z = p.z + (int64_t)b * p.N * HT;
+    const int64_t* perm = p.perm ? p.perm + (int64_t)b * p.perm_stride : nullptr;
+    for (int r = tid; r < M; r += NT) {
+        mem_pos[r] = r;
+        mem_src[r] = perm ? (int)perm[r] : r;
+    }
+    __syncthreads();
+
+    const int n_iter = (p.N - M + p.I - 1) / p.I;
+    for (int it = 0; it < n_iter; ++it) {
+        const int lo = M + it * p.I;
+        const int hi = min(lo + p.I, p.N);
+        const int L = M + (hi - lo);
+        // ---- candidate -> row of the logit table, cached in shared memory
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid * E + e;
+            int src = -1;
+            if (l < L) {
+                if (l < M) src = mem_src[l];
+                else { const int pp = lo + (l - M); src = perm ? (int)perm[pp] : pp; }
+            }
+            cand[l] = src;
+        }
+        // ---- pass 1: max per (h,t); E independent 32-byte row loads in flight per thread
+        float acc[HT];
+#pragma unroll
+        for (int c = 0; c < HT; ++c) acc[c] = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int src = cand[tid * E + e];
+            if (src >= 0) {
+                const float4* row = reinterpret_cast<const float4*>(z + (int64_t)src * HT);
+#pragma unroll
+                for (int c = 0; c < HT / 4; ++c) {
+                    const float4 v = __ldg(row + c);
+                    acc[4 * c] = fmaxf(acc[4 * c], v.x); acc[4 * c + 1] = fmaxf(acc[4 * c + 1], v.y);
+                    acc[4 * c + 2] = fmaxf(acc[4 * c + 2], v.z); acc[4 * c + 3] = fmaxf(acc[4 * c + 3], v.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < HT; ++c) acc[c] = ipsb::warp_max(acc[c]);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < HT; ++c) red[warp * HT + c] = acc[c];
+        }
+        __syncthreads();
+        if (tid < HT) {
+            float m = red[tid];
+            for (int w = 1; w < 32; ++w) m = fmaxf(m, red[w * HT + tid]);
+            red[32 * HT + tid] = m;
+        }
+        __syncthreads();
+        float mx[HT];
+#pragma unroll
+        for (int c = 0; c < HT; ++c) mx[c] = red[32 * HT + c];
+        if (tid < HT) red[33 * HT + tid] = red[32 * HT + tid];          // maxima kept for pass 3
+        __syncthreads();
+        // ---- pass 2: sums of exp
+#pragma unroll
+        for (int c = 0; c < HT; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int src = cand[tid * E + e];
+            if (src >= 0) {
+                const float4* row = reinterpret_cast<const float4*>(z + (int64_t)src * HT);
+#pragma unroll
+                for (int c = 0; c < HT / 4; ++c) {
+                    const float4 v = __ldg(row + c);
+                    acc[4 * c] += expf(v.x - mx[4 * c]); acc[4 * c + 1] += expf(v.y - mx[4 * c + 1]);
+                    acc[4 * c + 2] += expf(v.z - mx[4 * c + 2]); acc[4 * c + 3] += expf(v.w - mx[4 * c + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < HT; ++c) acc[c] = ipsb::warp_sum(acc[c]);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < HT; ++c) red[warp * HT + c] = acc[c];
+        }
+        __syncthreads();
+        if (tid < HT) {
+            float sm = red[tid];
+            for (int w = 1; w < 32; ++w) sm += red[w * HT + tid];
+            red[32 * HT + tid] = sm;
+        }
+        __syncthreads();
+        // ---- pass 3: scores -> ascending keys of the inverted order bits
+        const float* mxs = red + 32 * HT;   // sums now; keep maxima in registers
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid * E + e;
+            const int src = cand[l];
+            uint32_t key = 0u;
+            if (src >= 0) {
+                const float* zrow = z + (int64_t)src * HT;
+                float tok = 0.f;
+                for (int t = 0; t < p.T; ++t) {
+                    float hs = 0.f;
+                    for (int h = 0; h < p.H; ++h) {
+                        const int c = h * p.T + t;
+                        hs += expf(__ldg(zrow + c) - red[33 * HT + c]) / mxs[c];
+                    }
+                    tok += hs / (float)p.H;
+                }
+                key = order_bits(tok / (float)p.T);
+            }
+            keyA[l] = key;
+        }
+        __syncthreads();
+        // ---- radix SELECT of the M-th largest key: 4 passes of 8 bits, most significant first
+        uint32_t prefix = 0;
+        int remaining = M;                      // rank still to locate inside the current prefix class
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int l = tid * E + e;
+                if (l < L) {
+                    const uint32_t k = keyA[l];
+                    if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {                    // lane j owns bins [255-8j-7, 255-8j]: scan from the top
+                int c[8], tot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; tot += c[j]; }
+                int inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int before = inc - tot;   // keys in bins above this lane's range
+                if (before < remaining && remaining <= inc) {
+                    int run = before;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (run < remaining && remaining <= run + c[j]) { sel[0] = 255 - 8 * lane - j; sel[1] = remaining - run; }
+                        run += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (uint32_t)sel[0];
+            remaining = sel[1];
+            __syncthreads();
+        }
+        const uint32_t thr = prefix;            // key of the rank-M candidate; `remaining` of its equals are kept
+        // ---- stable compaction in buffer (= scan) order: keep key > thr, and the first `remaining` with key == thr
+        int ngt = 0, neq = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid * E + e;
+            if (l < L) { const uint32_t k = keyA[l]; ngt += (k > thr); neq += (k == thr); }
+        }
+        int inc_gt = ngt, inc_eq = neq;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc_gt, o), v = __shfl_up_sync(0xffffffffu, inc_eq, o);
+            if (lane >= o) { inc_gt += u; inc_eq += v; }
+        }
+        if (lane == 31) { wsum[warp] = inc_gt; wsum[32 + warp] = inc_eq; }
+        __syncthreads();
+        if (warp == 0) {
+            int a = wsum[lane], c2 = wsum[32 + lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, a, o), v = __shfl_up_sync(0xffffffffu, c2, o);
+                if (lane >= o) { a += u; c2 += v; }
+            }
+            wsum[lane] = a; wsum[32 + lane] = c2;
+        }
+        __syncthreads();
+        int gt_before = (inc_gt - ngt) + (warp ? wsum[warp - 1] : 0);
+        int eq_before = (inc_eq - neq) + (warp ? wsum[32 + warp - 1] : 0);
+        int* new_pos = mem_pos + 2 * M;         // second half of the double-buffered memory arrays
+        int* new_src = mem_src + 2 * M;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid * E + e;
+            if (l < L) {
+                const uint32_t k = keyA[l];
+                const bool keep = (k > thr) || (k == thr && eq_before < remaining);
+                if (keep) {
+                    const int dst = gt_before + (eq_before < remaining ? eq_before : remaining);
+                    new_pos[dst] = (l < M) ? mem_pos[l] : lo + (l - M);
+                    new_src[dst] = cand[l];
+                    fin_key[dst] = k;           // score bits of the survivors (needed for the final ordering)
+                }
+                gt_before += (k > thr);
+                eq_before += (k == thr);
+            }
+        }
+        __syncthreads();
+        for (int r = tid; r < M; r += NT) { mem_pos[r] = new_pos[r]; mem_src[r] = new_src[r]; }
+        __syncthreads();
+    }
+    // ---- final ordering: score descending, ties -> scanned first (memory is in scan order)
+    unsigned long long* keys64 = reinterpret_cast<unsigned long long*>(smem_raw);     // aliases keyA / cand (no longer needed)
+    const int Mpad = next_pow2(M);
+    uint32_t fk[(8192 + NT - 1) / NT];
+    for (int r = tid, j = 0; r < M; r += NT, ++j) fk[j] = fin_key[r];
+    __syncthreads();
+    for (int r = tid, j = 0; r < Mpad; r += NT, ++j)
+        keys64[r] = (r < M) ? (((unsigned long long)fk[j] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)r)) : 0ull;
+    __syncthreads();
+    bitonic_desc(keys64, Mpad);
+    for (int r = tid; r < M; r += NT) {
+        const unsigned long long k = keys64[r];
+        const int j = (int)key_pos(k);
+        p.out_pos[(int64_t)b * M + r] = mem_pos[j];
+        p.out_src[(int64_t)b * M + r] = mem_src[j];
+        if (p.out_score) p.out_score[(int64_t)b * M + r] = order_bits_inv((uint32_t)(k >> 32));
+    }
+}
+
+template <int HT, int E>
+int launch_reg(const LoopParams& p, int B, cudaStream_t st) {
+    size_t smem = (size_t)1024 * E * 8 + (size_t)p.M * 20 + (256 + 2 + 64) * 4 + 34 * HT * 4 + 64;
+    const size_t fin = (size_t)host_next_pow2(p.M) * 8;      // final 64-bit sort aliases the key / cand arrays
+    IPSB_REQUIRE(fin <= (size_t)1024 * E * 8, "select_loop: M too large for the final sort");
+    IPSB_REQUIRE(smem <= 227 * 1024, "select_loop: %zu bytes of shared memory needed", smem);
+    auto kern = select_loop_reg_kernel<HT, E>;
+    IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, 1024, smem, st>>>(p);
+    IPSB_LAUNCH_CHECK();
+    return 0;
 }
 
 // ---- standalone pieces (unit-level parity: P1 / P2) ----------------------------------
@@ -275,12 +536,17 @@ int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_str
     IPSB_REQUIRE(M < N, "select_loop: M=%d >= N=%d is the caller's shortcut (ips_net.py:185)", M, N);
     IPSB_REQUIRE(H * T <= kMaxHT, "select_loop: H*T=%d exceeds %d", H * T, kMaxHT);
     const int Lmax = M + (I < N - M ? I : N - M);
+    LoopParams p{z, perm, perm_batch_stride, N, H, T, M, I, mem_pos, mem_src, mem_score};
+    // long buffers: register-resident logits + radix sort (M must fit the 8192-entry scratch)
+    if (H * T == 8 && Lmax > 2048 && M <= 8192 && N < 65536 * 1024) {
+        if (Lmax <= 1024 * 4) return launch_reg<8, 4>(p, B, (cudaStream_t)stream);
+        if (Lmax <= 1024 * 10 && (size_t)M * 8 <= 56 * 1024) return launch_reg<8, 10>(p, B, (cudaStream_t)stream);
+    }
     const int Lpad = host_next_pow2(Lmax);
     IPSB_REQUIRE(Lpad <= kMaxLpad, "select_loop: M+I=%d exceeds the single-CTA limit %d", Lmax, kMaxLpad);
     const size_t smem = (size_t)Lpad * 8 + (size_t)(2 * M) * 4 + sizeof(Scratch) + 16;
     IPSB_REQUIRE(smem <= 227 * 1024, "select_loop: %zu bytes of shared memory needed (M=%d I=%d)", smem, M, I);
     IPSB_CUDA(cudaFuncSetAttribute(select_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LoopParams p{z, perm, perm_batch_stride, N, H, T, M, I, mem_pos, mem_src, mem_score};
     select_loop_kernel<<<B, Lpad <= 512 ? 256 : 1024, smem, (cudaStream_t)stream>>>(p);
     IPSB_LAUNCH_CHECK();
     return 0;

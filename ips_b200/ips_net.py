@@ -210,9 +210,8 @@ class IPSNet(nn.Module):
         if self.is_image:
             _, C, H, W = flat.shape
             if plan['stem']['mode'] == 3:
-                x = ops.stage_patches_padded(flat, n_rows, C, H, W, row_idx=row_idx, first_row=first_row)
-            else:
-                x = ops.stage_patches(flat, n_rows, C, H, W, dt, row_idx=row_idx, first_row=first_row)
+                return self._embed_pf(plan, flat, row_idx, first_row, n_rows, C, H, W)
+            x = ops.stage_patches(flat, n_rows, C, H, W, dt, row_idx=row_idx, first_row=first_row)
             x = self._conv(x, plan['stem'])
             x = ops.maxpool3x3s2(x, dt)
             for b in plan['blocks']:
@@ -226,6 +225,28 @@ class IPSNet(nn.Module):
             return ops.linear_bf16(a, plan['p_w'], plan['p_scale'], plan['p_shift'], relu=True)
         a = ops.layernorm_rows(rows.contiguous(), 1e-5)
         return ops.linear_f32(a, plan['p_w'], plan['p_scale'], plan['p_shift'], relu=True)
+
+    def _embed_pf(self, plan, flat, row_idx, first_row, n_rows, C, H, W):
+        """bf16 encoder on padded-flat activations (ips_b200/csrc/pf.cuh), one library call per layer;
+        the same kernel sequence the native executor issues."""
+        P = n_rows
+        x = ops.stage_patches_padded(flat, P, C, H, W, row_idx=row_idx, first_row=first_row)
+        x = self._conv(x, plan['stem'])                              # dense (P, H/2, W/2, 64)
+        h, w = x.shape[1], x.shape[2]
+        x = ops.maxpool3x3s2_pf(x)
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+
+        def conv(x, e, h, w, res=None, relu=True):
+            return ops.conv_bf16_pf(x, e['w'], e['scale'], e['shift'], res, P, h, w, e['cout'], e['kh'], e['kw'],
+                                    e['stride'], e['pad'], relu, True, True)
+        for b in plan['blocks']:
+            s = b['c1']['stride']
+            ho, wo = (h + 2 - 3) // s + 1, (w + 2 - 3) // s + 1
+            idt = x if b['ds'] is None else conv(x, b['ds'], h, w, relu=False)
+            y = conv(x, b['c1'], h, w)
+            x = conv(y, b['c2'], ho, wo, res=idt)
+            h, w = ho, wo
+        return ops.avgpool_pf(x, P, h, w)
 
     def _auto_chunk(self, patch_shape):
         if self.chunk_patches:

@@ -254,16 +254,19 @@ def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=F
     lib = _lib.load()
     need = lib.ipsb_resnet_workspace_bytes(desc, chunk, C, H, W)
     ws = workspace_cache.get('ws')
-    if ws is None or ws.numel() < need or ws.device != patches.device:
-        ws = torch.empty(need, dtype=torch.uint8, device=patches.device)
-        workspace_cache['ws'] = ws
+    key = (chunk, C, H, W, desc.dt)
+    fresh = ws is None or ws.numel() < need or ws.device != patches.device or workspace_cache.get('key') != key
+    if fresh:
+        if ws is None or ws.numel() < need or ws.device != patches.device:
+            ws = torch.empty(need, dtype=torch.uint8, device=patches.device)
+        workspace_cache['ws'], workspace_cache['key'] = ws, key
     z = torch.empty((rows, desc.HT), dtype=torch.float32, device=patches.device)
     emb = torch.empty((rows, desc.D), dtype=torch.float32, device=patches.device) if want_emb else None
     n_chunks = -(-rows // chunk)
     LAUNCHES += n_chunks * (4 + 2 * desc.n_blocks + sum(int(desc.blocks[i].has_ds) for i in range(desc.n_blocks))
                             + (1 if desc.add_tab else 0))
     _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), 0, rows, C, H, W, n_per_image, chunk, _p(ws), ws.numel(),
-                                      _p(emb), _p(z), _stream()))
+                                      int(fresh), _p(emb), _p(z), _stream()))
     return z, emb
 
 

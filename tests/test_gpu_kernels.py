@@ -315,7 +315,8 @@ def test_topm_stable(dev, L, M):
 
 
 def _loop_reference(z, perm, H, T, M, I):
-    """Python restatement of ips_net.py:213-241 on a logit table, stable tie-break."""
+    """Python restatement of ips_net.py:213-241 on a logit table.  Tie-break contract of the library:
+    the buffer is kept in scan order, equal scores resolve to the patch scanned first."""
     B, N, HT = z.shape
     out_pos, out_src = [], []
     for b in range(B):
@@ -328,14 +329,17 @@ def _loop_reference(z, perm, H, T, M, I):
             zz = z[b, order[cand]].view(1, -1, H, T).permute(0, 2, 3, 1)
             sc = torch.softmax(zz, -1).mean(1).transpose(1, 2).mean(-1)[0]
             top = torch.sort(sc, descending=True, stable=True)[1][:M]
-            mem = cand[top]
+            final = cand[top]                                    # best first (what the last iteration returns)
+            mem = final.sort()[0]                                # buffer kept in scan order
+        mem = final
         out_pos.append(mem)
         out_src.append(order[mem])
     return torch.stack(out_pos), torch.stack(out_src)
 
 
 @pytest.mark.parametrize('N,M,I,H,T', [(192, 10, 32, 8, 1), (900, 100, 100, 8, 4), (3000, 500, 500, 8, 1),
-                                       (50, 49, 7, 2, 2), (23000, 5000, 5000, 8, 1)])
+                                       (50, 49, 7, 2, 2), (23000, 5000, 5000, 8, 1), (9000, 1500, 1500, 8, 1),
+                                       (12345, 4000, 777, 8, 1)])
 @pytest.mark.parametrize('shuffle', ['none', 'batch', 'instance'])
 def test_select_loop(dev, N, M, I, H, T, shuffle):
     from ips_b200 import ops
