@@ -196,13 +196,22 @@ def run_ours(args):
         return ms.item()
 
     # ---- device-resident throughput ------------------------------------------------
+    seq = args.shard == 'sequence' and world > 1
+    if seq:                                        # one batch, patch axis sharded: same data on every rank's slice
+        from ips_b200.distributed import ips_sharded, shard_bounds
+        torch.manual_seed(1234)
+        lo_s, hi_s = shard_bounds(N, world)[rank]
+        x_local = x[:, lo_s:hi_s].contiguous()
+        step = lambda: ips_sharded(net, x_local, N)
+    else:
+        step = lambda: net.ips(x)
     for _ in range(max(args.warmup, 3)):
-        net.ips(x)
+        step()
     launches0 = ops.LAUNCHES
     with ClockSampler(local) as clk:
-        ms = timed(lambda: net.ips(x), args.steps)
+        ms = timed(step, args.steps)
     launches = ops.LAUNCHES - launches0
-    value = world * B * N * args.steps / (ms / 1e3)
+    value = (1 if seq else world) * B * N * args.steps / (ms / 1e3)
 
     # ---- end to end through the public API with HOST buffers ---------------------
     xh = x.cpu().pin_memory()
@@ -275,10 +284,11 @@ def run_ours(args):
         line = {
             'metric': 'ips_selection_patches_per_sec', 'value': value, 'unit': 'patches/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'higher_is_better': True, 'scaling': 'strong' if seq else 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': f'{args.workload}: IPSNet.ips, B={B} N={N} M={conf.M} I={conf.I} per GPU',
-                       'precision': args.precision, 'parallelism': f'dp{world} (independent batches, no collective)',
+                       'precision': args.precision, 'parallelism': (f'sp{world} (patch axis sharded; all-gather of logits, all-reduce of winners)' if seq
+                                       else f'dp{world} (independent batches, no collective)'),
                        'l2': f'input {in_bytes / 2**20:.0f} MiB per step > 126 MB L2, no flush needed'},
             'clocks': clk.summary(),
             'e2e': {'value': e2e_value, 'unit': 'patches/s', 'h2d_bytes_per_step': in_bytes,
@@ -300,6 +310,9 @@ def main():
     ap.add_argument('--workload', default='traffic', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--shard', default='batch', choices=['batch', 'sequence'],
+                    help="N>1: 'batch' = every rank scans its own batch (weak scaling); 'sequence' = ONE batch whose patch axis "
+                         "is sharded over the ranks (strong scaling, NCCL all-gather of logits + all-reduce of winners)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -162,7 +162,8 @@ IPSB_API int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patche
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the
  * pos-enc gather (:249-250): dst[b,m,:] = src[b*src_batch_stride + idx[b,m], :],
- * rows of row_bytes bytes (multiple of 4; 16-byte vector path when aligned). */
+ * rows of row_bytes bytes (multiple of 4; 16-byte vector path when aligned).  A negative index writes a zero
+ * row (used by the sequence-sharded gather, where a rank owns only part of the winners). */
 IPSB_API int ipsb_gather_rows(const void* src, int64_t src_batch_stride_rows, const int64_t* idx,
                      int B, int M, int64_t row_bytes, void* dst, void* stream);
 

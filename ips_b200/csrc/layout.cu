@@ -73,7 +73,8 @@ __global__ void gather_rows16_kernel(const unsigned char* __restrict__ src, int6
                                      unsigned char* __restrict__ dst) {
     const int64_t row = blockIdx.x;
     const int64_t b = row / M;
-    const int64_t srow = b * batch_stride_rows + idx[row];
+    const int64_t sel = idx[row];
+    const int64_t srow = b * batch_stride_rows + (sel < 0 ? 0 : sel);
     const unsigned char* s = src + srow * row_bytes;
     unsigned char* d = dst + row * row_bytes;
     const int64_t seg_lo = (int64_t)blockIdx.y * 16384;
@@ -86,7 +87,7 @@ __global__ void gather_rows16_kernel(const unsigned char* __restrict__ src, int6
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         ok[j] = off + j * step < seg_hi;
-        if (ok[j]) v[j] = ipsb::ld_stream16(s + off + j * step);
+        if (ok[j]) v[j] = sel < 0 ? make_int4(0, 0, 0, 0) : ipsb::ld_stream16(s + off + j * step);   // idx < 0: zero row
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -98,11 +99,12 @@ __global__ void gather_rows4_kernel(const uint32_t* __restrict__ src, int64_t ba
                                     uint32_t* __restrict__ dst) {
     const int64_t row = blockIdx.x;
     const int64_t b = row / M;
-    const uint32_t* s = src + (b * batch_stride_rows + idx[row]) * row_words;
+    const int64_t sel = idx[row];
+    const uint32_t* s = src + (b * batch_stride_rows + (sel < 0 ? 0 : sel)) * row_words;
     uint32_t* d = dst + row * row_words;
     for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < row_words;
          i += (int64_t)gridDim.y * blockDim.x)
-        d[i] = s[i];
+        d[i] = sel < 0 ? 0u : s[i];
 }
 
 // max_pool2d(3, 2, 1) channels-last, VEC channels per thread (16 bytes)

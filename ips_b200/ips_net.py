@@ -257,16 +257,17 @@ class IPSNet(nn.Module):
         return max(32, min(4096, (1024 * 10000) // max(px, 1)))      # ~1024 patches of 100x100: fills 148 SMs in every layer
 
     @torch.no_grad()
-    def patch_logits(self, patches):
+    def patch_logits(self, patches, pos_offset=0):
         """(B,N,...) -> (B,N,H*T) fp32 logit table on `self.device`, original patch order.
-        Host-resident input (lazy loading, conf.eager=False) is streamed chunk by chunk."""
+        Host-resident input (lazy loading, conf.eager=False) is streamed chunk by chunk.
+        `pos_offset`: index of patches[:, 0] in the full sequence (sequence-sharded runs)."""
         plan = self._get_plan()
         B, N = patches.shape[:2]
         rows = B * N
         flat = patches.reshape(rows, *patches.shape[2:])
         HT = plan['U'].shape[1]
         chunk = self._auto_chunk(patches.shape)
-        if self.is_image and flat.is_cuda and self.executor == 'native':
+        if self.is_image and flat.is_cuda and self.executor == 'native' and pos_offset == 0:
             if 'desc' not in plan:
                 plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
             z, _ = ops.resnet_logits(plan['desc'], flat.contiguous(), N, chunk, self._ws_cache)
@@ -274,7 +275,7 @@ class IPSNet(nn.Module):
         z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
         pos_idx = None
         if self.use_pos:
-            pos_idx = (torch.arange(rows, device=self.device) % N).contiguous()
+            pos_idx = (torch.arange(rows, device=self.device) % N + pos_offset).contiguous()
         for lo in range(0, rows, chunk):
             n = min(chunk, rows - lo)
             if flat.is_cuda:
