@@ -159,6 +159,19 @@ IPSB_API int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patche
                                 void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out,
                                 void* stream);
 
+/* ---------------------------------------------------------------- aggregator + heads, forward (no-grad)
+ * Replaces MultiHeadCrossAttention.forward / MLP.forward / get_preds in inference
+ * (architecture/transformer.py:85-132, architecture/ips_net.py:157-166); projections use the GEMM entry points.
+ * q_scaled: (T, H*Dk) = q_w(q) / sqrt(Dk); k: (B,M,H*Dk); v: (B,M,H*Dv); out: (B,T,H*Dv), Dv <= 64. */
+IPSB_API int ipsb_cross_attention_f32(const float* q_scaled, const float* k, const float* v, float* out,
+                                      int B, int M, int H, int Dk, int Dv, int T, void* stream);
+/* y = LayerNorm(x + r[row % r_rows]) * gamma + beta over rows of D (r may be NULL) */
+IPSB_API int ipsb_residual_layernorm_f32(const float* x, const float* r, int r_rows, const float* gamma, const float* beta,
+                                         float* y, int64_t rows, int D, float eps, void* stream);
+/* rows of n logits -> softmax (act 0) or sigmoid (act 1) */
+IPSB_API int ipsb_head_activation_f32(const float* logits, float* y, int rows, int n, int act, void* stream);
+IPSB_API int ipsb_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the
  * pos-enc gather (:249-250): dst[b,m,:] = src[b*src_batch_stride + idx[b,m], :],

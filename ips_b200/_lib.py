@@ -56,6 +56,10 @@ SIGNATURES = {
     'ipsb_scores_from_logits': [_ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_topm_stable': [_ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr],
     'ipsb_select_loop': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
+    'ipsb_cross_attention_f32': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
+    'ipsb_residual_layernorm_f32': [_ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
+    'ipsb_head_activation_f32': [_ptr, _ptr, _i32, _i32, _i32, _ptr],
+    'ipsb_add_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
     'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64, _i32,

@@ -347,8 +347,40 @@ class IPSNet(nn.Module):
         mem_pos = ops.gather_rows(self.pos_enc[0].contiguous(), mem_src, 0) if self.use_pos else None
         return mem_patch, mem_pos
 
+    @torch.no_grad()
+    def _forward_inference(self, mem_patch, mem_pos):
+        """`forward` in eval mode under no-grad (training/iterative.py:193-231 `evaluate`): every operator is a
+        library kernel -- encoder as in `ips`, then projections, cross-attention, LayerNorm, MLP, heads."""
+        ca, mlp = self.transf.crs_attn, self.transf.mlp
+        B, M = mem_patch.shape[:2]
+        f = lambda t: t.detach().float().contiguous()
+        emb = self.embed(mem_patch.reshape(B * M, *mem_patch.shape[2:]).contiguous())          # (B*M, D) fp32
+        if torch.is_tensor(mem_pos):
+            emb = ops.add(emb, mem_pos.reshape(B * M, -1).float().contiguous())
+        k = ops.linear_f32(emb, f(ca.k_w.weight)).view(B, M, -1)
+        v = ops.linear_f32(emb, f(ca.v_w.weight)).view(B, M, -1)
+        q_tok = f(ca.q[0])                                                                      # (T, D)
+        inv_t = torch.full((ca.H * ca.D_k,), 1.0 / ca.attention.temperature, device=emb.device)
+        q = ops.linear_f32(q_tok, f(ca.q_w.weight), scale=inv_t)                                # q / sqrt(D_k)
+        att = ops.cross_attention(q, k, v, ca.H, ca.D_k, ca.D_v)                                # (B, T, H*Dv)
+        T = q_tok.shape[0]
+        o = ops.linear_f32(att.view(B * T, -1), f(ca.fc.weight))
+        o = ops.residual_layernorm(o, q_tok, f(ca.layer_norm.weight), f(ca.layer_norm.bias), ca.layer_norm.eps)
+        hdn = ops.linear_f32(o, f(mlp.w_1.weight), shift=f(mlp.w_1.bias), relu=True)
+        h2 = ops.linear_f32(hdn, f(mlp.w_2.weight), shift=f(mlp.w_2.bias))
+        tok = ops.residual_layernorm(h2, o, f(mlp.layer_norm.weight), f(mlp.layer_norm.bias), mlp.layer_norm.eps).view(B, T, -1)
+        preds = {}
+        for task in self.tasks.values():
+            lin = self.output_layers[task['name']][0]
+            zl = ops.linear_f32(tok[:, task['id']].contiguous(), f(lin.weight), shift=f(lin.bias))
+            preds[task['name']] = ops.head_activation(zl, task['act_fn'])
+        return preds
+
     def forward(self, mem_patch, mem_pos=None):
-        """Encode + aggregate the selected patches with gradients (ips_net.py:264-283)."""
+        """Encode + aggregate the selected patches (ips_net.py:264-283).  Inference (eval mode, no grad) runs on
+        the library's kernels; the grad-mode train step uses PyTorch autograd on the same parameters."""
+        if not self.training and not torch.is_grad_enabled() and mem_patch.is_cuda:
+            return self._forward_inference(mem_patch, mem_pos)
         shape = mem_patch.shape
         B, M = shape[:2]
         mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)

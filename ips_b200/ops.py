@@ -324,6 +324,42 @@ def select_loop(z, perm, per_instance, H, T, M, I):
     return mem_pos, mem_src, score
 
 
+# ------------------------------------------------------------------ aggregator + heads (no-grad forward)
+
+def cross_attention(q_scaled, k, v, H, Dk, Dv):
+    """q_scaled (T,H*Dk), k (B,M,H*Dk), v (B,M,H*Dv) -> (B,T,H*Dv): softmax(q k^T) v per head."""
+    _chk(q_scaled, torch.float32, 'q'); _chk(k, torch.float32, 'k'); _chk(v, torch.float32, 'v')
+    B, M = k.shape[:2]
+    T = q_scaled.shape[0]
+    out = torch.empty((B, T, H * Dv), dtype=torch.float32, device=k.device)
+    _call('ipsb_cross_attention_f32', _p(q_scaled), _p(k), _p(v), _p(out), B, M, H, Dk, Dv, T, _stream())
+    return out
+
+
+def residual_layernorm(x, r, gamma, beta, eps):
+    """LayerNorm(x + r) * gamma + beta; x (rows, D), r (r_rows, D) broadcast over rows or None."""
+    _chk(x, torch.float32, 'x'); _chk(r, torch.float32, 'r'); _chk(gamma, torch.float32, 'gamma'); _chk(beta, torch.float32, 'beta')
+    rows, D = x.shape
+    y = torch.empty_like(x)
+    _call('ipsb_residual_layernorm_f32', _p(x), _p(r), 0 if r is None else r.shape[0], _p(gamma), _p(beta), _p(y), rows, D,
+          eps, _stream())
+    return y
+
+
+def head_activation(logits, act):
+    _chk(logits, torch.float32, 'logits')
+    y = torch.empty_like(logits)
+    _call('ipsb_head_activation_f32', _p(logits), _p(y), logits.shape[0], logits.shape[1], 1 if act == 'sigmoid' else 0, _stream())
+    return y
+
+
+def add(a, b):
+    _chk(a, torch.float32, 'a'); _chk(b, torch.float32, 'b')
+    y = torch.empty_like(a)
+    _call('ipsb_add_f32', _p(a), _p(b), _p(y), a.numel(), _stream())
+    return y
+
+
 # ------------------------------------------------------------------ torch.ops registration
 # Thin public aliases so the kernels are reachable as torch.ops.ips_b200.*; the
 # module code calls the Python functions above directly (lower dispatch overhead).

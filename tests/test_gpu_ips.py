@@ -188,3 +188,22 @@ def test_native_executor_equals_per_layer_calls(name, precision):
     net.executor = 'python'
     b = net.patch_logits(x)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('name', [n for n in CASE_NAMES if 'shortcut' not in n and 'instance' not in n])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_inference_forward_matches_oracle(name, precision):
+    """`net.eval(); net(mem_patch, mem_pos)` under no_grad (the reference's evaluate()) runs on the library's
+    kernels end to end and reproduces the oracle's probabilities (eval-mode BatchNorm, dropout off)."""
+    z, meta, conf, sd, patches = load_case(name)
+    net = _net(conf, sd, precision)
+    torch.manual_seed(meta['rng_seed'])
+    mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+    ref = O.forward(sd, conf, mem_patch, mem_pos, train=False)
+    net.eval()
+    with torch.no_grad():
+        got = net(mem_patch.to(DEV), None if mem_pos is None else mem_pos.to(DEV))
+    tol = dict(rtol=2e-4, atol=2e-6) if precision == 'fp32' else dict(rtol=5e-2, atol=5e-3)
+    for t in ref:
+        torch.testing.assert_close(got[t].cpu(), ref[t], **tol)
+    assert not net.training

@@ -362,3 +362,32 @@ def test_select_loop(dev, N, M, I, H, T, shuffle):
         assert torch.equal(pos.cpu(), ref_pos)
     sc = score.cpu()
     assert (sc[:, :-1] >= sc[:, 1:]).all()                        # best first
+
+
+# ------------------------------------------------------------------ aggregator + heads (no-grad forward)
+
+@pytest.mark.parametrize('B,M,H,Dk,Dv,T', [(2, 100, 8, 16, 16, 4), (3, 10, 8, 64, 64, 1), (1, 5000, 8, 64, 64, 1), (2, 7, 3, 8, 24, 2)])
+def test_cross_attention(dev, B, M, H, Dk, Dv, T):
+    from ips_b200 import ops
+    q = _rand(T, H * Dk, seed=50) / math.sqrt(Dk)
+    k, v = _rand(B, M, H * Dk, seed=51), _rand(B, M, H * Dv, seed=52)
+    qq = q.view(1, T, H, Dk).transpose(1, 2)
+    kk = k.view(B, M, H, Dk).transpose(1, 2)
+    vv = v.view(B, M, H, Dv).transpose(1, 2)
+    ref = torch.matmul(torch.softmax(torch.matmul(qq, kk.transpose(2, 3)), -1), vv).transpose(1, 2).reshape(B, T, H * Dv)
+    got = ops.cross_attention(q.to(dev), k.to(dev), v.to(dev), H, Dk, Dv).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_residual_layernorm_and_heads(dev):
+    from ips_b200 import ops
+    x, r = _rand(12, 128, seed=53), _rand(4, 128, seed=54)
+    g, b = torch.rand(128) + 0.5, _rand(128, seed=55)
+    ref = F.layer_norm(x + r.repeat(3, 1), (128,), g, b, 1e-6)
+    torch.testing.assert_close(ops.residual_layernorm(x.to(dev), r.to(dev), g.to(dev), b.to(dev), 1e-6).cpu(), ref, rtol=1e-5, atol=1e-5)
+    ref = F.layer_norm(x, (128,), g, b, 1e-6)
+    torch.testing.assert_close(ops.residual_layernorm(x.to(dev), None, g.to(dev), b.to(dev), 1e-6).cpu(), ref, rtol=1e-5, atol=1e-5)
+    z = _rand(9, 10, seed=56) * 3
+    torch.testing.assert_close(ops.head_activation(z.to(dev), 'softmax').cpu(), torch.softmax(z, -1), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(ops.head_activation(z.to(dev), 'sigmoid').cpu(), torch.sigmoid(z), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(ops.add(x.to(dev), x.to(dev)).cpu(), x + x)
