@@ -118,10 +118,14 @@ IPSB_API int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t*
  * scan order (shuffled position -> original index) or NULL for identity;
  * perm_batch_stride = N for per-instance permutations, 0 for a shared one.
  * Outputs (B,M): mem_pos = winners' shuffled positions (the reference's mem_idx),
- * mem_src = their original indices, mem_score = final-iteration scores; best first. */
+ * mem_src = their original indices, mem_score = final-iteration scores; best first.  Equal scores resolve to
+ * the patch scanned first.  workspace (ipsb_select_loop_workspace_bytes; may be NULL = slower single-CTA path)
+ * holds the scan-ordered logit table and the double-buffered memory set. */
+IPSB_API int64_t ipsb_select_loop_workspace_bytes(int B, int N, int HT, int M);
 IPSB_API int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_stride,
                      int B, int N, int H, int T, int M, int I,
-                     int64_t* mem_pos, int64_t* mem_src, float* mem_score, void* stream);
+                     int64_t* mem_pos, int64_t* mem_src, float* mem_score,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- native encoder executor
  * One call = the whole eval-mode patch encoder + logit projection for `n_rows` patches

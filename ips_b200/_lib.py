@@ -55,7 +55,8 @@ SIGNATURES = {
     'ipsb_logits': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_scores_from_logits': [_ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_topm_stable': [_ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr],
-    'ipsb_select_loop': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr],
+    'ipsb_select_loop_workspace_bytes': [_i32, _i32, _i32, _i32],
+    'ipsb_select_loop': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_cross_attention_f32': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_residual_layernorm_f32': [_ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
     'ipsb_head_activation_f32': [_ptr, _ptr, _i32, _i32, _i32, _ptr],
@@ -66,7 +67,7 @@ SIGNATURES = {
                            _ptr, _ptr, _ptr],
 }
 _RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64,
-            'ipsb_pf_rows': ctypes.c_int64}
+            'ipsb_pf_rows': ctypes.c_int64, 'ipsb_select_loop_workspace_bytes': ctypes.c_int64}
 
 _lib = None
 

@@ -9,8 +9,12 @@
 //
 // One CTA owns one image for the whole loop: the memory set lives in shared
 // memory across iterations, logits are re-read from the (L2 resident) table.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/ips_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -149,6 +153,9 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 int host_next_pow2(int v);
+}  // namespace
+extern "C" int64_t ipsb_select_loop_workspace_bytes(int B, int N, int HT, int M);
+namespace {
 
 struct LoopParams {
     const float* z;
@@ -473,6 +480,376 @@ int launch_reg(const LoopParams& p, int B, cudaStream_t st) {
     return 0;
 }
 
+// ---- cluster-parallel variant ------------------------------------------------------------------
+// A thread-block cluster of NC CTAs owns one image: CTA r holds buffer positions [r*S, (r+1)*S) --
+// their logits, scan positions and table rows -- in shared memory.  A pre-pass permutes the logit table
+// into scan order, so each iteration streams its chunk with coalesced loads and no dependent gathers.
+// Per iteration the CTAs exchange only small partials through distributed shared memory (per-(h,t) max and
+// sum, 256-bin radix-select histograms, survivor counts); the M survivors (logits, position, row, score
+// bits) move through a double-buffered global scratch that stays in L2.
+// Same semantics as the single-CTA kernels: buffer kept in scan order, equal scores -> scanned first.
+// histogram increment with warp aggregation: scores of one buffer share their leading bits, so most lanes hit the
+// same bin -- one shared-memory atomic per distinct bin per warp instead of one per lane
+__device__ __forceinline__ void hist_add(int* hist, uint32_t bin, bool active) {
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const uint32_t peers = __match_any_sync(act, bin);
+    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+}
+
+struct ClusterScratch {
+    float part_max[kMaxHT], part_sum[kMaxHT];   // this CTA's partials (read remotely)
+    float gmax[kMaxHT], gsum[kMaxHT];           // cluster-wide results
+    int hist[4][256];                           // this CTA's radix histograms (read remotely)
+    int tot[256];
+    int cnt[2];                                 // survivors above / equal to the threshold in this CTA
+    int sel[2];
+    int wsum[64];
+    Scratch red;
+};
+
+// zs[b, pos, :] = z[b, perm[pos], :], srcs[b, pos] = perm[pos]
+__global__ void permute_logits_kernel(const float* __restrict__ z, const int64_t* __restrict__ perm, int64_t perm_stride,
+                                      int N, int HT, float* __restrict__ zs, int* __restrict__ srcs, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / HT;
+        const int c = (int)(i - row * HT);
+        const int64_t b = row / N;
+        const int pos = (int)(row - b * N);
+        const int src = perm ? (int)perm[b * perm_stride + pos] : pos;
+        zs[i] = z[(b * N + src) * HT + c];
+        if (c == 0) srcs[row] = src;
+    }
+}
+
+struct ClusterArgs {
+    const float* zs;      // (B, N, HT) logits in scan order
+    const int* srcs;      // (B, N) table row of every scan position
+    float* m_z;           // (B, 2, M, HT) survivors' logits
+    int* m_pos;           // (B, 2, M)
+    int* m_src;           // (B, 2, M)
+    uint32_t* m_key;      // (B, M)
+    unsigned long long* m_runs;   // (B, NC * ceil(M / NC)) sorted runs of the final ordering
+    int slice_cap;
+};
+
+template <int NC>
+__global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(512, 1)
+select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int NT = 512;
+    const int cr = (NC == 1) ? 0 : (int)cluster.block_rank();
+    const int b = blockIdx.x / NC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HT = p.H * p.T, M = p.M, cap = a.slice_cap;
+    float* zl = reinterpret_cast<float*>(smem_raw);                     // [cap][HT] logits of this slice
+    uint32_t* key = reinterpret_cast<uint32_t*>(zl + (size_t)cap * HT); // [cap]
+    int* cand = reinterpret_cast<int*>(key + cap);                      // [cap] table rows
+    int* posl = cand + cap;                                             // [cap] scan positions
+    size_t front = (size_t)cap * (HT + 3) * 4;
+    { const size_t fs = (size_t)next_pow2((M + NC - 1) / NC) * 8; if (front < fs) front = fs; front = (front + 15) / 16 * 16; }
+    ClusterScratch* cs = reinterpret_cast<ClusterScratch*>(smem_raw + front);
+    uint32_t* allkey = reinterpret_cast<uint32_t*>(cs + 1);             // [M] final ordering
+
+    const float* zs = a.zs + (int64_t)b * p.N * HT;
+    const int* srcs = a.srcs + (int64_t)b * p.N;
+    float* z_buf[2] = {a.m_z + (int64_t)b * 2 * M * HT, a.m_z + (int64_t)b * 2 * M * HT + (int64_t)M * HT};
+    int* pos_buf[2] = {a.m_pos + (int64_t)b * 2 * M, a.m_pos + (int64_t)b * 2 * M + M};
+    int* src_buf[2] = {a.m_src + (int64_t)b * 2 * M, a.m_src + (int64_t)b * 2 * M + M};
+    uint32_t* key_buf = a.m_key + (int64_t)b * M;
+    auto csync = [&]() { if (NC == 1) __syncthreads(); else cluster.sync(); };
+
+    // initial memory buffer: the first M scan positions
+    for (int i = cr * NT + tid; i < M * HT; i += NC * NT) z_buf[0][i] = zs[i];
+    for (int r = cr * NT + tid; r < M; r += NC * NT) { pos_buf[0][r] = r; src_buf[0][r] = srcs[r]; }
+    __threadfence();
+    csync();
+
+    const bool pow2 = (HT & (HT - 1)) == 0;
+    const int nt_eff = (NT / HT) * HT;
+    const int n_iter = (p.N - M + p.I - 1) / p.I;
+    int cur = 0;
+    for (int it = 0; it < n_iter; ++it) {
+        const int lo = M + it * p.I;
+        const int hi = min(lo + p.I, p.N);
+        const int L = M + (hi - lo);
+        const int S = (L + NC - 1) / NC;                     // slice length
+        const int l0 = cr * S;
+        const int n_own = max(0, min(S, L - l0));
+        // ---- this slice's logits / positions / rows -> shared memory (coalesced 128-bit streams, 4 loads in flight)
+        {
+            const int hv = HT >> 2;                              // float4 granules per row (HT is a power of two >= 4) or 0
+            if (hv > 0) {
+                const int total4 = n_own * hv;
+                float4* zl4 = reinterpret_cast<float4*>(zl);
+                for (int e0 = tid; e0 < total4; e0 += 4 * NT) {
+                    float4 v4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * NT;
+                        if (e < total4) {
+                            const int i = e / hv, c4 = e - i * hv, l = l0 + i;
+                            const float* src_row = (l < M) ? z_buf[cur] + (int64_t)l * HT : zs + (int64_t)(lo + l - M) * HT;
+                            v4[u] = __ldg(reinterpret_cast<const float4*>(src_row) + c4);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * NT;
+                        if (e < total4) zl4[e] = v4[u];
+                    }
+                }
+            } else {
+                for (int e = tid; e < n_own * HT; e += NT) {
+                    const int i = e / HT, c = e - i * HT, l = l0 + i;
+                    zl[e] = (l < M) ? z_buf[cur][(int64_t)l * HT + c] : zs[(int64_t)(lo + l - M) * HT + c];
+                }
+            }
+        }
+        for (int i = tid; i < n_own; i += NT) {
+            const int l = l0 + i;
+            if (l < M) { posl[i] = pos_buf[cur][l]; cand[i] = src_buf[cur][l]; }
+            else { posl[i] = lo + (l - M); cand[i] = srcs[lo + (l - M)]; }
+        }
+        if (tid < 256) { cs->hist[0][tid] = 0; cs->hist[1][tid] = 0; cs->hist[2][tid] = 0; cs->hist[3][tid] = 0; }
+        __syncthreads();
+        // ---- per-(h,t) max over the whole buffer
+        const int ht = tid % HT;
+        float v = -INFINITY;
+        if (tid < nt_eff)
+            for (int e = tid; e < n_own * HT; e += nt_eff) v = fmaxf(v, zl[e]);
+        reduce_classes<true>(v, HT, pow2, nt_eff, &cs->red, cs->part_max);
+        csync();
+        if (tid < HT) {
+            float m = cs->part_max[tid];
+            if (NC > 1) for (int r = 0; r < NC; ++r) m = fmaxf(m, cluster.map_shared_rank(cs->part_max, r)[tid]);
+            cs->gmax[tid] = m;
+        }
+        __syncthreads();
+        // ---- per-(h,t) sum of exp
+        v = 0.f;
+        if (tid < nt_eff) {
+            const float m = cs->gmax[ht];
+            for (int e = tid; e < n_own * HT; e += nt_eff) v += expf(zl[e] - m);
+        }
+        reduce_classes<false>(v, HT, pow2, nt_eff, &cs->red, cs->part_sum);
+        csync();
+        if (tid < HT) {
+            float sm = 0.f;
+            if (NC > 1) { for (int r = 0; r < NC; ++r) sm += cluster.map_shared_rank(cs->part_sum, r)[tid]; }
+            else sm = cs->part_sum[tid];
+            cs->gsum[tid] = sm;
+        }
+        __syncthreads();
+        // ---- scores -> order bits; first radix histogram on the fly
+        for (int i0 = 0; i0 < n_own; i0 += NT) {             // warp-uniform trip count (hist_add uses warp votes)
+            const int i = i0 + tid;
+            uint32_t k = 0;
+            if (i < n_own) {
+                const float* zr = zl + (size_t)i * HT;
+                float tok = 0.f;
+                for (int t = 0; t < p.T; ++t) {
+                    float hs = 0.f;
+                    for (int h = 0; h < p.H; ++h) {
+                        const int c = h * p.T + t;
+                        hs += expf(zr[c] - cs->gmax[c]) / cs->gsum[c];
+                    }
+                    tok += hs / (float)p.H;
+                }
+                k = order_bits(tok / (float)p.T);
+                key[i] = k;
+            }
+            hist_add(cs->hist[0], k >> 24, i < n_own);
+        }
+        // ---- radix select of the rank-M key: 4 passes of 8 bits, histograms summed over the cluster
+        uint32_t prefix = 0;
+        int remaining = M;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (pass > 0) {
+                for (int i0 = 0; i0 < n_own; i0 += NT) {
+                    const int i = i0 + tid;
+                    const uint32_t k = (i < n_own) ? key[i] : 0u;
+                    hist_add(cs->hist[pass], (k >> shift) & 255u, i < n_own && (k >> (shift + 8)) == prefix);
+                }
+            }
+            csync();
+            if (tid < 256) {
+                int t = 0;
+                if (NC > 1) { for (int r = 0; r < NC; ++r) t += cluster.map_shared_rank(&cs->hist[pass][0], r)[tid]; }
+                else t = cs->hist[pass][tid];
+                cs->tot[tid] = t;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int c[8], tot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = cs->tot[255 - 8 * lane - j]; tot += c[j]; }
+                int inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int before = inc - tot;
+                if (before < remaining && remaining <= inc) {
+                    int run = before;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (run < remaining && remaining <= run + c[j]) { cs->sel[0] = 255 - 8 * lane - j; cs->sel[1] = remaining - run; }
+                        run += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (uint32_t)cs->sel[0];
+            remaining = cs->sel[1];
+            __syncthreads();
+        }
+        const uint32_t thr = prefix;
+        // ---- stable compaction in scan order: contiguous runs of E slice entries per thread
+        const int E = (S + NT - 1) / NT;
+        int ngt = 0, neq = 0;
+        for (int e = 0; e < E; ++e) {
+            const int i = tid * E + e;
+            if (i < n_own) { const uint32_t k = key[i]; ngt += (k > thr); neq += (k == thr); }
+        }
+        int inc_gt = ngt, inc_eq = neq;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc_gt, o), w = __shfl_up_sync(0xffffffffu, inc_eq, o);
+            if (lane >= o) { inc_gt += u; inc_eq += w; }
+        }
+        if (lane == 31) { cs->wsum[warp] = inc_gt; cs->wsum[32 + warp] = inc_eq; }
+        __syncthreads();
+        if (warp == 0) {
+            int g1 = lane < NT / 32 ? cs->wsum[lane] : 0, c2 = lane < NT / 32 ? cs->wsum[32 + lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, g1, o), w = __shfl_up_sync(0xffffffffu, c2, o);
+                if (lane >= o) { g1 += u; c2 += w; }
+            }
+            cs->wsum[lane] = g1; cs->wsum[32 + lane] = c2;
+            if (lane == NT / 32 - 1) { cs->cnt[0] = g1; cs->cnt[1] = c2; }
+        }
+        csync();
+        int gt_before = (inc_gt - ngt) + (warp ? cs->wsum[warp - 1] : 0);
+        int eq_before = (inc_eq - neq) + (warp ? cs->wsum[32 + warp - 1] : 0);
+        if (NC > 1) {
+            for (int r = 0; r < cr; ++r) {                   // survivors in the slices before this one
+                const int* rc = cluster.map_shared_rank(cs->cnt, r);
+                gt_before += rc[0];
+                eq_before += rc[1];
+            }
+        }
+        const int nxt = cur ^ 1;
+        for (int e = 0; e < E; ++e) {
+            const int i = tid * E + e;
+            if (i < n_own) {
+                const uint32_t k = key[i];
+                if ((k > thr) || (k == thr && eq_before < remaining)) {
+                    const int dst = gt_before + (eq_before < remaining ? eq_before : remaining);
+                    pos_buf[nxt][dst] = posl[i];
+                    src_buf[nxt][dst] = cand[i];
+                    key_buf[dst] = k;
+                    posl[i] = dst;                           // remembered for the cooperative logit copy below
+                } else {
+                    posl[i] = -1;
+                }
+                gt_before += (k > thr);
+                eq_before += (k == thr);
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < n_own * HT; e += NT) {         // survivors' logits -> next buffer, coalesced per row
+            const int i = e / HT, dst = posl[i];
+            if (dst >= 0) z_buf[nxt][(int64_t)dst * HT + (e - i * HT)] = zl[e];
+        }
+        __threadfence();
+        csync();                                             // new buffer visible to the whole cluster
+        cur = nxt;
+    }
+    // ---- final ordering (score descending, ties -> scanned first): every CTA sorts its share of the survivors
+    //      (bitonic, shared memory), the sorted runs are exchanged through the scratch, and each element's rank is
+    //      its place in its own run plus, by binary search, the number of larger elements in the other runs
+    {
+        const int Sm = (M + NC - 1) / NC;
+        const int j0 = cr * Sm;
+        const int n_mine = max(0, min(Sm, M - j0));
+        const int pad = next_pow2(Sm);
+        unsigned long long* run = reinterpret_cast<unsigned long long*>(smem_raw);           // [pad] (aliases zl: free now)
+        for (int r = tid; r < pad; r += NT)
+            run[r] = (r < n_mine) ? (((unsigned long long)key_buf[j0 + r] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(j0 + r))) : 0ull;
+        __syncthreads();
+        bitonic_desc(run, pad);
+        unsigned long long* g_runs = a.m_runs + (int64_t)b * NC * Sm;
+        for (int r = tid; r < n_mine; r += NT) g_runs[(int64_t)cr * Sm + r] = run[r];
+        __threadfence();
+        csync();
+        unsigned long long* all = reinterpret_cast<unsigned long long*>(allkey);             // [NC][Sm]
+        if (NC > 1) {
+            for (int r = tid; r < NC * Sm; r += NT) {
+                const int rr = r / Sm, k = r - rr * Sm;
+                all[r] = (k < max(0, min(Sm, M - rr * Sm))) ? g_runs[r] : 0ull;
+            }
+            __syncthreads();
+        }
+        for (int r = tid; r < n_mine; r += NT) {
+            const unsigned long long K = run[r];
+            int rank = r;
+            if (NC > 1) {
+                for (int rr = 0; rr < NC; ++rr) {
+                    if (rr == cr) continue;
+                    const unsigned long long* o = all + rr * Sm;
+                    const int n_o = max(0, min(Sm, M - rr * Sm));
+                    int lo_ = 0, hi_ = n_o;                      // first index whose element is < K (run is descending)
+                    while (lo_ < hi_) {
+                        const int mid = (lo_ + hi_) >> 1;
+                        if (o[mid] > K) lo_ = mid + 1; else hi_ = mid;
+                    }
+                    rank += lo_;
+                }
+            }
+            const int j = (int)key_pos(K);
+            p.out_pos[(int64_t)b * M + rank] = pos_buf[cur][j];
+            p.out_src[(int64_t)b * M + rank] = src_buf[cur][j];
+            if (p.out_score) p.out_score[(int64_t)b * M + rank] = order_bits_inv((uint32_t)(K >> 32));
+        }
+    }
+}
+
+template <int NC>
+int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    const int HT = p.H * p.T, M = p.M, N = p.N;
+    const int cap = (Lmax + NC - 1) / NC;
+    const int Sm = (M + NC - 1) / NC;
+    size_t front = (size_t)cap * (HT + 3) * 4;
+    if (front < (size_t)host_next_pow2(Sm) * 8) front = (size_t)host_next_pow2(Sm) * 8;     // final sort aliases the slice arrays
+    front = (front + 15) / 16 * 16;
+    const size_t smem = front + sizeof(ClusterScratch) + (size_t)NC * Sm * 8 + 64;
+    if (smem > 200 * 1024) return -1;                        // caller falls back
+    const int64_t need = ipsb_select_loop_workspace_bytes(B, N, HT, M);
+    IPSB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "select_loop: workspace of %lld bytes required", (long long)need);
+    char* ws = (char*)workspace;
+    ClusterArgs a;
+    auto take = [&](size_t bytes) { char* q = ws; ws += (bytes + 255) / 256 * 256; return q; };   // 256-byte aligned pieces
+    float* zs = (float*)take((size_t)B * N * HT * 4);
+    int* srcs = (int*)take((size_t)B * N * 4);
+    a.m_z = (float*)take((size_t)B * 2 * M * HT * 4);
+    a.m_pos = (int*)take((size_t)B * 2 * M * 4);
+    a.m_src = (int*)take((size_t)B * 2 * M * 4);
+    a.m_key = (uint32_t*)take((size_t)B * M * 4);
+    a.m_runs = (unsigned long long*)take((size_t)B * (M + 8) * 8);
+    a.zs = zs; a.srcs = srcs; a.slice_cap = cap;
+    const int64_t total = (int64_t)B * N * HT;
+    int64_t g = (total + 255) / 256;
+    if (g > (int64_t)ipsb::sm_count() * 8) g = (int64_t)ipsb::sm_count() * 8;
+    permute_logits_kernel<<<(unsigned)g, 256, 0, st>>>(p.z, p.perm, p.perm_stride, N, HT, zs, srcs, total);
+    IPSB_LAUNCH_CHECK();
+    auto kern = select_loop_cluster_kernel<NC>;
+    IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * NC, 512, smem, st>>>(p, a);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- standalone pieces (unit-level parity: P1 / P2) ----------------------------------
 
 __global__ void __launch_bounds__(1024) scores_kernel(const float* z, float* scores, int L, int H, int T) {
@@ -529,15 +906,27 @@ int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t* idx_out,
     return 0;
 }
 
+int64_t ipsb_select_loop_workspace_bytes(int B, int N, int HT, int M) {
+    return (int64_t)B * ((int64_t)N * (HT + 1) + 2ll * M * (HT + 2) + M) * 4 + (int64_t)B * (M + 8) * 8 + 7 * 256;
+}
+
 int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_stride,
                      int B, int N, int H, int T, int M, int I,
-                     int64_t* mem_pos, int64_t* mem_src, float* mem_score, void* stream) {
+                     int64_t* mem_pos, int64_t* mem_src, float* mem_score,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
     IPSB_REQUIRE(B > 0 && N > 0 && M > 0 && I > 0 && H > 0 && T > 0, "select_loop: bad shape");
     IPSB_REQUIRE(M < N, "select_loop: M=%d >= N=%d is the caller's shortcut (ips_net.py:185)", M, N);
     IPSB_REQUIRE(H * T <= kMaxHT, "select_loop: H*T=%d exceeds %d", H * T, kMaxHT);
     const int Lmax = M + (I < N - M ? I : N - M);
     LoopParams p{z, perm, perm_batch_stride, N, H, T, M, I, mem_pos, mem_src, mem_score};
-    // long buffers: register-resident logits + radix sort (M must fit the 8192-entry scratch)
+    // shared-memory-resident loop: one CTA per image, or a cluster of 8 CTAs per image for long buffers
+    const bool ht_pow2 = ((H * T) & (H * T - 1)) == 0;
+    if (ht_pow2 && workspace != nullptr && getenv("IPSB_SELECT_SINGLE_CTA") == nullptr) {
+        const int rc = (Lmax >= 2048) ? launch_cluster<8>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream)
+                                      : launch_cluster<1>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
+    // single-CTA long-buffer variant (kept as a cross-check, IPSB_SELECT_SINGLE_CTA=1)
     if (H * T == 8 && Lmax > 2048 && M <= 8192 && N < 65536 * 1024) {
         if (Lmax <= 1024 * 4) return launch_reg<8, 4>(p, B, (cudaStream_t)stream);
         if (Lmax <= 1024 * 10 && (size_t)M * 8 <= 56 * 1024) return launch_reg<8, 10>(p, B, (cudaStream_t)stream);

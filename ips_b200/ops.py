@@ -319,8 +319,10 @@ def select_loop(z, perm, per_instance, H, T, M, I):
     mem_pos = torch.empty((B, M), dtype=torch.int64, device=dev)
     mem_src = torch.empty((B, M), dtype=torch.int64, device=dev)
     score = torch.empty((B, M), dtype=torch.float32, device=dev)
+    need = _lib.load().ipsb_select_loop_workspace_bytes(B, N, H * T, M)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
     _call('ipsb_select_loop', _p(z), _p(perm), N if (perm is not None and per_instance) else 0,
-                                            B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score), _stream())
+                                            B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score), _p(ws), need, _stream())
     return mem_pos, mem_src, score
 
 
