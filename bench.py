@@ -217,11 +217,11 @@ def run_ours(args):
     xh = x.cpu().pin_memory()
     res_h = torch.empty((B, conf.M, *shape[2:]), dtype=torch.float32).pin_memory()
     idx_h = torch.empty((B, conf.M), dtype=torch.int64).pin_memory()
-    xd = torch.empty_like(x)
 
     def e2e_step():
-        xd.copy_(xh, non_blocking=True)            # H2D of this step's patches (pinned)
-        mem_patch, _ = net.ips(xd)
+        # public API with a HOST tensor (the reference's lazy mode, conf.eager=False): ips() streams it to the
+        # device chunk by chunk on a copy stream while the encoder works on the chunks that have arrived
+        mem_patch, _ = net.ips(xh)
         res_h.copy_(mem_patch, non_blocking=True)  # D2H of the step's result
         idx_h.copy_(net.last_mem_idx, non_blocking=True)
 
@@ -229,6 +229,44 @@ def run_ours(args):
     e2e_step()
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = world * B * N * e2e_steps / (ms_e2e / 1e3)
+
+    # ---- secondary metric: train images/s over the reference's track_efficiency bracket
+    #      (ips + forward + loss + backward + AdamW step; the grad-mode half runs on PyTorch autograd in round 1)
+    train = None
+    if not args.no_train:
+        import torch.nn.functional as Fn
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=conf.wd)
+        labels = {}
+        for task in conf.tasks.values():
+            if task['metric'] == 'multilabel_accuracy':
+                labels[task['name']] = (torch.rand(B, conf.n_class, device=dev) < 0.3).float()
+            elif task['act_fn'] == 'sigmoid':
+                labels[task['name']] = torch.randint(0, 2, (B,), device=dev).float()
+            else:
+                labels[task['name']] = torch.randint(0, conf.n_class, (B,), device=dev)
+
+        def train_step():
+            mem_patch, mem_pos = net.ips(x)
+            opt.zero_grad(set_to_none=True)
+            preds = net(mem_patch, mem_pos)
+            loss = 0
+            for task in conf.tasks.values():
+                pr = preds[task['name']].squeeze(-1)
+                if task['act_fn'] == 'softmax':
+                    loss = loss + Fn.nll_loss(torch.log(pr + conf.eps), labels[task['name']])
+                else:
+                    loss = loss + Fn.binary_cross_entropy(pr.view(-1), labels[task['name']].view(-1))
+            (loss / len(conf.tasks)).backward()
+            if world > 1:
+                from ips_b200.distributed import allreduce_gradients
+                allreduce_gradients(list(net.parameters()))
+            opt.step()
+
+        tsteps = max(2, min(args.steps, 5))
+        train_step(); train_step()
+        ms_t = timed(train_step, tsteps)
+        train = {'metric': 'train_images_per_sec', 'value': world * B * tsteps / (ms_t / 1e3), 'ms_per_step': ms_t / tsteps,
+                 'note': 'ips() on the library kernels; grad-mode forward/backward/AdamW on PyTorch autograd (round 1)'}
 
     # ---- roofline of the dominant kernel family (per-launch CUDA events, same work) ---
     roof = None
@@ -294,7 +332,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'patches/s', 'h2d_bytes_per_step': in_bytes,
                     'd2h_bytes_per_step': res_h.numel() * 4 + idx_h.numel() * 8, 'ms_per_step': ms_e2e / e2e_steps},
             'gpu_launches': launches,
-            'roofline': roof, 'cpu_baseline': cpu,
+            'roofline': roof, 'cpu_baseline': cpu, 'train': train,
         }
         print(json.dumps(line))
     if world > 1:
@@ -310,6 +348,7 @@ def main():
     ap.add_argument('--workload', default='traffic', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-train', action='store_true', help='skip the secondary train images/s measurement')
     ap.add_argument('--shard', default='batch', choices=['batch', 'sequence'],
                     help="N>1: 'batch' = every rank scans its own batch (weak scaling); 'sequence' = ONE batch whose patch axis "
                          "is sharded over the ranks (strong scaling, NCCL all-gather of logits + all-reduce of winners)")

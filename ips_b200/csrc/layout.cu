@@ -208,6 +208,44 @@ __global__ void rows_kernel(const float* __restrict__ x, T* __restrict__ y, int 
     for (int i = tid; i < F; i += blockDim.x) yr[i] = from_f32<T>((xr[i] - mean) * rstd);
 }
 
+// warp per row, the whole row in registers (V float4 per lane, all loads issued up front): one pass over HBM
+template <typename T, bool kNorm, int V>
+__global__ void __launch_bounds__(256) rows_warp_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t rows, float eps) {
+    constexpr int F = V * 128;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * F);
+    float4 v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int4 raw = ipsb::ld_stream16(xr + i * 32 + lane);
+        v[i] = *reinterpret_cast<const float4*>(&raw);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (kNorm) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        mean = ipsb::warp_sum(s) / (float)F;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        rstd = rsqrtf(ipsb::warp_sum(q) / (float)F + eps);
+    }
+    T* yr = y + row * F;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        __align__(8) T o[4] = {from_f32<T>((v[i].x - mean) * rstd), from_f32<T>((v[i].y - mean) * rstd),
+                               from_f32<T>((v[i].z - mean) * rstd), from_f32<T>((v[i].w - mean) * rstd)};
+        if (sizeof(T) == 2) *reinterpret_cast<uint2*>(yr + (i * 32 + lane) * 4) = *reinterpret_cast<const uint2*>(o);
+        else *reinterpret_cast<float4*>(yr + (i * 32 + lane) * 4) = *reinterpret_cast<const float4*>(o);
+    }
+}
+
 int grid_for(int64_t total, int threads) {
     int64_t g = ipsb::ceil_div(total, threads);
     const int64_t cap = (int64_t)ipsb::sm_count() * 16;
@@ -325,6 +363,13 @@ int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int F, float
 
 int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream) {
     IPSB_REQUIRE(rows > 0 && F > 0, "rows_to_bf16: bad shape");
+    if (F == 2048 && ((uintptr_t)x % 16 == 0)) {          // CAMELYON feature width: warp-per-row single-pass kernel
+        const unsigned g = (unsigned)((rows + 7) / 8);
+        if (layernorm) rows_warp_kernel<bf16, true, 16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, rows, eps);
+        else rows_warp_kernel<bf16, false, 16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, rows, eps);
+        IPSB_LAUNCH_CHECK();
+        return 0;
+    }
     if (layernorm)
         rows_kernel<bf16, true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, F, eps);
     else

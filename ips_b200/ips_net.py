@@ -285,6 +285,49 @@ class IPSNet(nn.Module):
             z[lo:lo + n] = ops.logits(emb, plan['U'], plan['posU'], None if pos_idx is None else pos_idx[lo:lo + n].contiguous())
         return z.view(B, N, HT)
 
+    @torch.no_grad()
+    def _stream_in(self, patches):
+        """Host-resident patches (lazy loading, `conf.eager: False`): copy them to the device chunk by chunk on a
+        side stream while the encoder already works on the chunks that have arrived.  Returns the device copy and
+        the logit table.  (The reference moves each chunk with `.to(device)` inside its loop, ips_net.py:206,223.)"""
+        plan = self._get_plan()
+        B, N = patches.shape[:2]
+        rows = B * N
+        flat_h = patches.reshape(rows, *patches.shape[2:])
+        if flat_h.dtype != torch.float32:
+            flat_h = flat_h.float()
+        HT = plan['U'].shape[1]
+        chunk = self._auto_chunk(patches.shape)
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        dev = torch.empty(flat_h.shape, dtype=torch.float32, device=self.device)
+        dev.record_stream(cs)
+        cs.wait_stream(main)
+        events = []
+        with torch.cuda.stream(cs):
+            for lo in range(0, rows, chunk):
+                n = min(chunk, rows - lo)
+                dev[lo:lo + n].copy_(flat_h[lo:lo + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
+        native = self.is_image and self.executor == 'native'
+        if native and 'desc' not in plan:
+            plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
+        pos_idx = (torch.arange(rows, device=self.device) % N).contiguous() if self.use_pos else None
+        for ci, lo in enumerate(range(0, rows, chunk)):
+            n = min(chunk, rows - lo)
+            main.wait_event(events[ci])
+            if native:
+                ops.resnet_logits(plan['desc'], dev, N, chunk, self._ws_cache, first_row=lo, n_rows=n, z=z)
+            else:
+                emb = self.embed(dev, first_row=lo, n_rows=n)
+                z[lo:lo + n] = ops.logits(emb, plan['U'], plan['posU'], None if pos_idx is None else pos_idx[lo:lo + n].contiguous())
+        return dev.view(patches.shape), z.view(B, N, HT)
+
     # ------------------------------------------------------------------ reference API
     def do_shuffle(self, patches, pos_enc):
         """Kept for API compatibility (ips_net.py:118-134): returns permuted copies like the
@@ -335,7 +378,10 @@ class IPSNet(nn.Module):
             perm = perm.to(device).contiguous()
 
         ca = self.transf.crs_attn
-        z = self.patch_logits(patches)                            # encode + project every patch once
+        if not patches.is_cuda:                                   # lazy loading: overlap H2D with the encoder
+            patches, z = self._stream_in(patches)
+        else:
+            z = self.patch_logits(patches)                        # encode + project every patch once
         _, mem_src, _ = ops.select_loop(z, perm, per_inst, ca.H, ca.n_token, M, I)
         self.last_mem_idx = mem_src
 

@@ -246,11 +246,13 @@ def make_resnet_desc(plan, dt, D, HT):
     return d
 
 
-def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False):
-    """Whole eval-mode encoder + logit projection of (rows,C,H,W) fp32 patches in ONE library call."""
+def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False, first_row=0, n_rows=None, z=None):
+    """Whole eval-mode encoder + logit projection of (rows,C,H,W) fp32 patches in ONE library call.
+    `first_row` / `n_rows` restrict the call to a row range (its logits land in z[first_row : first_row+n_rows])."""
     global LAUNCHES
     _chk(patches, torch.float32, 'patches')
-    rows, C, H, W = patches.shape
+    total_rows, C, H, W = patches.shape
+    rows = total_rows - first_row if n_rows is None else n_rows
     lib = _lib.load()
     need = lib.ipsb_resnet_workspace_bytes(desc, chunk, C, H, W)
     ws = workspace_cache.get('ws')
@@ -260,13 +262,16 @@ def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=F
         if ws is None or ws.numel() < need or ws.device != patches.device:
             ws = torch.empty(need, dtype=torch.uint8, device=patches.device)
         workspace_cache['ws'], workspace_cache['key'] = ws, key
-    z = torch.empty((rows, desc.HT), dtype=torch.float32, device=patches.device)
-    emb = torch.empty((rows, desc.D), dtype=torch.float32, device=patches.device) if want_emb else None
+    if z is None:
+        z = torch.empty((total_rows, desc.HT), dtype=torch.float32, device=patches.device)
+    emb = torch.empty((total_rows, desc.D), dtype=torch.float32, device=patches.device) if want_emb else None
     n_chunks = -(-rows // chunk)
     LAUNCHES += n_chunks * (4 + 2 * desc.n_blocks + sum(int(desc.blocks[i].has_ds) for i in range(desc.n_blocks))
                             + (1 if desc.add_tab else 0))
-    _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), 0, rows, C, H, W, n_per_image, chunk, _p(ws), ws.numel(),
-                                      int(fresh), _p(emb), _p(z), _stream()))
+    z_ptr = z.data_ptr() + first_row * desc.HT * 4
+    e_ptr = 0 if emb is None else emb.data_ptr() + first_row * desc.D * 4
+    _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), first_row, rows, C, H, W, n_per_image, chunk, _p(ws), ws.numel(),
+                                      int(fresh), e_ptr, z_ptr, _stream()))
     return z, emb
 
 
