@@ -42,28 +42,50 @@ __global__ void stage_kernel(const float* __restrict__ src, const int64_t* __res
     }
 }
 
-// same, into a zero-bordered (Hp, Wp) frame with the image at (pt, pl): feeds the TMA stem
-template <typename T, int CPAD>
+// same, into a zero-bordered (Hp, Wp) frame with the image at (pt, pl): feeds the TMA stem.
+// One thread = four consecutive frame pixels of one row (pl % 4 == 0, W % 4 == 0): C float4 plane loads
+// (coalesced along x) and one 32-byte channels-last store; border quads are written as zeros.
+template <int CPAD>
 __global__ void stage_padded_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx,
                                     int64_t first_row, int64_t n_rows, int C, int H, int W, int Hp, int Wp,
-                                    int pt, int pl, T* __restrict__ dst) {
-    const int64_t total = n_rows * Hp * Wp;
+                                    int pt, int pl, bool vec4, bf16* __restrict__ dst) {
+    const int qpr = (Wp + 3) >> 2;                              // quads per frame row
+    const int64_t total = n_rows * Hp * qpr;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / (Hp * Wp);
-        const int rem = (int)(i - r * (Hp * Wp));
-        const int y = rem / Wp - pt, x = rem % Wp - pl;
-        __align__(16) T out[CPAD];
-        if (y >= 0 && y < H && x >= 0 && x < W) {
+        const int64_t fr = i / qpr;                              // frame row index = r * Hp + y'
+        const int qx = (int)(i - fr * qpr);
+        const int64_t r = fr / Hp;
+        const int y = (int)(fr - r * Hp) - pt;
+        const int x0 = qx * 4 - pl;                              // image x of the quad's first pixel
+        __align__(16) bf16 out[4][CPAD];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) out[k][c] = __float2bfloat16_rn(0.f);
+        if (y >= 0 && y < H && x0 + 3 >= 0 && x0 < W) {
             const int64_t srow = row_idx ? row_idx[r] : first_row + r;
-            const float* s = src + srow * (int64_t)C * H * W + (int64_t)y * W + x;
-#pragma unroll
-            for (int c = 0; c < CPAD; ++c) out[c] = from_f32<T>(c < C ? __ldg(s + (int64_t)c * H * W) : 0.f);
-        } else {
-#pragma unroll
-            for (int c = 0; c < CPAD; ++c) out[c] = from_f32<T>(0.f);
+            const float* sp = src + srow * (int64_t)C * H * W + (int64_t)y * W + x0;
+            if (vec4 && x0 >= 0 && x0 + 3 < W) {                 // aligned interior quad: one float4 per plane
+                for (int c = 0; c < C; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(sp + (int64_t)c * H * W);
+                    out[0][c] = __float2bfloat16_rn(v.x); out[1][c] = __float2bfloat16_rn(v.y);
+                    out[2][c] = __float2bfloat16_rn(v.z); out[3][c] = __float2bfloat16_rn(v.w);
+                }
+            } else {
+                for (int k = 0; k < 4; ++k)
+                    if (x0 + k >= 0 && x0 + k < W)
+                        for (int c = 0; c < C; ++c) out[k][c] = __float2bfloat16_rn(__ldg(sp + (int64_t)c * H * W + k));
+            }
         }
-        *reinterpret_cast<uint2*>(dst + i * CPAD) = *reinterpret_cast<const uint2*>(out);
+        bf16* d = dst + (fr * Wp + qx * 4) * CPAD;
+        const int npx = min(4, Wp - qx * 4);
+        if (npx == 4) {
+            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(&out[0][0]);
+            *reinterpret_cast<uint4*>(d + 2 * CPAD) = *reinterpret_cast<const uint4*>(&out[2][0]);
+        } else {
+            for (int k = 0; k < npx; ++k) *reinterpret_cast<uint2*>(d + k * CPAD) = *reinterpret_cast<const uint2*>(&out[k][0]);
+        }
     }
 }
 
@@ -276,9 +298,11 @@ int ipsb_stage_patches(const float* src, const int64_t* row_idx, int64_t first_r
 int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
                               int C, int H, int W, int pad_top, int pad_left, int Hp, int Wp, void* dst, void* stream) {
     IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= 4 && Hp >= H + pad_top && Wp >= W + pad_left, "stage_padded: bad shape");
-    const int64_t total = n_rows * Hp * Wp;
-    stage_padded_kernel<bf16, 4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        src, row_idx, first_row, n_rows, C, H, W, Hp, Wp, pad_top, pad_left, (bf16*)dst);
+    IPSB_REQUIRE(Wp % 2 == 0, "stage_padded: frame width %d must be even", Wp);
+    const bool vec4 = W % 4 == 0 && pad_left % 4 == 0 && ((uintptr_t)src % 16 == 0);
+    const int64_t total = n_rows * Hp * ((Wp + 3) / 4);
+    stage_padded_kernel<4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src, row_idx, first_row, n_rows, C, H, W, Hp, Wp, pad_top, pad_left, vec4, (bf16*)dst);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -37,7 +37,8 @@ struct HaloParams {
     int dbg;              // IPSB_DEBUG bits: 1 skip stores, 2 skip MMAs, 4 load A only for the first tile of a CTA
     int cblocks;          // Cin / 64
     int total_tiles;
-    int a_rows;           // rows per A block = 130 + 2*Wp
+    int a_rows;           // rows per TMA box of the A block (single tile: 130 + 2*Wp)
+    int n_boxes;          // boxes per A block (2 when two tiles share a block)
     uint32_t a_slot_bytes;
     int64_t pix_rows;     // P * Sp: rows [G0, G0 + pix_rows) hold pixels / pads of real patches
 };
@@ -49,7 +50,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-template <int BN, int SA, int SB, bool RESB>
+template <int BN, int SA, int SB, bool RESB, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const HaloParams p) {
@@ -77,11 +78,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (tid == 0) {
         for (int s = 0; s < SA; ++s) { umma::mbar_init(a_full(s), 1); umma::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < SB; ++s) { umma::mbar_init(b_full(s), 1); umma::mbar_init(b_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), PAIR ? 256 : 128); }
         umma::mbar_init(resb_bar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * BN);
+    constexpr int MT = PAIR ? 2 : 1;                 // M tiles computed per pipeline step (they share every weight slab)
+    if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * MT * BN);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -96,15 +98,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int ks = 0; ks < n_slabs; ++ks) tma_load_2d(b0 + ks * B_SLAB_BYTES, &tmB, resb_bar, ks * BK, 0);
             }
             uint32_t ia = 0, ib = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {     // PAIR: `tile` counts pairs of M tiles
                 for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
                     const int sa = ia % SA;
                     umma::mbar_wait(a_empty(sa), ((ia / SA) & 1) ^ 1);
-                    if ((p.dbg & 4) && ia >= (uint32_t)SA) { umma::mbar_arrive(a_full(sa)); }
-                    else {
-                    umma::mbar_expect_tx(a_full(sa), (uint32_t)p.a_rows * 128u);
-                    tma_load_2d(smem0 + sa * p.a_slot_bytes, &tmA, a_full(sa), cb * BK, tile * TILE_M);
-                    }
+                    umma::mbar_expect_tx(a_full(sa), (uint32_t)(p.a_rows * p.n_boxes) * 128u);
+                    for (int bx = 0; bx < p.n_boxes; ++bx)
+                        tma_load_2d(smem0 + sa * p.a_slot_bytes + (uint32_t)(bx * p.a_rows) * 128u, &tmA, a_full(sa), cb * BK,
+                                    tile * (MT * TILE_M) + bx * p.a_rows);
                     if (!RESB) {
                         for (int tap = 0; tap < 9; ++tap, ++ib) {
                             const int sb = ib % SB;
@@ -127,7 +128,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t acc = tcount & 1;
                 umma::mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1);
                 umma::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * (MT * BN);
                 for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
                     const int sa = ia % SA;
                     umma::mbar_wait(a_full(sa), (ia / SA) & 1);
@@ -147,10 +148,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         const uint64_t adesc = umma::smem_desc_sw128(a_base + (uint32_t)(r * p.Wp + s) * 128u);
                         const uint64_t bdesc = umma::smem_desc_sw128(b_addr);
-                        if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma::mma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (cb | tap | k) != 0);
+                        for (int mt = 0; mt < MT; ++mt) {            // both tiles of a pair reuse the weight slab
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma::mma_bf16(d_tmem + mt * BN, adesc + (uint64_t)(mt * (TILE_M * 128 / 16)) + 2u * k, bdesc + 2u * k,
+                                               idesc, (cb | tap | k) != 0);
                         }
                         if (!RESB) { umma::mma_commit(b_empty(sb)); ++ib; }
                     }
@@ -171,21 +174,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sc_smem[p.Cout + i] = p.shift ? p.shift[i] : 0.f;
         }
         umma::named_bar_sync(1, 256);
-        uint32_t tcount = wg;
+        // single tiles: the warpgroups alternate tiles (accumulator = tile parity); pairs: both warpgroups work on
+        // every pair, warpgroup w draining the w-th tile of the pair
+        uint32_t tcount = PAIR ? 0 : wg;
         const uint32_t stage = out_stage0 + (uint32_t)wg * epi::STAGE_BYTES;
         const bool issuer = (row == 0);
-        for (int tile = blockIdx.x + wg * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tcount += 2) {
+        for (int step = blockIdx.x + (PAIR ? 0 : wg * gridDim.x); step < p.total_tiles;
+             step += (PAIR ? 1 : 2) * gridDim.x, tcount += (PAIR ? 1 : 2)) {
+            const int tile = PAIR ? 2 * step + wg : step;            // M tile (128 PF rows) this warpgroup drains
+            const uint32_t acc = PAIR ? (tcount & 1) : (uint32_t)wg;
             const int rel = tile * TILE_M + row;                     // row index relative to G0 (fits int32: checked on the host)
             const bool in_range = rel < (int)p.pix_rows;             // rows of real patches (pixels or their pads)
             const int rem = rel % p.Sp;
             const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
             const bool pixel = in_range && yy < p.H && xx < p.W;     // pad rows are stored as zeros
             const int64_t g = (int64_t)p.G0 + rel;
-            umma::mbar_wait(tfull_bar(wg), (tcount >> 1) & 1);
+            umma::mbar_wait(tfull_bar(acc), (tcount >> 1) & 1);
             umma::tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (PAIR ? acc * 2 * BN + wg * BN : wg * BN);
             const int g0 = p.G0 + tile * TILE_M;
-            epi::drain_tile<BN, bf16>(t_row, tempty_bar(wg), sc_smem, sc_smem + p.Cout, pixel,
+            epi::drain_tile<BN, bf16>(t_row, tempty_bar(acc), sc_smem, sc_smem + p.Cout, pixel,
                                       (p.res && pixel) ? p.res + g * p.Cout : nullptr, p.relu, stage, row, 2u + (uint32_t)wg, issuer,
                                       [&](int s0, uint32_t src) { if (!(p.dbg & 1)) epi::tma_store_2d(&tmC, src, s0, g0); });
         }
@@ -194,7 +202,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * MT * BN);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -212,12 +220,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int BN, int SA, int SB, bool RESB>
+template <int BN, int SA, int SB, bool RESB, bool PAIR>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p, cudaStream_t st) {
     const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? 9 * p.cblocks : SB) * BN * 128 + 2 * epi::STAGE_BYTES + 1024 +
                         8 * (2 * SA + 2 * SB + 5) + 32 + 8 * (size_t)p.Cout;
     IPSB_REQUIRE(smem <= 227 * 1024, "conv_halo: %zu bytes of shared memory", smem);
-    auto kern = conv_halo_kernel<BN, SA, SB, RESB>;
+    auto kern = conv_halo_kernel<BN, SA, SB, RESB, PAIR>;
     static size_t configured = 0;
     if (configured < smem) {
         IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -248,9 +256,17 @@ int conv3x3_halo(const void* x, const void* w, const float* scale, const float* 
     p.pix_rows = P * (int64_t)g.Sp;
     IPSB_REQUIRE(p.pix_rows + TILE_M < (1ll << 31), "conv3x3_halo: too many rows");
     p.total_tiles = (int)((p.pix_rows + TILE_M - 1) / TILE_M);
-    p.a_rows = TILE_M + 2 * g.Wp + 2;
+    const bool pair = (Cout == 128) && getenv("IPSB_HALO_NOPAIR") == nullptr;     // streamed weights: two M tiles share every slab
+    if (pair) {
+        p.total_tiles = (p.total_tiles + 1) / 2;                 // pipeline steps = pairs of tiles
+        p.n_boxes = 2;
+        p.a_rows = (TILE_M + g.Wp + 1 + 7) / 8 * 8;              // two boxes cover 256 + 2*Wp + 2 rows (8-row aligned halves)
+    } else {
+        p.n_boxes = 1;
+        p.a_rows = TILE_M + 2 * g.Wp + 2;
+    }
     IPSB_REQUIRE(p.a_rows <= 256, "conv3x3_halo: width %d too large for one TMA box", W);
-    p.a_slot_bytes = (uint32_t)((p.a_rows * 128 + 1023) / 1024 * 1024);
+    p.a_slot_bytes = (uint32_t)((p.a_rows * p.n_boxes * 128 + 1023) / 1024 * 1024);
 
     alignas(64) CUtensorMap tmA, tmB;
     {
@@ -286,10 +302,11 @@ int conv3x3_halo(const void* x, const void* w, const float* scale, const float* 
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv3x3_halo: cuTensorMapEncodeTiled(output) failed with %d", (int)r);
     }
     if (Cout == 64) {
-        if ((size_t)9 * p.cblocks * 64 * 128 <= 80 * 1024) return launch<64, 4, 1, true>(tmA, tmB, tmC, p, st);
-        return launch<64, 4, 6, false>(tmA, tmB, tmC, p, st);
+        if ((size_t)9 * p.cblocks * 64 * 128 <= 80 * 1024) return launch<64, 4, 1, true, false>(tmA, tmB, tmC, p, st);
+        return launch<64, 4, 6, false, false>(tmA, tmB, tmC, p, st);
     }
-    return launch<128, 4, 5, false>(tmA, tmB, tmC, p, st);
+    if (pair) return launch<128, 3, 4, false, true>(tmA, tmB, tmC, p, st);
+    return launch<128, 4, 5, false, false>(tmA, tmB, tmC, p, st);
 }
 
 }  // namespace ipsb
