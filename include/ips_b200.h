@@ -94,6 +94,20 @@ IPSB_API int ipsb_avgpool_pf(const void* x, float* y, int64_t P, int H, int W, i
  * K % 64 == 0, N % 64 == 0.  tcgen05 path for the Linear layers. */
 IPSB_API int ipsb_linear_bf16_umma(const void* a, const void* w, const float* scale, const float* shift,
                           float* y, int64_t M, int N, int K, int relu, void* stream);
+/* General tensor-core GEMM of the grad-mode step (forward / data-gradient / weight-gradient of nn.Linear):
+ *   mode 0 (NT): a (M,K), b (N,K)   c = a b^T        mode 1 (NN): a (M,K), b (K,N)   c = a b
+ *   mode 2 (TN): a (K,M), b (K,N)   c = a^T b   (contraction over rows; split along K into fp32 partials in
+ *   `workspace`, ipsb_gemm_workspace_bytes, then reduced deterministically; needs M % 128 == 0)
+ * a, b bf16 row-major; c (M,N) fp32 (c_is_f32) or bf16; c = act(c * scale[N] + shift[N]); N % 64 == 0; row strides 16-byte aligned. */
+IPSB_API int64_t ipsb_gemm_workspace_bytes(int mode, int64_t M, int N, int64_t K);
+IPSB_API int ipsb_gemm_bf16(int mode, const void* a, const void* b, const float* scale, const float* shift, void* c, int c_is_f32,
+                   int64_t M, int N, int64_t K, int relu, void* workspace, int64_t workspace_bytes, void* stream);
+/* fp32 CUDA-core GEMM in the same three layouts (any sizes with K % 4 == 0 / N % 4 == 0 as the layout needs): exact mode
+ * of the train step and the fallback for shapes the tensor-core kernel does not take (class heads). */
+IPSB_API int ipsb_gemm_f32(int mode, const float* a, const float* b, const float* shift, float* c, int64_t M, int N, int64_t K,
+                  int relu, void* stream);
+IPSB_API int ipsb_colsum_f32(const float* x, const float* y, float* out, int64_t rows, int cols, void* stream);   /* sum_r x*y */
+IPSB_API int ipsb_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 /* fp32 (rows,F) -> bf16 with optional no-affine LayerNorm fused (projector prologue) */
 IPSB_API int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);
 

@@ -50,6 +50,11 @@ SIGNATURES = {
     'ipsb_maxpool3x3s2_pf': [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_avgpool_pf': [_ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_linear_bf16_umma': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
+    'ipsb_gemm_workspace_bytes': [_i32, _i64, _i32, _i64],
+    'ipsb_gemm_bf16': [_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i64, _i32, _i64, _i32, _ptr, _i64, _ptr],
+    'ipsb_gemm_f32': [_i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i64, _i32, _ptr],
+    'ipsb_colsum_f32': [_ptr, _ptr, _ptr, _i64, _i32, _ptr],
+    'ipsb_cast_bf16': [_ptr, _ptr, _i64, _ptr],
     'ipsb_rows_to_bf16': [_ptr, _ptr, _i64, _i32, _i32, _f32, _ptr],
     'ipsb_score_basis': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_logits': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
@@ -67,7 +72,8 @@ SIGNATURES = {
                            _ptr, _ptr, _ptr],
 }
 _RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64,
-            'ipsb_pf_rows': ctypes.c_int64, 'ipsb_select_loop_workspace_bytes': ctypes.c_int64}
+            'ipsb_pf_rows': ctypes.c_int64, 'ipsb_select_loop_workspace_bytes': ctypes.c_int64,
+            'ipsb_gemm_workspace_bytes': ctypes.c_int64}
 
 _lib = None
 

@@ -268,6 +268,30 @@ __global__ void __launch_bounds__(256) rows_warp_kernel(const float* __restrict_
     }
 }
 
+// out[c] = sum_r x[r, c] (bias gradients, BatchNorm statistics); one block per 32 columns, fixed order
+__global__ void colsum_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t rows, int cols) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < cols)
+        for (int64_t r = w; r < rows; r += 8) s += y ? x[r * cols + c] * y[r * cols + c] : x[r * cols + c];
+    part[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0 && c < cols) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        out[c] = t;
+    }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        __align__(8) bf16 o[4] = {__float2bfloat16_rn(v.x), __float2bfloat16_rn(v.y), __float2bfloat16_rn(v.z), __float2bfloat16_rn(v.w)};
+        reinterpret_cast<uint2*>(y)[i] = *reinterpret_cast<const uint2*>(o);
+    }
+}
+
 int grid_for(int64_t total, int threads) {
     int64_t g = ipsb::ceil_div(total, threads);
     const int64_t cap = (int64_t)ipsb::sm_count() * 16;
@@ -381,6 +405,21 @@ int ipsb_avgpool(const void* x, float* y, int64_t P, int HW, int C, int dt, void
 int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int F, float eps, void* stream) {
     IPSB_REQUIRE(rows > 0 && F > 0, "layernorm: bad shape");
     rows_kernel<float, true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, y, F, eps);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+/* out[c] = sum_r x[r,c] * (y ? y[r,c] : 1) */
+int ipsb_colsum_f32(const float* x, const float* y, float* out, int64_t rows, int cols, void* stream) {
+    IPSB_REQUIRE(rows > 0 && cols > 0, "colsum: bad shape");
+    colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, y, out, rows, cols);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
+    IPSB_REQUIRE(n > 0 && n % 4 == 0 && ((uintptr_t)x % 16 == 0), "cast_bf16: n=%lld must be a multiple of 4", (long long)n);
+    cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n / 4);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

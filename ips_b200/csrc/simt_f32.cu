@@ -23,6 +23,21 @@ struct DenseA {
         return *reinterpret_cast<const float4*>(a + row * K + k);
     }
 };
+// A stored (K, M): the contraction index is the slow one (weight-gradient products)
+struct DenseAT {
+    const float* a;
+    int K;
+    int64_t lda;          // = M
+    __device__ __forceinline__ float4 load(int64_t row, int64_t M, int k) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row >= M) return v;
+        if (k + 0 < K) v.x = a[(int64_t)(k + 0) * lda + row];
+        if (k + 1 < K) v.y = a[(int64_t)(k + 1) * lda + row];
+        if (k + 2 < K) v.z = a[(int64_t)(k + 2) * lda + row];
+        if (k + 3 < K) v.w = a[(int64_t)(k + 3) * lda + row];
+        return v;
+    }
+};
 struct ConvA {
     const float* x;
     ConvGeom g;
@@ -190,6 +205,30 @@ int ipsb_linear_f32(const float* a, const float* w, const float* scale, const fl
     DenseA A{a, K};
     dim3 grid((unsigned)ipsb::ceil_div(M, BM), (unsigned)ipsb::ceil_div(N, BN));
     gemm_simt_kernel<DenseA, true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, w, scale, shift, nullptr, y, M, N, K, relu);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// fp32 CUDA-core GEMM in the three layouts of the train step (any M, N, K with K % 4 == 0 for modes 0/1, N % 4 == 0 for
+// modes 1/2): mode 0 (NT) a (M,K) b (N,K); mode 1 (NN) a (M,K) b (K,N); mode 2 (TN) a (K,M) b (K,N).  c = a-op b + shift.
+int ipsb_gemm_f32(int mode, const float* a, const float* b, const float* shift, float* c, int64_t M, int N, int64_t K,
+                  int relu, void* stream) {
+    IPSB_REQUIRE(mode >= 0 && mode <= 2 && M > 0 && N > 0 && K > 0 && K < (1ll << 31), "gemm_f32: bad arguments");
+    dim3 grid((unsigned)ipsb::ceil_div(M, BM), (unsigned)ipsb::ceil_div(N, BN));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        IPSB_REQUIRE(K % 4 == 0, "gemm_f32 NT: K=%lld must be a multiple of 4", (long long)K);
+        DenseA A{a, (int)K};
+        gemm_simt_kernel<DenseA, true><<<grid, 256, 0, st>>>(A, b, nullptr, shift, nullptr, c, M, N, (int)K, relu);
+    } else if (mode == 1) {
+        IPSB_REQUIRE(K % 4 == 0 && N % 4 == 0, "gemm_f32 NN: K=%lld and N=%d must be multiples of 4", (long long)K, N);
+        DenseA A{a, (int)K};
+        gemm_simt_kernel<DenseA, false><<<grid, 256, 0, st>>>(A, b, nullptr, shift, nullptr, c, M, N, (int)K, relu);
+    } else {
+        IPSB_REQUIRE(N % 4 == 0, "gemm_f32 TN: N=%d must be a multiple of 4", N);
+        DenseAT A{a, (int)K, M};
+        gemm_simt_kernel<DenseAT, false><<<grid, 256, 0, st>>>(A, b, nullptr, shift, nullptr, c, M, N, (int)K, relu);
+    }
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .autograd import Linear
 from .transformer import Transformer, pos_enc_1d
 from .utils import scan_order
 
@@ -70,7 +71,7 @@ def _conv_patch_encoder(enc_type, n_chan_in, n_res_blocks):
 
 
 def _projector(n_chan_in, D):
-    return nn.Sequential(nn.LayerNorm(n_chan_in, eps=1e-05, elementwise_affine=False), nn.Linear(n_chan_in, D),
+    return nn.Sequential(nn.LayerNorm(n_chan_in, eps=1e-05, elementwise_affine=False), Linear(n_chan_in, D),
                          nn.BatchNorm1d(D), nn.ReLU())
 
 
@@ -87,7 +88,7 @@ class IPSNet(nn.Module):
         out = nn.ModuleDict()
         for task in tasks.values():
             act = nn.Softmax(dim=-1) if task['act_fn'] == 'softmax' else nn.Sigmoid()
-            out[task['name']] = nn.Sequential(nn.Linear(self.D, self.n_class), act)
+            out[task['name']] = nn.Sequential(Linear(self.D, self.n_class), act)
         return out
 
     def __init__(self, device, conf):
@@ -116,6 +117,9 @@ class IPSNet(nn.Module):
         self.pos_enc = pos_enc_1d(conf.D, conf.N).unsqueeze(0).to(device) if conf.use_pos else None
         self.output_layers = self.get_output_layers(conf.tasks)
 
+        for m in self.modules():                     # train-step GEMMs follow the same precision switch as ips()
+            if isinstance(m, Linear):
+                m.precision = self.precision
         self._plan = None
         self._plan_key = None
         self.last_mem_idx = None      # (B,M) original-order indices of the last ips() call (notebook cell 9)

@@ -331,6 +331,55 @@ def select_loop(z, perm, per_instance, H, T, M, I):
     return mem_pos, mem_src, score
 
 
+def gemm_bf16(mode, a, b, scale=None, shift=None, relu=False, out_dtype=torch.float32):
+    """Tensor-core GEMM, bf16 operands, fp32 accumulate.  mode 'nt': a (M,K) b (N,K) -> a b^T;
+    'nn': a (M,K) b (K,N) -> a b;  'tn': a (K,M) b (K,N) -> a^T b (split-K, deterministic)."""
+    _chk(a, torch.bfloat16, 'a'); _chk(b, torch.bfloat16, 'b'); _chk(scale, torch.float32, 'scale'); _chk(shift, torch.float32, 'shift')
+    code = {'nt': 0, 'nn': 1, 'tn': 2}[mode]
+    if code == 0:
+        (M, K), N = a.shape, b.shape[0]
+    elif code == 1:
+        (M, K), N = a.shape, b.shape[1]
+    else:
+        (K, M), N = a.shape, b.shape[1]
+    c = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    need = _lib.load().ipsb_gemm_workspace_bytes(code, M, N, K)
+    ws = torch.empty(need, dtype=torch.uint8, device=a.device) if need else None
+    _call('ipsb_gemm_bf16', code, _p(a), _p(b), _p(scale), _p(shift), _p(c), int(out_dtype == torch.float32), M, N, K, int(relu),
+          _p(ws), need, _stream())
+    return c
+
+
+def gemm_f32(mode, a, b, shift=None, relu=False):
+    """fp32 CUDA-core GEMM in the 'nt' / 'nn' / 'tn' layouts of gemm_bf16."""
+    _chk(a, torch.float32, 'a'); _chk(b, torch.float32, 'b'); _chk(shift, torch.float32, 'shift')
+    code = {'nt': 0, 'nn': 1, 'tn': 2}[mode]
+    if code == 0:
+        (M, K), N = a.shape, b.shape[0]
+    elif code == 1:
+        (M, K), N = a.shape, b.shape[1]
+    else:
+        (K, M), N = a.shape, b.shape[1]
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _call('ipsb_gemm_f32', code, _p(a), _p(b), _p(shift), _p(c), M, N, K, int(relu), _stream())
+    return c
+
+
+def colsum(x, y=None):
+    """sum over rows of x (or of x*y): (rows, cols) -> (cols,)"""
+    _chk(x, torch.float32, 'x'); _chk(y, torch.float32, 'y')
+    out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+    _call('ipsb_colsum_f32', _p(x), _p(y), _p(out), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+def cast_bf16(x):
+    _chk(x, torch.float32, 'x')
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _call('ipsb_cast_bf16', _p(x), _p(y), x.numel(), _stream())
+    return y
+
+
 # ------------------------------------------------------------------ aggregator + heads (no-grad forward)
 
 def cross_attention(q_scaled, k, v, H, Dk, Dv):

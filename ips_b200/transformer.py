@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .autograd import Linear
 
 
 def pos_enc_1d(D, len_seq):
@@ -43,10 +44,10 @@ class MultiHeadCrossAttention(nn.Module):
         self.q = nn.Parameter(torch.empty((1, n_token, D)))
         bound = math.sqrt(1 / D_k)
         nn.init.uniform_(self.q, a=-bound, b=bound)
-        self.q_w = nn.Linear(D, H * D_k, bias=False)
-        self.k_w = nn.Linear(D, H * D_k, bias=False)
-        self.v_w = nn.Linear(D, H * D_v, bias=False)
-        self.fc = nn.Linear(H * D_v, D, bias=False)
+        self.q_w = Linear(D, H * D_k, bias=False)
+        self.k_w = Linear(D, H * D_k, bias=False)
+        self.v_w = Linear(D, H * D_v, bias=False)
+        self.fc = Linear(H * D_v, D, bias=False)
         self.attention = _Temperature(D_k ** 0.5, attn_dropout)
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(D, eps=1e-6)
@@ -87,8 +88,8 @@ class MultiHeadCrossAttention(nn.Module):
 class MLP(nn.Module):
     def __init__(self, D, D_inner, dropout=0.1):
         super().__init__()
-        self.w_1 = nn.Linear(D, D_inner)
-        self.w_2 = nn.Linear(D_inner, D)
+        self.w_1 = Linear(D, D_inner)
+        self.w_2 = Linear(D_inner, D)
         self.layer_norm = nn.LayerNorm(D, eps=1e-6)
         self.dropout = nn.Dropout(dropout)
 

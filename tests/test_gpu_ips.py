@@ -207,3 +207,34 @@ def test_inference_forward_matches_oracle(name, precision):
     for t in ref:
         torch.testing.assert_close(got[t].cpu(), ref[t], **tol)
     assert not net.training
+
+
+@pytest.mark.parametrize('name', ['camelyon_small', 'camelyon_batch', 'mnist_small', 'traffic_small'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_train_step_gradients_match_oracle(name, precision):
+    """Grad-mode forward + loss + backward (train-mode BatchNorm, dropout 0): every nn.Linear runs forward AND
+    backward on the library's GEMM kernels (NT / NN / TN); loss and gradients against the CPU oracle."""
+    z, meta, conf, sd, patches = load_case(name)
+    net = _net(conf, sd, precision)
+    torch.backends.cudnn.allow_tf32 = False          # the conv encoder's grad-mode half is still cuDNN: keep it fp32
+    torch.manual_seed(meta['rng_seed'])
+    mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+    labels = O.make_labels(conf, meta['B'], meta['label_seed'])
+    preds = net(mem_patch.to(DEV), None if mem_pos is None else mem_pos.to(DEV))
+    loss = O.loss_fn(conf, preds, {k: v.to(DEV) for k, v in labels.items()})
+    loss.backward()
+    ref_loss = float(z['loss'])
+    tol = 1e-4 if precision == 'fp32' else 2e-2
+    assert abs(loss.item() - ref_loss) <= tol * max(1.0, abs(ref_loss))
+    grads = dict(net.named_parameters())
+    for key in z.files:
+        if not key.startswith('gradnorm_'):
+            continue
+        g = grads[key[9:]].grad
+        got, want = g.double().norm().item(), float(z[key])
+        assert abs(got - want) <= (1e-3 if precision == 'fp32' else 6e-2) * max(want, 1e-6), (key, got, want)
+        if precision == 'fp32':
+            want_v = z['grad_' + key[9:]]
+            # element-wise, relative to the slice's scale (train-mode BatchNorm over a handful of patches amplifies
+            # the cuDNN-vs-CPU rounding of the conv encoder in individual small entries)
+            np.testing.assert_allclose(g.reshape(-1)[:256].cpu().numpy(), want_v, rtol=2e-3, atol=2e-2 * float(np.abs(want_v).max()))

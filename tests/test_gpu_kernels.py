@@ -391,3 +391,31 @@ def test_residual_layernorm_and_heads(dev):
     torch.testing.assert_close(ops.head_activation(z.to(dev), 'softmax').cpu(), torch.softmax(z, -1), rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(ops.head_activation(z.to(dev), 'sigmoid').cpu(), torch.sigmoid(z), rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(ops.add(x.to(dev), x.to(dev)).cpu(), x + x)
+
+
+# ------------------------------------------------------------------ general tensor-core GEMM (train step)
+
+@pytest.mark.parametrize('mode', ['nt', 'nn', 'tn'])
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (512, 2048, 8000), (1000, 512, 2048), (256, 128, 130000), (384, 192, 72)])
+def test_gemm_bf16_modes(dev, mode, M, N, K):
+    """NT / NN / TN products against fp32 matmul of the same bf16 operands (MN-major operands, split-K)."""
+    from ips_b200 import ops
+    if mode == 'tn' and M % 128:
+        pytest.skip('TN split-K needs M % 128 == 0')
+    if mode != 'tn' and K > 10000:
+        K = 4096
+    g = torch.Generator().manual_seed(60)
+    x = (torch.randn(M, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    w = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    ref = x.float() @ w.float().t()
+    if mode == 'nt':
+        got = ops.gemm_bf16('nt', x.to(dev), w.to(dev))
+    elif mode == 'nn':
+        got = ops.gemm_bf16('nn', x.to(dev), w.t().contiguous().to(dev))
+    else:
+        got = ops.gemm_bf16('tn', x.t().contiguous().to(dev), w.t().contiguous().to(dev))
+    torch.testing.assert_close(got.cpu(), ref, rtol=2e-3, atol=2e-3)
+    if mode == 'nt':
+        shift = torch.randn(N, generator=g)
+        got = ops.gemm_bf16('nt', x.to(dev), w.to(dev), shift=shift.to(dev), relu=True, out_dtype=torch.bfloat16)
+        torch.testing.assert_close(got.cpu().float(), torch.relu(ref + shift), rtol=2e-2, atol=2e-2)
