@@ -277,8 +277,8 @@ def run_ours(args):
         ms_t = timed(train_step, tsteps)
         train = {'metric': 'train_images_per_sec', 'value': world * B_train * tsteps / (ms_t / 1e3), 'ms_per_step': ms_t / tsteps,
                  'images_per_step': B_train, 'ips_calls_per_step': n_calls,
-                 'note': 'ips() and every nn.Linear forward/backward on the library kernels; conv encoder backward, BatchNorm, '
-                         'LayerNorm, attention core and AdamW on PyTorch (round 1)'}
+                 'note': 'ips(), every nn.Linear, LayerNorm, BatchNorm1d and the attention core run forward AND backward on the '
+                         'library kernels; the conv encoder\'s grad-mode half, elementwise glue and AdamW are PyTorch (round 1)'}
 
     # ---- roofline of the dominant kernel family (per-launch CUDA events, same work) ---
     roof = None

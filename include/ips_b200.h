@@ -106,7 +106,8 @@ IPSB_API int ipsb_gemm_bf16(int mode, const void* a, const void* b, const float*
  * of the train step and the fallback for shapes the tensor-core kernel does not take (class heads). */
 IPSB_API int ipsb_gemm_f32(int mode, const float* a, const float* b, const float* shift, float* c, int64_t M, int N, int64_t K,
                   int relu, void* stream);
-IPSB_API int ipsb_colsum_f32(const float* x, const float* y, float* out, int64_t rows, int cols, void* stream);   /* sum_r x*y */
+IPSB_API int ipsb_colsum_f32(const float* x, const float* y, float* out, float* scratch /* 64*cols floats or NULL */, int64_t rows,
+                    int cols, void* stream);   /* out[c] = sum_r x[r,c] * (y ? y[r,c] : 1) */
 IPSB_API int ipsb_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 /* fp32 (rows,F) -> bf16 with optional no-affine LayerNorm fused (projector prologue) */
 IPSB_API int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);
@@ -189,6 +190,29 @@ IPSB_API int ipsb_residual_layernorm_f32(const float* x, const float* r, int r_r
 /* rows of n logits -> softmax (act 0) or sigmoid (act 1) */
 IPSB_API int ipsb_head_activation_f32(const float* logits, float* y, int rows, int n, int act, void* stream);
 IPSB_API int ipsb_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- grad-mode operators (fp32), forward + backward
+ * BatchNorm1d in batch-statistics mode (ips_net.py:58 under net.train()), LayerNorm backward
+ * (transformer.py:107,130) and the cross-attention core with a dropout mask (transformer.py:29-41,98). */
+IPSB_API int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch /* 128*cols floats */, int64_t rows, int cols,
+                      void* stream);   /* biased variance, two-stage deterministic reduction */
+IPSB_API int ipsb_bn_apply_f32(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
+                      int64_t rows, int cols, int relu, void* stream);
+/* sums (2*cols) = [dbeta, dgamma]; dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*(y>0) when relu */
+IPSB_API int ipsb_bn_backward_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                         const float* gamma, float* sums, float* dx, float* scratch /* 128*cols floats */, int64_t rows, int cols,
+                         int relu, void* stream);
+/* dx of y = LayerNorm(x)*gamma+beta (gamma may be NULL); xhat (optional) returns the normalised input for dgamma */
+IPSB_API int ipsb_layernorm_backward_f32(const float* dy, const float* x, const float* gamma, float* dx, float* xhat, int64_t rows,
+                                int D, float eps, void* stream);
+/* q_scaled (T,H*Dk), k (B,M,H*Dk), v (B,M,H*Dv), mask (B,H,T,M) of 0/1 or NULL, keep_scale = 1/(1-p);
+ * prob (B,H,T,M) softmax weights (saved for the backward), out (B,T,H*Dv) */
+IPSB_API int ipsb_attention_train_fwd_f32(const float* q_scaled, const float* k, const float* v, const float* mask, float keep_scale,
+                                 float* prob, float* out, int B, int M, int H, int Dk, int Dv, int T, void* stream);
+/* dq_part (B,T,H*Dk) is per batch element (sum over B = dq); dk (B,M,H*Dk); dv (B,M,H*Dv) */
+IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k, const float* v, const float* mask, float keep_scale,
+                                 const float* prob, const float* dout, float* dq_part, float* dk, float* dv,
+                                 int B, int M, int H, int Dk, int Dv, int T, void* stream);
 
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the

@@ -53,7 +53,7 @@ SIGNATURES = {
     'ipsb_gemm_workspace_bytes': [_i32, _i64, _i32, _i64],
     'ipsb_gemm_bf16': [_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i64, _i32, _i64, _i32, _ptr, _i64, _ptr],
     'ipsb_gemm_f32': [_i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i64, _i32, _ptr],
-    'ipsb_colsum_f32': [_ptr, _ptr, _ptr, _i64, _i32, _ptr],
+    'ipsb_colsum_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
     'ipsb_cast_bf16': [_ptr, _ptr, _i64, _ptr],
     'ipsb_rows_to_bf16': [_ptr, _ptr, _i64, _i32, _i32, _f32, _ptr],
     'ipsb_score_basis': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
@@ -66,6 +66,12 @@ SIGNATURES = {
     'ipsb_residual_layernorm_f32': [_ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
     'ipsb_head_activation_f32': [_ptr, _ptr, _i32, _i32, _i32, _ptr],
     'ipsb_add_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
+    'ipsb_bn_stats_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
+    'ipsb_bn_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
+    'ipsb_bn_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
+    'ipsb_layernorm_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
+    'ipsb_attention_train_fwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
+    'ipsb_attention_train_bwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
     'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64, _i32,

@@ -89,3 +89,108 @@ class Linear(nn.Linear):
         if not x.is_cuda:
             return super().forward(x)
         return LinearFn.apply(x, self.weight, self.bias, self.precision)
+
+
+# ---------------------------------------------------------------------------------------------------
+# non-GEMM operators of the grad-mode step
+# ---------------------------------------------------------------------------------------------------
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class BatchNormTrainFn(torch.autograd.Function):
+    """BatchNorm over rows in batch-statistics mode with an optional fused ReLU (nn.BatchNorm1d + nn.ReLU under
+    net.train(), architecture/ips_net.py:58-59).  Updates the running statistics like nn.BatchNorm1d."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        x = x.contiguous().float()
+        rows, cols = x.shape
+        mean = torch.empty(cols, dtype=torch.float32, device=x.device)
+        var = torch.empty_like(mean)
+        scratch = torch.empty(128 * cols, dtype=torch.float32, device=x.device)
+        ops._call('ipsb_bn_stats_f32', _p(x), _p(mean), _p(var), _p(scratch), rows, cols, ops._stream())
+        with torch.no_grad():
+            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+            running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows / max(rows - 1, 1))
+        rstd = torch.rsqrt(var + eps)
+        y = torch.empty_like(x)
+        g, b = gamma.contiguous().float(), beta.contiguous().float()
+        ops._call('ipsb_bn_apply_f32', _p(x), _p(mean), _p(rstd), _p(g), _p(b), _p(y), rows, cols, int(relu), ops._stream())
+        ctx.save_for_backward(x, y, mean, rstd, g)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, g = ctx.saved_tensors
+        rows, cols = x.shape
+        dy = dy.contiguous().float()
+        sums = torch.empty(2 * cols, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        scratch = torch.empty(128 * cols, dtype=torch.float32, device=x.device)
+        ops._call('ipsb_bn_backward_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(sums), _p(dx), _p(scratch), rows, cols,
+                  int(ctx.relu), ops._stream())
+        return dx, sums[cols:], sums[:cols], None, None, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm over the last dimension, optional affine (nn.LayerNorm, architecture/transformer.py:107,130 and the
+    affine-free projector prologue, ips_net.py:56)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous().float()
+        D = x2.shape[1]
+        if gamma is None:
+            y = ops.layernorm_rows(x2, eps)
+        else:
+            y = ops.residual_layernorm(x2, None, gamma.contiguous().float(), beta.contiguous().float(), eps)
+        ctx.save_for_backward(x2, None if gamma is None else gamma.contiguous().float())
+        ctx.eps, ctx.shape, ctx.affine = eps, shape, gamma is not None
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g = ctx.saved_tensors
+        rows, D = x2.shape
+        dy2 = dy.reshape(rows, D).contiguous().float()
+        dx = torch.empty_like(x2)
+        xhat = torch.empty_like(x2) if ctx.affine else None
+        ops._call('ipsb_layernorm_backward_f32', _p(dy2), _p(x2), _p(g), _p(dx), _p(xhat), rows, D, ctx.eps, ops._stream())
+        dg = db = None
+        if ctx.affine:
+            dg, db = ops.colsum(dy2, xhat), ops.colsum(dy2)
+        return dx.view(ctx.shape), dg, db, None
+
+
+class CrossAttentionFn(torch.autograd.Function):
+    """softmax(q k^T) (dropout) v per head and query token (architecture/transformer.py:29-41).  q is already divided by
+    the temperature; `mask` (B,H,T,M) of 0/1 floats or None is the attention-dropout keep mask."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, keep_scale, H, Dk, Dv):
+        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        B, M = k.shape[:2]
+        T = q.shape[0]
+        prob = torch.empty((B, H, T, M), dtype=torch.float32, device=k.device)
+        out = torch.empty((B, T, H * Dv), dtype=torch.float32, device=k.device)
+        ops._call('ipsb_attention_train_fwd_f32', _p(q), _p(k), _p(v), _p(mask), float(keep_scale), _p(prob), _p(out),
+                  B, M, H, Dk, Dv, T, ops._stream())
+        ctx.save_for_backward(q, k, v, prob, mask)
+        ctx.dims = (B, M, H, Dk, Dv, T, float(keep_scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, prob, mask = ctx.saved_tensors
+        B, M, H, Dk, Dv, T, keep_scale = ctx.dims
+        dout = dout.contiguous().float()
+        dq_part = torch.empty((B, T * H * Dk), dtype=torch.float32, device=k.device)
+        dk, dv = torch.empty_like(k), torch.empty_like(v)
+        ops._call('ipsb_attention_train_bwd_f32', _p(q), _p(k), _p(v), _p(mask), keep_scale, _p(prob), _p(dout), _p(dq_part),
+                  _p(dk), _p(dv), B, M, H, Dk, Dv, T, ops._stream())
+        dq = ops.colsum(dq_part).view(T, H * Dk)
+        return dq, dk, dv, None, None, None, None, None

@@ -272,15 +272,17 @@ __global__ void __launch_bounds__(256) rows_warp_kernel(const float* __restrict_
 __global__ void colsum_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t rows, int cols) {
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    const int R = gridDim.y;                      // row chunks: out is (R, cols) partials when R > 1
+    const int64_t per = (rows + R - 1) / R, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float s = 0.f;
     if (c < cols)
-        for (int64_t r = w; r < rows; r += 8) s += y ? x[r * cols + c] * y[r * cols + c] : x[r * cols + c];
+        for (int64_t r = r0 + w; r < r1; r += 8) s += y ? x[r * cols + c] * y[r * cols + c] : x[r * cols + c];
     part[w][threadIdx.x & 31] = s;
     __syncthreads();
     if (w == 0 && c < cols) {
         float t = 0.f;
         for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
-        out[c] = t;
+        out[(int64_t)blockIdx.y * cols + c] = t;
     }
 }
 
@@ -410,9 +412,14 @@ int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int F, float
 }
 
 /* out[c] = sum_r x[r,c] * (y ? y[r,c] : 1) */
-int ipsb_colsum_f32(const float* x, const float* y, float* out, int64_t rows, int cols, void* stream) {
+int ipsb_colsum_f32(const float* x, const float* y, float* out, float* scratch, int64_t rows, int cols, void* stream) {
     IPSB_REQUIRE(rows > 0 && cols > 0, "colsum: bad shape");
-    colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, y, out, rows, cols);
+    if (rows <= 4096 || scratch == nullptr) {
+        colsum_kernel<<<dim3((cols + 31) / 32, 1), 256, 0, (cudaStream_t)stream>>>(x, y, out, rows, cols);
+    } else {                                     // long columns: 64 row chunks -> partials -> second pass over the 64 partial rows
+        colsum_kernel<<<dim3((cols + 31) / 32, 64), 256, 0, (cudaStream_t)stream>>>(x, y, scratch, rows, cols);
+        colsum_kernel<<<dim3((cols + 31) / 32, 1), 256, 0, (cudaStream_t)stream>>>(scratch, nullptr, out, 64, cols);
+    }
     IPSB_LAUNCH_CHECK();
     return 0;
 }

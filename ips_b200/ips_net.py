@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .autograd import Linear
+from .autograd import Linear, LayerNormFn, BatchNormTrainFn
 from .transformer import Transformer, pos_enc_1d
 from .utils import scan_order
 
@@ -433,7 +433,18 @@ class IPSNet(nn.Module):
             return self._forward_inference(mem_patch, mem_pos)
         shape = mem_patch.shape
         B, M = shape[:2]
-        mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
+        if not self.is_image and mem_patch.is_cuda and self.training:
+            # feature projector on the library's kernels, forward and backward: LayerNorm -> Linear -> BatchNorm1d
+            # (batch statistics, running-stat update) + ReLU
+            ln, lin, bn = self.encoder[0], self.encoder[1], self.encoder[2]
+            h = LayerNormFn.apply(mem_patch.reshape(B * M, -1), None, None, ln.eps)
+            h = lin(h)
+            mem_emb = BatchNormTrainFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, True)
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            mem_emb = mem_emb.view(B, M, -1)
+        else:
+            mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
         if torch.is_tensor(mem_pos):
             mem_emb = mem_emb + mem_pos
         return self.get_preds(self.transf(mem_emb))

@@ -369,7 +369,8 @@ def colsum(x, y=None):
     """sum over rows of x (or of x*y): (rows, cols) -> (cols,)"""
     _chk(x, torch.float32, 'x'); _chk(y, torch.float32, 'y')
     out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
-    _call('ipsb_colsum_f32', _p(x), _p(y), _p(out), x.shape[0], x.shape[1], _stream())
+    scratch = torch.empty(64 * x.shape[1], dtype=torch.float32, device=x.device) if x.shape[0] > 4096 else None
+    _call('ipsb_colsum_f32', _p(x), _p(y), _p(out), _p(scratch), x.shape[0], x.shape[1], _stream())
     return out
 
 

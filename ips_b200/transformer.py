@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .autograd import Linear
+from .autograd import Linear, LayerNormFn, CrossAttentionFn
 
 
 def pos_enc_1d(D, len_seq):
@@ -76,6 +76,17 @@ class MultiHeadCrossAttention(nn.Module):
     def forward(self, x):
         B, L = x.shape[:2]
         H, Dk, Dv, T = self.H, self.D_k, self.D_v, self.n_token
+        if x.is_cuda:                       # library kernels forward and backward (autograd.py)
+            q = self.q_w(self.q)[0] / self.attention.temperature                      # (T, H*Dk)
+            k, v = self.k_w(x), self.v_w(x)                                             # (B, L, H*Dk / H*Dv)
+            mask, keep = None, 1.0
+            pd = self.attention.dropout.p
+            if self.training and pd > 0:
+                mask = (torch.rand((B, H, T, L), device=x.device) >= pd).float()
+                keep = 1.0 / (1.0 - pd)
+            out = CrossAttentionFn.apply(q, k, v, mask, keep, H, Dk, Dv)                # (B, T, H*Dv)
+            out = self.dropout(self.fc(out)) + self.q
+            return LayerNormFn.apply(out, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
         q = self.q_w(self.q).view(1, T, H, Dk).transpose(1, 2)
         k = self.k_w(x).view(B, L, H, Dk).transpose(1, 2)
         v = self.v_w(x).view(B, L, H, Dv).transpose(1, 2)
@@ -94,7 +105,10 @@ class MLP(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x):
-        return self.layer_norm(self.dropout(self.w_2(torch.relu(self.w_1(x)))) + x)
+        h = self.dropout(self.w_2(torch.relu(self.w_1(x)))) + x
+        if x.is_cuda:
+            return LayerNormFn.apply(h, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+        return self.layer_norm(h)
 
 
 class Transformer(nn.Module):

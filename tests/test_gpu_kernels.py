@@ -419,3 +419,72 @@ def test_gemm_bf16_modes(dev, mode, M, N, K):
         shift = torch.randn(N, generator=g)
         got = ops.gemm_bf16('nt', x.to(dev), w.to(dev), shift=shift.to(dev), relu=True, out_dtype=torch.bfloat16)
         torch.testing.assert_close(got.cpu().float(), torch.relu(ref + shift), rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------ grad-mode operators vs torch autograd
+
+def test_batchnorm_train_fn(dev):
+    from ips_b200.autograd import BatchNormTrainFn
+    x = _rand(300, 70, seed=70) * 2 + 0.5
+    g, b = torch.rand(70) + 0.5, _rand(70, seed=71)
+    dy = _rand(300, 70, seed=72)
+    bn = torch.nn.BatchNorm1d(70)
+    with torch.no_grad():
+        bn.weight.copy_(g); bn.bias.copy_(b)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.relu(bn(xr)); yr.backward(dy)
+    xg = x.to(dev).requires_grad_(True)
+    gg, bg = g.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    rm, rv = torch.zeros(70, device=dev), torch.ones(70, device=dev)
+    y = BatchNormTrainFn.apply(xg, gg, bg, rm, rv, 0.1, 1e-5, True)
+    y.backward(dy.to(dev))
+    torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(gg.grad.cpu(), bn.weight.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(bg.grad.cpu(), bn.bias.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(rm.cpu(), bn.running_mean, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(rv.cpu(), bn.running_var, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('affine', [True, False])
+def test_layernorm_fn(dev, affine):
+    from ips_b200.autograd import LayerNormFn
+    x, dy = _rand(2, 9, 128, seed=73) * 3, _rand(2, 9, 128, seed=74)
+    g, b = (torch.rand(128) + 0.5, _rand(128, seed=75)) if affine else (None, None)
+    xr = x.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True) if affine else None
+    br = b.clone().requires_grad_(True) if affine else None
+    F.layer_norm(xr, (128,), gr, br, 1e-6).backward(dy)
+    xg = x.to(dev).requires_grad_(True)
+    gg = g.to(dev).requires_grad_(True) if affine else None
+    bg = b.to(dev).requires_grad_(True) if affine else None
+    y = LayerNormFn.apply(xg, gg, bg, 1e-6)
+    y.backward(dy.to(dev))
+    torch.testing.assert_close(y.detach().cpu(), F.layer_norm(x, (128,), g, b, 1e-6), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-5)
+    if affine:
+        torch.testing.assert_close(gg.grad.cpu(), gr.grad, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(bg.grad.cpu(), br.grad, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize('B,M,H,Dk,Dv,T,drop', [(2, 50, 8, 16, 16, 4, 0.0), (3, 10, 8, 64, 64, 1, 0.3), (1, 700, 8, 64, 64, 1, 0.1)])
+def test_cross_attention_fn(dev, B, M, H, Dk, Dv, T, drop):
+    from ips_b200.autograd import CrossAttentionFn
+    q = _rand(T, H * Dk, seed=76) / math.sqrt(Dk)
+    k, v = _rand(B, M, H * Dk, seed=77), _rand(B, M, H * Dv, seed=78)
+    dout = _rand(B, T, H * Dv, seed=79)
+    mask = (torch.rand(B, H, T, M) >= drop).float() if drop > 0 else None
+    keep = 1.0 / (1.0 - drop)
+    qr, kr, vr = q.clone().requires_grad_(True), k.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    a = torch.softmax(torch.matmul(qr.view(1, T, H, Dk).transpose(1, 2), kr.view(B, M, H, Dk).transpose(1, 2).transpose(2, 3)), -1)
+    if mask is not None:
+        a = a * mask * keep
+    ref = torch.matmul(a, vr.view(B, M, H, Dv).transpose(1, 2)).transpose(1, 2).reshape(B, T, H * Dv)
+    ref.backward(dout)
+    qg, kg, vg = (t.to(dev).requires_grad_(True) for t in (q, k, v))
+    out = CrossAttentionFn.apply(qg, kg, vg, None if mask is None else mask.to(dev), keep, H, Dk, Dv)
+    out.backward(dout.to(dev))
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(kg.grad.cpu(), kr.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(vg.grad.cpu(), vr.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(qg.grad.cpu(), qr.grad, rtol=1e-3, atol=1e-4)
