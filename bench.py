@@ -138,7 +138,7 @@ def run_reference(args):
     if rank != 0:
         return
     t_start = time.perf_counter()
-    rate, cores, sample = cpu_reference_rate(args.workload, sample_images=2, repeats=max(1, min(args.steps, 3)))
+    rate, cores, sample = cpu_reference_rate(args.workload, sample_images=16, repeats=max(1, min(args.steps, 5)))
     conf, B, N = conf_for(args.workload, 'fp32')
     line = {
         'impl': 'reference', 'metric': 'ips_selection_patches_per_sec', 'value': rate, 'unit': 'patches/s',
@@ -327,7 +327,7 @@ def run_ours(args):
     # ---- CPU baseline on rank 0 at N=1 -------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, cores, sample = cpu_reference_rate(args.workload, sample_images=2, repeats=3)
+        rate, cores, sample = cpu_reference_rate(args.workload, sample_images=16, repeats=3)
         cpu = {'value': rate, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': sample}
 
     if rank == 0:
