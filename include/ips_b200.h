@@ -53,6 +53,15 @@ IPSB_API int ipsb_stage_patches(const float* src, const int64_t* row_idx, int64_
 IPSB_API int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows,
                               int C, int H, int W, int pad_top, int pad_left, int Hp, int Wp, void* dst, void* stream);
 
+/* Space-to-depth staging for the stem (mode 4 of ipsb_conv_bf16_umma): frame pixel (Y',X') of a patch holds 16 bf16,
+ * channel (dy*2+dx)*4+c = in(2Y'+dy-4, 2X'+dx-4, c); (H/2+3) x (W/2+3) frame pixels per patch.  The 7x7/2 stem is then a
+ * 4x4 stride-1 convolution whose 16 taps are shifted views of one block of frame rows (weights (Cout,256),
+ * k = (a*4+b)*16 + (dy*2+dx)*4 + c = w[2a+dy-1, 2b+dx-1, c]).  The stem output keeps the frame's row order
+ * (output (oy,ox) of patch p at row p*Sp + oy*(W/2+3) + ox, Sp = (H/2+3)*(W/2+3)); ipsb_maxpool3x3s2_pf_strided reads it. */
+IPSB_API int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows, int C, int H, int W,
+                           void* dst, void* stream);
+IPSB_API int ipsb_maxpool3x3s2_pf_strided(const void* x, void* y, int64_t P, int H, int W, int C, int in_Wp, int in_Sp, void* stream);
+
 /* ---------------------------------------------------------------- encoder, fp32 SIMT ("exact" mode)
  * Replaces: conv2d + eval-mode batch_norm [+ residual add] [+ relu] of the
  * truncated torchvision ResNet (ips_net.py:17-52).  x: (P,H,W,Cin) NHWC fp32,
@@ -75,6 +84,7 @@ IPSB_API int ipsb_layernorm_rows_f32(const float* x, float* y, int64_t rows, int
  * Same contract as ipsb_conv_f32 with x,res,y bf16 NHWC and w (Cout, K) bf16
  * K-major, K = kh*kw*Cin padded to a multiple of 64.  mode 0: Cin % 64 == 0, TMA-fed
  * (M tile = box of output pixels); mode 2: same contract through a cp.async gather;
+ * mode 4: the stem on the space-to-depth frame (H, W = image size, Cin = 16), shifted-window kernel;
  * mode 3: the stem on the zero-bordered frame of ipsb_stage_patches_padded (H, W = frame size), TMA-fed;
  * mode 1: the 7x7/2 stem on 4-channel-padded input (K laid out r*32+(s+1)*4+c, 256). */
 IPSB_API int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const float* shift,

@@ -41,6 +41,8 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
 // stride-1 3x3 convolution on padded-flat activations (umma_conv_halo.cu)
 int conv3x3_halo(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
                  int64_t P, int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
+int conv_stem_s2d(const void* x, const void* w, const float* scale, const float* shift, void* y, int64_t P, int H, int W,
+                  int Cout, int relu, cudaStream_t st);
 int conv_stem_tma(const void* x, const void* w, const float* scale, const float* shift, void* y,
                   int64_t P, int H, int W, int Cout, int relu, cudaStream_t st);
 

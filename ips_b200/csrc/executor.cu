@@ -15,7 +15,7 @@ inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
 // largest activation (elements per patch) of each of the three rotating buffers
 int64_t max_act_elems(const ipsb_resnet_desc* net, int H, int W, int64_t* staged_elems) {
-    *staged_elems = (net->stem.mode == 3) ? (int64_t)(H + 6) * (W + 6) * 4 : (int64_t)H * W * 4;
+    *staged_elems = (net->stem.mode >= 3) ? (int64_t)(H + 6) * (W + 6) * 4 : (int64_t)H * W * 4;
     int h = out_dim(H, 7, 2, 3), w = out_dim(W, 7, 2, 3);
     int64_t mx = (int64_t)h * w * net->stem.cout;
     h = out_dim(h, 3, 2, 1); w = out_dim(w, 3, 2, 1);
@@ -54,7 +54,8 @@ PfPlan make_pf_plan(const ipsb_resnet_desc* net, int64_t chunk, int H, int W) {
     PfPlan pl;
     pl.staged_bytes = align256(chunk * (int64_t)(H + 6) * (W + 6) * 4 * 2);
     int h = out_dim(H, 7, 2, 3), w = out_dim(W, 7, 2, 3);
-    pl.stem_bytes = align256(chunk * (int64_t)h * w * net->stem.cout * 2);
+    pl.stem_bytes = (net->stem.mode == 4) ? align256(chunk * (int64_t)(h + 3) * (w + 3) * net->stem.cout * 2)   // wide row order
+                                          : align256(chunk * (int64_t)h * w * net->stem.cout * 2);
     h = out_dim(h, 3, 2, 1); w = out_dim(w, 3, 2, 1);
     pl.n_groups = net->n_blocks / 2;
     pl.total = pl.staged_bytes + pl.stem_bytes;
@@ -82,7 +83,7 @@ extern "C" {
 int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W) {
     (void)C;
     const int64_t tail = align256(chunk * net->D * 4) + align256(chunk * 8) + 1024;
-    if (net->dt == IPSB_BF16 && net->stem.mode == 3) return make_pf_plan(net, chunk, H, W).total + tail;
+    if (net->dt == IPSB_BF16 && net->stem.mode >= 3) return make_pf_plan(net, chunk, H, W).total + tail;
     int64_t staged;
     const int64_t act = max_act_elems(net, H, W, &staged);
     const int64_t es = (int64_t)esize(net->dt);
@@ -118,6 +119,17 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         const pf::Geo gq = pf::make(P, hq, wq);
         for (int64_t s0 = 0; s0 < P; s0 += sub) {
             const int64_t Ps = (P - s0 < sub) ? P - s0 : sub;
+            if (st.mode == 4) {               // space-to-depth frame -> shifted-window stem -> strided max-pool
+                rc = ipsb_stage_patches_s2d(patches, nullptr, first_row + lo + s0, Ps, C, H, W, staged, stream);
+                if (rc) return rc;
+                rc = ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H, W, 16, st.cout, 7, 7, 2, 3, 1, 4,
+                                         stream);
+                if (rc) return rc;
+                rc = ipsb_maxpool3x3s2_pf_strided(stem_out, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, hs, wsz, st.cout,
+                                                  wsz + 3, (hs + 3) * (wsz + 3), stream);
+                if (rc) return rc;
+                continue;
+            }
             rc = ipsb_stage_patches_padded(patches, nullptr, first_row + lo + s0, Ps, C, H, W, 3, 4, H + 6, W + 6, staged, stream);
             if (rc) return rc;
             rc = ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H + 6, W + 6, 4, st.cout, 7, 7, 2, 3,
@@ -173,7 +185,7 @@ int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_
     IPSB_REQUIRE(net && patches && z_out && workspace, "resnet_logits: null argument");
     IPSB_REQUIRE(n_rows > 0 && chunk > 0 && net->n_blocks > 0 && net->n_blocks <= 8 && net->n_blocks % 2 == 0, "resnet_logits: bad sizes");
     IPSB_REQUIRE(workspace_bytes >= ipsb_resnet_workspace_bytes(net, chunk, C, H, W), "resnet_logits: workspace too small");
-    if (net->dt == IPSB_BF16 && net->stem.mode == 3)
+    if (net->dt == IPSB_BF16 && net->stem.mode >= 3)
         return resnet_logits_pf(net, patches, first_row, n_rows, C, H, W, n_per_image, chunk, workspace, zero_init, emb_out,
                                 z_out, stream);
     const int dt = net->dt;

@@ -89,6 +89,45 @@ __global__ void stage_padded_kernel(const float* __restrict__ src, const int64_t
     }
 }
 
+// space-to-depth staging for the stem: one thread per 2x2 input block.  Frame pixel (Y', X') of patch r holds 16 bf16:
+// channel (dy*2+dx)*4 + c = in(2Y'+dy-4, 2X'+dx-4, c) (zero outside the image / for c >= C); Ys x Wp frame pixels per patch.
+__global__ void stage_s2d_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx, int64_t first_row,
+                                 int64_t n_rows, int C, int H, int W, int Ys, int Wp, bf16* __restrict__ dst) {
+    const int64_t total = n_rows * Ys * Wp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / (Ys * Wp);
+        const int rem = (int)(i - r * (Ys * Wp));
+        const int Yp = rem / Wp, Xp = rem - Yp * Wp;
+        __align__(16) bf16 out[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] = __float2bfloat16_rn(0.f);
+        const int y0 = 2 * Yp - 4, x0 = 2 * Xp - 4;
+        if (y0 + 1 >= 0 && y0 < H && x0 + 1 >= 0 && x0 < W) {
+            const int64_t srow = row_idx ? row_idx[r] : first_row + r;
+            const float* sp = src + srow * (int64_t)C * H * W;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = y0 + dy;
+                if (y < 0 || y >= H) continue;
+                for (int c = 0; c < C; ++c) {
+                    const float* rowp = sp + ((int64_t)c * H + y) * W;
+                    if (x0 >= 0 && x0 + 1 < W) {         // x0 is even: aligned pair
+                        const float2 v = *reinterpret_cast<const float2*>(rowp + x0);
+                        out[(dy * 2 + 0) * 4 + c] = __float2bfloat16_rn(v.x);
+                        out[(dy * 2 + 1) * 4 + c] = __float2bfloat16_rn(v.y);
+                    } else {
+                        if (x0 >= 0 && x0 < W) out[(dy * 2 + 0) * 4 + c] = __float2bfloat16_rn(rowp[x0]);
+                        if (x0 + 1 >= 0 && x0 + 1 < W) out[(dy * 2 + 1) * 4 + c] = __float2bfloat16_rn(rowp[x0 + 1]);
+                    }
+                }
+            }
+        }
+        uint4* d = reinterpret_cast<uint4*>(dst + i * 16);
+        d[0] = *reinterpret_cast<const uint4*>(&out[0]);
+        d[1] = *reinterpret_cast<const uint4*>(&out[8]);
+    }
+}
+
 // dst row (b,m) <- src row; grid.x = rows, grid.y = 16 KB segments of a row
 __global__ void gather_rows16_kernel(const unsigned char* __restrict__ src, int64_t batch_stride_rows,
                                      const int64_t* __restrict__ idx, int M, int64_t row_bytes,
@@ -132,7 +171,7 @@ __global__ void gather_rows4_kernel(const uint32_t* __restrict__ src, int64_t ba
 // max_pool2d(3, 2, 1) channels-last, VEC channels per thread (16 bytes)
 template <typename T, int VEC>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t P, int H, int W, int C,
-                               int Ho, int Wo, int oG0, int oWp, int oSp) {
+                               int Ho, int Wo, int oG0, int oWp, int oSp, int iWp, int iSp) {
     const int cv = C / VEC;
     const int64_t total = P * Ho * Wo * cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -151,7 +190,7 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = ox * 2 - 1 + dx;
                 if (ix < 0 || ix >= W) continue;
-                const T* s = x + ((p * H + iy) * W + ix) * (int64_t)C + c0;
+                const T* s = x + (p * iSp + (int64_t)iy * iWp + ix) * (int64_t)C + c0;
                 __align__(16) T v[VEC];
                 *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(s);
 #pragma unroll
@@ -358,11 +397,11 @@ int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, in
     if (dt == IPSB_BF16) {
         IPSB_REQUIRE(C % 8 == 0, "maxpool: C=%d not a multiple of 8", C);
         const int64_t total = P * Ho * Wo * (C / 8);
-        maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, P, H, W, C, Ho, Wo, 0, Wo, Ho * Wo);
+        maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, P, H, W, C, Ho, Wo, 0, Wo, Ho * Wo, W, H * W);
     } else if (dt == IPSB_F32) {
         IPSB_REQUIRE(C % 4 == 0, "maxpool: C=%d not a multiple of 4", C);
         const int64_t total = P * Ho * Wo * (C / 4);
-        maxpool_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, P, H, W, C, Ho, Wo, 0, Wo, Ho * Wo);
+        maxpool_kernel<float, 4><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)y, P, H, W, C, Ho, Wo, 0, Wo, Ho * Wo, W, H * W);
     } else {
         return ipsb::fail("maxpool: unknown dtype %d", dt);
     }
@@ -370,13 +409,28 @@ int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, in
     return 0;
 }
 
-int ipsb_maxpool3x3s2_pf(const void* x, void* y, int64_t P, int H, int W, int C, void* stream) {
+int ipsb_maxpool3x3s2_pf_strided(const void* x, void* y, int64_t P, int H, int W, int C, int in_Wp, int in_Sp, void* stream) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    IPSB_REQUIRE(C % 8 == 0, "maxpool_pf: C=%d not a multiple of 8", C);
+    IPSB_REQUIRE(C % 8 == 0 && in_Wp >= W && in_Sp >= H * in_Wp - (in_Wp - W), "maxpool_pf: bad arguments (C=%d)", C);
     const pf::Geo g = pf::make(P, Ho, Wo);
     const int64_t total = P * Ho * Wo * (C / 8);
     maxpool_kernel<bf16, 8><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, P, H, W, C,
-                                                                                   Ho, Wo, g.G0, g.Wp, g.Sp);
+                                                                                   Ho, Wo, g.G0, g.Wp, g.Sp, in_Wp, in_Sp);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_maxpool3x3s2_pf(const void* x, void* y, int64_t P, int H, int W, int C, void* stream) {
+    return ipsb_maxpool3x3s2_pf_strided(x, y, P, H, W, C, W, H * W, stream);
+}
+
+int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows, int C, int H, int W,
+                           void* dst, void* stream) {
+    IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= 4 && H % 2 == 0 && W % 2 == 0 && ((uintptr_t)src % 8 == 0),
+                 "stage_s2d: needs C <= 4 and even H, W");
+    const int Ys = H / 2 + 3, Wp = W / 2 + 3;
+    stage_s2d_kernel<<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(src, row_idx, first_row, n_rows, C, H, W,
+                                                                                       Ys, Wp, (bf16*)dst);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

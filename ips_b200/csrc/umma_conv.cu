@@ -269,6 +269,10 @@ int ipsb_conv_bf16_umma(const void* x, const void* w, const float* scale, const 
     if (mode == 0)      // TMA-fed path: the M tile is a box of output pixels
         return ipsb::conv_tma(x, w, scale, shift, res, y, P, H, W, Cin, Cout, kh, kw, stride, pad, relu, false,
                               (cudaStream_t)stream);
+    if (mode == 4) {    // space-to-depth stem: x is the s2d frame of ipsb_stage_patches_s2d for HxW images, y the wide row order
+        IPSB_REQUIRE(Cin == 16 && kh == 7 && kw == 7 && stride == 2, "conv_umma mode 4 is the 7x7/2 stem on the s2d frame");
+        return ipsb::conv_stem_s2d(x, w, scale, shift, y, P, H, W, Cout, relu, (cudaStream_t)stream);
+    }
     if (mode == 3) {    // TMA-fed stem: x is the zero-bordered (P, H, W, 4) frame, image = (H-6) x (W-6)
         IPSB_REQUIRE(Cin == 4 && kh == 7 && kw == 7 && stride == 2, "conv_umma mode 3 is the 7x7/2 stem");
         return ipsb::conv_stem_tma(x, w, scale, shift, y, P, H - 6, W - 6, Cout, relu, (cudaStream_t)stream);

@@ -50,7 +50,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-template <int BN, int SA, int SB, bool RESB, bool PAIR>
+// K-major operand with 32-byte rows (16 bf16): 8-row atoms of 256 bytes, SWIZZLE_32B (tools/probe_sw32.cu)
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t addr) {
+    const uint32_t lo = ((addr >> 4) & 0x3fffu) | (1u << 16);
+    const uint32_t hi = (256u >> 4) | (1u << 14) | (6u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int BN, int SA, int SB, bool RESB, bool PAIR, bool S2D>
 __global__ void __launch_bounds__(320, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const HaloParams p) {
@@ -58,7 +65,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem0 = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b0 = smem0 + SA * p.a_slot_bytes;                                   // weight ring or resident slabs
-    const uint32_t out_stage0 = b0 + (RESB ? (uint32_t)(9 * p.cblocks) : (uint32_t)SB) * B_SLAB_BYTES;   // 2 x 16 KB epilogue staging
+    const uint32_t out_stage0 = b0 + (RESB ? (uint32_t)(S2D ? 4 : 9 * p.cblocks) : (uint32_t)SB) * B_SLAB_BYTES;   // 2 x 16 KB epilogue staging
     const uint32_t bar0 = out_stage0 + 2u * epi::STAGE_BYTES;
     auto a_full = [&](int s) { return bar0 + 8u * s; };
     auto a_empty = [&](int s) { return bar0 + 8u * (SA + s); };
@@ -88,7 +95,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const int n_slabs = 9 * p.cblocks;
+    // S2D (7x7/2 stem as a 4x4 stride-1 convolution on the 2x2 space-to-depth input): 16 taps of 16 channels,
+    // A rows of 32 bytes (SWIZZLE_32B), the (Cout, 256) weights resident as four 64-wide slabs
+    constexpr int ROW_BYTES = S2D ? 32 : 128;
+    constexpr int NTAPS = S2D ? 16 : 9;
+    const int n_slabs = S2D ? 4 : 9 * p.cblocks;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -102,12 +113,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
                     const int sa = ia % SA;
                     umma::mbar_wait(a_empty(sa), ((ia / SA) & 1) ^ 1);
-                    umma::mbar_expect_tx(a_full(sa), (uint32_t)(p.a_rows * p.n_boxes) * 128u);
+                    umma::mbar_expect_tx(a_full(sa), (uint32_t)(p.a_rows * p.n_boxes) * ROW_BYTES);
                     for (int bx = 0; bx < p.n_boxes; ++bx)
-                        tma_load_2d(smem0 + sa * p.a_slot_bytes + (uint32_t)(bx * p.a_rows) * 128u, &tmA, a_full(sa), cb * BK,
+                        tma_load_2d(smem0 + sa * p.a_slot_bytes + (uint32_t)(bx * p.a_rows) * ROW_BYTES, &tmA, a_full(sa), cb * BK,
                                     tile * (MT * TILE_M) + bx * p.a_rows);
                     if (!RESB) {
-                        for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        for (int tap = 0; tap < NTAPS; ++tap, ++ib) {
                             const int sb = ib % SB;
                             umma::mbar_wait(b_empty(sb), ((ib / SB) & 1) ^ 1);
                             umma::mbar_expect_tx(b_full(sb), B_SLAB_BYTES);
@@ -134,7 +145,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     umma::mbar_wait(a_full(sa), (ia / SA) & 1);
                     umma::tc_fence_after();
                     const uint32_t a_base = smem0 + sa * p.a_slot_bytes;
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < NTAPS; ++tap) {
+                        if (S2D) {       // tap (a, b) of the 4x4 window: rows shifted by a*Wp + b, K slice tap*16 of the weights
+                            const int ta = tap >> 2, tb = tap & 3;
+                            const uint64_t adesc = desc_sw32(a_base + (uint32_t)(ta * p.Wp + tb) * 32u);
+                            const uint64_t bdesc = umma::smem_desc_sw128(b0 + ta * B_SLAB_BYTES) + (uint64_t)(2 * tb);
+                            umma::mma_bf16(d_tmem, adesc, bdesc, idesc, tap != 0);
+                            continue;
+                        }
                         const int r = tap / 3, s = tap - 3 * r;
                         uint32_t b_addr;
                         int sb = 0;
@@ -187,7 +205,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool in_range = rel < (int)p.pix_rows;             // rows of real patches (pixels or their pads)
             const int rem = rel % p.Sp;
             const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
-            const bool pixel = in_range && yy < p.H && xx < p.W;     // pad rows are stored as zeros
+            const bool pixel = in_range && (S2D || (yy < p.H && xx < p.W));   // pad rows are stored as zeros (S2D: no pads)
             const int64_t g = (int64_t)p.G0 + rel;
             umma::mbar_wait(tfull_bar(acc), (tcount >> 1) & 1);
             umma::tc_fence_after();
@@ -220,12 +238,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int BN, int SA, int SB, bool RESB, bool PAIR>
+template <int BN, int SA, int SB, bool RESB, bool PAIR, bool S2D = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? 9 * p.cblocks : SB) * BN * 128 + 2 * epi::STAGE_BYTES + 1024 +
+    const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? (S2D ? 4 : 9 * p.cblocks) : SB) * BN * 128 + 2 * epi::STAGE_BYTES + 1024 +
                         8 * (2 * SA + 2 * SB + 5) + 32 + 8 * (size_t)p.Cout;
     IPSB_REQUIRE(smem <= 227 * 1024, "conv_halo: %zu bytes of shared memory", smem);
-    auto kern = conv_halo_kernel<BN, SA, SB, RESB, PAIR>;
+    auto kern = conv_halo_kernel<BN, SA, SB, RESB, PAIR, S2D>;
     static size_t configured = 0;
     if (configured < smem) {
         IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -307,6 +325,61 @@ int conv3x3_halo(const void* x, const void* w, const float* scale, const float* 
     }
     if (pair) return launch<128, 3, 4, false, true>(tmA, tmB, tmC, p, st);
     return launch<128, 4, 5, false, false>(tmA, tmB, tmC, p, st);
+}
+
+
+// 7x7/2 pad-3 stem on the space-to-depth frame of ipsb_stage_patches_s2d: x (P * Sp rows, 16) bf16 with Sp = (H/2+3)*(W/2+3);
+// w (Cout=64, 256) bf16, k = (a*4+b)*16 + (dy*2+dx)*4 + c; y (P * Sp rows, 64) bf16 in the same "wide" row order
+// (output (oy, ox) of patch p at row p*Sp + oy*(W/2+3) + ox; the other rows hold don't-care values).
+int conv_stem_s2d(const void* x, const void* w, const float* scale, const float* shift, void* y, int64_t P, int H, int W,
+                  int Cout, int relu, cudaStream_t st) {
+    IPSB_REQUIRE(Cout == 64 && H % 2 == 0 && W % 2 == 0, "conv_stem_s2d: needs Cout=64 and even H, W");
+    EncodeTiledFn enc = encode_fn();
+    IPSB_REQUIRE(enc != nullptr, "conv_stem_s2d: cuTensorMapEncodeTiled not available from the driver");
+    const int Ho = H / 2, Wo = W / 2, Wp = Wo + 3, Sp = (Ho + 3) * Wp;
+    HaloParams p;
+    p.scale = scale; p.shift = shift; p.res = nullptr; p.y = (bf16*)y;
+    p.P = (int)P; p.H = Ho; p.W = Wo; p.Wp = Wp; p.Sp = Sp; p.G0 = 0; p.Cout = Cout; p.relu = relu; p.dbg = 0;
+    p.cblocks = 1;
+    p.pix_rows = P * (int64_t)Sp;
+    IPSB_REQUIRE(p.pix_rows + TILE_M < (1ll << 31), "conv_stem_s2d: too many rows");
+    p.total_tiles = (int)((p.pix_rows + TILE_M - 1) / TILE_M);
+    p.n_boxes = 2;
+    p.a_rows = ((TILE_M + 3 * Wp + 3 + 1) / 2 + 7) / 8 * 8;         // two boxes cover 128 + 3*Wp + 3 rows
+    IPSB_REQUIRE(p.a_rows <= 256, "conv_stem_s2d: width %d too large", W);
+    p.a_slot_bytes = (uint32_t)((p.a_rows * 2 * 32 + 1023) / 1024 * 1024);
+    alignas(64) CUtensorMap tmA, tmB, tmC;
+    {
+        cuuint64_t dims[2] = {16, (cuuint64_t)p.pix_rows};
+        cuuint64_t strides[1] = {32};
+        cuuint32_t box[2] = {16, (cuuint32_t)p.a_rows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_stem_s2d: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {256, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {512};
+        cuuint32_t box[2] = {64, 64};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_stem_s2d: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)p.pix_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)TILE_M};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_stem_s2d: cuTensorMapEncodeTiled(output) failed with %d", (int)r);
+    }
+    return launch<64, 6, 1, true, false, true>(tmA, tmB, tmC, p, st);
 }
 
 }  // namespace ipsb

@@ -127,9 +127,13 @@ class IPSNet(nn.Module):
         # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
         self.executor = os.environ.get('IPS_B200_EXECUTOR', 'native')
         self._ws_cache = {}
-        # bf16 stem: 3 = TMA-fed (zero-bordered staged frame, even patch sizes), 1 = cp.async gather
+        # bf16 stem: 4 = shifted-window kernel on the space-to-depth frame, 3 = TMA-fed im2col rows (both need even
+        # patch sizes), 1 = cp.async gather
         ps = getattr(conf, 'patch_size', [0, 0])
-        self.stem_tma = self.is_image and ps[0] % 2 == 0 and ps[1] % 2 == 0 and os.environ.get('IPS_B200_STEM', 'tma') == 'tma'
+        stem = os.environ.get('IPS_B200_STEM', 's2d')
+        even = self.is_image and ps[0] % 2 == 0 and ps[1] % 2 == 0
+        self.stem_mode = {'s2d': 4, 'tma': 3}.get(stem, 1) if even else 1
+        self.stem_tma = self.stem_mode >= 3
         ops.register_custom_ops()
 
     # ------------------------------------------------------------------ derived parameters
@@ -145,12 +149,18 @@ class IPSNet(nn.Module):
         w = conv.weight.detach().float()
         cout, cin, kh, kw = w.shape
         e = dict(cin=4 if stem else cin, cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0],
-                 mode=(3 if self.precision == 'bf16' and self.stem_tma else 1) if stem else 0)
+                 mode=(self.stem_mode if self.precision == 'bf16' else 1) if stem else 0)
         e['scale'], e['shift'] = _fold_bn(bn)
         if stem:                                                  # channels padded to 4
             w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
             w4[:, :cin] = w
-            if self.precision == 'bf16':                          # k = r*32 + (s+1)*4 + c, 8x8 taps
+            if self.precision == 'bf16' and e['mode'] == 4:       # k = (a*4+b)*16 + (dy*2+dx)*4 + c = w[2a+dy-1, 2b+dx-1, c]
+                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
+                wp[:, 1:kh + 1, 1:kw + 1] = w4.permute(0, 2, 3, 1)
+                wp = wp.view(cout, 4, 2, 4, 2, 4).permute(0, 1, 3, 2, 4, 5)
+                e['w'] = wp.reshape(cout, 256).to(torch.bfloat16).contiguous()
+                e['cin'] = 16
+            elif self.precision == 'bf16':                        # k = r*32 + (s+1)*4 + c, 8x8 taps
                 wp = torch.zeros((cout, 8, 8, 4), device=w.device)
                 wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
                 e['w'] = wp.reshape(cout, 256).to(torch.bfloat16).contiguous()
@@ -213,7 +223,7 @@ class IPSNet(nn.Module):
             n_rows = flat.shape[0] - first_row if row_idx is None else row_idx.numel()
         if self.is_image:
             _, C, H, W = flat.shape
-            if plan['stem']['mode'] == 3:
+            if plan['stem']['mode'] >= 3:
                 return self._embed_pf(plan, flat, row_idx, first_row, n_rows, C, H, W)
             x = ops.stage_patches(flat, n_rows, C, H, W, dt, row_idx=row_idx, first_row=first_row)
             x = self._conv(x, plan['stem'])
@@ -234,10 +244,17 @@ class IPSNet(nn.Module):
         """bf16 encoder on padded-flat activations (ips_b200/csrc/pf.cuh), one library call per layer;
         the same kernel sequence the native executor issues."""
         P = n_rows
-        x = ops.stage_patches_padded(flat, P, C, H, W, row_idx=row_idx, first_row=first_row)
-        x = self._conv(x, plan['stem'])                              # dense (P, H/2, W/2, 64)
-        h, w = x.shape[1], x.shape[2]
-        x = ops.maxpool3x3s2_pf(x)
+        if plan['stem']['mode'] == 4:
+            e = plan['stem']
+            x = ops.stage_patches_s2d(flat, P, C, H, W, row_idx=row_idx, first_row=first_row)
+            x = ops.conv_stem_s2d(x, e['w'], e['scale'], e['shift'], P, H, W, e['cout'])   # wide row order
+            h, w = H // 2, W // 2
+            x = ops.maxpool3x3s2_pf_strided(x, P, h, w, e['cout'], w + 3, (h + 3) * (w + 3))
+        else:
+            x = ops.stage_patches_padded(flat, P, C, H, W, row_idx=row_idx, first_row=first_row)
+            x = self._conv(x, plan['stem'])                              # dense (P, H/2, W/2, 64)
+            h, w = x.shape[1], x.shape[2]
+            x = ops.maxpool3x3s2_pf(x)
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
 
         def conv(x, e, h, w, res=None, relu=True):

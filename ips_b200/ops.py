@@ -77,6 +77,36 @@ def stage_patches_padded(src, n_rows, C, H, W, row_idx=None, first_row=0):
     return out
 
 
+def stage_patches_s2d(src, n_rows, C, H, W, row_idx=None, first_row=0):
+    """(rows,C,H,W) fp32 -> space-to-depth frame (n_rows * (H/2+3)*(W/2+3), 16) bf16 for the shifted-window stem."""
+    _chk(src, torch.float32, 'src')
+    _chk(row_idx, torch.int64, 'row_idx')
+    Sp = (H // 2 + 3) * (W // 2 + 3)
+    out = torch.empty((n_rows * Sp, 16), dtype=torch.bfloat16, device=src.device)
+    _call('ipsb_stage_patches_s2d', _p(src), _p(row_idx), first_row, n_rows, C, H, W, _p(out), _stream())
+    return out
+
+
+def conv_stem_s2d(frame, w_nk, scale, shift, P, H, W, Cout=64, relu=True):
+    """7x7/2 stem on the s2d frame; returns the wide-row-order output (P * Sp, Cout) bf16."""
+    _chk(frame, torch.bfloat16, 'frame'); _chk(w_nk, torch.bfloat16, 'w')
+    Sp = (H // 2 + 3) * (W // 2 + 3)
+    y = torch.empty((P * Sp, Cout), dtype=torch.bfloat16, device=frame.device)
+    _call('ipsb_conv_bf16_umma', _p(frame), _p(w_nk), _p(scale), _p(shift), 0, _p(y), P, H, W, 16, Cout, 7, 7, 2, 3, int(relu), 4,
+          _stream())
+    return y
+
+
+def maxpool3x3s2_pf_strided(x, P, H, W, C, in_Wp, in_Sp, out=None):
+    """max-pool of a (P, H, W, C) map stored with row pitch in_Wp / patch pitch in_Sp (in pixels) -> PF (rows, C)."""
+    _chk(x, torch.bfloat16, 'x')
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.zeros((pf_geo(P, Ho, Wo)[0], C), dtype=torch.bfloat16, device=x.device)
+    _call('ipsb_maxpool3x3s2_pf_strided', _p(x), _p(out), P, H, W, C, in_Wp, in_Sp, _stream())
+    return out
+
+
 def gather_rows(src, idx, batch_stride_rows):
     """dst[b,m] = src_rows[b*batch_stride_rows + idx[b,m]]; src viewed as rows of src.shape[-k:]."""
     _chk(idx, torch.int64, 'idx')

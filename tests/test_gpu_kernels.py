@@ -488,3 +488,41 @@ def test_cross_attention_fn(dev, B, M, H, Dk, Dv, T, drop):
     torch.testing.assert_close(kg.grad.cpu(), kr.grad, rtol=1e-3, atol=1e-5)
     torch.testing.assert_close(vg.grad.cpu(), vr.grad, rtol=1e-3, atol=1e-5)
     torch.testing.assert_close(qg.grad.cpu(), qr.grad, rtol=1e-3, atol=1e-4)
+
+
+def _stem_s2d_weights(w):
+    """(64, C, 7, 7) -> (64, 256) with k = (a*4+b)*16 + (dy*2+dx)*4 + c = w[2a+dy-1, 2b+dx-1, c]."""
+    Cout, C = w.shape[:2]
+    out = torch.zeros(Cout, 4, 4, 2, 2, 4)
+    for a in range(4):
+        for dy in range(2):
+            r = 2 * a + dy - 1
+            if not 0 <= r < 7:
+                continue
+            for b in range(4):
+                for dx in range(2):
+                    s = 2 * b + dx - 1
+                    if 0 <= s < 7:
+                        out[:, a, b, dy, dx, :C] = w[:, :, r, s]
+    return out.reshape(Cout, 256)
+
+
+@pytest.mark.parametrize('C,H,W,P', [(3, 100, 100, 9), (1, 50, 50, 37), (3, 20, 36, 5)])
+def test_stem_s2d(dev, C, H, W, P):
+    """7x7/2 stem as a shifted-window 4x4 convolution on the space-to-depth frame + strided max-pool."""
+    from ips_b200 import ops
+    x = _rand(P, C, H, W, seed=80)
+    w = _rand(64, C, 7, 7, seed=81, scale=math.sqrt(2.0 / (49 * C))).to(torch.bfloat16)
+    scale, shift = torch.rand(64) + 0.5, _rand(64, seed=82, scale=0.1)
+    frame = ops.stage_patches_s2d(x.to(dev), P, C, H, W)
+    y = ops.conv_stem_s2d(frame, _stem_s2d_weights(w.float()).to(torch.bfloat16).to(dev), scale.to(dev), shift.to(dev), P, H, W)
+    Ho, Wo, Wp = H // 2, W // 2, W // 2 + 3
+    Sp = (Ho + 3) * Wp
+    got = y.view(P, Sp, 64)[:, :Ho * Wp].view(P, Ho, Wp, 64)[:, :, :Wo].cpu().float()
+    xb = x.to(torch.bfloat16).float()
+    ref = torch.relu(F.conv2d(xb, w.float(), stride=2, padding=3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2)
+    pooled = ops.maxpool3x3s2_pf_strided(y, P, Ho, Wo, 64, Wp, Sp)
+    Hq, Wq = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
+    refp = F.max_pool2d(got.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(ops.from_pf(pooled, P, Hq, Wq).cpu(), refp)
