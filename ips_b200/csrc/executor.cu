@@ -1,6 +1,7 @@
 // Native executor for the eval-mode ResNet patch encoder: issues the whole layer sequence
 // of one chunk (stage -> stem -> maxpool -> BasicBlocks -> avgpool -> logits) from C++, so an
 // ips() call costs one library call instead of ~25 Python round trips per chunk.
+#include <cstdlib>
 #include "common.cuh"
 #include "pf.cuh"
 #include "../../include/ips_b200.h"
@@ -116,6 +117,7 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         const int64_t per_patch = (int64_t)hs * wsz * st.cout * 2;
         int64_t sub = P;                      // (sub-chunking to keep the stem output in L2 measured slower: smaller grids)
         (void)per_patch;
+        if (const char* e = getenv("IPSB_STEM_SUB")) { sub = atoll(e); if (sub <= 0 || sub > P) sub = P; }
         const pf::Geo gq = pf::make(P, hq, wq);
         for (int64_t s0 = 0; s0 < P; s0 += sub) {
             const int64_t Ps = (P - s0 < sub) ? P - s0 : sub;

@@ -57,23 +57,29 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t addr) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+// epilogue warpgroups: the stem (16 short MMAs per tile) is epilogue-bound with two, so it gets four
+template <bool S2D> struct EpiWgs { static constexpr int N = S2D ? 4 : 2; };
+
 template <int BN, int SA, int SB, bool RESB, bool PAIR, bool S2D>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(64 + 128 * EpiWgs<S2D>::N, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const HaloParams p) {
     constexpr int B_SLAB_BYTES = BN * 128;
+    constexpr int NWG = EpiWgs<S2D>::N;              // epilogue warpgroups
+    constexpr int NACC = PAIR ? 2 : NWG;             // TMEM accumulator stages (pairs: two stages of two tiles)
+    static_assert(!PAIR || NWG == 2, "paired tiles use two warpgroups");
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem0 = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b0 = smem0 + SA * p.a_slot_bytes;                                   // weight ring or resident slabs
-    const uint32_t out_stage0 = b0 + (RESB ? (uint32_t)(S2D ? 4 : 9 * p.cblocks) : (uint32_t)SB) * B_SLAB_BYTES;   // 2 x 16 KB epilogue staging
-    const uint32_t bar0 = out_stage0 + 2u * epi::STAGE_BYTES;
+    const uint32_t out_stage0 = b0 + (RESB ? (uint32_t)(S2D ? 4 : 9 * p.cblocks) : (uint32_t)SB) * B_SLAB_BYTES;   // NWG x 16 KB epilogue staging
+    const uint32_t bar0 = out_stage0 + (uint32_t)NWG * epi::STAGE_BYTES;
     auto a_full = [&](int s) { return bar0 + 8u * s; };
     auto a_empty = [&](int s) { return bar0 + 8u * (SA + s); };
     auto b_full = [&](int s) { return bar0 + 8u * (2 * SA + s); };
     auto b_empty = [&](int s) { return bar0 + 8u * (2 * SA + SB + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + 2 + a); };
-    const uint32_t resb_bar = bar0 + 8u * (2 * SA + 2 * SB + 4);
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + NACC + a); };
+    const uint32_t resb_bar = bar0 + 8u * (2 * SA + 2 * SB + 2 * NACC);
     const uint32_t tmem_slot = resb_bar + 8u;
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - umma::smem_u32(smem_raw)));
@@ -85,12 +91,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (tid == 0) {
         for (int s = 0; s < SA; ++s) { umma::mbar_init(a_full(s), 1); umma::mbar_init(a_empty(s), 1); }
         for (int s = 0; s < SB; ++s) { umma::mbar_init(b_full(s), 1); umma::mbar_init(b_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), PAIR ? 256 : 128); }
+        for (int a = 0; a < NACC; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), PAIR ? 256 : 128); }
         umma::mbar_init(resb_bar, 1);
         umma::fence_barrier_init();
     }
     constexpr int MT = PAIR ? 2 : 1;                 // M tiles computed per pipeline step (they share every weight slab)
-    if (warp == 1) umma::tmem_alloc(tmem_slot, 2 * MT * BN);
+    if (warp == 1) umma::tmem_alloc(tmem_slot, NACC * MT * BN);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -131,13 +137,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {                                            // the whole warp runs the loop; the elected lane issues
+            const uint32_t leader = umma::elect_one();
             constexpr uint32_t idesc = umma::idesc_bf16_f32(TILE_M, BN);
             if (RESB) umma::mbar_wait(resb_bar, 0);
             uint32_t ia = 0, ib = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t acc = tcount & 1;
-                umma::mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1);
+                const uint32_t acc = tcount % NACC;
+                umma::mbar_wait(tempty_bar(acc), ((tcount / NACC) & 1) ^ 1);
                 umma::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (MT * BN);
                 for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
@@ -150,7 +157,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const int ta = tap >> 2, tb = tap & 3;
                             const uint64_t adesc = desc_sw32(a_base + (uint32_t)(ta * p.Wp + tb) * 32u);
                             const uint64_t bdesc = umma::smem_desc_sw128(b0 + ta * B_SLAB_BYTES) + (uint64_t)(2 * tb);
-                            umma::mma_bf16(d_tmem, adesc, bdesc, idesc, tap != 0);
+                            umma::mma_bf16_w(d_tmem, adesc, bdesc, idesc, tap != 0, leader);
                             continue;
                         }
                         const int r = tap / 3, s = tap - 3 * r;
@@ -170,14 +177,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int mt = 0; mt < MT; ++mt) {            // both tiles of a pair reuse the weight slab
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                umma::mma_bf16(d_tmem + mt * BN, adesc + (uint64_t)(mt * (TILE_M * 128 / 16)) + 2u * k, bdesc + 2u * k,
-                                               idesc, (cb | tap | k) != 0);
+                                umma::mma_bf16_w(d_tmem + mt * BN, adesc + (uint64_t)(mt * (TILE_M * 128 / 16)) + 2u * k, bdesc + 2u * k,
+                                                 idesc, (cb | tap | k) != 0, leader);
                         }
-                        if (!RESB) { umma::mma_commit(b_empty(sb)); ++ib; }
+                        if (!RESB) { umma::mma_commit_w(b_empty(sb), leader); ++ib; }
                     }
-                    umma::mma_commit(a_empty(sa));
+                    umma::mma_commit_w(a_empty(sa), leader);
                 }
-                umma::mma_commit(tfull_bar(acc));
+                umma::mma_commit_w(tfull_bar(acc), leader);
             }
         }
         __syncwarp();
@@ -187,18 +194,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int wg = (warp - 2) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        for (int i = tid - 64; i < p.Cout; i += 256) {
+        for (int i = tid - 64; i < p.Cout; i += 128 * NWG) {
             sc_smem[i] = p.scale ? p.scale[i] : 1.f;
             sc_smem[p.Cout + i] = p.shift ? p.shift[i] : 0.f;
         }
-        umma::named_bar_sync(1, 256);
+        umma::named_bar_sync(1, 128 * NWG);
         // single tiles: the warpgroups alternate tiles (accumulator = tile parity); pairs: both warpgroups work on
         // every pair, warpgroup w draining the w-th tile of the pair
         uint32_t tcount = PAIR ? 0 : wg;
         const uint32_t stage = out_stage0 + (uint32_t)wg * epi::STAGE_BYTES;
         const bool issuer = (row == 0);
         for (int step = blockIdx.x + (PAIR ? 0 : wg * gridDim.x); step < p.total_tiles;
-             step += (PAIR ? 1 : 2) * gridDim.x, tcount += (PAIR ? 1 : 2)) {
+             step += (PAIR ? 1 : NWG) * gridDim.x, tcount += (PAIR ? 1 : NWG)) {
             const int tile = PAIR ? 2 * step + wg : step;            // M tile (128 PF rows) this warpgroup drains
             const uint32_t acc = PAIR ? (tcount & 1) : (uint32_t)wg;
             const int rel = tile * TILE_M + row;                     // row index relative to G0 (fits int32: checked on the host)
@@ -207,7 +214,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
             const bool pixel = in_range && (S2D || (yy < p.H && xx < p.W));   // pad rows are stored as zeros (S2D: no pads)
             const int64_t g = (int64_t)p.G0 + rel;
-            umma::mbar_wait(tfull_bar(acc), (tcount >> 1) & 1);
+            umma::mbar_wait(tfull_bar(acc), (tcount / NACC) & 1);
             umma::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (PAIR ? acc * 2 * BN + wg * BN : wg * BN);
             const int g0 = p.G0 + tile * TILE_M;
@@ -220,7 +227,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * MT * BN);
+    if (warp == 1) umma::tmem_dealloc(tmem_base, NACC * MT * BN);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -240,8 +247,8 @@ EncodeTiledFn encode_fn() {
 
 template <int BN, int SA, int SB, bool RESB, bool PAIR, bool S2D = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? (S2D ? 4 : 9 * p.cblocks) : SB) * BN * 128 + 2 * epi::STAGE_BYTES + 1024 +
-                        8 * (2 * SA + 2 * SB + 5) + 32 + 8 * (size_t)p.Cout;
+    const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? (S2D ? 4 : 9 * p.cblocks) : SB) * BN * 128 + EpiWgs<S2D>::N * epi::STAGE_BYTES + 1024 +
+                        8 * (2 * SA + 2 * SB + 2 * EpiWgs<S2D>::N + 1) + 32 + 8 * (size_t)p.Cout;
     IPSB_REQUIRE(smem <= 227 * 1024, "conv_halo: %zu bytes of shared memory", smem);
     auto kern = conv_halo_kernel<BN, SA, SB, RESB, PAIR, S2D>;
     static size_t configured = 0;
@@ -250,7 +257,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         configured = smem;
     }
     const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
-    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
+    kern<<<grid, 64 + 128 * EpiWgs<S2D>::N, smem, st>>>(tmA, tmB, tmC, p);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

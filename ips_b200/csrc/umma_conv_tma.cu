@@ -157,7 +157,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {                                            // the whole warp runs the loop; the elected lane issues
+            const uint32_t leader = umma::elect_one();
             constexpr uint32_t idesc = umma::idesc_bf16_f32(TILE_M, BN);
             if (RESB) umma::mbar_wait(resb_bar, 0);
             uint32_t it = 0, tcount = 0;
@@ -181,10 +182,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
 #pragma unroll
                     for (int k = 0; k < MMAS_PER_STAGE; ++k)
-                        umma::mma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ks | k) != 0);
-                    umma::mma_commit(empty_bar(stage));
+                        umma::mma_bf16_w(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ks | k) != 0, leader);
+                    umma::mma_commit_w(empty_bar(stage), leader);
                 }
-                umma::mma_commit(tfull_bar(acc));
+                umma::mma_commit_w(tfull_bar(acc), leader);
             }
         }
         __syncwarp();

@@ -123,7 +123,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {                                            // the whole warp runs the loop; the elected lane issues
+            const uint32_t leader = umma::elect_one();
             constexpr uint32_t idesc = umma::idesc_bf16_f32(TILE_M, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -144,11 +145,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // K-major: 32 bytes further along the row; MN-major: 16 k rows = 2 KB further down
                         const uint64_t adesc = A_MN ? desc_mn128(a_addr + k * 2048) : umma::smem_desc_sw128(a_addr) + 2u * k;
                         const uint64_t bdesc = B_MN ? desc_mn128(a_addr + A_BYTES + k * 2048) : umma::smem_desc_sw128(a_addr + A_BYTES) + 2u * k;
-                        umma::mma_bf16(d_tmem, adesc, bdesc, idesc, (ks > ks0) || (k != 0));
+                        umma::mma_bf16_w(d_tmem, adesc, bdesc, idesc, (ks > ks0) || (k != 0), leader);
                     }
-                    umma::mma_commit(empty_bar(stage));
+                    umma::mma_commit_w(empty_bar(stage), leader);
                 }
-                umma::mma_commit(tfull_bar(acc));
+                umma::mma_commit_w(tfull_bar(acc), leader);
             }
         }
         __syncwarp();

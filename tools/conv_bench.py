@@ -64,3 +64,26 @@ for name, Cin, Cout, H in [('l1', 64, 64, 25), ('l2', 128, 128, 13), ('m_l1', 64
     ms = e0.elapsed_time(e1) / 20
     fl = 2.0 * P * H * H * Cout * 9 * Cin
     print(f'{name:5s} P={P} {H}x{H} {Cin}->{Cout}  {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (algorithmic)')
+
+# ---- space-to-depth stem chain: staging, shifted-window stem, strided max-pool
+print('--- s2d stem chain')
+if not only or only == 's2d':
+    for C, H in [(3, 100), (1, 50)]:
+        x = torch.randn(P, C, H, H, device=dev)
+        w = (torch.randn(64, 256, device=dev) / 16).to(torch.bfloat16)
+        scale = torch.ones(64, device=dev); shift = torch.zeros(64, device=dev)
+        Ho, Wp = H // 2, H // 2 + 3
+        Sp = (Ho + 3) * Wp
+        frame = ops.stage_patches_s2d(x, P, C, H, H)
+        y = ops.conv_stem_s2d(frame, w, scale, shift, P, H, H)
+        pooled = ops.maxpool3x3s2_pf_strided(y, P, Ho, Ho, 64, Wp, Sp)
+        for name, f in [('stage', lambda: ops.stage_patches_s2d(x, P, C, H, H)),
+                        ('stem', lambda: ops.conv_stem_s2d(frame, w, scale, shift, P, H, H)),
+                        ('pool', lambda: ops.maxpool3x3s2_pf_strided(y, P, Ho, Ho, 64, Wp, Sp, out=pooled))]:
+            for _ in range(3): f()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20): f()
+            e1.record(); torch.cuda.synchronize()
+            print(f'{name:5s} C={C} {H}x{H} P={P}  {e0.elapsed_time(e1) / 20 * 1e3:8.1f} us')
