@@ -3,7 +3,11 @@
 // One warpgroup (128 threads, thread = accumulator row) drains one TMEM accumulator in slabs
 // of 128 bytes per row (64 bf16 / 32 fp32 channels): tcgen05.ld -> folded BatchNorm from shared
 // memory, residual, ReLU -> 128B-swizzled staging tile in shared memory -> ONE TMA tensor store
-// per slab.  Stores therefore leave the SM as full 128-byte lines issued by the TMA unit
+// per slab.  A residual arrives the same way in reverse: one TMA load drops the residual slab INTO the
+// staging tile (same box, same swizzle), each thread reads its own 16-byte chunks and overwrites them
+// with the result (a warp's direct 16-byte loads of 32 different residual rows cost the 64-channel
+// layers 30 us per launch).  The load for a tile's first slab is issued before the warpgroup waits
+// for its accumulator, so its latency hides behind the other warpgroup's tile.  Stores therefore leave the SM as full 128-byte lines issued by the TMA unit
 // (a warp's direct 16-byte stores to 32 different rows were measured at < 2 TB/s chip-wide and
 // bound the 64-channel layers).  The TMA unit clips rows outside the tensor, so ragged tiles
 // need no masking.
@@ -25,6 +29,14 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_ld_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_ld_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -34,18 +46,20 @@ template <> struct Slab<bf16> { static constexpr int COLS = 64; };
 template <> struct Slab<float> { static constexpr int COLS = 32; };
 
 // 32 accumulator columns of one row -> staging row (swizzled 16-byte chunks)
+// has_res: the staging row already holds the residual slab (TMA-loaded); it is read and overwritten in place
 template <typename OutT>
 __device__ __forceinline__ void stage32(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
-                                        const bf16* res32, int relu, uint32_t row_smem, int row, int chunk0);
+                                        bool has_res, int relu, uint32_t row_smem, int row, int chunk0);
 
 template <>
 __device__ __forceinline__ void stage32<bf16>(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
-                                              const bf16* res32, int relu, uint32_t row_smem, int row, int chunk0) {
+                                              bool has_res, int relu, uint32_t row_smem, int row, int chunk0) {
     const float4* sc4 = reinterpret_cast<const float4*>(sc);
     const float4* sh4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {                 // 8 channels = one 16-byte chunk
         uint32_t w[4] = {0u, 0u, 0u, 0u};
+        const uint32_t chunk_addr = row_smem + (((uint32_t)(chunk0 + g) ^ (uint32_t)(row & 7)) << 4);
         if (pixel) {
             const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
             float o[8];
@@ -57,8 +71,9 @@ __device__ __forceinline__ void stage32<bf16>(const uint32_t (&v)[32], const flo
             o[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, h1.y);
             o[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, h1.z);
             o[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, h1.w);
-            if (res32 != nullptr) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res32 + g * 8);
+            if (has_res) {
+                uint4 rv;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(chunk_addr));
                 const bf16* rb = reinterpret_cast<const bf16*>(&rv);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rb[i]);
@@ -73,16 +88,15 @@ __device__ __forceinline__ void stage32<bf16>(const uint32_t (&v)[32], const flo
                 w[i] = *reinterpret_cast<uint32_t*>(&h);
             }
         }
-        const uint32_t chunk = (uint32_t)(chunk0 + g);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                     ::"r"(row_smem + ((chunk ^ (uint32_t)(row & 7)) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                     ::"r"(chunk_addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
     }
 }
 
 template <>
 __device__ __forceinline__ void stage32<float>(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
-                                               const bf16* res32, int relu, uint32_t row_smem, int row, int chunk0) {
-    (void)res32;
+                                               bool has_res, int relu, uint32_t row_smem, int row, int chunk0) {
+    (void)has_res;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {                 // 4 channels = one 16-byte chunk
         float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -104,23 +118,41 @@ __device__ __forceinline__ void stage32<float>(const uint32_t (&v)[32], const fl
     }
 }
 
+// Issued by the warpgroup's store thread before it waits for the accumulator: the residual of the tile's first slab
+// lands in the staging tile.  load(slab_col0, dst, bar) must issue the TMA load of a 128-row x 128-byte box.
+template <class Load>
+__device__ __forceinline__ void prefetch_residual(bool issuer, uint32_t res_bar, uint32_t res_bytes, uint32_t stage, const Load& load) {
+    if (issuer) {
+        bulk_wait_read0();                             // the previous store has finished reading the staging tile
+        umma::mbar_expect_tx(res_bar, res_bytes);
+        load(0, stage, res_bar);
+    }
+}
+
 // Drain one accumulator (BN fp32 columns of this thread's row) through the staging tile.
 //   t_row      TMEM address of this thread's lane + the accumulator's first column
 //   sc / sh    shared-memory scale / shift for the BN columns of this tile
 //   pixel      row carries a real output (else zeros are staged)
-//   res_row    residual row (bf16, BN channels) or null
+//   has_res    a residual is added (prefetch_residual was called for this tile); res_bar / res_phase: its mbarrier,
+//              res_bytes: bytes one residual box deposits (rows of the M-tile box x 128)
 //   stage      this warpgroup's 16 KB staging tile (1024-byte aligned), bar_id: its named barrier
-//   issue(slab_col0, stage) is called by ONE thread per slab and must issue the TMA store.
-template <int BN, typename OutT, class Issue>
+//   issue(slab_col0, stage) is called by ONE thread per slab and must issue the TMA store,
+//   load(slab_col0, stage, bar) the TMA load of the residual slab.
+template <int BN, typename OutT, class Issue, class Load>
 __device__ __forceinline__ void drain_tile(uint32_t t_row, uint32_t tempty_bar, const float* sc, const float* sh, bool pixel,
-                                           const bf16* res_row, int relu, uint32_t stage, int row, uint32_t bar_id,
-                                           bool issuer, const Issue& issue) {
+                                           bool has_res, uint32_t res_bar, uint32_t res_bytes, uint32_t& res_phase, int relu, uint32_t stage, int row,
+                                           uint32_t bar_id, bool issuer, const Issue& issue, const Load& load) {
     constexpr int COLS = Slab<OutT>::COLS;
     const uint32_t row_smem = stage + (uint32_t)row * 128u;
 #pragma unroll 1
     for (int s0 = 0; s0 < BN; s0 += COLS) {
-        if (issuer) bulk_wait_read0();                 // previous store has finished reading the staging tile
-        umma::named_bar_sync(bar_id, 128);
+        if (has_res) {                                 // residual slab has landed (implies the staging tile was free)
+            umma::mbar_wait(res_bar, res_phase);
+            res_phase ^= 1u;
+        } else {
+            if (issuer) bulk_wait_read0();             // previous store has finished reading the staging tile
+            umma::named_bar_sync(bar_id, 128);
+        }
 #pragma unroll
         for (int c0 = 0; c0 < COLS; c0 += 32) {
             uint32_t v[32];
@@ -130,14 +162,18 @@ __device__ __forceinline__ void drain_tile(uint32_t t_row, uint32_t tempty_bar, 
                 umma::tc_fence_before();
                 umma::mbar_arrive(tempty_bar);
             }
-            stage32<OutT>(v, sc + s0 + c0, sh + s0 + c0, pixel, res_row ? res_row + s0 + c0 : nullptr, relu, row_smem, row,
-                          c0 * (int)sizeof(OutT) / 16);
+            stage32<OutT>(v, sc + s0 + c0, sh + s0 + c0, pixel, has_res, relu, row_smem, row, c0 * (int)sizeof(OutT) / 16);
         }
         umma::fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA unit
         umma::named_bar_sync(bar_id, 128);
         if (issuer) {
             issue(s0, stage);
             bulk_commit();
+            if (has_res && s0 + COLS < BN) {           // next slab's residual (latency exposed; budget is the other warpgroup's tile)
+                bulk_wait_read0();
+                umma::mbar_expect_tx(res_bar, res_bytes);
+                load(s0 + COLS, stage, res_bar);
+            }
         }
     }
 }

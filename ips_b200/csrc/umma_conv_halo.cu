@@ -63,7 +63,7 @@ template <bool S2D> struct EpiWgs { static constexpr int N = S2D ? 4 : 2; };
 template <int BN, int SA, int SB, bool RESB, bool PAIR, bool S2D>
 __global__ void __launch_bounds__(64 + 128 * EpiWgs<S2D>::N, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const HaloParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const HaloParams p) {
     constexpr int B_SLAB_BYTES = BN * 128;
     constexpr int NWG = EpiWgs<S2D>::N;              // epilogue warpgroups
     constexpr int NACC = PAIR ? 2 : NWG;             // TMEM accumulator stages (pairs: two stages of two tiles)
@@ -80,7 +80,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SA + 2 * SB + NACC + a); };
     const uint32_t resb_bar = bar0 + 8u * (2 * SA + 2 * SB + 2 * NACC);
-    const uint32_t tmem_slot = resb_bar + 8u;
+    auto res_bar = [&](int w) { return resb_bar + 8u + 8u * w; };      // residual slab landed in warpgroup w's staging tile
+    const uint32_t tmem_slot = resb_bar + 8u + 8u * NWG;
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - umma::smem_u32(smem_raw)));
     const uint32_t sc_addr = (tmem_slot + 4u + 15u) & ~15u;
@@ -93,6 +94,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < SB; ++s) { umma::mbar_init(b_full(s), 1); umma::mbar_init(b_empty(s), 1); }
         for (int a = 0; a < NACC; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), PAIR ? 256 : 128); }
         umma::mbar_init(resb_bar, 1);
+        for (int w = 0; w < NWG; ++w) umma::mbar_init(res_bar(w), 1);
         umma::fence_barrier_init();
     }
     constexpr int MT = PAIR ? 2 : 1;                 // M tiles computed per pipeline step (they share every weight slab)
@@ -204,6 +206,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t tcount = PAIR ? 0 : wg;
         const uint32_t stage = out_stage0 + (uint32_t)wg * epi::STAGE_BYTES;
         const bool issuer = (row == 0);
+        const bool has_res = p.res != nullptr;
+        uint32_t res_phase = 0;
         for (int step = blockIdx.x + (PAIR ? 0 : wg * gridDim.x); step < p.total_tiles;
              step += (PAIR ? 1 : NWG) * gridDim.x, tcount += (PAIR ? 1 : NWG)) {
             const int tile = PAIR ? 2 * step + wg : step;            // M tile (128 PF rows) this warpgroup drains
@@ -213,14 +217,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int rem = rel % p.Sp;
             const int yy = rem / p.Wp, xx = rem - yy * p.Wp;
             const bool pixel = in_range && (S2D || (yy < p.H && xx < p.W));   // pad rows are stored as zeros (S2D: no pads)
-            const int64_t g = (int64_t)p.G0 + rel;
+            const int g0 = p.G0 + tile * TILE_M;
+            auto load_res = [&](int s0, uint32_t dst, uint32_t bar) { epi::tma_ld_2d(dst, &tmR, bar, s0, g0); };
+            if (has_res) epi::prefetch_residual(issuer, res_bar(wg), epi::STAGE_BYTES, stage, load_res);
             umma::mbar_wait(tfull_bar(acc), (tcount / NACC) & 1);
             umma::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (PAIR ? acc * 2 * BN + wg * BN : wg * BN);
-            const int g0 = p.G0 + tile * TILE_M;
-            epi::drain_tile<BN, bf16>(t_row, tempty_bar(acc), sc_smem, sc_smem + p.Cout, pixel,
-                                      (p.res && pixel) ? p.res + g * p.Cout : nullptr, p.relu, stage, row, 2u + (uint32_t)wg, issuer,
-                                      [&](int s0, uint32_t src) { if (!(p.dbg & 1)) epi::tma_store_2d(&tmC, src, s0, g0); });
+            epi::drain_tile<BN, bf16>(t_row, tempty_bar(acc), sc_smem, sc_smem + p.Cout, pixel, has_res, res_bar(wg), epi::STAGE_BYTES, res_phase,
+                                      p.relu, stage, row, 2u + (uint32_t)wg, issuer,
+                                      [&](int s0, uint32_t src) { if (!(p.dbg & 1)) epi::tma_store_2d(&tmC, src, s0, g0); }, load_res);
         }
         if (issuer) epi::bulk_wait0();
     }
@@ -246,9 +251,10 @@ EncodeTiledFn encode_fn() {
 }
 
 template <int BN, int SA, int SB, bool RESB, bool PAIR, bool S2D = false>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, const HaloParams& p,
+           cudaStream_t st) {
     const size_t smem = (size_t)SA * p.a_slot_bytes + (size_t)(RESB ? (S2D ? 4 : 9 * p.cblocks) : SB) * BN * 128 + EpiWgs<S2D>::N * epi::STAGE_BYTES + 1024 +
-                        8 * (2 * SA + 2 * SB + 2 * EpiWgs<S2D>::N + 1) + 32 + 8 * (size_t)p.Cout;
+                        8 * (2 * SA + 2 * SB + 3 * EpiWgs<S2D>::N + 1) + 32 + 8 * (size_t)p.Cout;
     IPSB_REQUIRE(smem <= 227 * 1024, "conv_halo: %zu bytes of shared memory", smem);
     auto kern = conv_halo_kernel<BN, SA, SB, RESB, PAIR, S2D>;
     static size_t configured = 0;
@@ -257,7 +263,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         configured = smem;
     }
     const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
-    kern<<<grid, 64 + 128 * EpiWgs<S2D>::N, smem, st>>>(tmA, tmB, tmC, p);
+    kern<<<grid, 64 + 128 * EpiWgs<S2D>::N, smem, st>>>(tmA, tmB, tmC, tmR, p);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
@@ -315,23 +321,24 @@ int conv3x3_halo(const void* x, const void* w, const float* scale, const float* 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv3x3_halo: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
-    alignas(64) CUtensorMap tmC;
-    {   // output rows [G0 + pix_rows) as a 2-D tensor; rows past the last patch are clipped by the TMA unit
+    alignas(64) CUtensorMap tmC, tmR;
+    for (int i = 0; i < 2; ++i) {   // output (and residual) rows [G0 + pix_rows) as a 2-D tensor; rows past the last patch are clipped
+        void* base = (i == 0) ? y : const_cast<void*>(res ? res : y);
         cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)(g.G0 + p.pix_rows)};
         cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)TILE_M};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, estr,
+        CUresult r = enc(i == 0 ? &tmC : &tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv3x3_halo: cuTensorMapEncodeTiled(output) failed with %d", (int)r);
     }
     if (Cout == 64) {
-        if ((size_t)9 * p.cblocks * 64 * 128 <= 80 * 1024) return launch<64, 4, 1, true, false>(tmA, tmB, tmC, p, st);
-        return launch<64, 4, 6, false, false>(tmA, tmB, tmC, p, st);
+        if ((size_t)9 * p.cblocks * 64 * 128 <= 80 * 1024) return launch<64, 4, 1, true, false>(tmA, tmB, tmC, tmR, p, st);
+        return launch<64, 4, 6, false, false>(tmA, tmB, tmC, tmR, p, st);
     }
-    if (pair) return launch<128, 3, 4, false, true>(tmA, tmB, tmC, p, st);
-    return launch<128, 4, 5, false, false>(tmA, tmB, tmC, p, st);
+    if (pair) return launch<128, 3, 4, false, true>(tmA, tmB, tmC, tmR, p, st);
+    return launch<128, 4, 5, false, false>(tmA, tmB, tmC, tmR, p, st);
 }
 
 
@@ -386,7 +393,7 @@ int conv_stem_s2d(const void* x, const void* w, const float* scale, const float*
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_stem_s2d: cuTensorMapEncodeTiled(output) failed with %d", (int)r);
     }
-    return launch<64, 6, 1, true, false, true>(tmA, tmB, tmC, p, st);
+    return launch<64, 6, 1, true, false, true>(tmA, tmB, tmC, tmC, p, st);
 }
 
 }  // namespace ipsb

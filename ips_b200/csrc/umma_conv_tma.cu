@@ -84,7 +84,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TmaConvParams& p, int til
 template <int BN, int STAGES, bool STEM, bool RESB, typename OutT>
 __global__ void __launch_bounds__(320, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const TmaConvParams p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TmaConvParams p) {
     constexpr int B_SLAB_BYTES = BN * 128;
     constexpr int A_BYTES = STEM ? TILE_M * 64 : A_STAGE_BYTES;             // stem: 64-byte rows (one filter row)
     constexpr int STAGE_BYTES = A_BYTES + (RESB ? 0 : B_SLAB_BYTES);
@@ -99,7 +99,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
     const uint32_t resb_bar = bar0 + 8u * (2 * STAGES + 4);
-    const uint32_t tmem_slot = resb_bar + 8u;
+    auto res_bar = [&](int w) { return resb_bar + 8u + 8u * w; };      // residual slab landed in warpgroup w's staging tile
+    const uint32_t tmem_slot = resb_bar + 24u;
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - umma::smem_u32(smem_raw)));
     const uint32_t sc_addr = (tmem_slot + 4u + 15u) & ~15u;                          // scale[Cout], shift[Cout]
@@ -117,6 +118,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma::mbar_init(tempty_bar(a), 128);
         }
         umma::mbar_init(resb_bar, 1);
+        umma::mbar_init(res_bar(0), 1); umma::mbar_init(res_bar(1), 1);
         umma::fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -206,18 +208,24 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t tcount = wg;
         const uint32_t stage = out_stage0 + (uint32_t)wg * epi::STAGE_BYTES;
         const bool issuer = (row == 0);
+        const bool has_res = p.res != nullptr;
+        uint32_t res_phase = 0;
+        const uint32_t res_bytes = (uint32_t)(p.bw * p.bh * p.bp) * 128u;     // one residual box
         for (int tile = blockIdx.x + wg * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tcount += 2) {
             const TileCoord tc = decode_tile(p, tile, BN);
             const int pp = tc.p0 + pi, oy = tc.oy0 + yi, ox = tc.ox0 + xi;
             const bool valid = pi < p.bp && pp < p.P && oy < p.Ho && ox < p.Wo;
-            const int64_t m = p.out_G0 + (int64_t)pp * p.out_Sp + oy * p.out_Wp + ox;
+            auto load_res = [&](int s0, uint32_t dst, uint32_t bar) {
+                epi::tma_ld_4d(dst, &tmR, bar, tc.n0 + s0, tc.ox0, tc.oy0, tc.p0);
+            };
+            if (has_res) epi::prefetch_residual(issuer, res_bar(wg), res_bytes, stage, load_res);
             umma::mbar_wait(tfull_bar(wg), (tcount >> 1) & 1);
             umma::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
-            epi::drain_tile<BN, OutT>(t_row, tempty_bar(wg), sc_smem + tc.n0, sc_smem + p.Cout + tc.n0, valid,
-                                      (p.res && valid) ? p.res + m * p.Cout + tc.n0 : nullptr, p.relu, stage, row,
-                                      2u + (uint32_t)wg, issuer,
-                                      [&](int s0, uint32_t src) { epi::tma_store_4d(&tmC, src, tc.n0 + s0, tc.ox0, tc.oy0, tc.p0); });
+            epi::drain_tile<BN, OutT>(t_row, tempty_bar(wg), sc_smem + tc.n0, sc_smem + p.Cout + tc.n0, valid, has_res, res_bar(wg),
+                                      res_bytes, res_phase, p.relu, stage, row, 2u + (uint32_t)wg, issuer,
+                                      [&](int s0, uint32_t src) { epi::tma_store_4d(&tmC, src, tc.n0 + s0, tc.ox0, tc.oy0, tc.p0); },
+                                      load_res);
         }
         if (issuer) epi::bulk_wait0();
     }
@@ -246,9 +254,10 @@ EncodeTiledFn encode_fn() {
 }
 
 template <int BN, int STAGES, bool STEM, bool RESB, typename OutT>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TmaConvParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, const TmaConvParams& p,
+           cudaStream_t st) {
     const size_t smem = (size_t)STAGES * ((STEM ? TILE_M * 64 : A_STAGE_BYTES) + (RESB ? 0 : BN * 128)) +
-                        (RESB ? (size_t)p.b_slabs * BN * 128 : 0) + 2 * epi::STAGE_BYTES + 1024 + 8 * (2 * STAGES + 5) + 32 +
+                        (RESB ? (size_t)p.b_slabs * BN * 128 : 0) + 2 * epi::STAGE_BYTES + 1024 + 8 * (2 * STAGES + 7) + 32 +
                         8 * (size_t)p.Cout;
     IPSB_REQUIRE(smem <= 227 * 1024, "conv_tma: %zu bytes of shared memory", smem);
     auto kern = conv_tma_kernel<BN, STAGES, STEM, RESB, OutT>;
@@ -258,19 +267,19 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         configured = smem;
     }
     const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
-    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
+    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmC, tmR, p);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
 
 template <bool STEM, typename OutT>
-int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TmaConvParams& p, int BN, bool resb,
-             cudaStream_t st) {
-    if (!STEM && BN == 256) return launch<256, 3, false, false, OutT>(tmA, tmB, tmC, p, st);
-    if (!STEM && BN == 128) return launch<128, 5, false, false, OutT>(tmA, tmB, tmC, p, st);
-    if (STEM) return launch<64, 8, true, true, OutT>(tmA, tmB, tmC, p, st);
-    if (resb) return launch<64, 6, false, true, OutT>(tmA, tmB, tmC, p, st);
-    return launch<64, 6, false, false, OutT>(tmA, tmB, tmC, p, st);
+int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, const TmaConvParams& p,
+             int BN, bool resb, cudaStream_t st) {
+    if (!STEM && BN == 256) return launch<256, 3, false, false, OutT>(tmA, tmB, tmC, tmR, p, st);
+    if (!STEM && BN == 128) return launch<128, 5, false, false, OutT>(tmA, tmB, tmC, tmR, p, st);
+    if (STEM) return launch<64, 8, true, true, OutT>(tmA, tmB, tmC, tmR, p, st);
+    if (resb) return launch<64, 6, false, true, OutT>(tmA, tmB, tmC, tmR, p, st);
+    return launch<64, 6, false, false, OutT>(tmA, tmB, tmC, tmR, p, st);
 }
 
 // choose the pixel box (bw x bh x bp <= 128) with the most useful accumulator rows
@@ -374,13 +383,15 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
         IPSB_REQUIRE(r == CUDA_SUCCESS, "conv_tma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     if (int rc = encode_weights(enc, &tmB, w, kh * kw * Cin, Cout, BN)) return rc;
-    alignas(64) CUtensorMap tmC;
+    alignas(64) CUtensorMap tmC, tmR;
     if (out_f32) {
+        IPSB_REQUIRE(res == nullptr, "conv_tma: a residual needs the bf16 output path");
         if (int rc = encode_output<float>(enc, &tmC, y, p, out_pf)) return rc;
-        return dispatch<false, float>(tmA, tmB, tmC, p, BN, resb, st);
+        return dispatch<false, float>(tmA, tmB, tmC, tmC, p, BN, resb, st);
     }
     if (int rc = encode_output<bf16>(enc, &tmC, y, p, out_pf)) return rc;
-    return dispatch<false, bf16>(tmA, tmB, tmC, p, BN, resb, st);
+    if (int rc = encode_output<bf16>(enc, &tmR, res ? const_cast<void*>(res) : y, p, out_pf)) return rc;   // same geometry as the output
+    return dispatch<false, bf16>(tmA, tmB, tmC, tmR, p, BN, resb, st);
 }
 
 // 7x7 stride-2 pad-3 stem.  x: (P, H+6, W+6, 4) bf16 with a zero border (3 rows above, 4 columns left);
@@ -417,7 +428,7 @@ int conv_stem_tma(const void* x, const void* w, const float* scale, const float*
     if (int rc = encode_weights(enc, &tmB, w, 256, Cout, 64)) return rc;
     alignas(64) CUtensorMap tmC;
     if (int rc = encode_output<bf16>(enc, &tmC, y, p, false)) return rc;
-    return dispatch<true, bf16>(tmA, tmB, tmC, p, 64, true, st);
+    return dispatch<true, bf16>(tmA, tmB, tmC, tmC, p, 64, true, st);
 }
 
 }  // namespace ipsb

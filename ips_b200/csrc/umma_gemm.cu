@@ -172,9 +172,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
             const int out_row0 = (int)(sp * p.split_stride_rows) + mt * TILE_M;
-            epi::drain_tile<BN, OutT>(t_row, tempty_bar(wg), sc_smem + nt * BN, sc_smem + Npad + nt * BN, true, nullptr, p.relu,
-                                      stage, row, 2u + (uint32_t)wg, issuer,
-                                      [&](int s0, uint32_t src) { epi::tma_store_2d(&tmC, src, nt * BN + s0, out_row0); });
+            uint32_t no_phase = 0;
+            epi::drain_tile<BN, OutT>(t_row, tempty_bar(wg), sc_smem + nt * BN, sc_smem + Npad + nt * BN, true, false, 0u, 0u, no_phase,
+                                      p.relu, stage, row, 2u + (uint32_t)wg, issuer,
+                                      [&](int s0, uint32_t src) { epi::tma_store_2d(&tmC, src, nt * BN + s0, out_row0); },
+                                      [](int, uint32_t, uint32_t) {});
         }
         if (issuer) epi::bulk_wait0();
     }
