@@ -61,6 +61,11 @@ IPSB_API int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx,
 IPSB_API int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows, int C, int H, int W,
                            void* dst, void* stream);
 IPSB_API int ipsb_maxpool3x3s2_pf_strided(const void* x, void* y, int64_t P, int H, int W, int C, int in_Wp, int in_Sp, void* stream);
+/* conv1 -> bn1 -> relu -> maxpool (architecture/ips_net.py:17-39) in one kernel: s2d frame of P patches of HxW ->
+ * padded-flat (ipsb_pf_rows(P, Hq, Wq), 64) bf16 with Hq = (H/2 - 1)/2 + 1; the stem output stays in shared memory.
+ * w: (64, 256) bf16 in the mode-4 packing; y's pad rows must already be zero (they are not written). */
+IPSB_API int ipsb_stem_pool_s2d(const void* frame, const void* w, const float* scale, const float* shift, void* y, int64_t P, int H, int W,
+                       int relu, void* stream);
 
 /* ---------------------------------------------------------------- encoder, fp32 SIMT ("exact" mode)
  * Replaces: conv2d + eval-mode batch_norm [+ residual add] [+ relu] of the

@@ -124,6 +124,12 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
             if (st.mode == 4) {               // space-to-depth frame -> shifted-window stem -> strided max-pool
                 rc = ipsb_stage_patches_s2d(patches, nullptr, first_row + lo + s0, Ps, C, H, W, staged, stream);
                 if (rc) return rc;
+                if (st.cout == 64 && !getenv("IPSB_STEM_UNFUSED")) {   // stem + pool fused: the stem output stays on chip
+                    rc = ipsb_stem_pool_s2d(staged, st.w, st.scale, st.shift, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, H, W,
+                                            1, stream);
+                    if (rc) return rc;
+                    continue;
+                }
                 rc = ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H, W, 16, st.cout, 7, 7, 2, 3, 1, 4,
                                          stream);
                 if (rc) return rc;

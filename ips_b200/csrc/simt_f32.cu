@@ -151,33 +151,54 @@ __global__ void score_basis_kernel(const float* __restrict__ q_tok, const float*
     }
 }
 
-// z[row, ht] = emb[row,:] . U[:,ht] (+ add); thread per (row, ht), U^T staged in smem
+// z[row, ht] = emb[row,:] . U[:,ht] (+ add).  One warp per row: lane l owns the float4 groups l, l+32, ... of the row
+// (coalesced 512-byte reads), accumulates 8 columns at a time against U^T staged in shared memory and the warp reduces
+// with shuffles.  The summation order of a row is fixed by D alone, so a row's logits do not depend on how rows are
+// chunked or sharded.
 __global__ void __launch_bounds__(256)
 logits_kernel(const float* __restrict__ emb, const float* __restrict__ U, const float* __restrict__ add_tab,
               const int64_t* __restrict__ add_idx, float* __restrict__ z, int64_t rows, int D, int HT) {
-    extern __shared__ __align__(16) float Ut[];   // [HT][D+4]
-    const int ld = D + 4;
+    extern __shared__ __align__(16) float Ut[];   // [HT][D]
     for (int i = threadIdx.x; i < D * HT; i += blockDim.x) {
         const int d = i / HT, c = i - d * HT;
-        Ut[c * ld + d] = U[i];
+        Ut[c * D + d] = U[i];
     }
     __syncthreads();
-    const int rpb = blockDim.x / HT;
-    const int r_in = threadIdx.x / HT, c = threadIdx.x - r_in * HT;
-    if (r_in >= rpb) return;
-    for (int64_t row = (int64_t)blockIdx.x * rpb + r_in; row < rows; row += (int64_t)gridDim.x * rpb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int n4 = D >> 2;
+    for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < rows; row += (int64_t)gridDim.x * wpb) {
         const float4* e = reinterpret_cast<const float4*>(emb + row * D);
-        const float4* u = reinterpret_cast<const float4*>(Ut + c * ld);
-        float s = 0.f;
-        for (int d4 = 0; d4 < D / 4; ++d4) {
-            const float4 ev = e[d4], uv = u[d4];
-            s = fmaf(ev.x, uv.x, s);
-            s = fmaf(ev.y, uv.y, s);
-            s = fmaf(ev.z, uv.z, s);
-            s = fmaf(ev.w, uv.w, s);
+        for (int c0 = 0; c0 < HT; c0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            for (int d4 = lane; d4 < n4; d4 += 32) {
+                const float4 ev = e[d4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (c0 + j < HT) {
+                        const float4 uv = reinterpret_cast<const float4*>(Ut + (c0 + j) * D)[d4];
+                        acc[j] = fmaf(ev.x, uv.x, acc[j]);
+                        acc[j] = fmaf(ev.y, uv.y, acc[j]);
+                        acc[j] = fmaf(ev.z, uv.z, acc[j]);
+                        acc[j] = fmaf(ev.w, uv.w, acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            }
+            if (lane < 8 && c0 + lane < HT) {
+                float s = acc[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) s = (lane == j) ? acc[j] : s;
+                const int c = c0 + lane;
+                if (add_tab) s += add_tab[(add_idx ? add_idx[row] : row) * HT + c];
+                z[row * HT + c] = s;
+            }
         }
-        if (add_tab) s += add_tab[(add_idx ? add_idx[row] : row) * HT + c];
-        z[row * HT + c] = s;
     }
 }
 
@@ -244,11 +265,10 @@ int ipsb_score_basis(const float* q_tok, const float* q_w, const float* k_w, flo
 int ipsb_logits(const float* emb, const float* U, const float* add_tab, const int64_t* add_idx,
                 float* z, int64_t rows, int D, int HT, void* stream) {
     IPSB_REQUIRE(rows > 0 && D % 4 == 0 && HT > 0 && HT <= 32, "logits: bad shape rows=%lld D=%d HT=%d", (long long)rows, D, HT);
-    const size_t smem = (size_t)HT * (D + 4) * sizeof(float);
+    const size_t smem = (size_t)HT * D * sizeof(float);
     IPSB_REQUIRE(smem <= 200 * 1024, "logits: D*HT too large for shared memory");
     IPSB_CUDA(cudaFuncSetAttribute(logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int rpb = 256 / HT;
-    int64_t g = ipsb::ceil_div(rows, rpb);
+    int64_t g = ipsb::ceil_div(rows, 8);              // 8 warps = 8 rows per block pass
     const int64_t cap = (int64_t)ipsb::sm_count() * 4;
     if (g > cap) g = cap;
     logits_kernel<<<(unsigned)g, 256, smem, (cudaStream_t)stream>>>(emb, U, add_tab, add_idx, z, rows, D, HT);

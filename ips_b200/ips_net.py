@@ -247,9 +247,12 @@ class IPSNet(nn.Module):
         if plan['stem']['mode'] == 4:
             e = plan['stem']
             x = ops.stage_patches_s2d(flat, P, C, H, W, row_idx=row_idx, first_row=first_row)
-            x = ops.conv_stem_s2d(x, e['w'], e['scale'], e['shift'], P, H, W, e['cout'])   # wide row order
             h, w = H // 2, W // 2
-            x = ops.maxpool3x3s2_pf_strided(x, P, h, w, e['cout'], w + 3, (h + 3) * (w + 3))
+            if e['cout'] == 64 and not os.environ.get('IPSB_STEM_UNFUSED'):
+                x = ops.stem_pool_s2d(x, e['w'], e['scale'], e['shift'], P, H, W)          # stem output stays on chip
+            else:
+                x = ops.conv_stem_s2d(x, e['w'], e['scale'], e['shift'], P, H, W, e['cout'])   # wide row order
+                x = ops.maxpool3x3s2_pf_strided(x, P, h, w, e['cout'], w + 3, (h + 3) * (w + 3))
         else:
             x = ops.stage_patches_padded(flat, P, C, H, W, row_idx=row_idx, first_row=first_row)
             x = self._conv(x, plan['stem'])                              # dense (P, H/2, W/2, 64)

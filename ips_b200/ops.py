@@ -97,6 +97,16 @@ def conv_stem_s2d(frame, w_nk, scale, shift, P, H, W, Cout=64, relu=True):
     return y
 
 
+def stem_pool_s2d(frame, w_nk, scale, shift, P, H, W, relu=True, out=None):
+    """Fused 7x7/2 stem + BN + ReLU + 3x3/2 max-pool on the s2d frame -> padded-flat (rows, 64) bf16."""
+    _chk(frame, torch.bfloat16, 'frame'); _chk(w_nk, torch.bfloat16, 'w')
+    Hq, Wq = (H // 2 - 1) // 2 + 1, (W // 2 - 1) // 2 + 1
+    if out is None:
+        out = torch.zeros((pf_geo(P, Hq, Wq)[0], 64), dtype=torch.bfloat16, device=frame.device)
+    _call('ipsb_stem_pool_s2d', _p(frame), _p(w_nk), _p(scale), _p(shift), _p(out), P, H, W, int(relu), _stream())
+    return out
+
+
 def maxpool3x3s2_pf_strided(x, P, H, W, C, in_Wp, in_Sp, out=None):
     """max-pool of a (P, H, W, C) map stored with row pitch in_Wp / patch pitch in_Sp (in pixels) -> PF (rows, C)."""
     _chk(x, torch.bfloat16, 'x')

@@ -526,3 +526,19 @@ def test_stem_s2d(dev, C, H, W, P):
     Hq, Wq = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
     refp = F.max_pool2d(got.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(ops.from_pf(pooled, P, Hq, Wq).cpu(), refp)
+
+
+@pytest.mark.parametrize('C,H,W,P', [(3, 100, 100, 9), (1, 50, 50, 37), (3, 20, 36, 5), (3, 100, 100, 160)])
+def test_stem_pool_fused(dev, C, H, W, P):
+    """Fused stem + max-pool kernel == unfused stem kernel followed by the strided max-pool, bit for bit."""
+    from ips_b200 import ops
+    x = _rand(P, C, H, W, seed=90)
+    w = _stem_s2d_weights(_rand(64, C, 7, 7, seed=91, scale=math.sqrt(2.0 / (49 * C)))).to(torch.bfloat16).to(dev)
+    scale, shift = (torch.rand(64) + 0.5).to(dev), _rand(64, seed=92, scale=0.1).to(dev)
+    frame = ops.stage_patches_s2d(x.to(dev), P, C, H, W)
+    Ho, Wo, Wp = H // 2, W // 2, W // 2 + 3
+    y = ops.conv_stem_s2d(frame, w, scale, shift, P, H, W)
+    ref = ops.maxpool3x3s2_pf_strided(y, P, Ho, Wo, 64, Wp, (Ho + 3) * Wp)
+    got = ops.stem_pool_s2d(frame, w, scale, shift, P, H, W)
+    assert got.shape == ref.shape
+    assert torch.equal(got, ref)

@@ -79,7 +79,8 @@ if not only or only == 's2d':
         pooled = ops.maxpool3x3s2_pf_strided(y, P, Ho, Ho, 64, Wp, Sp)
         for name, f in [('stage', lambda: ops.stage_patches_s2d(x, P, C, H, H)),
                         ('stem', lambda: ops.conv_stem_s2d(frame, w, scale, shift, P, H, H)),
-                        ('pool', lambda: ops.maxpool3x3s2_pf_strided(y, P, Ho, Ho, 64, Wp, Sp, out=pooled))]:
+                        ('pool', lambda: ops.maxpool3x3s2_pf_strided(y, P, Ho, Ho, 64, Wp, Sp, out=pooled)),
+                        ('fused', lambda: ops.stem_pool_s2d(frame, w, scale, shift, P, H, H, out=pooled))]:
             for _ in range(3): f()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
