@@ -183,7 +183,9 @@ typedef struct {
     const float* add_tab; /* (N, HT) positional contribution or NULL */
 } ipsb_resnet_desc;
 
-/* bytes of scratch needed for chunks of `chunk` patches of (C,H,W) */
+/* bytes of scratch needed for chunks of `chunk` patches of (C,H,W): one "lane".  On the bf16 path a workspace of
+ * L x this size (L <= 4) lets ipsb_resnet_logits run L chunks concurrently on internal streams (fork from / join
+ * into `stream` with events), which fills the SMs a persistent kernel's last partial wave leaves idle. */
 IPSB_API int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W);
 /* patches: (rows,C,H,W) fp32 NCHW on the device; row r reads patch first_row + r; add_tab row = (first_row + r) % n_per_image.
  * emb_out (n_rows, D) fp32 may be NULL; z_out (n_rows, HT) fp32.  zero_init != 0 on the first use of a workspace

@@ -55,7 +55,9 @@ PfPlan make_pf_plan(const ipsb_resnet_desc* net, int64_t chunk, int H, int W) {
     PfPlan pl;
     pl.staged_bytes = align256(chunk * (int64_t)(H + 6) * (W + 6) * 4 * 2);
     int h = out_dim(H, 7, 2, 3), w = out_dim(W, 7, 2, 3);
-    pl.stem_bytes = (net->stem.mode == 4) ? align256(chunk * (int64_t)(h + 3) * (w + 3) * net->stem.cout * 2)   // wide row order
+    const bool fused = net->stem.mode == 4 && net->stem.cout == 64 && !getenv("IPSB_STEM_UNFUSED");   // stem output stays on chip
+    pl.stem_bytes = fused ? 0
+                  : (net->stem.mode == 4) ? align256(chunk * (int64_t)(h + 3) * (w + 3) * net->stem.cout * 2)   // wide row order
                                           : align256(chunk * (int64_t)h * w * net->stem.cout * 2);
     h = out_dim(h, 3, 2, 1); w = out_dim(w, 3, 2, 1);
     pl.n_groups = net->n_blocks / 2;
@@ -69,6 +71,32 @@ PfPlan make_pf_plan(const ipsb_resnet_desc* net, int64_t chunk, int H, int W) {
         pl.total += 4 * pl.group_bytes[g];
     }
     return pl;
+}
+
+// Internal streams for running several chunks concurrently ("lanes").  Every kernel of the bf16 path is a persistent
+// grid of one CTA per SM; with two chunks in flight the block scheduler fills the SMs a kernel's last partial wave of
+// tiles leaves idle (and the HBM-bound staging kernel of one chunk overlaps the tensor-bound kernels of the other).
+constexpr int MAX_LANES = 4;
+struct LaneStreams {
+    int device = -1;
+    cudaStream_t s[MAX_LANES] = {};
+    cudaEvent_t done[MAX_LANES] = {};
+    cudaEvent_t fork = nullptr;
+};
+int lane_streams(LaneStreams** out) {
+    static thread_local LaneStreams ls;
+    int dev = 0;
+    IPSB_CUDA(cudaGetDevice(&dev));
+    if (ls.device != dev) {
+        for (int i = 0; i < MAX_LANES; ++i) {
+            IPSB_CUDA(cudaStreamCreateWithFlags(&ls.s[i], cudaStreamNonBlocking));
+            IPSB_CUDA(cudaEventCreateWithFlags(&ls.done[i], cudaEventDisableTiming));
+        }
+        IPSB_CUDA(cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming));
+        ls.device = dev;
+    }
+    *out = &ls;
+    return 0;
 }
 
 int run_conv_pf(const ipsb_conv_desc& c, const void* x, const void* res, void* y, int64_t P, int H, int W, int relu,
@@ -92,22 +120,38 @@ int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, 
 }
 
 static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
-                            int C, int H, int W, int64_t n_per_image, int64_t chunk, void* workspace, int zero_init,
-                            float* emb_out, float* z_out, void* stream) {
+                            int C, int H, int W, int64_t n_per_image, int64_t chunk, void* workspace, int64_t lane_bytes, int lanes,
+                            int zero_init, float* emb_out, float* z_out, void* caller_stream) {
     const PfPlan pl = make_pf_plan(net, chunk, H, W);
-    char* ws = (char*)workspace;
-    void* staged = ws;               ws += pl.staged_bytes;
-    void* stem_out = ws;             ws += pl.stem_bytes;
-    void* gb[4][4];
-    char* pf_begin = ws;
-    for (int g = 0; g < pl.n_groups; ++g)
-        for (int i = 0; i < 4; ++i) { gb[g][i] = ws; ws += pl.group_bytes[g]; }
+    const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
+    if (lanes > n_chunks) lanes = (int)n_chunks;
+    LaneStreams* ls = nullptr;
+    if (lanes > 1) {
+        if (int rc = lane_streams(&ls)) return rc;
+    }
+    size_t pf_bytes = 0;
+    for (int g = 0; g < pl.n_groups; ++g) pf_bytes += 4 * (size_t)pl.group_bytes[g];
     if (zero_init)   // pad rows of the padded-flat buffers must be zero; kernels keep them zero afterwards
-        IPSB_CUDA(cudaMemsetAsync(pf_begin, 0, (size_t)(ws - pf_begin), (cudaStream_t)stream));
-    float* emb_ws = (float*)ws;      ws += align256(chunk * net->D * 4);
-    int64_t* pos_idx = (int64_t*)ws;
+        for (int l = 0; l < lanes; ++l)
+            IPSB_CUDA(cudaMemsetAsync((char*)workspace + l * lane_bytes + pl.staged_bytes + pl.stem_bytes, 0, pf_bytes,
+                                      (cudaStream_t)caller_stream));
+    if (lanes > 1) {
+        IPSB_CUDA(cudaEventRecord(ls->fork, (cudaStream_t)caller_stream));
+        for (int l = 0; l < lanes; ++l) IPSB_CUDA(cudaStreamWaitEvent(ls->s[l], ls->fork, 0));
+    }
 
-    for (int64_t lo = 0; lo < n_rows; lo += chunk) {
+    int64_t ci = 0;
+    for (int64_t lo = 0; lo < n_rows; lo += chunk, ++ci) {
+        const int lane = (int)(ci % lanes);
+        void* stream = lanes > 1 ? (void*)ls->s[lane] : caller_stream;
+        char* ws = (char*)workspace + lane * lane_bytes;
+        void* staged = ws;               ws += pl.staged_bytes;
+        void* stem_out = ws;             ws += pl.stem_bytes;
+        void* gb[4][4];
+        for (int g = 0; g < pl.n_groups; ++g)
+            for (int i = 0; i < 4; ++i) { gb[g][i] = ws; ws += pl.group_bytes[g]; }
+        float* emb_ws = (float*)ws;      ws += align256(chunk * net->D * 4);
+        int64_t* pos_idx = (int64_t*)ws;
         const int64_t P = (n_rows - lo < chunk) ? n_rows - lo : chunk;
         // stage -> stem -> max-pool in sub-chunks whose stem output (the largest activation) stays in L2
         int rc = 0;
@@ -184,6 +228,11 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         rc = ipsb_logits(emb, net->U, net->add_tab, idx, z_out + lo * net->HT, P, net->D, net->HT, stream);
         if (rc) return rc;
     }
+    if (lanes > 1)
+        for (int l = 0; l < lanes; ++l) {
+            IPSB_CUDA(cudaEventRecord(ls->done[l], ls->s[l]));
+            IPSB_CUDA(cudaStreamWaitEvent((cudaStream_t)caller_stream, ls->done[l], 0));
+        }
     return 0;
 }
 
@@ -192,10 +241,14 @@ int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_
                        void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out, void* stream) {
     IPSB_REQUIRE(net && patches && z_out && workspace, "resnet_logits: null argument");
     IPSB_REQUIRE(n_rows > 0 && chunk > 0 && net->n_blocks > 0 && net->n_blocks <= 8 && net->n_blocks % 2 == 0, "resnet_logits: bad sizes");
-    IPSB_REQUIRE(workspace_bytes >= ipsb_resnet_workspace_bytes(net, chunk, C, H, W), "resnet_logits: workspace too small");
-    if (net->dt == IPSB_BF16 && net->stem.mode >= 3)
-        return resnet_logits_pf(net, patches, first_row, n_rows, C, H, W, n_per_image, chunk, workspace, zero_init, emb_out,
-                                z_out, stream);
+    const int64_t lane_bytes = ipsb_resnet_workspace_bytes(net, chunk, C, H, W);
+    IPSB_REQUIRE(workspace_bytes >= lane_bytes, "resnet_logits: workspace too small");
+    if (net->dt == IPSB_BF16 && net->stem.mode >= 3) {
+        int lanes = (int)(workspace_bytes / lane_bytes);        // a workspace of L lanes runs L chunks concurrently
+        if (lanes > MAX_LANES) lanes = MAX_LANES;
+        return resnet_logits_pf(net, patches, first_row, n_rows, C, H, W, n_per_image, chunk, workspace, lane_bytes, lanes, zero_init,
+                                emb_out, z_out, stream);
+    }
     const int dt = net->dt;
     const int64_t es = (int64_t)esize(dt);
     int64_t staged_elems;

@@ -12,7 +12,7 @@
 // Work unit = GROUP: R pooled rows of one patch.  They need stem rows 2*pr0-1 .. 2*(pr0+R-1)+1, i.e. the (2R+1)*Wp
 // consecutive flat rows starting one image row above -> NT tiles of 128 rows.  Per group:
 //   producer warp    TMA-loads each tile's block of frame rows (128 + 3*Wp + 3 rows of 32 bytes)
-//   MMA warp         16 tcgen05.mma (M=128, N=64, K=16) per tile into one of four TMEM accumulators
+//   MMA warp         16 tcgen05.mma (M=128, N=64, K=16) per tile into one of eight TMEM accumulators
 //   4 epilogue WGs   tile t of the CTA goes to warpgroup t%4: tcgen05.ld -> BN + ReLU -> bf16 -> the group's staging
 //                    buffer in shared memory (NT x 16 KB, 128-byte rows, XOR-swizzled chunks); after a barrier all
 //                    512 threads max-pool out of shared memory and write the padded-flat layer-1 input with
@@ -35,7 +35,8 @@ namespace {
 using bf16 = __nv_bfloat16;
 constexpr int TILE_M = 128;
 constexpr int BN = 64;
-constexpr int NWG = 4;                     // epilogue warpgroups = TMEM accumulator stages
+constexpr int NWG = 4;                     // epilogue warpgroups
+constexpr int NACC = 8;                    // TMEM accumulator stages (all 512 columns): the MMA warp runs a group ahead of the pool
 constexpr int B_SLAB_BYTES = BN * 128;     // (64, 64) bf16 slab of the (64, 256) weights
 constexpr int THREADS = 64 + 128 * NWG;
 
@@ -84,8 +85,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto a_full = [&](int s) { return bar0 + 8u * s; };
     auto a_empty = [&](int s) { return bar0 + 8u * (SA + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SA + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SA + NWG + a); };
-    const uint32_t resb_bar = bar0 + 8u * (2 * SA + 2 * NWG);
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SA + NACC + a); };
+    const uint32_t resb_bar = bar0 + 8u * (2 * SA + 2 * NACC);
     const uint32_t tmem_slot = resb_bar + 8u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - umma::smem_u32(smem_raw)));
     const uint32_t sc_addr = (tmem_slot + 4u + 15u) & ~15u;
@@ -94,11 +95,11 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < SA; ++s) { umma::mbar_init(a_full(s), 1); umma::mbar_init(a_empty(s), 1); }
-        for (int a = 0; a < NWG; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < NACC; ++a) { umma::mbar_init(tfull_bar(a), 1); umma::mbar_init(tempty_bar(a), 128); }
         umma::mbar_init(resb_bar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_slot, NWG * BN);
+    if (warp == 1) umma::tmem_alloc(tmem_slot, NACC * BN);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -132,8 +133,8 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t tc = 0;
         for (int grp = blockIdx.x; grp < p.total_groups; grp += gridDim.x) {
             for (int j = 0; j < p.NT; ++j, ++tc) {
-                const uint32_t acc = tc % NWG;
-                umma::mbar_wait(tempty_bar(acc), ((tc / NWG) & 1) ^ 1);
+                const uint32_t acc = tc % NACC;
+                umma::mbar_wait(tempty_bar(acc), ((tc / NACC) & 1) ^ 1);
                 const int sa = tc % SA;
                 umma::mbar_wait(a_full(sa), (tc / SA) & 1);
                 umma::tc_fence_after();
@@ -170,9 +171,10 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < p.NT; ++j) {
                 const uint32_t tc = tc0 + j;
                 if ((int)(tc % NWG) != wg) continue;
-                umma::mbar_wait(tfull_bar(wg), (tc / NWG) & 1);
+                const uint32_t acc = tc % NACC;
+                umma::mbar_wait(tfull_bar(acc), (tc / NACC) & 1);
                 umma::tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 const uint32_t row_smem = stage0 + (uint32_t)(j * TILE_M + row) * 128u;
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -181,7 +183,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     umma::tmem_ld_wait();
                     if (c0 + 32 >= BN) {                              // accumulator fully read: hand it back to the MMA warp
                         umma::tc_fence_before();
-                        umma::mbar_arrive(tempty_bar(wg));
+                        umma::mbar_arrive(tempty_bar(acc));
                     }
                     epi::stage32<bf16>(v, sc_smem + c0, sc_smem + BN + c0, true, false, p.relu, row_smem, row, c0 / 8);
                 }
@@ -218,7 +220,7 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem_base, NWG * BN);
+    if (warp == 1) umma::tmem_dealloc(tmem_base, NACC * BN);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -261,7 +263,7 @@ int ipsb_stem_pool_s2d(const void* frame, const void* w, const float* scale, con
     p.a_slot_bytes = (uint32_t)((p.a_rows * 2 * 32 + 1023) / 1024 * 1024);
     constexpr int SA = 4;
     // pooled rows per group: fewest tiles per patch with the staging buffer within shared memory
-    const size_t fixed = (size_t)SA * p.a_slot_bytes + 4 * B_SLAB_BYTES + 2048 + 8 * (2 * SA + 2 * NWG + 2) + 8 * BN;
+    const size_t fixed = (size_t)SA * p.a_slot_bytes + 4 * B_SLAB_BYTES + 2048 + 8 * (2 * SA + 2 * NACC + 2) + 8 * BN;
     const int nt_max = (int)((227 * 1024 - fixed) / epi::STAGE_BYTES);
     int best_cost = 1 << 30;
     p.R = 0;

@@ -123,7 +123,9 @@ class IPSNet(nn.Module):
         self._plan = None
         self._plan_key = None
         self.last_mem_idx = None      # (B,M) original-order indices of the last ips() call (notebook cell 9)
-        self.chunk_patches = int(getattr(conf, 'chunk_patches', 0))   # 0 = auto
+        self.chunk_patches = int(os.environ.get('IPS_B200_CHUNK', getattr(conf, 'chunk_patches', 0)))   # 0 = auto
+        # chunks in flight inside the native executor (internal streams); 1 = strictly sequential
+        self.lanes = int(os.environ.get('IPS_B200_LANES', getattr(conf, 'lanes', 2)))
         # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
         self.executor = os.environ.get('IPS_B200_EXECUTOR', 'native')
         self._ws_cache = {}
@@ -272,13 +274,21 @@ class IPSNet(nn.Module):
             h, w = ho, wo
         return ops.avgpool_pf(x, P, h, w)
 
-    def _auto_chunk(self, patch_shape):
+    def _auto_chunk(self, patch_shape, rows=None):
+        """Patches per encoder launch.  Large chunks waste less of each persistent kernel's last wave of tiles; with
+        `lanes` chunks in flight the rows are split evenly over the lanes, capped by the activation workspace
+        (~1.3 GB per 1024 patches of 100x100)."""
         if self.chunk_patches:
             return self.chunk_patches
         if not self.is_image:
             return 16384
         px = patch_shape[-1] * patch_shape[-2]
-        return max(32, min(4096, (1024 * 10000) // max(px, 1)))      # ~1024 patches of 100x100: fills 148 SMs in every layer
+        cap = max(32, min(8192, (2048 * 10000) // max(px, 1)))
+        if rows is None:
+            return cap
+        per_lane = -(-rows // max(1, self.lanes))
+        n = -(-per_lane // cap)                                        # chunks per lane
+        return max(32, -(-(-(-per_lane // n)) // 8) * 8)
 
     @torch.no_grad()
     def patch_logits(self, patches, pos_offset=0):
@@ -290,11 +300,11 @@ class IPSNet(nn.Module):
         rows = B * N
         flat = patches.reshape(rows, *patches.shape[2:])
         HT = plan['U'].shape[1]
-        chunk = self._auto_chunk(patches.shape)
+        chunk = self._auto_chunk(patches.shape, rows)
         if self.is_image and flat.is_cuda and self.executor == 'native' and pos_offset == 0:
             if 'desc' not in plan:
                 plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
-            z, _ = ops.resnet_logits(plan['desc'], flat.contiguous(), N, chunk, self._ws_cache)
+            z, _ = ops.resnet_logits(plan['desc'], flat.contiguous(), N, chunk, self._ws_cache, lanes=self.lanes)
             return z.view(B, N, HT)
         z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
         pos_idx = None
@@ -321,7 +331,9 @@ class IPSNet(nn.Module):
         if flat_h.dtype != torch.float32:
             flat_h = flat_h.float()
         HT = plan['U'].shape[1]
-        chunk = self._auto_chunk(patches.shape)
+        # smaller chunks than the resident path: the encoder starts as soon as the first chunk has arrived
+        chunk = self.chunk_patches or (max(32, min(4096, (1024 * 10000) // max(patches.shape[-1] * patches.shape[-2], 1)))
+                                       if self.is_image else 16384)
         main = torch.cuda.current_stream(self.device)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)

@@ -286,17 +286,18 @@ def make_resnet_desc(plan, dt, D, HT):
     return d
 
 
-def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False, first_row=0, n_rows=None, z=None):
+def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False, first_row=0, n_rows=None, z=None, lanes=1):
     """Whole eval-mode encoder + logit projection of (rows,C,H,W) fp32 patches in ONE library call.
-    `first_row` / `n_rows` restrict the call to a row range (its logits land in z[first_row : first_row+n_rows])."""
+    `first_row` / `n_rows` restrict the call to a row range (its logits land in z[first_row : first_row+n_rows]).
+    `lanes` > 1 sizes the workspace for that many chunks in flight on the library's internal streams."""
     global LAUNCHES
     _chk(patches, torch.float32, 'patches')
     total_rows, C, H, W = patches.shape
     rows = total_rows - first_row if n_rows is None else n_rows
     lib = _lib.load()
-    need = lib.ipsb_resnet_workspace_bytes(desc, chunk, C, H, W)
+    need = lib.ipsb_resnet_workspace_bytes(desc, chunk, C, H, W) * max(1, int(lanes))
     ws = workspace_cache.get('ws')
-    key = (chunk, C, H, W, desc.dt)
+    key = (chunk, C, H, W, desc.dt, int(lanes))
     fresh = ws is None or ws.numel() < need or ws.device != patches.device or workspace_cache.get('key') != key
     if fresh:
         if ws is None or ws.numel() < need or ws.device != patches.device:
@@ -310,7 +311,7 @@ def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=F
                             + (1 if desc.add_tab else 0))
     z_ptr = z.data_ptr() + first_row * desc.HT * 4
     e_ptr = 0 if emb is None else emb.data_ptr() + first_row * desc.D * 4
-    _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), first_row, rows, C, H, W, n_per_image, chunk, _p(ws), ws.numel(),
+    _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), first_row, rows, C, H, W, n_per_image, chunk, _p(ws), need,
                                       int(fresh), e_ptr, z_ptr, _stream()))
     return z, emb
 
