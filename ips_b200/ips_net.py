@@ -331,8 +331,9 @@ class IPSNet(nn.Module):
         if flat_h.dtype != torch.float32:
             flat_h = flat_h.float()
         HT = plan['U'].shape[1]
-        # smaller chunks than the resident path: the encoder starts as soon as the first chunk has arrived
-        chunk = self.chunk_patches or (max(32, min(4096, (1024 * 10000) // max(patches.shape[-1] * patches.shape[-2], 1)))
+        # smaller chunks than the resident path: the encoder starts as soon as the first chunk has arrived and only the
+        # last chunk's compute is exposed after the copy (traffic, 369 MB over PCIe: raw copy 6.7 ms, ips() 8.0 ms)
+        chunk = self.chunk_patches or (max(32, min(4096, (512 * 10000) // max(patches.shape[-1] * patches.shape[-2], 1)))
                                        if self.is_image else 16384)
         main = torch.cuda.current_stream(self.device)
         if getattr(self, '_copy_stream', None) is None:
