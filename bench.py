@@ -324,6 +324,17 @@ def run_ours(args):
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s',
                     'launches_per_step': counts[dom], 'kernel_ms_per_step': per[dom]}
         roof['kernel_ms_all'] = {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+        # DRAM bytes per launch of the same kernel family, from the committed ncu launch list of this command
+        # (tools/launch_traffic.py -> profiles/r01_traffic.json; cold-cache, serialised replays)
+        try:
+            if args.workload == 'traffic' and args.precision == 'bf16' and dom.startswith('conv/gemm'):
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_traffic.json')) as f:
+                    tj = json.load(f)['conv_family']
+                roof['traffic'] = tj['dram_bytes'] / tj['launches']
+                roof['traffic_note'] = ('dram read+write bytes per launch averaged over the %d conv-family launches of one step '
+                                        '(ncu, profiles/r01_traffic.json); algorithmic = FLOP-bound family' % tj['launches'])
+        except Exception:
+            pass
 
     # ---- CPU baseline on rank 0 at N=1 -------------------------------------------------
     cpu = None

@@ -33,6 +33,13 @@ int fail(const char* fmt, ...);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int sm_count();
+// Persistent-kernel grid: the fewest CTAs that finish `units` work items in the same number of rounds as `max_ctas`
+// would (192 units on 148 SMs take 2 rounds either way -> 96 CTAs); the SMs left free run the other lane's kernels.
+static inline int balanced_grid(int64_t units, int max_ctas) {
+    if (units <= max_ctas) return (int)units;
+    const int64_t rounds = (units + max_ctas - 1) / max_ctas;
+    return (int)((units + rounds - 1) / rounds);
+}
 
 // TMA-fed tcgen05 implicit GEMM (umma_conv_tma.cu)
 int conv_tma(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,

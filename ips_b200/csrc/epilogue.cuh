@@ -138,7 +138,8 @@ __device__ __forceinline__ void prefetch_residual(bool issuer, uint32_t res_bar,
 //   stage      this warpgroup's 16 KB staging tile (1024-byte aligned), bar_id: its named barrier
 //   issue(slab_col0, stage) is called by ONE thread per slab and must issue the TMA store,
 //   load(slab_col0, stage, bar) the TMA load of the residual slab.
-template <int BN, typename OutT, class Issue, class Load>
+//   CLUSTER_RELEASE: tempty_bar is a shared::cluster address (the leader CTA's barrier of a CTA pair)
+template <int BN, typename OutT, bool CLUSTER_RELEASE = false, class Issue, class Load>
 __device__ __forceinline__ void drain_tile(uint32_t t_row, uint32_t tempty_bar, const float* sc, const float* sh, bool pixel,
                                            bool has_res, uint32_t res_bar, uint32_t res_bytes, uint32_t& res_phase, int relu, uint32_t stage, int row,
                                            uint32_t bar_id, bool issuer, const Issue& issue, const Load& load) {
@@ -160,7 +161,8 @@ __device__ __forceinline__ void drain_tile(uint32_t t_row, uint32_t tempty_bar, 
             umma::tmem_ld_wait();
             if (s0 + c0 + 32 >= BN) {                  // accumulator fully read: hand it back to the MMA warp
                 umma::tc_fence_before();
-                umma::mbar_arrive(tempty_bar);
+                if (CLUSTER_RELEASE) umma::mbar_arrive_cluster(tempty_bar);
+                else                 umma::mbar_arrive(tempty_bar);
             }
             stage32<OutT>(v, sc + s0 + c0, sh + s0 + c0, pixel, has_res, relu, row_smem, row, c0 * (int)sizeof(OutT) / 16);
         }

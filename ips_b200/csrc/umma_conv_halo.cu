@@ -262,7 +262,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
+    const int grid = ipsb::balanced_grid(p.total_tiles, ipsb::sm_count());
     kern<<<grid, 64 + 128 * EpiWgs<S2D>::N, smem, st>>>(tmA, tmB, tmC, tmR, p);
     IPSB_LAUNCH_CHECK();
     return 0;

@@ -20,6 +20,7 @@
 //
 // Replaces conv2d + batch_norm(eval) + add + relu (architecture/ips_net.py:17-52) and
 // nn.Linear (ips_net.py:57) of the reference.
+#include <cstdlib>
 #include <cuda.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -236,6 +237,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------- host side
+}  // namespace
+namespace ipsb {
+// CTA-pair kernel for the 256-wide layers (umma_conv_pair.cu); -1 = pairs cannot be scheduled on this device
+int conv_pair_launch(const CUtensorMap& tmA, const CUtensorMap& tmBh, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                     const float* scale, const float* shift, bool has_res, int P, int Ho, int Wo, int Cout, int kw, int stride, int pad,
+                     int relu, int bw, int bh, int bp, int tiles_x, int tiles_y, int n_tiles_n, int m_tiles, int KS, int cblocks,
+                     uint32_t a_bytes, cudaStream_t st);
+}
+namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -266,7 +276,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = p.total_tiles < ipsb::sm_count() ? p.total_tiles : ipsb::sm_count();
+    const int grid = ipsb::balanced_grid(p.total_tiles, ipsb::sm_count());
     kern<<<grid, 320, smem, st>>>(tmA, tmB, tmC, tmR, p);
     IPSB_LAUNCH_CHECK();
     return 0;
@@ -391,6 +401,15 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
     }
     if (int rc = encode_output<bf16>(enc, &tmC, y, p, out_pf)) return rc;
     if (int rc = encode_output<bf16>(enc, &tmR, res ? const_cast<void*>(res) : y, p, out_pf)) return rc;   // same geometry as the output
+    const int m_tiles = p.total_tiles / p.n_tiles_n;
+    static const bool pair_ok = !getenv("IPSB_NO_PAIR");
+    if (pair_ok && BN == 256 && m_tiles >= 2) {        // 256-wide layers: CTA pairs (tcgen05.mma.cta_group::2)
+        alignas(64) CUtensorMap tmBh;
+        if (int rc = encode_weights(enc, &tmBh, w, kh * kw * Cin, Cout, BN / 2)) return rc;      // half slabs
+        const int rc = conv_pair_launch(tmA, tmBh, tmC, tmR, scale, shift, res != nullptr, (int)P, Ho, Wo, Cout, kw, stride, pad, relu,
+                                        p.bw, p.bh, p.bp, p.tiles_x, p.tiles_y, p.n_tiles_n, m_tiles, p.KS, p.cblocks, p.a_bytes, st);
+        if (rc >= 0) return rc;
+    }
     return dispatch<false, bf16>(tmA, tmB, tmC, tmR, p, BN, resb, st);
 }
 

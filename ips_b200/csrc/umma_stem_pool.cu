@@ -303,7 +303,7 @@ int ipsb_stem_pool_s2d(const void* frame, const void* w, const float* scale, con
         IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = p.total_groups < ipsb::sm_count() ? p.total_groups : ipsb::sm_count();
+    const int grid = ipsb::balanced_grid(p.total_groups, ipsb::sm_count());
     kern<<<grid, THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
     IPSB_LAUNCH_CHECK();
     return 0;
