@@ -61,6 +61,23 @@ IPSB_API int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx,
 IPSB_API int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows, int C, int H, int W,
                            void* dst, void* stream);
 IPSB_API int ipsb_maxpool3x3s2_pf_strided(const void* x, void* y, int64_t P, int H, int W, int C, int in_Wp, int in_Sp, void* stream);
+/* On-device patchify: the reference cuts images into patches on the CPU workers
+ * (`img.unfold(1, ph, sh).unfold(2, pw, sw).permute(1, 2, 0, 3, 4).reshape(-1, C, ph, pw)`,
+ * data/megapixel_mnist/mnist_dataset.py:47-53, data/traffic/traffic_dataset.py:337-343).  With an ipsb_image_geo the
+ * staging kernel and the final gather read the patch rectangles straight out of (B, C, img_h, img_w) fp32 images:
+ * patch n of an image is grid row n / n_cols, column n % n_cols, n_cols = (img_w - pw) / stride_w + 1; overlapping
+ * strides are allowed.  n_per_image must equal the number of grid cells. */
+typedef struct {
+    int32_t img_h, img_w;
+    int32_t stride_h, stride_w;
+    int32_t n_per_image;
+} ipsb_image_geo;
+IPSB_API int ipsb_stage_image_s2d(const float* img, const ipsb_image_geo* geo, int64_t first_row, int64_t n_rows, int C, int H, int W,
+                         void* dst, void* stream);
+/* out (B, M, C, H, W) fp32 <- patch idx[b, m] of image b (idx NULL: all patches in order = patchify; idx < 0: zeros) */
+IPSB_API int ipsb_gather_patches_image(const float* img, const ipsb_image_geo* geo, const int64_t* idx, int B, int M, int C, int H, int W,
+                              float* out, void* stream);
+
 /* conv1 -> bn1 -> relu -> maxpool (architecture/ips_net.py:17-39) in one kernel: s2d frame of P patches of HxW ->
  * padded-flat (ipsb_pf_rows(P, Hq, Wq), 64) bf16 with Hq = (H/2 - 1)/2 + 1; the stem output stays in shared memory.
  * w: (64, 256) bf16 in the mode-4 packing; y's pad rows must already be zero (they are not written). */
@@ -194,6 +211,11 @@ IPSB_API int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patche
                                 int C, int H, int W, int64_t n_per_image, int64_t chunk,
                                 void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out,
                                 void* stream);
+/* same, reading the patches out of whole images (bf16 path with the space-to-depth stem only); H, W = patch size */
+IPSB_API int ipsb_resnet_logits_image(const ipsb_resnet_desc* net, const float* images, const ipsb_image_geo* geo, int64_t first_row,
+                                      int64_t n_rows, int C, int H, int W, int64_t chunk,
+                                      void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out,
+                                      void* stream);
 
 /* ---------------------------------------------------------------- aggregator + heads, forward (no-grad)
  * Replaces MultiHeadCrossAttention.forward / MLP.forward / get_preds in inference

@@ -32,6 +32,12 @@ class ResnetDesc(ctypes.Structure):
                 ('D', ctypes.c_int32), ('HT', ctypes.c_int32), ('U', _ptr), ('add_tab', _ptr)]
 
 
+class ImageGeo(ctypes.Structure):
+    """ipsb_image_geo"""
+    _fields_ = [('img_h', ctypes.c_int32), ('img_w', ctypes.c_int32), ('stride_h', ctypes.c_int32), ('stride_w', ctypes.c_int32),
+                ('n_per_image', ctypes.c_int32)]
+
+
 # name -> argtypes (restype is int status unless listed in _RESTYPE)
 SIGNATURES = {
     'ipsb_abi_version': [],
@@ -40,6 +46,8 @@ SIGNATURES = {
     'ipsb_stage_patches': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_stage_patches_padded': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_stage_patches_s2d': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
+    'ipsb_stage_image_s2d': [_ptr, ctypes.POINTER(ImageGeo), _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
+    'ipsb_gather_patches_image': [_ptr, ctypes.POINTER(ImageGeo), _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_maxpool3x3s2_pf_strided': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_stem_pool_s2d': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_conv_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
@@ -79,6 +87,8 @@ SIGNATURES = {
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
     'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64, _i32,
                            _ptr, _ptr, _ptr],
+    'ipsb_resnet_logits_image': [ctypes.POINTER(ResnetDesc), _ptr, ctypes.POINTER(ImageGeo), _i64, _i64, _i32, _i32, _i32, _i64,
+                                 _ptr, _i64, _i32, _ptr, _ptr, _ptr],
 }
 _RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64,
             'ipsb_pf_rows': ctypes.c_int64, 'ipsb_select_loop_workspace_bytes': ctypes.c_int64,

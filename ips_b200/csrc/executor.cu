@@ -121,7 +121,7 @@ int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, 
 
 static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,
                             int C, int H, int W, int64_t n_per_image, int64_t chunk, void* workspace, int64_t lane_bytes, int lanes,
-                            int zero_init, float* emb_out, float* z_out, void* caller_stream) {
+                            int zero_init, float* emb_out, float* z_out, void* caller_stream, const ipsb_image_geo* img_geo = nullptr) {
     const PfPlan pl = make_pf_plan(net, chunk, H, W);
     const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
     if (lanes > n_chunks) lanes = (int)n_chunks;
@@ -166,7 +166,8 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         for (int64_t s0 = 0; s0 < P; s0 += sub) {
             const int64_t Ps = (P - s0 < sub) ? P - s0 : sub;
             if (st.mode == 4) {               // space-to-depth frame -> shifted-window stem -> strided max-pool
-                rc = ipsb_stage_patches_s2d(patches, nullptr, first_row + lo + s0, Ps, C, H, W, staged, stream);
+                rc = img_geo ? ipsb_stage_image_s2d(patches, img_geo, first_row + lo + s0, Ps, C, H, W, staged, stream)
+                             : ipsb_stage_patches_s2d(patches, nullptr, first_row + lo + s0, Ps, C, H, W, staged, stream);
                 if (rc) return rc;
                 if (st.cout == 64 && !getenv("IPSB_STEM_UNFUSED")) {   // stem + pool fused: the stem output stays on chip
                     rc = ipsb_stem_pool_s2d(staged, st.w, st.scale, st.shift, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, H, W,
@@ -234,6 +235,20 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
             IPSB_CUDA(cudaStreamWaitEvent((cudaStream_t)caller_stream, ls->done[l], 0));
         }
     return 0;
+}
+
+int ipsb_resnet_logits_image(const ipsb_resnet_desc* net, const float* images, const ipsb_image_geo* geo, int64_t first_row,
+                             int64_t n_rows, int C, int H, int W, int64_t chunk,
+                             void* workspace, int64_t workspace_bytes, int zero_init, float* emb_out, float* z_out, void* stream) {
+    IPSB_REQUIRE(net && images && geo && z_out && workspace, "resnet_logits_image: null argument");
+    IPSB_REQUIRE(n_rows > 0 && chunk > 0 && net->n_blocks > 0 && net->n_blocks <= 8 && net->n_blocks % 2 == 0, "resnet_logits_image: bad sizes");
+    IPSB_REQUIRE(net->dt == IPSB_BF16 && net->stem.mode == 4, "resnet_logits_image: needs the bf16 path with the space-to-depth stem");
+    const int64_t lane_bytes = ipsb_resnet_workspace_bytes(net, chunk, C, H, W);
+    IPSB_REQUIRE(workspace_bytes >= lane_bytes, "resnet_logits_image: workspace too small");
+    int lanes = (int)(workspace_bytes / lane_bytes);
+    if (lanes > MAX_LANES) lanes = MAX_LANES;
+    return resnet_logits_pf(net, images, first_row, n_rows, C, H, W, geo->n_per_image, chunk, workspace, lane_bytes, lanes, zero_init,
+                            emb_out, z_out, stream, geo);
 }
 
 int ipsb_resnet_logits(const ipsb_resnet_desc* net, const float* patches, int64_t first_row, int64_t n_rows,

@@ -91,7 +91,23 @@ __global__ void stage_padded_kernel(const float* __restrict__ src, const int64_t
 
 // space-to-depth staging for the stem: one thread per 2x2 input block.  Frame pixel (Y', X') of patch r holds 16 bf16:
 // channel (dy*2+dx)*4 + c = in(2Y'+dy-4, 2X'+dx-4, c) (zero outside the image / for c >= C); Ys x Wp frame pixels per patch.
-__global__ void stage_s2d_kernel(const float* __restrict__ src, const int64_t* __restrict__ row_idx, int64_t first_row,
+// The source is either a tensor of patches (geo.n_cols == 0: patch r starts at r*C*H*W, rows of W floats) or whole images
+// (B, C, img_h, img_w) cut into a grid of patches on the fly (ipsb_image_geo: patch n of an image = row n / n_cols,
+// column n % n_cols of the grid, at stride (sh, sw) -- the reference's CPU `unfold`, data/*/..._dataset.py).
+struct SrcGeo {
+    int64_t img_stride, chan_stride, row_stride;    // floats between images / channels / pixel rows
+    int n_per_image, n_cols, sh, sw;
+    int pair_ok;                                    // 8-byte loads of aligned pixel pairs are safe
+};
+__device__ __forceinline__ const float* patch_base(const float* src, const SrcGeo& g, int64_t srow, int C, int H, int W) {
+    if (g.n_cols == 0) return src + srow * (int64_t)C * H * W;
+    const int64_t b = srow / g.n_per_image;
+    const int n = (int)(srow - b * g.n_per_image);
+    const int pr = n / g.n_cols, pc = n - pr * g.n_cols;
+    return src + b * g.img_stride + (int64_t)pr * g.sh * g.row_stride + (int64_t)pc * g.sw;
+}
+
+__global__ void stage_s2d_kernel(const float* __restrict__ src, const SrcGeo geo, const int64_t* __restrict__ row_idx, int64_t first_row,
                                  int64_t n_rows, int C, int H, int W, int Ys, int Wp, bf16* __restrict__ dst) {
     const int64_t total = n_rows * Ys * Wp;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -104,14 +120,14 @@ __global__ void stage_s2d_kernel(const float* __restrict__ src, const int64_t* _
         const int y0 = 2 * Yp - 4, x0 = 2 * Xp - 4;
         if (y0 + 1 >= 0 && y0 < H && x0 + 1 >= 0 && x0 < W) {
             const int64_t srow = row_idx ? row_idx[r] : first_row + r;
-            const float* sp = src + srow * (int64_t)C * H * W;
+            const float* sp = patch_base(src, geo, srow, C, H, W);
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
                 const int y = y0 + dy;
                 if (y < 0 || y >= H) continue;
                 for (int c = 0; c < C; ++c) {
-                    const float* rowp = sp + ((int64_t)c * H + y) * W;
-                    if (x0 >= 0 && x0 + 1 < W) {         // x0 is even: aligned pair
+                    const float* rowp = sp + (int64_t)c * geo.chan_stride + (int64_t)y * geo.row_stride;
+                    if (geo.pair_ok && x0 >= 0 && x0 + 1 < W) {         // x0 is even: aligned pair
                         const float2 v = *reinterpret_cast<const float2*>(rowp + x0);
                         out[(dy * 2 + 0) * 4 + c] = __float2bfloat16_rn(v.x);
                         out[(dy * 2 + 1) * 4 + c] = __float2bfloat16_rn(v.y);
@@ -125,6 +141,26 @@ __global__ void stage_s2d_kernel(const float* __restrict__ src, const int64_t* _
         uint4* d = reinterpret_cast<uint4*>(dst + i * 16);
         d[0] = *reinterpret_cast<const uint4*>(&out[0]);
         d[1] = *reinterpret_cast<const uint4*>(&out[8]);
+    }
+}
+
+// out[b, m, c, y, x] = img[b, c, pr*sh + y, pc*sw + x] for patch n = idx[b, m] (idx == null: n = m, i.e. patchify);
+// one block per (patch, channel), threads along the pixels of the patch
+__global__ void gather_patches_image_kernel(const float* __restrict__ img, const SrcGeo geo, const int64_t* __restrict__ idx,
+                                            int M, int C, int H, int W, float* __restrict__ out) {
+    const int64_t pm = blockIdx.x;                       // b * M + m
+    const int c = blockIdx.y;
+    const int64_t b = pm / M;
+    const int64_t n = idx ? idx[pm] : pm - b * M;
+    float* d = out + (pm * C + c) * (int64_t)H * W;
+    if (n < 0) {                                         // not owned (sharded assembly): zero patch
+        for (int i = threadIdx.x; i < H * W; i += blockDim.x) d[i] = 0.f;
+        return;
+    }
+    const float* s = patch_base(img, geo, b * geo.n_per_image + n, C, H, W) + (int64_t)c * geo.chan_stride;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        d[i] = s[(int64_t)y * geo.row_stride + x];
     }
 }
 
@@ -429,8 +465,46 @@ int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t fir
     IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= 4 && H % 2 == 0 && W % 2 == 0 && ((uintptr_t)src % 8 == 0),
                  "stage_s2d: needs C <= 4 and even H, W");
     const int Ys = H / 2 + 3, Wp = W / 2 + 3;
-    stage_s2d_kernel<<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(src, row_idx, first_row, n_rows, C, H, W,
+    const SrcGeo geo{0, (int64_t)H * W, (int64_t)W, 0, 0, 0, 0, 1};
+    stage_s2d_kernel<<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(src, geo, row_idx, first_row, n_rows, C, H, W,
                                                                                        Ys, Wp, (bf16*)dst);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int make_src_geo(const ipsb_image_geo* g, int C, int H, int W, const float* img, SrcGeo* out) {
+    IPSB_REQUIRE(g && g->img_h >= H && g->img_w >= W && g->stride_h > 0 && g->stride_w > 0, "image geometry: bad sizes");
+    const int n_rows_grid = (g->img_h - H) / g->stride_h + 1, n_cols = (g->img_w - W) / g->stride_w + 1;
+    IPSB_REQUIRE(g->n_per_image == n_rows_grid * n_cols, "image geometry: n_per_image=%d but the grid has %d x %d patches",
+                 g->n_per_image, n_rows_grid, n_cols);
+    out->chan_stride = (int64_t)g->img_h * g->img_w;
+    out->img_stride = out->chan_stride * C;
+    out->row_stride = g->img_w;
+    out->n_per_image = g->n_per_image; out->n_cols = n_cols; out->sh = g->stride_h; out->sw = g->stride_w;
+    out->pair_ok = (g->img_w % 2 == 0) && (g->stride_w % 2 == 0) && ((uintptr_t)img % 8 == 0);
+    return 0;
+}
+
+int ipsb_stage_image_s2d(const float* img, const ipsb_image_geo* g, int64_t first_row, int64_t n_rows, int C, int H, int W,
+                         void* dst, void* stream) {
+    IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= 4 && H % 2 == 0 && W % 2 == 0, "stage_image_s2d: needs C <= 4 and even H, W");
+    SrcGeo geo;
+    if (int rc = make_src_geo(g, C, H, W, img, &geo)) return rc;
+    const int Ys = H / 2 + 3, Wp = W / 2 + 3;
+    stage_s2d_kernel<<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(img, geo, nullptr, first_row, n_rows, C, H, W,
+                                                                                       Ys, Wp, (bf16*)dst);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_gather_patches_image(const float* img, const ipsb_image_geo* g, const int64_t* idx, int B, int M, int C, int H, int W,
+                              float* out, void* stream) {
+    IPSB_REQUIRE(B > 0 && M > 0 && C > 0, "gather_patches_image: bad sizes");
+    SrcGeo geo;
+    if (int rc = make_src_geo(g, C, H, W, img, &geo)) return rc;
+    IPSB_REQUIRE(idx != nullptr || M == g->n_per_image, "gather_patches_image: patchify needs M == n_per_image");
+    dim3 grid((unsigned)(B * (int64_t)M), (unsigned)C);
+    gather_patches_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, geo, idx, M, C, H, W, out);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -132,6 +132,7 @@ class IPSNet(nn.Module):
         # bf16 stem: 4 = shifted-window kernel on the space-to-depth frame, 3 = TMA-fed im2col rows (both need even
         # patch sizes), 1 = cp.async gather
         ps = getattr(conf, 'patch_size', [0, 0])
+        self.patch_size = tuple(ps)
         stem = os.environ.get('IPS_B200_STEM', 's2d')
         even = self.is_image and ps[0] % 2 == 0 and ps[1] % 2 == 0
         self.stem_mode = {'s2d': 4, 'tma': 3}.get(stem, 1) if even else 1
@@ -398,15 +399,26 @@ class IPSNet(nn.Module):
         return preds
 
     @torch.no_grad()
-    def ips(self, patches):
-        """Iterative Patch Selection (ips_net.py:169-262): returns (mem_patch, mem_pos)."""
+    def ips(self, patches, out=None, row_offset=0):
+        """Iterative Patch Selection (ips_net.py:169-262): returns (mem_patch, mem_pos).
+
+        `out=(mem_patch_buf, mem_pos_buf)`, `row_offset=n_prep`: write the winners straight into rows
+        [n_prep, n_prep + B) of the train-step buffers of `init_batch` instead of allocating and copying
+        (`fill_batch`, training/iterative.py:31-50).  The returned tensors are views of the buffers."""
         M, I, D = self.M, self.I, self.D
         device = self.device
         B, N = patches.shape[:2]
         if M >= N:                                               # shortcut, :185-188
             pos_enc = self.pos_enc.expand(B, -1, -1) if self.use_pos else None
             self.last_mem_idx = None
-            return patches.to(device), pos_enc
+            mem_patch = patches.to(device)
+            if out is not None:
+                out[0][row_offset:row_offset + B, :N] = mem_patch
+                mem_patch = out[0][row_offset:row_offset + B, :N]
+                if self.use_pos:
+                    out[1][row_offset:row_offset + B, :N] = pos_enc
+                    pos_enc = out[1][row_offset:row_offset + B, :N]
+            return mem_patch, pos_enc
         if torch.device(device).type != 'cuda':
             raise RuntimeError('ips_b200.IPSNet.ips needs a CUDA device: there is no CPU implementation')
 
@@ -422,12 +434,64 @@ class IPSNet(nn.Module):
         _, mem_src, _ = ops.select_loop(z, perm, per_inst, ca.H, ca.n_token, M, I)
         self.last_mem_idx = mem_src
 
+        o_patch, o_pos = self._out_views(out, row_offset, B, M)
         if patches.is_cuda:
-            mem_patch = ops.gather_rows(patches.contiguous(), mem_src, N)
+            mem_patch = ops.gather_rows(patches.contiguous(), mem_src, N, out=o_patch)
         else:                                                    # lazy loading: gather on the host, :244-247
             host_idx = mem_src.cpu()
             mem_patch = torch.stack([patches[b, host_idx[b]] for b in range(B)]).to(device)
-        mem_pos = ops.gather_rows(self.pos_enc[0].contiguous(), mem_src, 0) if self.use_pos else None
+            if o_patch is not None:
+                o_patch.copy_(mem_patch)
+                mem_patch = o_patch
+        mem_pos = ops.gather_rows(self.pos_enc[0].contiguous(), mem_src, 0, out=o_pos) if self.use_pos else None
+        return mem_patch, mem_pos
+
+    def _out_views(self, out, row_offset, B, M):
+        """Rows [row_offset, row_offset + B) of the caller's (B_total, M, ...) buffers, or (None, None)."""
+        if out is None:
+            return None, None
+        buf_patch, buf_pos = out
+        if buf_patch.shape[1] != M or row_offset + B > buf_patch.shape[0]:
+            raise ValueError('ips_b200: out buffer of shape %s cannot take %d x %d winners at row %d'
+                             % (tuple(buf_patch.shape), B, M, row_offset))
+        o_pos = buf_pos[row_offset:row_offset + B] if (self.use_pos and buf_pos is not None) else None
+        return buf_patch[row_offset:row_offset + B], o_pos
+
+    @torch.no_grad()
+    def ips_image(self, images, patch_size=None, patch_stride=None, out=None, row_offset=0):
+        """`ips` on whole images (B, C, Himg, Wimg): the patch grid the reference's data loaders cut on the CPU
+        (`unfold(1, ph, sh).unfold(2, pw, sw)`, mnist_dataset.py:47-53, traffic_dataset.py:337-343; patch n = grid row
+        n // n_cols, column n % n_cols) is read straight out of the images by the staging kernel and by the final
+        gather.  Same result as `ips(patchify(images))`, same RNG consumption."""
+        if not self.is_image:
+            raise ValueError('ips_image needs an image configuration')
+        ph, pw = patch_size or self.patch_size
+        sh, sw = patch_stride or (ph, pw)
+        if not images.is_cuda:
+            images = images.to(self.device, non_blocking=True)
+        images = images.float().contiguous()
+        B, C = images.shape[:2]
+        geo, N = ops.image_geo(images, (ph, pw), (sh, sw))
+        M, I = self.M, self.I
+        plan = self._get_plan()
+        direct = (self.precision == 'bf16' and self.executor == 'native' and plan['stem']['mode'] == 4
+                  and plan['stem']['cout'] == 64 and M < N)
+        if not direct:                                            # other modes: patchify on the device, then the usual path
+            return self.ips(ops.gather_patches_image(images, geo, None, (ph, pw)), out=out, row_offset=row_offset)
+        perm, per_inst = scan_order(self.shuffle, self.shuffle_style, B, N, images.device)
+        if perm is not None:
+            perm = perm.to(self.device).contiguous()
+        ca = self.transf.crs_attn
+        HT = plan['U'].shape[1]
+        if 'desc' not in plan:
+            plan['desc'] = ops.make_resnet_desc(plan, ops.BF16, self.D, HT)
+        chunk = self._auto_chunk((ph, pw), B * N)
+        z, _ = ops.resnet_logits(plan['desc'], images, N, chunk, self._ws_cache, lanes=self.lanes, geo=geo, patch_size=(ph, pw))
+        _, mem_src, _ = ops.select_loop(z.view(B, N, HT), perm, per_inst, ca.H, ca.n_token, M, I)
+        self.last_mem_idx = mem_src
+        o_patch, o_pos = self._out_views(out, row_offset, B, M)
+        mem_patch = ops.gather_patches_image(images, geo, mem_src, (ph, pw), out=o_patch)
+        mem_pos = ops.gather_rows(self.pos_enc[0].contiguous(), mem_src, 0, out=o_pos) if self.use_pos else None
         return mem_patch, mem_pos
 
     @torch.no_grad()

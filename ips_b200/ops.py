@@ -5,6 +5,8 @@ CUDA stream to the library, and returns freshly allocated outputs.  The main
 entry points are also registered as PyTorch custom ops under ``torch.ops.ips_b200``
 (see the bottom of the file).  No function here has a non-CUDA implementation.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -117,8 +119,9 @@ def maxpool3x3s2_pf_strided(x, P, H, W, C, in_Wp, in_Sp, out=None):
     return out
 
 
-def gather_rows(src, idx, batch_stride_rows):
-    """dst[b,m] = src_rows[b*batch_stride_rows + idx[b,m]]; src viewed as rows of src.shape[-k:]."""
+def gather_rows(src, idx, batch_stride_rows, out=None):
+    """dst[b,m] = src_rows[b*batch_stride_rows + idx[b,m]]; src viewed as rows of src.shape[-k:].
+    `out`: contiguous (B, M, *row_shape) destination, e.g. a row range of the train-step buffer."""
     _chk(idx, torch.int64, 'idx')
     if not src.is_cuda or not src.is_contiguous():
         raise RuntimeError('ips_b200: gather source must be a contiguous CUDA tensor')
@@ -127,7 +130,10 @@ def gather_rows(src, idx, batch_stride_rows):
     row_bytes = src.element_size()
     for s in row_shape:
         row_bytes *= s
-    out = torch.empty((B, M, *row_shape), dtype=src.dtype, device=src.device)
+    if out is None:
+        out = torch.empty((B, M, *row_shape), dtype=src.dtype, device=src.device)
+    elif tuple(out.shape) != (B, M, *row_shape) or out.dtype != src.dtype or not out.is_contiguous() or out.device != src.device:
+        raise RuntimeError('ips_b200: gather destination must be a contiguous %s tensor on the source device' % ((B, M, *row_shape),))
     _call('ipsb_gather_rows', _p(src), batch_stride_rows, _p(idx), B, M, row_bytes, _p(out), _stream())
     return out
 
@@ -286,13 +292,38 @@ def make_resnet_desc(plan, dt, D, HT):
     return d
 
 
-def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False, first_row=0, n_rows=None, z=None, lanes=1):
+def image_geo(images, patch_size, patch_stride):
+    """ipsb_image_geo + patches per image for (B, C, Himg, Wimg) images cut like the reference's `unfold` calls."""
+    Himg, Wimg = images.shape[-2:]
+    ph, pw = patch_size
+    sh, sw = patch_stride
+    n_rows, n_cols = (Himg - ph) // sh + 1, (Wimg - pw) // sw + 1
+    return _lib.ImageGeo(Himg, Wimg, sh, sw, n_rows * n_cols), n_rows * n_cols
+
+
+def gather_patches_image(images, geo, idx, patch_size, out=None):
+    """(B, M, C, ph, pw) fp32 <- patch idx[b, m] of image b; idx None = every patch in grid order (on-device patchify)."""
+    _chk(images, torch.float32, 'images'); _chk(idx, torch.int64, 'idx')
+    B, C = images.shape[:2]
+    M = geo.n_per_image if idx is None else idx.shape[1]
+    if out is None:
+        out = torch.empty((B, M, C, *patch_size), dtype=torch.float32, device=images.device)
+    _call('ipsb_gather_patches_image', _p(images), ctypes.byref(geo), _p(idx), B, M, C, patch_size[0], patch_size[1], _p(out), _stream())
+    return out
+
+
+def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False, first_row=0, n_rows=None, z=None, lanes=1,
+                  geo=None, patch_size=None):
     """Whole eval-mode encoder + logit projection of (rows,C,H,W) fp32 patches in ONE library call.
     `first_row` / `n_rows` restrict the call to a row range (its logits land in z[first_row : first_row+n_rows]).
     `lanes` > 1 sizes the workspace for that many chunks in flight on the library's internal streams."""
     global LAUNCHES
     _chk(patches, torch.float32, 'patches')
-    total_rows, C, H, W = patches.shape
+    if geo is None:
+        total_rows, C, H, W = patches.shape
+    else:                                          # `patches` holds whole images (B, C, Himg, Wimg): on-device patchify
+        C, (H, W) = patches.shape[1], patch_size
+        total_rows = patches.shape[0] * geo.n_per_image
     rows = total_rows - first_row if n_rows is None else n_rows
     lib = _lib.load()
     need = lib.ipsb_resnet_workspace_bytes(desc, chunk, C, H, W) * max(1, int(lanes))
@@ -311,8 +342,12 @@ def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=F
                             + (1 if desc.add_tab else 0))
     z_ptr = z.data_ptr() + first_row * desc.HT * 4
     e_ptr = 0 if emb is None else emb.data_ptr() + first_row * desc.D * 4
-    _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), first_row, rows, C, H, W, n_per_image, chunk, _p(ws), need,
-                                      int(fresh), e_ptr, z_ptr, _stream()))
+    if geo is None:
+        _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), first_row, rows, C, H, W, n_per_image, chunk, _p(ws), need,
+                                          int(fresh), e_ptr, z_ptr, _stream()))
+    else:
+        _lib.check(lib.ipsb_resnet_logits_image(desc, _p(patches), ctypes.byref(geo), first_row, rows, C, H, W, chunk, _p(ws), need,
+                                                int(fresh), e_ptr, z_ptr, _stream()))
     return z, emb
 
 

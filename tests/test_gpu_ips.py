@@ -190,6 +190,25 @@ def test_native_executor_equals_per_layer_calls(name, precision):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize('pre,rows', [('traffic', 700), ('mnist', 1900)])
+def test_lanes_and_chunking_do_not_change_logits(pre, rows):
+    """A patch's logits are a property of the patch: the same bits whatever the chunk size, the number of chunks in
+    flight (internal streams), the tile a row lands in, single CTA or CTA pair."""
+    conf = O.preset(pre, attn_dropout=0.0, dropout=0.0)
+    sd = O.make_state(conf, 41, q_gain=12.0)
+    g = torch.Generator(device=DEV).manual_seed(42)
+    x = torch.randn((1, rows, conf.n_chan_in, *conf.patch_size), generator=g, device=DEV)
+    ref = None
+    for lanes, chunk in ((1, 0), (2, 0), (3, 100), (2, 257), (4, 64)):
+        net = _net(conf.replace(lanes=lanes, chunk_patches=chunk, N=rows), sd, 'bf16')
+        z = net.patch_logits(x)
+        z2 = net.patch_logits(x)                   # second call: reused workspace, no re-zeroing
+        assert torch.equal(z, z2)
+        if ref is None:
+            ref = z
+        assert torch.equal(z, ref), (lanes, chunk)
+
+
 @pytest.mark.parametrize('name', [n for n in CASE_NAMES if 'shortcut' not in n and 'instance' not in n])
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_inference_forward_matches_oracle(name, precision):
@@ -238,3 +257,57 @@ def test_train_step_gradients_match_oracle(name, precision):
             # element-wise, relative to the slice's scale (train-mode BatchNorm over a handful of patches amplifies
             # the cuDNN-vs-CPU rounding of the conv encoder in individual small entries)
             np.testing.assert_allclose(g.reshape(-1)[:256].cpu().numpy(), want_v, rtol=2e-3, atol=2e-2 * float(np.abs(want_v).max()))
+
+
+def _unfold(images, ph, pw, sh, sw):
+    """The reference's CPU patchify (mnist_dataset.py:47-53), batched."""
+    p = images.unfold(2, ph, sh).unfold(3, pw, sw)              # (B, C, nr, nc, ph, pw)
+    B, C, nr, nc = p.shape[:4]
+    return p.permute(0, 2, 3, 1, 4, 5).reshape(B, nr * nc, C, ph, pw).contiguous()
+
+
+@pytest.mark.parametrize('pre,img,stride,precision', [('traffic', (300, 500), None, 'bf16'), ('mnist', (250, 300), (25, 25), 'bf16'),
+                                                      ('mnist', (250, 300), (25, 25), 'fp32'), ('traffic', (301, 507), (67, 101), 'bf16')])
+def test_ips_image_equals_ips_of_unfolded_patches(pre, img, stride, precision):
+    """On-device patchify: reading the patch grid straight out of the images gives the same winners,
+    bit for bit, as ips() on the reference's unfolded patch tensor -- also for overlapping and odd strides."""
+    conf = O.preset(pre, attn_dropout=0.0, dropout=0.0)
+    ph, pw = conf.patch_size
+    sh, sw = stride or (ph, pw)
+    B = 3
+    g = torch.Generator(device=DEV).manual_seed(52)
+    images = torch.randn((B, conf.n_chan_in, *img), generator=g, device=DEV)
+    patches = _unfold(images, ph, pw, sh, sw)
+    N = patches.shape[1]
+    conf = conf.replace(N=N, M=min(conf.M, 20), I=min(conf.I, 20))
+    sd = O.make_state(conf, 51, q_gain=12.0)
+    net = _net(conf, sd, precision)
+    from ips_b200 import ops
+    geo, n = ops.image_geo(images, (ph, pw), (sh, sw))
+    assert n == N and torch.equal(ops.gather_patches_image(images, geo, None, (ph, pw)), patches)
+    torch.manual_seed(5)
+    a_patch, a_pos = net.ips(patches)
+    a_idx = net.last_mem_idx.clone()
+    torch.manual_seed(5)
+    b_patch, b_pos = net.ips_image(images, (ph, pw), (sh, sw))
+    assert torch.equal(a_idx, net.last_mem_idx)
+    assert torch.equal(a_patch, b_patch)
+    assert (a_pos is None and b_pos is None) or torch.equal(a_pos, b_pos)
+
+
+def test_ips_writes_into_train_buffers():
+    """Batch assembly: ips(out=..., row_offset=n_prep) fills the init_batch buffers in place
+    exactly as fill_batch (training/iterative.py:31-50) would."""
+    z, meta, conf, sd, patches = load_case('mnist_small')
+    net = _net(conf, sd, 'fp32')
+    B = patches.shape[0]
+    x = patches.to(DEV)
+    torch.manual_seed(2)
+    ref_patch, ref_pos = net.ips(x)
+    buf_patch = torch.zeros((2 * B + 1, conf.M, *x.shape[2:]), device=DEV)
+    buf_pos = torch.zeros((2 * B + 1, conf.M, conf.D), device=DEV)
+    torch.manual_seed(2)
+    got_patch, got_pos = net.ips(x, out=(buf_patch, buf_pos), row_offset=B)
+    assert got_patch.data_ptr() == buf_patch[B].data_ptr()
+    assert torch.equal(buf_patch[B:2 * B], ref_patch) and torch.equal(buf_pos[B:2 * B], ref_pos)
+    assert float(buf_patch[:B].abs().max()) == 0.0 and float(buf_patch[2 * B:].abs().max()) == 0.0
