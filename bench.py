@@ -253,32 +253,42 @@ def run_ours(args):
         n_calls = B_train // B
         labels_t = {k: (v.repeat(n_calls, *([1] * (v.dim() - 1)))) for k, v in labels.items()}
 
+        # forward + loss + backward + AdamW of the B_train x M winners as ONE CUDA graph over static buffers; every
+        # ips() call writes its winners straight into them (ips_b200/train.py)
+        from ips_b200.train import GraphedTrainStep
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=conf.wd, capturable=True)
+        hook = None
+        if world > 1:
+            from ips_b200.distributed import allreduce_gradients
+            hook = allreduce_gradients
+        gstep = GraphedTrainStep(net, conf, opt, B_train, grad_hook=hook)
+        for k, v in labels_t.items():
+            gstep.labels[k].copy_(v)
+        for i in range(n_calls):
+            net.ips(x, out=gstep.buffers, row_offset=i * B)
+        graphed = True
+        try:
+            gstep.capture()
+        except Exception as e:                      # e.g. a collective that cannot be captured: eager step
+            graphed = False
+            sys.stderr.write('train step: CUDA-graph capture failed (%s); running eagerly\n' % (e,))
+
         def train_step():
-            parts = [net.ips(x) for _ in range(n_calls)]
-            mem_patch = torch.cat([p_[0] for p_ in parts], 0) if n_calls > 1 else parts[0][0]
-            mem_pos = None if parts[0][1] is None else (torch.cat([p_[1] for p_ in parts], 0) if n_calls > 1 else parts[0][1])
-            opt.zero_grad(set_to_none=True)
-            preds = net(mem_patch, mem_pos)
-            loss = 0
-            for task in conf.tasks.values():
-                pr = preds[task['name']].squeeze(-1)
-                if task['act_fn'] == 'softmax':
-                    loss = loss + Fn.nll_loss(torch.log(pr + conf.eps), labels_t[task['name']])
-                else:
-                    loss = loss + Fn.binary_cross_entropy(pr.view(-1), labels_t[task['name']].view(-1))
-            (loss / len(conf.tasks)).backward()
-            if world > 1:
-                from ips_b200.distributed import allreduce_gradients
-                allreduce_gradients(list(net.parameters()))
-            opt.step()
+            for i in range(n_calls):
+                net.ips(x, out=gstep.buffers, row_offset=i * B)
+            if graphed:
+                gstep()
+            else:
+                gstep._step()
 
         tsteps = max(2, min(args.steps, 5))
         train_step(); train_step()
         ms_t = timed(train_step, tsteps)
         train = {'metric': 'train_images_per_sec', 'value': world * B_train * tsteps / (ms_t / 1e3), 'ms_per_step': ms_t / tsteps,
                  'images_per_step': B_train, 'ips_calls_per_step': n_calls,
+                 'graphed': graphed,
                  'note': 'ips(), every nn.Linear, LayerNorm, BatchNorm1d and the attention core run forward AND backward on the '
-                         'library kernels; the conv encoder\'s grad-mode half, elementwise glue and AdamW are PyTorch (round 1)'}
+                         'library kernels (conv encoder: tcgen05 forward, dgrad and wgrad), replayed as one CUDA graph; pooling / residual / ReLU glue and AdamW are PyTorch ops inside the graph'}
 
     # ---- roofline of the dominant kernel family (per-launch CUDA events, same work) ---
     roof = None

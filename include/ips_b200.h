@@ -78,6 +78,11 @@ IPSB_API int ipsb_stage_image_s2d(const float* img, const ipsb_image_geo* geo, i
 IPSB_API int ipsb_gather_patches_image(const float* img, const ipsb_image_geo* geo, const int64_t* idx, int B, int M, int C, int H, int W,
                               float* out, void* stream);
 
+/* im2col rows for the weight-gradient GEMM of the conv encoder's backward pass (A12): x (P,H,W,C) bf16 channels-last ->
+ * out (P*Ho*Wo, Kp) bf16, column (r*kw+s)*C + c, zero beyond kh*kw*C; Kp a multiple of 8. */
+IPSB_API int ipsb_im2col_bf16(const void* x, void* out, int64_t P, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp,
+                              void* stream);
+
 /* conv1 -> bn1 -> relu -> maxpool (architecture/ips_net.py:17-39) in one kernel: s2d frame of P patches of HxW ->
  * padded-flat (ipsb_pf_rows(P, Hq, Wq), 64) bf16 with Hq = (H/2 - 1)/2 + 1; the stem output stays in shared memory.
  * w: (64, 256) bf16 in the mode-4 packing; y's pad rows must already be zero (they are not written). */

@@ -48,6 +48,7 @@ SIGNATURES = {
     'ipsb_stage_patches_s2d': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_stage_image_s2d': [_ptr, ctypes.POINTER(ImageGeo), _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_gather_patches_image': [_ptr, ctypes.POINTER(ImageGeo), _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
+    'ipsb_im2col_bf16': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_maxpool3x3s2_pf_strided': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_stem_pool_s2d': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_conv_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],

@@ -8,6 +8,11 @@ time; an operator without an entry here still runs on PyTorch autograd.
     grad input     NN GEMM   dx = dy W
     grad weight    TN GEMM   dW = dy^T x   (MN-major operands, split-K, deterministic)
     grad bias      column sum
+
+`ConvFn` / `StemConvFn` -- bias-free conv2d of the patch encoder on channels-last activations (A12)
+    forward        tcgen05 implicit GEMM (the kernels of the selection pass)
+    grad input     the same kernel on dy (zero-dilated for stride 2) with flipped, transposed weights
+    grad weight    im2col rows (`ipsb_im2col_bf16`) x dy as a TN GEMM (split over the pixels, deterministic)
 """
 import torch
 from torch import nn
@@ -194,3 +199,124 @@ class CrossAttentionFn(torch.autograd.Function):
                   _p(dk), _p(dv), B, M, H, Dk, Dv, T, ops._stream())
         dq = ops.colsum(dq_part).view(T, H * Dk)
         return dq, dk, dv, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# conv encoder, grad mode (architecture/ips_net.py:17-52 under net.train(): `self.encoder(...)` at :273-274)
+# ----------------------------------------------------------------------------------------
+
+_CONST = {}
+
+
+def _ones_zeros(n, device):
+    key = (n, str(device))
+    if key not in _CONST:
+        _CONST[key] = (torch.ones(n, dtype=torch.float32, device=device), torch.zeros(n, dtype=torch.float32, device=device))
+    return _CONST[key]
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def _conv_wgrad(xb, dyb, kh, kw, stride, pad):
+    """dW[co, r, s, c] = sum_m dy[m, co] * im2col(x)[m, (r, s, c)] -> (Cout, kh, kw, C) fp32."""
+    P, H, W, C = xb.shape
+    Cout = dyb.shape[-1]
+    K = kh * kw * C
+    dy2 = dyb.reshape(-1, Cout)
+    # the long side (K = kh*kw*C) goes to the GEMM's M (multiple of 128), Cout to its N: dW^T = im2col(x)^T dy
+    xcol = ops.im2col_bf16(xb, kh, kw, stride, pad, _round_up(K, 128))
+    dw = ops.gemm_bf16('tn', xcol, dy2)[:K].t()                         # (Kp, Cout) -> (Cout, K)
+    return dw.reshape(Cout, kh, kw, C)
+
+
+class ConvFn(torch.autograd.Function):
+    """y = conv2d(x, weight, stride, pad) without bias; x, y channels-last (P, H, W, C) fp32, bf16 tensor-core math."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        xb = ops.cast_bf16(x.contiguous().float())
+        Cout, Cin, kh, kw = weight.shape
+        w_nk = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).to(torch.bfloat16).contiguous()
+        one, zero = _ones_zeros(Cout, x.device)
+        y = ops.conv_bf16(xb, w_nk, one, zero, None, Cout, kh, kw, stride, pad, False, 0)
+        ctx.save_for_backward(xb, weight)
+        ctx.stride, ctx.pad = stride, pad
+        return y.float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight = ctx.saved_tensors
+        stride, pad = ctx.stride, ctx.pad
+        Cout, Cin, kh, kw = weight.shape
+        P, H, W, _ = xb.shape
+        Ho, Wo = dy.shape[1], dy.shape[2]
+        dyb = ops.cast_bf16(dy.contiguous().float())
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # dx = conv(dy zero-dilated to the input grid, weights flipped and transposed, pad k-1-p)
+            wt = weight.detach().float().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout).to(torch.bfloat16).contiguous()
+            g = dyb
+            if stride != 1:
+                g = torch.zeros((P, H, W, Cout), dtype=torch.bfloat16, device=dy.device)
+                g[:, ::stride, ::stride][:, :Ho, :Wo] = dyb
+            one, zero = _ones_zeros(Cin, dy.device)
+            dx = ops.conv_bf16(g, wt, one, zero, None, Cin, kh, kw, 1, kh - 1 - pad, False, 0).float()
+        if ctx.needs_input_grad[1]:
+            dw = _conv_wgrad(xb, dyb, kh, kw, stride, pad).permute(0, 3, 1, 2).contiguous()
+        return dx, dw, None, None
+
+
+class StemConvFn(torch.autograd.Function):
+    """The 7x7/2 stem on (P, C, H, W) fp32 patches -> (P, H/2, W/2, 64) fp32 channels-last (no input gradient)."""
+
+    @staticmethod
+    def forward(ctx, patches, weight):
+        P, C, H, W = patches.shape
+        Cout, Cin, kh, kw = weight.shape
+        xb = ops.stage_patches(patches.contiguous().float(), P, C, H, W, ops.BF16)          # (P,H,W,4) bf16
+        wp = torch.zeros((Cout, 8, 8, 4), dtype=torch.float32, device=patches.device)       # k = r*32 + (s+1)*4 + c
+        wp[:, :kh, 1:kw + 1, :Cin] = weight.detach().float().permute(0, 2, 3, 1)
+        one, zero = _ones_zeros(Cout, patches.device)
+        y = ops.conv_bf16(xb, wp.reshape(Cout, 256).to(torch.bfloat16), one, zero, None, Cout, kh, kw, 2, 3, False, 1)
+        ctx.save_for_backward(xb, weight)
+        return y.float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight = ctx.saved_tensors
+        Cout, Cin, kh, kw = weight.shape
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dyb = ops.cast_bf16(dy.contiguous().float())
+            dw = _conv_wgrad(xb, dyb, kh, kw, 2, 3)[..., :Cin].permute(0, 3, 1, 2).contiguous()
+        return None, dw
+
+
+def _bn2d_train(x, bn, relu):
+    """nn.BatchNorm2d in batch-statistics mode on channels-last activations (rows = pixels)."""
+    C = x.shape[-1]
+    y = BatchNormTrainFn.apply(x.reshape(-1, C), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    return y.view(x.shape)
+
+
+def conv_encoder_train(encoder, patches):
+    """Grad-mode forward of the truncated ResNet-18 (`encoder` = the nn.Sequential of ips_net.py:34-50) on
+    (P, C, H, W) patches; every convolution and BatchNorm runs forward and backward on the library's kernels.
+    Max-pool, residual add, ReLU and the average pool are PyTorch elementwise / reduction glue."""
+    mods = list(encoder.children())
+    x = StemConvFn.apply(patches, mods[0].weight)
+    x = _bn2d_train(x, mods[1], True)
+    x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+    for layer in mods[4:-1]:
+        for blk in layer:
+            idt = x
+            y = _bn2d_train(ConvFn.apply(x, blk.conv1.weight, blk.stride, 1), blk.bn1, True)
+            y = _bn2d_train(ConvFn.apply(y, blk.conv2.weight, 1, 1), blk.bn2, False)
+            if blk.downsample is not None:
+                idt = _bn2d_train(ConvFn.apply(x, blk.downsample[0].weight, blk.stride, 0), blk.downsample[1], False)
+            x = torch.relu(y + idt)
+    return x.mean(dim=(1, 2))

@@ -164,6 +164,48 @@ __global__ void gather_patches_image_kernel(const float* __restrict__ img, const
     }
 }
 
+// im2col of a channels-last bf16 tensor for the weight-gradient GEMM: out[m, (r*kw+s)*C + c] = x[p, oy*stride+r-pad,
+// ox*stride+s-pad, c] (zero outside), m = (p*Ho + oy)*Wo + ox; columns >= kh*kw*C are zero.  One thread per 16-byte chunk.
+__global__ void im2col_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t M, int H, int W, int C, int Ho, int Wo,
+                                   int kh, int kw, int stride, int pad, int Kp) {
+    const int chunks = Kp / 8;
+    const int K = kh * kw * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M * chunks; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / chunks;
+        const int k0 = (int)(i - m * chunks) * 8;
+        const int ox = (int)(m % Wo);
+        const int64_t t = m / Wo;
+        const int oy = (int)(t % Ho);
+        const int64_t p = t / Ho;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (C % 8 == 0) {
+            if (k0 < K) {
+                const int tap = k0 / C, c0 = k0 - tap * C;
+                const int r = tap / kw, sx = tap - r * kw;
+                const int iy = oy * stride + r - pad, ix = ox * stride + sx - pad;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                    v = *reinterpret_cast<const uint4*>(x + ((p * H + iy) * W + ix) * (int64_t)C + c0);
+            }
+        } else {
+            __align__(16) bf16 e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j;
+                float val = 0.f;
+                if (k < K) {
+                    const int tap = k / C, c = k - tap * C;
+                    const int r = tap / kw, sx = tap - r * kw;
+                    const int iy = oy * stride + r - pad, ix = ox * stride + sx - pad;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __bfloat162float(x[((p * H + iy) * W + ix) * (int64_t)C + c]);
+                }
+                e[j] = __float2bfloat16_rn(val);
+            }
+            v = *reinterpret_cast<const uint4*>(e);
+        }
+        *reinterpret_cast<uint4*>(out + m * Kp + k0) = v;
+    }
+}
+
 // dst row (b,m) <- src row; grid.x = rows, grid.y = 16 KB segments of a row
 __global__ void gather_rows16_kernel(const unsigned char* __restrict__ src, int64_t batch_stride_rows,
                                      const int64_t* __restrict__ idx, int M, int64_t row_bytes,
@@ -505,6 +547,16 @@ int ipsb_gather_patches_image(const float* img, const ipsb_image_geo* g, const i
     IPSB_REQUIRE(idx != nullptr || M == g->n_per_image, "gather_patches_image: patchify needs M == n_per_image");
     dim3 grid((unsigned)(B * (int64_t)M), (unsigned)C);
     gather_patches_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, geo, idx, M, C, H, W, out);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_im2col_bf16(const void* x, void* out, int64_t P, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp, void* stream) {
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    IPSB_REQUIRE(P > 0 && Ho > 0 && Wo > 0 && Kp % 8 == 0 && Kp >= kh * kw * C, "im2col: bad sizes (Kp=%d, K=%d)", Kp, kh * kw * C);
+    const int64_t M = P * Ho * Wo;
+    im2col_bf16_kernel<<<grid_for(M * (Kp / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, M, H, W, C, Ho, Wo, kh, kw,
+                                                                                     stride, pad, Kp);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

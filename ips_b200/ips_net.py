@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .autograd import Linear, LayerNormFn, BatchNormTrainFn
+from .autograd import Linear, LayerNormFn, BatchNormTrainFn, conv_encoder_train
 from .transformer import Transformer, pos_enc_1d
 from .utils import scan_order
 
@@ -126,6 +126,8 @@ class IPSNet(nn.Module):
         self.chunk_patches = int(os.environ.get('IPS_B200_CHUNK', getattr(conf, 'chunk_patches', 0)))   # 0 = auto
         # chunks in flight inside the native executor (internal streams); 1 = strictly sequential
         self.lanes = int(os.environ.get('IPS_B200_LANES', getattr(conf, 'lanes', 2)))
+        # grad-mode conv encoder: 'native' = library kernels forward and backward (bf16 precision), 'torch' = cuDNN autograd
+        self.train_encoder = os.environ.get('IPS_B200_TRAIN_ENCODER', getattr(conf, 'train_encoder', 'native'))
         # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
         self.executor = os.environ.get('IPS_B200_EXECUTOR', 'native')
         self._ws_cache = {}
@@ -540,6 +542,10 @@ class IPSNet(nn.Module):
             with torch.no_grad():
                 bn.num_batches_tracked += 1
             mem_emb = mem_emb.view(B, M, -1)
+        elif (self.is_image and mem_patch.is_cuda and self.training and self.precision == 'bf16'
+              and self.train_encoder == 'native' and self.encoder[0].out_channels == 64):
+            # conv encoder on the library's kernels, forward and backward (ips_b200/autograd.py::conv_encoder_train)
+            mem_emb = conv_encoder_train(self.encoder, mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
         else:
             mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
         if torch.is_tensor(mem_pos):

@@ -99,6 +99,18 @@ def conv_stem_s2d(frame, w_nk, scale, shift, P, H, W, Cout=64, relu=True):
     return y
 
 
+def im2col_bf16(x, kh, kw, stride, pad, Kp=None):
+    """(P,H,W,C) bf16 channels-last -> (P*Ho*Wo, Kp) bf16 im2col rows, column (r*kw+s)*C + c, zero padded to Kp."""
+    _chk(x, torch.bfloat16, 'x')
+    P, H, W, C = x.shape
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    K = kh * kw * C
+    Kp = K if Kp is None else Kp
+    out = torch.empty((P * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
+    _call('ipsb_im2col_bf16', _p(x), _p(out), P, H, W, C, kh, kw, stride, pad, Kp, _stream())
+    return out
+
+
 def stem_pool_s2d(frame, w_nk, scale, shift, P, H, W, relu=True, out=None):
     """Fused 7x7/2 stem + BN + ReLU + 3x3/2 max-pool on the s2d frame -> padded-flat (rows, 64) bf16."""
     _chk(frame, torch.bfloat16, 'frame'); _chk(w_nk, torch.bfloat16, 'w')

@@ -1,0 +1,112 @@
+"""Train-step runtime: the grad-mode half of one batch as ONE CUDA graph.
+
+The reference's step (training/iterative.py:124-171) is
+    for each loader batch:  mem_patch_iter, mem_pos_iter = net.ips(patches)      # no-grad selection
+                            fill_batch(mem_patch, mem_pos, labels, ...)          # copy into the train buffers
+    preds = net(mem_patch, mem_pos); loss = compute_loss(...); loss.backward(); optimizer.step()
+The second half touches only B x M selected patches: ~500 small kernels whose launch latency, not their work,
+sets the step time.  `GraphedTrainStep` captures forward + loss + backward + optimizer step once into a CUDA graph
+over static buffers -- `net.ips(..., out=step.buffers, row_offset=n_prep)` writes the winners straight into them
+ -- and replays it per batch.  RNG-consuming ops (dropout) stay correct under replay through
+PyTorch's graph-safe CUDA generator.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def compute_loss(conf, preds, labels):
+    """Mean over tasks of NLLLoss(log(p + eps)) / BCELoss(p) (training/iterative.py:83-98, criteria main.py:53-61)."""
+    loss = 0
+    for task in conf.tasks.values():
+        p = preds[task['name']].squeeze(-1)
+        y = labels[task['name']]
+        if task['act_fn'] == 'softmax':
+            loss = loss + F.nll_loss(torch.log(p + conf.eps), y)
+        else:
+            loss = loss + F.binary_cross_entropy(p.view(-1), y.view(-1).to(p.dtype))
+    return loss / len(conf.tasks)
+
+
+class GraphedTrainStep:
+    """forward + loss + backward + optimizer.step of an IPSNet as a replayable CUDA graph.
+
+    buffers   `mem_patch` (B, M, ...), `mem_pos` (B, M, D) or None, `labels` {task: tensor}: static inputs; fill them
+              (e.g. `net.ips(x, out=(step.mem_patch, step.mem_pos), row_offset=n_prep)`, `step.labels[k].copy_(...)`)
+              and call the object.
+    optimizer must be created with `capturable=True` (its step counter lives on the device).
+    grad_hook optional callable run after backward inside the graph (e.g. NCCL all-reduce of the gradients).
+    """
+
+    def __init__(self, net, conf, optimizer, batch_size, loss_fn=compute_loss, grad_hook=None, warmup=3):
+        dev = net.device
+        self.net, self.conf, self.opt, self.loss_fn, self.grad_hook = net, conf, optimizer, loss_fn, grad_hook
+        M = min(net.M, getattr(conf, 'N', net.M)) if getattr(conf, 'N', None) else net.M
+        if conf.is_image:
+            self.mem_patch = torch.zeros((batch_size, M, conf.n_chan_in, *conf.patch_size), device=dev)
+        else:
+            self.mem_patch = torch.zeros((batch_size, M, conf.n_chan_in), device=dev)
+        self.mem_pos = torch.zeros((batch_size, M, net.D), device=dev) if net.use_pos else None
+        self.labels = {}
+        for task in conf.tasks.values():
+            if task['metric'] == 'multilabel_accuracy':
+                self.labels[task['name']] = torch.zeros((batch_size, conf.n_class), dtype=torch.float32, device=dev)
+            elif task['act_fn'] == 'sigmoid':
+                self.labels[task['name']] = torch.zeros((batch_size,), dtype=torch.float32, device=dev)
+            else:
+                self.labels[task['name']] = torch.zeros((batch_size,), dtype=torch.int64, device=dev)
+        self.loss = torch.zeros((), device=dev)
+        self.graph = None
+        self._warmup = warmup
+
+    @property
+    def buffers(self):
+        return self.mem_patch, self.mem_pos
+
+    def _step(self):
+        self.opt.zero_grad(set_to_none=False)
+        preds = self.net(self.mem_patch, self.mem_pos)
+        loss = self.loss_fn(self.conf, preds, self.labels)
+        loss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook([p for p in self.net.parameters() if p.grad is not None])
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def capture(self, restore_state=True):
+        """Warm up on a side stream (lazy workspaces, kernel attributes, autograd buffers, optimizer state), then
+        capture.  The warm-up steps are real steps on whatever the buffers hold; with `restore_state` the parameters,
+        BatchNorm statistics and optimizer state are put back in place afterwards (the graph keeps their addresses)."""
+        dev = self.net.device
+        snap = None
+        if restore_state:
+            snap = ([p.detach().clone() for p in self.net.parameters()], [b.detach().clone() for b in self.net.buffers()],
+                    {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for p, st in self.opt.state.items()})
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        if snap is not None:
+            with torch.no_grad():
+                for p, v in zip(self.net.parameters(), snap[0]):
+                    p.copy_(v)
+                for b, v in zip(self.net.buffers(), snap[1]):
+                    b.copy_(v)
+                for p, st in self.opt.state.items():
+                    old = snap[2].get(id(p))
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.copy_(old[k]) if old is not None else v.zero_()
+        return self
+
+    def __call__(self):
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.loss

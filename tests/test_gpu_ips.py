@@ -311,3 +311,51 @@ def test_ips_writes_into_train_buffers():
     assert got_patch.data_ptr() == buf_patch[B].data_ptr()
     assert torch.equal(buf_patch[B:2 * B], ref_patch) and torch.equal(buf_pos[B:2 * B], ref_pos)
     assert float(buf_patch[:B].abs().max()) == 0.0 and float(buf_patch[2 * B:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('name', ['traffic_small', 'mnist_small', 'camelyon_batch'])
+def test_graphed_train_step_equals_eager(name):
+    """The CUDA-graph train step (forward + loss + backward + AdamW) replays to the same parameters as the eager
+    step from the same state, and keeps doing so on new buffer contents."""
+    from ips_b200.train import GraphedTrainStep, compute_loss
+    z, meta, conf, sd, patches = load_case(name)
+    conf = conf.replace(attn_dropout=0.0, dropout=0.0)
+    B = meta['B']
+
+    def fresh():
+        net = _net(conf, sd, 'bf16')
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=conf.wd, capturable=True)
+        return net, opt
+
+    batches = []
+    g = torch.Generator().manual_seed(77)
+    for i in range(2):
+        torch.manual_seed(meta['rng_seed'] + i)
+        mp, mpos, _ = O.ips(sd, conf, patches + 0.05 * i * torch.randn(patches.shape, generator=g), perm='draw', tie='topk')
+        batches.append((mp.to(DEV), None if mpos is None else mpos.to(DEV),
+                        {k: v.to(DEV) for k, v in O.make_labels(conf, B, meta['label_seed'] + i).items()}))
+
+    net_e, opt_e = fresh()
+    losses_e = []
+    for mp, mpos, lab in batches:
+        opt_e.zero_grad(set_to_none=False)
+        loss = compute_loss(conf, net_e(mp, mpos), lab)
+        loss.backward()
+        opt_e.step()
+        losses_e.append(loss.item())
+
+    net_g, opt_g = fresh()
+    step = GraphedTrainStep(net_g, conf, opt_g, B)
+    step.mem_patch.copy_(batches[0][0])
+    step.capture()
+    losses_g = []
+    for mp, mpos, lab in batches:
+        step.mem_patch.copy_(mp)
+        if mpos is not None:
+            step.mem_pos.copy_(mpos)
+        for k, v in lab.items():
+            step.labels[k].copy_(v)
+        losses_g.append(step().item())
+    assert np.allclose(losses_g, losses_e, rtol=1e-4, atol=1e-5), (losses_g, losses_e)
+    for (k, a), b in zip(net_e.state_dict().items(), net_g.state_dict().values()):
+        torch.testing.assert_close(b.float(), a.float(), rtol=1e-3, atol=1e-5, msg=k)

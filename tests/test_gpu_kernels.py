@@ -542,3 +542,47 @@ def test_stem_pool_fused(dev, C, H, W, P):
     got = ops.stem_pool_s2d(frame, w, scale, shift, P, H, W)
     assert got.shape == ref.shape
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize('case', [(64, 64, 3, 1, 1, 13, 13), (64, 128, 3, 2, 1, 13, 13), (64, 128, 1, 2, 0, 13, 13),
+                                  (128, 256, 3, 2, 1, 7, 7), (256, 256, 3, 1, 1, 4, 4), (256, 512, 1, 2, 0, 7, 7)])
+def test_conv_autograd_fn(dev, case):
+    """ConvFn: forward, grad input (same kernel, flipped weights, zero-dilated dy for stride 2) and grad weight
+    (im2col x dy, TN GEMM) against torch autograd on the same bf16-rounded operands."""
+    from ips_b200.autograd import ConvFn
+    Cin, Cout, k, s, p, H, W = case
+    P = 11
+    x = _rand(P, H, W, Cin, seed=60).to(torch.bfloat16).float()
+    w = _rand(Cout, Cin, k, k, seed=61, scale=math.sqrt(2.0 / (Cin * k * k))).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv2d(xr.permute(0, 3, 1, 2), wr, stride=s, padding=p).permute(0, 2, 3, 1)
+    dy = _rand(*yr.shape, seed=62).to(torch.bfloat16).float()
+    yr.backward(dy)
+    xd = x.to(dev).requires_grad_(True)
+    wd = w.to(dev).requires_grad_(True)
+    y = ConvFn.apply(xd, wd, s, p)
+    y.backward(dy.to(dev))
+    torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-2, atol=1e-2)
+    for got, ref in ((xd.grad.cpu(), xr.grad), (wd.grad.cpu(), wr.grad)):
+        assert got.shape == ref.shape
+        err = (got - ref).abs().max() / ref.abs().max()
+        assert err < 1e-2, err
+
+
+@pytest.mark.parametrize('C,H,W', [(3, 100, 100), (1, 50, 50), (3, 20, 36)])
+def test_stem_conv_autograd_fn(dev, C, H, W):
+    from ips_b200.autograd import StemConvFn
+    P = 7
+    x = _rand(P, C, H, W, seed=63).to(torch.bfloat16).float()
+    w = _rand(64, C, 7, 7, seed=64, scale=math.sqrt(2.0 / (49 * C))).to(torch.bfloat16).float()
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv2d(x, wr, stride=2, padding=3).permute(0, 2, 3, 1)
+    dy = _rand(*yr.shape, seed=65).to(torch.bfloat16).float()
+    yr.backward(dy)
+    wd = w.to(dev).requires_grad_(True)
+    y = StemConvFn.apply(x.to(dev), wd)
+    y.backward(dy.to(dev))
+    torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-2, atol=1e-2)
+    err = (wd.grad.cpu() - wr.grad).abs().max() / wr.grad.abs().max()
+    assert err < 1e-2, err
