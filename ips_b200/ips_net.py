@@ -138,6 +138,10 @@ class IPSNet(nn.Module):
         stem = os.environ.get('IPS_B200_STEM', 's2d')
         even = self.is_image and ps[0] % 2 == 0 and ps[1] % 2 == 0
         self.stem_mode = {'s2d': 4, 'tma': 3}.get(stem, 1) if even else 1
+        if self.stem_mode == 4 and ps[1] > 240:      # the shifted-window stem keeps 128 + 3*(W/2+3) + 3 frame rows per tile in two TMA boxes
+            self.stem_mode = 1
+        if self.stem_mode == 3 and max(ps) > 480:
+            self.stem_mode = 1
         self.stem_tma = self.stem_mode >= 3
         ops.register_custom_ops()
 

@@ -359,3 +359,22 @@ def test_graphed_train_step_equals_eager(name):
     assert np.allclose(losses_g, losses_e, rtol=1e-4, atol=1e-5), (losses_g, losses_e)
     for (k, a), b in zip(net_e.state_dict().items(), net_g.state_dict().values()):
         torch.testing.assert_close(b.float(), a.float(), rtol=1e-3, atol=1e-5, msg=k)
+
+
+@pytest.mark.parametrize('patch', [(256, 320), (30, 18), (240, 64)])
+def test_ips_unusual_patch_sizes(patch):
+    """Patch sizes beyond the shipped configs: wide patches fall back from the shifted-window stem to the gather
+    stem; the bf16 selection still agrees with the fp32 CPU oracle on a conditioned fixture."""
+    conf = O.preset('traffic', attn_dropout=0.0, dropout=0.0, patch_size=list(patch), N=24, M=4, I=6)
+    sd = O.make_state(conf, 61, q_gain=12.0)
+    patches = O.make_patches(conf, 2, 24, 62)
+    net = _net(conf, sd, 'bf16')
+    torch.manual_seed(9)
+    mp, _ = net.ips(patches.to(DEV))
+    got = net.last_mem_idx.cpu()
+    torch.manual_seed(9)
+    _, _, o_src = O.ips(sd, conf, patches, perm='draw', tie='stable')
+    overlap = np.mean([len(set(got[b].tolist()) & set(o_src[b].tolist())) / conf.M for b in range(2)])
+    assert overlap >= 0.75, overlap
+    for b in range(2):
+        assert torch.equal(mp[b].cpu(), patches[b, got[b]])
