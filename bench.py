@@ -202,7 +202,7 @@ def run_ours(args):
         torch.manual_seed(1234)
         lo_s, hi_s = shard_bounds(N, world)[rank]
         x_local = x[:, lo_s:hi_s].contiguous()
-        step = lambda: ips_sharded(net, x_local, N)
+        step = lambda: ips_sharded(net, x_local, N, mode=args.shard_mode)
     else:
         step = lambda: net.ips(x)
     for _ in range(max(args.warmup, 3)):
@@ -359,7 +359,7 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'strong' if seq else 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': f'{args.workload}: IPSNet.ips, B={B} N={N} M={conf.M} I={conf.I} per GPU',
-                       'precision': args.precision, 'parallelism': (f'sp{world} (patch axis sharded; all-gather of logits, all-reduce of winners)' if seq
+                       'precision': args.precision, 'parallelism': ((f'sp{world} (patch axis sharded; all-gather of logits, replicated loop, all-reduce of winners)' if args.shard_mode == 'exact' else f'sp{world} (patch axis sharded; local top-M per rank, all-gather of M candidates, global re-score, all-reduce of winners)') if seq
                                        else f'dp{world} (independent batches, no collective)'),
                        'l2': f'input {in_bytes / 2**20:.0f} MiB per step > 126 MB L2, no flush needed'},
             'clocks': clk.summary(),
@@ -383,6 +383,9 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary train images/s measurement')
+    ap.add_argument('--shard-mode', default='merge', choices=['exact', 'merge'],
+                    help="--shard sequence: 'merge' = local top-M per rank + candidate merge (north_star; the loop shards), "
+                         "'exact' = logit table all-gathered, loop replicated (bit-identical to one GPU)")
     ap.add_argument('--shard', default='batch', choices=['batch', 'sequence'],
                     help="N>1: 'batch' = every rank scans its own batch (weak scaling); 'sequence' = ONE batch whose patch axis "
                          "is sharded over the ranks (strong scaling, NCCL all-gather of logits + all-reduce of winners)")

@@ -12,6 +12,12 @@ Two modes:
   local-top-M + candidate merge, which changes the softmax context.  The selected
   patches are then assembled with one all-reduce (each rank contributes the rows it owns).
 
+  `mode='merge'` is the scalable schedule of `north_star` / SURVEY 8e: every rank runs the selection loop on ITS slice
+  only (N/R patches, local top-M), the R*M candidates' logits and indices are all-gathered (M*(H*T*4+8) bytes per rank)
+  and every rank re-scores them in one buffer and keeps the global stable top-M.  It matches the sharded-schedule
+  oracle (`oracle/ips_oracle.py::ips_sharded`, parity P5) exactly, and the sequential scan whenever H*n_token == 1;
+  with several heads it differs from the sequential scan in a fraction of a percent of the picks (F5).
+
 `allreduce_gradients` is the data-parallel gradient exchange of the train step.
 """
 import torch
@@ -47,6 +53,12 @@ class _CudaBackend:
         from . import ops
         return ops.gather_rows(local_patches.contiguous(), local_idx.contiguous(), local_patches.shape[1])
 
+    def merge(self, zc, M):
+        """(B, L, HT) candidate logits -> positions (B, M) of the stable top-M of their scores in ONE buffer."""
+        from . import ops
+        ca = self.net.transf.crs_attn
+        return ops.topm_stable(ops.scores_from_logits(zc.contiguous(), ca.H, ca.n_token), M)[1]
+
 
 def gather_logit_table(z_local, N, group=None):
     """All-gather per-rank (B, n_r, HT) slices (n_r may differ by one) into (B, N, HT)."""
@@ -65,10 +77,54 @@ def gather_logit_table(z_local, N, group=None):
     return out
 
 
-def ips_sharded(net, local_patches, N, group=None, backend=None):
+def local_scan_order(net, B, n_local, device):
+    """This rank's scan order of its own slice in 'merge' mode: the reference's shuffle (utils/utils.py:33-58) applied
+    to the slice.  The equivalent single-process permutation is cat_r(lo_r + local_order_r) (block-wise shuffle)."""
+    from .utils import scan_order
+    return scan_order(net.shuffle, net.shuffle_style, B, n_local, device)
+
+
+def _ips_sharded_merge(net, local_patches, N, group, be, lo, hi):
+    R = dist.get_world_size(group)
+    B, n = local_patches.shape[:2]
+    M, dev = net.M, local_patches.device
+    perm, per_inst = local_scan_order(net, B, n, torch.device('cpu'))
+    if perm is not None:
+        perm = perm.to(dev).contiguous()
+    z_local = be.logits(local_patches)                                        # (B, n, HT), true positions via pos_offset
+    if n > M:
+        cand_local = be.select(z_local, perm, per_inst)                       # (B, M) local indices, best first
+    elif perm is None:
+        cand_local = torch.arange(n, device=dev).unsqueeze(0).expand(B, -1).contiguous()
+    else:                                                                     # short slice: everything, in scan order
+        cand_local = (perm if per_inst else perm[:1].expand(B, -1)).contiguous()
+    m = cand_local.shape[1]
+    HT = z_local.shape[-1]
+    zc = be.gather(z_local, cand_local)                                       # (B, m, HT): the candidates' logits
+    # all-gather the candidates (slices not longer than M contribute fewer than M): pad to M rows
+    m_max = min(M, -(-N // R))
+    pad_z = torch.zeros((B, m_max, HT), dtype=zc.dtype, device=dev)
+    pad_i = torch.full((B, m_max), -1, dtype=torch.int64, device=dev)
+    pad_z[:, :m] = zc
+    pad_i[:, :m] = cand_local + lo
+    all_z = [torch.empty_like(pad_z) for _ in range(R)]
+    all_i = [torch.empty_like(pad_i) for _ in range(R)]
+    dist.all_gather(all_z, pad_z, group=group)
+    dist.all_gather(all_i, pad_i, group=group)
+    counts = [min(M, b - a) if (b - a) > M else (b - a) for a, b in shard_bounds(N, R)]
+    zc_all = torch.cat([all_z[r][:, :counts[r]] for r in range(R)], dim=1)
+    cand = torch.cat([all_i[r][:, :counts[r]] for r in range(R)], dim=1)      # (B, <= R*M) original indices, rank order
+    if cand.shape[1] <= M:
+        return cand
+    pos = be.merge(zc_all, M)                                                 # identical on every rank
+    return torch.gather(cand, 1, pos)
+
+
+def ips_sharded(net, local_patches, N, group=None, backend=None, mode='exact'):
     """Sequence-sharded `IPSNet.ips`.  `local_patches` is this rank's slice (B, n_r, ...) of the patch axis in
-    rank order (`shard_bounds(N, world)`).  Returns (mem_patch, mem_pos) on every rank, identical to
-    `net.ips` on the full tensor with the same scan order."""
+    rank order (`shard_bounds(N, world)`).  Returns (mem_patch, mem_pos) on every rank.
+    mode 'exact': identical to `net.ips` on the full tensor with the same scan order (logit table all-gathered, loop
+    replicated).  mode 'merge': local top-M per rank + one global re-score of the R*M candidates (the loop shards)."""
     R = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lo, hi = shard_bounds(N, R)[rank]
@@ -80,6 +136,11 @@ def ips_sharded(net, local_patches, N, group=None, backend=None):
     be = backend or _CudaBackend(net)
     be.pos_offset = lo
     dev = local_patches.device
+    if mode == 'merge':
+        mem_src = _ips_sharded_merge(net, local_patches, N, group, be, lo, hi)
+        return _assemble(net, be, local_patches, mem_src, lo, hi, group)
+    if mode != 'exact':
+        raise ValueError("mode must be 'exact' or 'merge'")
 
     # scan order: drawn once (same RNG calls as the reference) on rank 0, broadcast to all ranks
     from .utils import scan_order
@@ -99,8 +160,12 @@ def ips_sharded(net, local_patches, N, group=None, backend=None):
     z_local = be.logits(local_patches)                               # (B, n_r, HT)
     z = gather_logit_table(z_local, N, group)                         # (B, N, HT) everywhere
     mem_src = be.select(z, perm, per_inst)                            # (B, M) original indices, identical on all ranks
-    net.last_mem_idx = mem_src
+    return _assemble(net, be, local_patches, mem_src, lo, hi, group)
 
+
+def _assemble(net, be, local_patches, mem_src, lo, hi, group):
+    """Winners (original indices, identical on all ranks) -> (mem_patch, mem_pos): every rank contributes its rows."""
+    net.last_mem_idx = mem_src
     owned = (mem_src >= lo) & (mem_src < hi)
     local_idx = torch.where(owned, mem_src - lo, torch.full_like(mem_src, -1))      # -1 -> zero row
     mem_patch = be.gather(local_patches, local_idx)

@@ -54,10 +54,64 @@ class OracleBackend:
             out.append(order[final])
         return torch.stack(out)
 
+    def merge(self, zc, M):
+        conf = self.conf
+        zz = zc.view(zc.shape[0], -1, conf.H, conf.n_token).permute(0, 2, 3, 1)
+        sc = torch.softmax(zz, -1).mean(1).transpose(1, 2).mean(-1)
+        return torch.sort(sc, dim=-1, descending=True, stable=True)[1][:, :M]
+
     def gather(self, local, local_idx):
         rows = [torch.stack([local[b, i] if i >= 0 else torch.zeros_like(local[b, 0]) for i in local_idx[b].tolist()])
                 for b in range(local.shape[0])]
         return torch.stack(rows)
+
+
+def _worker_merge(rank, world, port, case, ret):
+    """north_star schedule: local top-M per rank, all-gather of the candidates, one global re-score."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from ips_b200 import IPSNet, Struct
+        from ips_b200.distributed import ips_sharded, shard_bounds
+        from golden_util import load_case
+        z, meta, conf, sd, patches = load_case(case)
+        N = patches.shape[1]
+        net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+        net.load_state_dict(sd)
+        lo, hi = shard_bounds(N, world)[rank]
+        torch.manual_seed(100 + rank)                           # every rank shuffles its own slice
+        mem_patch, mem_pos = ips_sharded(net, patches[:, lo:hi].contiguous(), N, backend=OracleBackend(sd, conf), mode='merge')
+        ret['idx%d' % rank] = net.last_mem_idx
+        if rank == 0:
+            ret.update(mem_patch=mem_patch, mem_pos=mem_pos)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', ['camelyon_batch', 'mnist_small'])
+def test_sharded_merge_schedule_world2(case):
+    """P5: the local-top-M + merge schedule equals the sharded-schedule oracle run in one process."""
+    from golden_util import load_case
+    from ips_b200.distributed import shard_bounds
+    z, meta, conf, sd, patches = load_case(case)
+    B, N = patches.shape[:2]
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_merge, args=(2, port, case, ret), nprocs=2, join=True)
+    blocks = []
+    for r, (lo, hi) in enumerate(shard_bounds(N, 2)):           # the equivalent block-wise permutation
+        torch.manual_seed(100 + r)
+        blocks.append(O.draw_permutation(conf, B, hi - lo) + lo)
+    perm = torch.cat(blocks, dim=1)
+    o_patch, o_pos, o_src = O.ips_sharded(sd, conf, patches, R=2, perm=perm, tie='stable')
+    assert torch.equal(ret['idx0'], ret['idx1'])
+    assert torch.equal(ret['idx0'], o_src)
+    assert torch.equal(ret['mem_patch'], o_patch)
+    if conf.use_pos:
+        assert torch.equal(ret['mem_pos'], o_pos)
 
 
 def _worker(rank, world, port, case, ret):
