@@ -107,27 +107,48 @@ __device__ __forceinline__ const float* patch_base(const float* src, const SrcGe
     return src + b * g.img_stride + (int64_t)pr * g.sh * g.row_stride + (int64_t)pc * g.sw;
 }
 
+// VEC2: one thread stages TWO horizontally adjacent frame pixels from one 16-byte load per (row, channel).
+template <bool VEC2>
 __global__ void stage_s2d_kernel(const float* __restrict__ src, const SrcGeo geo, const int64_t* __restrict__ row_idx, int64_t first_row,
                                  int64_t n_rows, int C, int H, int W, int Ys, int Wp, bf16* __restrict__ dst) {
-    const int64_t total = n_rows * Ys * Wp;
+    const int Wt = VEC2 ? (Wp + 1) / 2 : Wp;              // threads per frame row
+    const int64_t total = n_rows * Ys * Wt;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / (Ys * Wp);
-        const int rem = (int)(i - r * (Ys * Wp));
-        const int Yp = rem / Wp, Xp = rem - Yp * Wp;
-        __align__(16) bf16 out[16];
+        const int64_t r = i / (Ys * Wt);
+        const int rem = (int)(i - r * (Ys * Wt));
+        const int Yp = rem / Wt, Xt = rem - Yp * Wt;
+        const int Xp = VEC2 ? 2 * Xt : Xt;
+        __align__(16) bf16 out[VEC2 ? 32 : 16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) out[k] = __float2bfloat16_rn(0.f);
+        for (int k = 0; k < (VEC2 ? 32 : 16); ++k) out[k] = __float2bfloat16_rn(0.f);
         const int y0 = 2 * Yp - 4, x0 = 2 * Xp - 4;
-        if (y0 + 1 >= 0 && y0 < H && x0 + 1 >= 0 && x0 < W) {
+        const int xs = VEC2 ? 4 : 2;                      // input columns covered by this thread
+        if (y0 + 1 >= 0 && y0 < H && x0 + xs - 1 >= 0 && x0 < W) {
             const int64_t srow = row_idx ? row_idx[r] : first_row + r;
             const float* sp = patch_base(src, geo, srow, C, H, W);
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
                 const int y = y0 + dy;
                 if (y < 0 || y >= H) continue;
-                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {             // compile-time indices keep `out` in registers
+                    if (c >= C) break;
                     const float* rowp = sp + (int64_t)c * geo.chan_stride + (int64_t)y * geo.row_stride;
-                    if (geo.pair_ok && x0 >= 0 && x0 + 1 < W) {         // x0 is even: aligned pair
+                    if (VEC2) {
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (x0 >= 0 && x0 + 3 < W) {      // x0 is a multiple of 4: aligned quad
+                            const float4 q = *reinterpret_cast<const float4*>(rowp + x0);
+                            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (x0 + j >= 0 && x0 + j < W) v[j] = rowp[x0 + j];
+                        }
+                        out[(dy * 2 + 0) * 4 + c] = __float2bfloat16_rn(v[0]);
+                        out[(dy * 2 + 1) * 4 + c] = __float2bfloat16_rn(v[1]);
+                        out[16 + (dy * 2 + 0) * 4 + c] = __float2bfloat16_rn(v[2]);
+                        out[16 + (dy * 2 + 1) * 4 + c] = __float2bfloat16_rn(v[3]);
+                    } else if (geo.pair_ok && x0 >= 0 && x0 + 1 < W) {         // x0 is even: aligned pair
                         const float2 v = *reinterpret_cast<const float2*>(rowp + x0);
                         out[(dy * 2 + 0) * 4 + c] = __float2bfloat16_rn(v.x);
                         out[(dy * 2 + 1) * 4 + c] = __float2bfloat16_rn(v.y);
@@ -138,9 +159,13 @@ __global__ void stage_s2d_kernel(const float* __restrict__ src, const SrcGeo geo
                 }
             }
         }
-        uint4* d = reinterpret_cast<uint4*>(dst + i * 16);
+        uint4* d = reinterpret_cast<uint4*>(dst + ((r * Ys + Yp) * Wp + Xp) * 16);
         d[0] = *reinterpret_cast<const uint4*>(&out[0]);
         d[1] = *reinterpret_cast<const uint4*>(&out[8]);
+        if (VEC2 && Xp + 1 < Wp) {
+            d[2] = *reinterpret_cast<const uint4*>(&out[16]);
+            d[3] = *reinterpret_cast<const uint4*>(&out[24]);
+        }
     }
 }
 
@@ -508,8 +533,12 @@ int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t fir
                  "stage_s2d: needs C <= 4 and even H, W");
     const int Ys = H / 2 + 3, Wp = W / 2 + 3;
     const SrcGeo geo{0, (int64_t)H * W, (int64_t)W, 0, 0, 0, 0, 1};
-    stage_s2d_kernel<<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(src, geo, row_idx, first_row, n_rows, C, H, W,
-                                                                                       Ys, Wp, (bf16*)dst);
+    if (W % 4 == 0 && ((uintptr_t)src % 16 == 0))       // rows and patches start 16-byte aligned: two frame pixels per thread
+        stage_s2d_kernel<true><<<grid_for(n_rows * Ys * ((Wp + 1) / 2), 256), 256, 0, (cudaStream_t)stream>>>(
+            src, geo, row_idx, first_row, n_rows, C, H, W, Ys, Wp, (bf16*)dst);
+    else
+        stage_s2d_kernel<false><<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(src, geo, row_idx, first_row, n_rows,
+                                                                                                  C, H, W, Ys, Wp, (bf16*)dst);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
@@ -533,8 +562,13 @@ int ipsb_stage_image_s2d(const float* img, const ipsb_image_geo* g, int64_t firs
     SrcGeo geo;
     if (int rc = make_src_geo(g, C, H, W, img, &geo)) return rc;
     const int Ys = H / 2 + 3, Wp = W / 2 + 3;
-    stage_s2d_kernel<<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(img, geo, nullptr, first_row, n_rows, C, H, W,
-                                                                                       Ys, Wp, (bf16*)dst);
+    const bool quad = (g->img_w % 4 == 0) && (g->stride_w % 4 == 0) && ((uintptr_t)img % 16 == 0);
+    if (quad)
+        stage_s2d_kernel<true><<<grid_for(n_rows * Ys * ((Wp + 1) / 2), 256), 256, 0, (cudaStream_t)stream>>>(
+            img, geo, nullptr, first_row, n_rows, C, H, W, Ys, Wp, (bf16*)dst);
+    else
+        stage_s2d_kernel<false><<<grid_for(n_rows * Ys * Wp, 256), 256, 0, (cudaStream_t)stream>>>(img, geo, nullptr, first_row, n_rows,
+                                                                                                  C, H, W, Ys, Wp, (bf16*)dst);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
