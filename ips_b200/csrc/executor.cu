@@ -153,15 +153,12 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         float* emb_ws = (float*)ws;      ws += align256(chunk * net->D * 4);
         int64_t* pos_idx = (int64_t*)ws;
         const int64_t P = (n_rows - lo < chunk) ? n_rows - lo : chunk;
-        // stage -> stem -> max-pool in sub-chunks whose stem output (the largest activation) stays in L2
+        // stage -> stem (+ max-pool)
         int rc = 0;
         const ipsb_conv_desc& st = net->stem;
         const int hs = out_dim(H, 7, 2, 3), wsz = out_dim(W, 7, 2, 3);
         const int hq = out_dim(hs, 3, 2, 1), wq = out_dim(wsz, 3, 2, 1);
-        const int64_t per_patch = (int64_t)hs * wsz * st.cout * 2;
-        int64_t sub = P;                      // (sub-chunking to keep the stem output in L2 measured slower: smaller grids)
-        (void)per_patch;
-        if (const char* e = getenv("IPSB_STEM_SUB")) { sub = atoll(e); if (sub <= 0 || sub > P) sub = P; }
+        const int64_t sub = P;                // (sub-chunks that keep the stem output in L2 measured slower: smaller grids)
         const pf::Geo gq = pf::make(P, hq, wq);
         for (int64_t s0 = 0; s0 < P; s0 += sub) {
             const int64_t Ps = (P - s0 < sub) ? P - s0 : sub;

@@ -34,7 +34,6 @@ struct HaloParams {
     const bf16* res;      // PF, same geometry as the output, or null
     bf16* y;              // PF output
     int P, H, W, Wp, Sp, G0, Cout, relu;
-    int dbg;              // IPSB_DEBUG bits: 1 skip stores, 2 skip MMAs, 4 load A only for the first tile of a CTA
     int cblocks;          // Cin / 64
     int total_tiles;
     int a_rows;           // rows per TMA box of the A block (single tile: 130 + 2*Wp)
@@ -225,7 +224,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (PAIR ? acc * 2 * BN + wg * BN : wg * BN);
             epi::drain_tile<BN, bf16>(t_row, tempty_bar(acc), sc_smem, sc_smem + p.Cout, pixel, has_res, res_bar(wg), epi::STAGE_BYTES, res_phase,
                                       p.relu, stage, row, 2u + (uint32_t)wg, issuer,
-                                      [&](int s0, uint32_t src) { if (!(p.dbg & 1)) epi::tma_store_2d(&tmC, src, s0, g0); }, load_res);
+                                      [&](int s0, uint32_t src) { epi::tma_store_2d(&tmC, src, s0, g0); }, load_res);
         }
         if (issuer) epi::bulk_wait0();
     }
@@ -283,7 +282,6 @@ int conv3x3_halo(const void* x, const void* w, const float* scale, const float* 
     p.scale = scale; p.shift = shift; p.res = (const bf16*)res; p.y = (bf16*)y;
     p.P = (int)P; p.H = H; p.W = W; p.Wp = g.Wp; p.Sp = g.Sp; p.G0 = g.G0; p.Cout = Cout; p.relu = relu;
     p.cblocks = Cin / BK;
-    { const char* e = getenv("IPSB_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     p.pix_rows = P * (int64_t)g.Sp;
     IPSB_REQUIRE(p.pix_rows + TILE_M < (1ll << 31), "conv3x3_halo: too many rows");
     p.total_tiles = (int)((p.pix_rows + TILE_M - 1) / TILE_M);
@@ -353,7 +351,7 @@ int conv_stem_s2d(const void* x, const void* w, const float* scale, const float*
     const int Ho = H / 2, Wo = W / 2, Wp = Wo + 3, Sp = (Ho + 3) * Wp;
     HaloParams p;
     p.scale = scale; p.shift = shift; p.res = nullptr; p.y = (bf16*)y;
-    p.P = (int)P; p.H = Ho; p.W = Wo; p.Wp = Wp; p.Sp = Sp; p.G0 = 0; p.Cout = Cout; p.relu = relu; p.dbg = 0;
+    p.P = (int)P; p.H = Ho; p.W = Wo; p.Wp = Wp; p.Sp = Sp; p.G0 = 0; p.Cout = Cout; p.relu = relu;
     p.cblocks = 1;
     p.pix_rows = P * (int64_t)Sp;
     IPSB_REQUIRE(p.pix_rows + TILE_M < (1ll << 31), "conv_stem_s2d: too many rows");
