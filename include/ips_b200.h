@@ -233,6 +233,11 @@ IPSB_API int ipsb_residual_layernorm_f32(const float* x, const float* r, int r_r
                                          float* y, int64_t rows, int D, float eps, void* stream);
 /* rows of n logits -> softmax (act 0) or sigmoid (act 1) */
 IPSB_API int ipsb_head_activation_f32(const float* logits, float* y, int rows, int n, int act, void* stream);
+/* Head activation + loss + gradient in one kernel: get_preds (ips_net.py:157-166) followed by compute_loss
+ * (training/iterative.py:83-98).  act 0: softmax, loss = mean_b -log(p[class_idx[b]] + eps); act 1: sigmoid, BCELoss against
+ * float targets (rows, n).  loss (1), dlogits (rows, n) = d loss / d logits or NULL, probs (rows, n) or NULL. */
+IPSB_API int ipsb_head_loss_f32(const float* logits, const int64_t* class_idx, const float* targets, int rows, int n, int act, float eps,
+                                float* loss, float* dlogits, float* probs, void* stream);
 IPSB_API int ipsb_add_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------- grad-mode operators (fp32), forward + backward

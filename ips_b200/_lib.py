@@ -76,6 +76,7 @@ SIGNATURES = {
     'ipsb_select_loop': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_cross_attention_f32': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_residual_layernorm_f32': [_ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
+    'ipsb_head_loss_f32': [_ptr, _ptr, _ptr, _i32, _i32, _i32, _f32, _ptr, _ptr, _ptr, _ptr],
     'ipsb_head_activation_f32': [_ptr, _ptr, _i32, _i32, _i32, _ptr],
     'ipsb_add_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_bn_stats_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],

@@ -320,3 +320,33 @@ def conv_encoder_train(encoder, patches):
                 idt = _bn2d_train(ConvFn.apply(x, blk.downsample[0].weight, blk.stride, 0), blk.downsample[1], False)
             x = torch.relu(y + idt)
     return x.mean(dim=(1, 2))
+
+
+# ----------------------------------------------------------------------------------------
+# heads + loss (get_preds, ips_net.py:157-166, + compute_loss, training/iterative.py:83-98) in one kernel
+# ----------------------------------------------------------------------------------------
+
+class HeadLossFn(torch.autograd.Function):
+    """loss = NLLLoss(log(softmax(z) + eps), y) or BCELoss(sigmoid(z), t), mean reduction; the kernel also writes
+    d loss / d z, so backward is a scale."""
+
+    @staticmethod
+    def forward(ctx, z, labels, act_fn, eps):
+        z2 = z.reshape(z.shape[0], -1).contiguous().float()
+        rows, n = z2.shape
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z2)
+        if act_fn == 'softmax':
+            cls = labels.reshape(rows).contiguous().to(torch.int64)
+            ops._call('ipsb_head_loss_f32', _p(z2), _p(cls), 0, rows, n, 0, float(eps), _p(loss), _p(dz), 0, ops._stream())
+        else:
+            tgt = labels.reshape(rows, n).contiguous().float()
+            ops._call('ipsb_head_loss_f32', _p(z2), 0, _p(tgt), rows, n, 1, float(eps), _p(loss), _p(dz), 0, ops._stream())
+        ctx.save_for_backward(dz)
+        ctx.shape = z.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return (dz * g).view(ctx.shape), None, None, None

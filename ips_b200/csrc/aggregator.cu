@@ -106,6 +106,59 @@ __global__ void head_activation_kernel(const float* __restrict__ zl, float* __re
     for (int i = 0; i < n; ++i) yr[i] = expf(zr[i] - mx) / den;
 }
 
+// Head activation + loss + its gradient in one pass (get_preds, ips_net.py:157-166, + compute_loss,
+// training/iterative.py:83-98).  act 0: p = softmax(z), loss_b = -log(p[y_b] + eps) (NLLLoss of log(p + eps), mean over
+// the batch); act 1: p = sigmoid(z), BCELoss(p, t) with PyTorch's log clamp at -100, mean over all B*n elements.
+// One block; warp w owns rows w, w + nwarps, ...; per-warp partial sums are combined in a fixed order (deterministic).
+__global__ void head_loss_kernel(const float* __restrict__ zl, const int64_t* __restrict__ cls, const float* __restrict__ tgt,
+                                 int rows, int n, int act, float eps, float* __restrict__ loss, float* __restrict__ dz,
+                                 float* __restrict__ probs) {
+    __shared__ float part[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float acc = 0.f;
+    for (int row = warp; row < rows; row += nwarps) {
+        const float* zr = zl + (int64_t)row * n;
+        if (act == 0) {
+            float mx = -INFINITY;
+            for (int i = lane; i < n; i += 32) mx = fmaxf(mx, zr[i]);
+            mx = ipsb::warp_max(mx);
+            float den = 0.f;
+            for (int i = lane; i < n; i += 32) den += expf(zr[i] - mx);
+            den = ipsb::warp_sum(den);
+            const int y = (int)cls[row];
+            const float py = expf(zr[y] - mx) / den;
+            acc += -logf(py + eps);
+            const float g = py / (py + eps) / (float)rows;              // d loss / d z_j = g * (p_j - [j == y])
+            for (int i = lane; i < n; i += 32) {
+                const float pj = expf(zr[i] - mx) / den;
+                if (probs) probs[(int64_t)row * n + i] = pj;
+                if (dz) dz[(int64_t)row * n + i] = g * (pj - (i == y ? 1.f : 0.f));
+            }
+        } else {
+            float a = 0.f;
+            for (int i = lane; i < n; i += 32) {
+                const float p = 1.f / (1.f + expf(-zr[i]));
+                const float t = tgt[(int64_t)row * n + i];
+                const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+                a += -(t * lp + (1.f - t) * lq);
+                if (probs) probs[(int64_t)row * n + i] = p;
+                if (dz) {                                                // clamped branches have zero slope
+                    const float gp = (logf(p) > -100.f ? t * (1.f - p) : 0.f) - (logf(1.f - p) > -100.f ? (1.f - t) * p : 0.f);
+                    dz[(int64_t)row * n + i] = -gp / ((float)rows * (float)n);
+                }
+            }
+            acc += ipsb::warp_sum(a) / (float)n;
+        }
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < nwarps; ++w) tot += part[w];
+        *loss = tot / (float)rows;
+    }
+}
+
 __global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = a[i] + b[i];
@@ -136,6 +189,15 @@ int ipsb_residual_layernorm_f32(const float* x, const float* r, int r_rows, cons
 int ipsb_head_activation_f32(const float* logits, float* y, int rows, int n, int act, void* stream) {
     IPSB_REQUIRE(rows > 0 && n > 0 && (act == 0 || act == 1), "head_activation: bad arguments");
     head_activation_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, y, rows, n, act);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_head_loss_f32(const float* logits, const int64_t* class_idx, const float* targets, int rows, int n, int act, float eps,
+                       float* loss, float* dlogits, float* probs, void* stream) {
+    IPSB_REQUIRE(rows > 0 && n > 0 && loss != nullptr && (act == 0 ? class_idx != nullptr : (act == 1 && targets != nullptr)),
+                 "head_loss: bad arguments");
+    head_loss_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(logits, class_idx, targets, rows, n, act, eps, loss, dlogits, probs);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

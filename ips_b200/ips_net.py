@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .autograd import Linear, LayerNormFn, BatchNormTrainFn, conv_encoder_train
+from .autograd import Linear, LayerNormFn, BatchNormTrainFn, HeadLossFn, conv_encoder_train
 from .transformer import Transformer, pos_enc_1d
 from .utils import scan_order
 
@@ -529,10 +529,10 @@ class IPSNet(nn.Module):
             preds[task['name']] = ops.head_activation(zl, task['act_fn'])
         return preds
 
-    def forward(self, mem_patch, mem_pos=None):
+    def forward(self, mem_patch, mem_pos=None, tokens_only=False):
         """Encode + aggregate the selected patches (ips_net.py:264-283).  Inference (eval mode, no grad) runs on
         the library's kernels; the grad-mode train step uses PyTorch autograd on the same parameters."""
-        if not self.training and not torch.is_grad_enabled() and mem_patch.is_cuda:
+        if not self.training and not torch.is_grad_enabled() and mem_patch.is_cuda and not tokens_only:
             return self._forward_inference(mem_patch, mem_pos)
         shape = mem_patch.shape
         B, M = shape[:2]
@@ -554,4 +554,18 @@ class IPSNet(nn.Module):
             mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
         if torch.is_tensor(mem_pos):
             mem_emb = mem_emb + mem_pos
-        return self.get_preds(self.transf(mem_emb))
+        tok = self.transf(mem_emb)
+        return tok if tokens_only else self.get_preds(tok)
+
+    def loss(self, mem_patch, mem_pos, labels, eps=1e-6):
+        """`compute_loss(net, mem_patch, mem_pos, criterions, labels, conf)` of training/iterative.py:65-100 with the
+        head activations, the losses and their gradients fused into one kernel per task: mean over
+        tasks of NLLLoss(log(softmax + eps)) / BCELoss(sigmoid).  Returns the scalar loss (on the device, no sync)."""
+        tok = self.forward(mem_patch, mem_pos, tokens_only=True)
+        if not tok.is_cuda:
+            raise RuntimeError('ips_b200.IPSNet.loss needs a CUDA device')
+        total = 0
+        for task in self.tasks.values():
+            z = self.output_layers[task['name']][0](tok[:, task['id']])
+            total = total + HeadLossFn.apply(z, labels[task['name']], task['act_fn'], eps)
+        return total / len(self.tasks)

@@ -27,6 +27,11 @@ def compute_loss(conf, preds, labels):
     return loss / len(conf.tasks)
 
 
+def fused_loss(conf, net, mem_patch, mem_pos, labels):
+    """forward + heads + loss with the head activation / loss / gradient kernel (`IPSNet.loss`)."""
+    return net.loss(mem_patch, mem_pos, labels, conf.eps)
+
+
 class GraphedTrainStep:
     """forward + loss + backward + optimizer.step of an IPSNet as a replayable CUDA graph.
 
@@ -37,7 +42,7 @@ class GraphedTrainStep:
     grad_hook optional callable run after backward inside the graph (e.g. NCCL all-reduce of the gradients).
     """
 
-    def __init__(self, net, conf, optimizer, batch_size, loss_fn=compute_loss, grad_hook=None, warmup=3):
+    def __init__(self, net, conf, optimizer, batch_size, loss_fn=compute_loss, grad_hook=None, warmup=3, fuse_loss=True):
         dev = net.device
         self.net, self.conf, self.opt, self.loss_fn, self.grad_hook = net, conf, optimizer, loss_fn, grad_hook
         M = min(net.M, getattr(conf, 'N', net.M)) if getattr(conf, 'N', None) else net.M
@@ -57,6 +62,7 @@ class GraphedTrainStep:
         self.loss = torch.zeros((), device=dev)
         self.graph = None
         self._warmup = warmup
+        self.fuse_loss = fuse_loss and loss_fn is compute_loss      # heads + loss + gradient in one kernel per task
 
     @property
     def buffers(self):
@@ -64,8 +70,10 @@ class GraphedTrainStep:
 
     def _step(self):
         self.opt.zero_grad(set_to_none=False)
-        preds = self.net(self.mem_patch, self.mem_pos)
-        loss = self.loss_fn(self.conf, preds, self.labels)
+        if self.fuse_loss:
+            loss = fused_loss(self.conf, self.net, self.mem_patch, self.mem_pos, self.labels)
+        else:
+            loss = self.loss_fn(self.conf, self.net(self.mem_patch, self.mem_pos), self.labels)
         loss.backward()
         if self.grad_hook is not None:
             self.grad_hook([p for p in self.net.parameters() if p.grad is not None])

@@ -378,3 +378,28 @@ def test_ips_unusual_patch_sizes(patch):
     assert overlap >= 0.75, overlap
     for b in range(2):
         assert torch.equal(mp[b].cpu(), patches[b, got[b]])
+
+
+@pytest.mark.parametrize('name', ['mnist_small', 'traffic_small', 'camelyon_batch'])
+def test_fused_head_loss_matches_compute_loss(name):
+    """IPSNet.loss (heads + NLL/BCE + gradient in one kernel per task) == compute_loss on the
+    probabilities of forward(): value and every parameter gradient."""
+    from ips_b200.train import compute_loss
+    z, meta, conf, sd, patches = load_case(name)
+    conf = conf.replace(attn_dropout=0.0, dropout=0.0)
+    torch.manual_seed(meta['rng_seed'])
+    mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+    labels = {k: v.to(DEV) for k, v in O.make_labels(conf, meta['B'], meta['label_seed']).items()}
+    mp, mpos = mem_patch.to(DEV), None if mem_pos is None else mem_pos.to(DEV)
+    res = []
+    for fused in (False, True):
+        net = _net(conf, sd, 'fp32')
+        loss = net.loss(mp, mpos, labels, conf.eps) if fused else compute_loss(conf, net(mp, mpos), labels)
+        loss.backward()
+        res.append((loss.item(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * max(1.0, abs(res[0][0]))
+    assert res[0][1].keys() == res[1][1].keys()
+    scale = max(float(g.abs().max()) for g in res[0][1].values())      # (some gradients are pure rounding noise: bias before BN)
+    for k in res[0][1]:
+        a, b = res[0][1][k], res[1][1][k]
+        assert (a - b).abs().max() <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, k
