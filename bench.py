@@ -214,7 +214,7 @@ def run_ours(args):
     value = (1 if seq else world) * B * N * args.steps / (ms / 1e3)
 
     # ---- end to end through the public API with HOST buffers ---------------------
-    xh = x.cpu().pin_memory()
+    xh = (x.to(torch.bfloat16) if args.features == 'bf16' and not conf.is_image else x).cpu().pin_memory()
     res_h = torch.empty((B, conf.M, *shape[2:]), dtype=torch.float32).pin_memory()
     idx_h = torch.empty((B, conf.M), dtype=torch.int64).pin_memory()
 
@@ -363,7 +363,7 @@ def run_ours(args):
                                        else f'dp{world} (independent batches, no collective)'),
                        'l2': f'input {in_bytes / 2**20:.0f} MiB per step > 126 MB L2, no flush needed'},
             'clocks': clk.summary(),
-            'e2e': {'value': e2e_value, 'unit': 'patches/s', 'h2d_bytes_per_step': in_bytes,
+            'e2e': {'value': e2e_value, 'unit': 'patches/s', 'h2d_bytes_per_step': xh.numel() * xh.element_size(),
                     'd2h_bytes_per_step': res_h.numel() * 4 + idx_h.numel() * 8, 'ms_per_step': ms_e2e / e2e_steps},
             'gpu_launches': launches,
             'roofline': roof, 'cpu_baseline': cpu, 'train': train,
@@ -383,6 +383,8 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary train images/s measurement')
+    ap.add_argument('--features', default='fp32', choices=['fp32', 'bf16'],
+                    help='feature-bag workloads: dtype of the HOST features of the e2e leg (bf16 = flat bf16 bags, SURVEY 8f N4)')
     ap.add_argument('--shard-mode', default='merge', choices=['exact', 'merge'],
                     help="--shard sequence: 'merge' = local top-M per rank + candidate merge (north_star; the loop shards), "
                          "'exact' = logit table all-gathered, loop replicated (bit-identical to one GPU)")

@@ -148,6 +148,9 @@ IPSB_API int ipsb_colsum_f32(const float* x, const float* y, float* out, float* 
 IPSB_API int ipsb_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 /* fp32 (rows,F) -> bf16 with optional no-affine LayerNorm fused (projector prologue) */
 IPSB_API int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);
+/* the same for features already stored as bf16 (flat bf16 feature bags halve the bytes of the CAMELYON path);
+ * LayerNorm statistics in fp32 on the exactly-upcast values */
+IPSB_API int ipsb_rows_bf16_to_bf16(const void* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);
 
 /* ---------------------------------------------------------------- scoring
  * The learned-query score is linear in the embedding before the softmax:

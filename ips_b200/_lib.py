@@ -68,6 +68,7 @@ SIGNATURES = {
     'ipsb_colsum_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
     'ipsb_cast_bf16': [_ptr, _ptr, _i64, _ptr],
     'ipsb_rows_to_bf16': [_ptr, _ptr, _i64, _i32, _i32, _f32, _ptr],
+    'ipsb_rows_bf16_to_bf16': [_ptr, _ptr, _i64, _i32, _i32, _f32, _ptr],
     'ipsb_score_basis': [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],
     'ipsb_logits': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_scores_from_logits': [_ptr, _ptr, _i32, _i32, _i32, _i32, _ptr],

@@ -410,6 +410,78 @@ __global__ void __launch_bounds__(256) rows_warp_kernel(const float* __restrict_
     }
 }
 
+// bf16 feature bags (features stored as bf16 halve the bytes of the CAMELYON path): warp per row, the row
+// (V x 256 bf16) in registers, LayerNorm statistics in fp32 on the exactly-upcast values -> bf16 GEMM operand
+template <bool kNorm, int V>
+__global__ void __launch_bounds__(256) rows_warp_bf16in_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t rows, float eps) {
+    constexpr int F = V * 256;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int4* xr = reinterpret_cast<const int4*>(x + row * F);
+    float v[V][8];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int4 raw = ipsb::ld_stream16(xr + i * 32 + lane);
+        const bf16* e = reinterpret_cast<const bf16*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(e[j]);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (kNorm) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        mean = ipsb::warp_sum(s) / (float)F;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+        rstd = rsqrtf(ipsb::warp_sum(q) / (float)F + eps);
+    }
+    int4* yr = reinterpret_cast<int4*>(y + row * F);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        __align__(16) bf16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn((v[i][j] - mean) * rstd);
+        yr[i * 32 + lane] = *reinterpret_cast<const int4*>(o);
+    }
+}
+
+// generic width: one block per row, fp32 two-pass statistics
+template <bool kNorm>
+__global__ void rows_bf16in_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int F, float eps) {
+    __shared__ float red[8];
+    __shared__ float stat[2];
+    const bf16* xr = x + (int64_t)blockIdx.x * F;
+    bf16* yr = y + (int64_t)blockIdx.x * F;
+    const int tid = threadIdx.x;
+    float mean = 0.f, rstd = 1.f;
+    if (kNorm) {
+        float s = 0.f;
+        for (int i = tid; i < F; i += blockDim.x) s += __bfloat162float(xr[i]);
+        s = ipsb::warp_sum(s);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) { float t = 0.f; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; stat[0] = t / (float)F; }
+        __syncthreads();
+        mean = stat[0];
+        float q = 0.f;
+        for (int i = tid; i < F; i += blockDim.x) { const float d = __bfloat162float(xr[i]) - mean; q += d * d; }
+        q = ipsb::warp_sum(q);
+        if ((tid & 31) == 0) red[tid >> 5] = q;
+        __syncthreads();
+        if (tid == 0) { float t = 0.f; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; stat[1] = rsqrtf(t / (float)F + eps); }
+        __syncthreads();
+        rstd = stat[1];
+    }
+    for (int i = tid; i < F; i += blockDim.x) yr[i] = __float2bfloat16_rn((__bfloat162float(xr[i]) - mean) * rstd);
+}
+
 // out[c] = sum_r x[r, c] (bias gradients, BatchNorm statistics); one block per 32 columns, fixed order
 __global__ void colsum_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t rows, int cols) {
     __shared__ float part[8][33];
@@ -658,6 +730,22 @@ int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernor
         rows_kernel<bf16, true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, F, eps);
     else
         rows_kernel<bf16, false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, F, eps);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_rows_bf16_to_bf16(const void* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream) {
+    IPSB_REQUIRE(rows > 0 && F > 0, "rows_bf16_to_bf16: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F == 2048 && ((uintptr_t)x % 16 == 0)) {
+        const unsigned g = (unsigned)((rows + 7) / 8);
+        if (layernorm) rows_warp_bf16in_kernel<true, 8><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, eps);
+        else rows_warp_bf16in_kernel<false, 8><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, eps);
+    } else if (layernorm) {
+        rows_bf16in_kernel<true><<<(unsigned)rows, 256, 0, st>>>((const bf16*)x, (bf16*)y, F, eps);
+    } else {
+        rows_bf16in_kernel<false><<<(unsigned)rows, 256, 0, st>>>((const bf16*)x, (bf16*)y, F, eps);
+    }
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -246,7 +246,7 @@ class IPSNet(nn.Module):
         if self.precision == 'bf16':
             a = ops.rows_to_bf16(rows.contiguous(), layernorm=True, eps=1e-5)
             return ops.linear_bf16(a, plan['p_w'], plan['p_scale'], plan['p_shift'], relu=True)
-        a = ops.layernorm_rows(rows.contiguous(), 1e-5)
+        a = ops.layernorm_rows(rows.contiguous().float(), 1e-5)
         return ops.linear_f32(a, plan['p_w'], plan['p_scale'], plan['p_shift'], relu=True)
 
     def _embed_pf(self, plan, flat, row_idx, first_row, n_rows, C, H, W):
@@ -322,7 +322,7 @@ class IPSNet(nn.Module):
             if flat.is_cuda:
                 emb = self.embed(flat, first_row=lo, n_rows=n)
             else:
-                emb = self.embed(flat[lo:lo + n].to(self.device, non_blocking=True).float().contiguous())
+                emb = self.embed(flat[lo:lo + n].to(self.device, non_blocking=True).contiguous())
             z[lo:lo + n] = ops.logits(emb, plan['U'], plan['posU'], None if pos_idx is None else pos_idx[lo:lo + n].contiguous())
         return z.view(B, N, HT)
 
@@ -335,7 +335,8 @@ class IPSNet(nn.Module):
         B, N = patches.shape[:2]
         rows = B * N
         flat_h = patches.reshape(rows, *patches.shape[2:])
-        if flat_h.dtype != torch.float32:
+        keep_bf16 = (not self.is_image) and flat_h.dtype == torch.bfloat16 and self.precision == 'bf16'   # bf16 feature bags
+        if flat_h.dtype != torch.float32 and not keep_bf16:
             flat_h = flat_h.float()
         HT = plan['U'].shape[1]
         # smaller chunks than the resident path: the encoder starts as soon as the first chunk has arrived and only the
@@ -346,7 +347,7 @@ class IPSNet(nn.Module):
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         cs = self._copy_stream
-        dev = torch.empty(flat_h.shape, dtype=torch.float32, device=self.device)
+        dev = torch.empty(flat_h.shape, dtype=flat_h.dtype, device=self.device)
         dev.record_stream(cs)
         cs.wait_stream(main)
         events = []
@@ -441,7 +442,12 @@ class IPSNet(nn.Module):
         self.last_mem_idx = mem_src
 
         o_patch, o_pos = self._out_views(out, row_offset, B, M)
-        if patches.is_cuda:
+        if patches.is_cuda and patches.dtype == torch.bfloat16:   # bf16 feature bag: the winners go to the train step as fp32
+            mem_patch = ops.gather_rows(patches.contiguous(), mem_src, N).float()
+            if o_patch is not None:
+                o_patch.copy_(mem_patch)
+                mem_patch = o_patch
+        elif patches.is_cuda:
             mem_patch = ops.gather_rows(patches.contiguous(), mem_src, N, out=o_patch)
         else:                                                    # lazy loading: gather on the host, :244-247
             host_idx = mem_src.cpu()

@@ -175,8 +175,13 @@ def layernorm_rows(x, eps):
 
 
 def rows_to_bf16(x, layernorm, eps=1e-5):
-    _chk(x, torch.float32, 'x')
+    """(rows, F) fp32 or bf16 features -> bf16 GEMM operand, optionally LayerNorm'ed (no affine) in fp32."""
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.dtype == torch.bfloat16:
+        _chk(x, torch.bfloat16, 'x')
+        _call('ipsb_rows_bf16_to_bf16', _p(x), _p(y), x.shape[0], x.shape[1], int(layernorm), eps, _stream())
+        return y
+    _chk(x, torch.float32, 'x')
     _call('ipsb_rows_to_bf16', _p(x), _p(y), x.shape[0], x.shape[1], int(layernorm), eps, _stream())
     return y
 

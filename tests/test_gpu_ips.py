@@ -403,3 +403,20 @@ def test_fused_head_loss_matches_compute_loss(name):
     for k in res[0][1]:
         a, b = res[0][1][k], res[1][1][k]
         assert (a - b).abs().max() <= 1e-4 * float(a.abs().max()) + 1e-6 * scale, k
+
+
+def test_bf16_feature_bag_equals_upcast_fp32():
+    """bf16-stored feature bags: ips() on the bf16 tensor -- device-resident or streamed from the host --
+    selects exactly what it selects on the same values upcast to fp32, and returns the winners as fp32."""
+    conf = O.preset('camelyon', attn_dropout=0.0, dropout=0.0, M=50, I=70)
+    sd = O.make_state(conf, 71, q_gain=12.0)
+    xb = O.make_patches(conf, 2, 1000, 72).to(torch.bfloat16)
+    net = _net(conf, sd, 'bf16')
+    torch.manual_seed(4)
+    ref_patch, _ = net.ips(xb.float().to(DEV))
+    ref_idx = net.last_mem_idx.clone()
+    for src in (xb.to(DEV), xb.pin_memory()):
+        torch.manual_seed(4)
+        got_patch, _ = net.ips(src)
+        assert torch.equal(net.last_mem_idx, ref_idx)
+        assert got_patch.dtype == torch.float32 and torch.equal(got_patch, ref_patch)

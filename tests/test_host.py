@@ -95,3 +95,25 @@ def test_grad_mode_forward_matches_golden(name):
     assert abs(loss.item() - float(z['loss'])) <= 1e-5 * max(1.0, abs(float(z['loss'])))
     g = net.transf.crs_attn.q.grad.reshape(-1)[:256].numpy()
     np.testing.assert_allclose(g, z['grad_transf.crs_attn.q'], rtol=1e-3, atol=1e-7)
+
+
+def test_feature_bag_roundtrip(tmp_path):
+    """Flat feature-bag file: write fp32 / bf16 bags, read them back memory-mapped with the item layout
+    of the reference's CamelyonFeatures."""
+    import torch
+    from ips_b200.io import FeatureBagWriter, FeatureBags
+    g = torch.Generator().manual_seed(3)
+    slides = [torch.randn(n, 64, generator=g) for n in (5, 130, 1)]
+    tasks = {'task0': {'name': 'metastases'}}
+    for dtype in ('fp32', 'bf16'):
+        path = str(tmp_path / ('bags_%s.bin' % dtype))
+        with FeatureBagWriter(path, 64, dtype) as w:
+            for i, s in enumerate(slides):
+                w.add('slide%d' % i, s, label=i % 2)
+        ds = FeatureBags(path, tasks)
+        assert len(ds) == 3 and ds.slide_names == ['slide0', 'slide1', 'slide2']
+        for i, s in enumerate(slides):
+            item = ds[i]
+            want = s if dtype == 'fp32' else s.to(torch.bfloat16)
+            assert item['input'].dtype == want.dtype and torch.equal(item['input'], want)
+            assert item['metastases'] == i % 2
