@@ -51,6 +51,17 @@ template <typename OutT>
 __device__ __forceinline__ void stage32(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
                                         bool has_res, int relu, uint32_t row_smem, int row, int chunk0);
 
+// packed helpers: two fp32 lanes per instruction (FFMA2 / FADD2), ReLU on the rounded bf16 pair (HMNMX2)
+__device__ __forceinline__ uint64_t fma2(uint32_t v0, uint32_t v1, float s0, float s1, float h0, float h1) {
+    uint64_t o;
+    asm("{\n\t.reg .b64 a, b, c;\n\t"
+        "mov.b64 a, {%1, %2};\n\tmov.b64 b, {%3, %4};\n\tmov.b64 c, {%5, %6};\n\t"
+        "fma.rn.f32x2 %0, a, b, c;\n\t}"
+        : "=l"(o)
+        : "r"(v0), "r"(v1), "r"(__float_as_uint(s0)), "r"(__float_as_uint(s1)), "r"(__float_as_uint(h0)), "r"(__float_as_uint(h1)));
+    return o;
+}
+
 template <>
 __device__ __forceinline__ void stage32<bf16>(const uint32_t (&v)[32], const float* sc, const float* sh, bool pixel,
                                               bool has_res, int relu, uint32_t row_smem, int row, int chunk0) {
@@ -62,30 +73,24 @@ __device__ __forceinline__ void stage32<bf16>(const uint32_t (&v)[32], const flo
         const uint32_t chunk_addr = row_smem + (((uint32_t)(chunk0 + g) ^ (uint32_t)(row & 7)) << 4);
         if (pixel) {
             const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], h0 = sh4[2 * g], h1 = sh4[2 * g + 1];
-            float o[8];
-            o[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, h0.x);
-            o[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, h0.y);
-            o[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, h0.z);
-            o[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, h0.w);
-            o[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, h1.x);
-            o[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, h1.y);
-            o[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, h1.z);
-            o[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, h1.w);
-            if (has_res) {
-                uint4 rv;
+            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res)
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(chunk_addr));
-                const bf16* rb = reinterpret_cast<const bf16*>(&rv);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] += __bfloat162float(rb[i]);
-            }
-            if (relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
-            }
+            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-                w[i] = *reinterpret_cast<uint32_t*>(&h);
+                const uint64_t o = fma2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1], s[2 * i], s[2 * i + 1], h[2 * i], h[2 * i + 1]);
+                float lo = __uint_as_float((uint32_t)o), hi = __uint_as_float((uint32_t)(o >> 32));
+                if (has_res) {                     // bf16 -> fp32 is a 16-bit shift
+                    lo += __uint_as_float(rr[i] << 16);
+                    hi += __uint_as_float(rr[i] & 0xffff0000u);
+                }
+                __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+                uint32_t u = *reinterpret_cast<uint32_t*>(&p);
+                if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(u) : "r"(0u));   // ReLU after rounding == rounding after ReLU
+                w[i] = u;
             }
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"

@@ -52,6 +52,7 @@ struct StemPoolParams {
     int a_rows, n_boxes;     // TMA boxes of one tile's block of frame rows
     uint32_t a_slot_bytes;
     int relu;
+    uint32_t per_row_magic;  // ceil(2^32 / (Wq * 8)): idx / per_row by multiply-high
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -191,18 +192,18 @@ stem_pool_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma::named_bar_sync(1, 128 * NWG);                       // the group's stem rows are staged
             const int rg = min(p.R, p.Hq - pr0);
             for (int idx = et; idx < rg * per_row; idx += 128 * NWG) {
-                const int pr = idx / per_row, rem = idx - pr * per_row;
+                const int pr = (int)(((uint64_t)(uint32_t)idx * p.per_row_magic) >> 32);      // idx / per_row
+                const int rem = idx - pr * per_row;
                 const int px = rem >> 3, ch = rem & 7;
                 uint32_t m0 = 0xff80ff80u, m1 = m0, m2 = m0, m3 = m0;  // -inf
+                // window rows / columns outside the image are clamped onto the border pixel: a duplicate does not change a max
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
-                    const int yy = 2 * (pr0 + pr) - 1 + dy;
-                    if (yy < 0 || yy >= p.Ho) continue;
-                    const int lrow = (2 * pr + dy) * p.Wp;
+                    const int yy = min(max(2 * (pr0 + pr) - 1 + dy, 0), p.Ho - 1);
+                    const int lrow = (yy - (2 * pr0 - 1)) * p.Wp;
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        const int xx = 2 * px - 1 + dx;
-                        if (xx < 0 || xx >= p.Wo) continue;
+                        const int xx = min(max(2 * px - 1 + dx, 0), p.Wo - 1);
                         const uint32_t l = (uint32_t)(lrow + xx);
                         uint32_t a, b, c, d;
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -275,6 +276,7 @@ int ipsb_stem_pool_s2d(const void* frame, const void* w, const float* scale, con
     }
     IPSB_REQUIRE(p.R > 0, "stem_pool: width %d does not fit the staging buffer", W);
     p.total_groups = (int)(P * p.GPP);
+    p.per_row_magic = (uint32_t)(((1ull << 32) + (uint64_t)(p.Wq * 8) - 1) / (uint64_t)(p.Wq * 8));
     alignas(64) CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[2] = {16, (cuuint64_t)frame_rows};
