@@ -246,13 +246,13 @@ IPSB_API int ipsb_add_f32(const float* a, const float* b, float* y, int64_t n, v
 /* ---------------------------------------------------------------- grad-mode operators (fp32), forward + backward
  * BatchNorm1d in batch-statistics mode (ips_net.py:58 under net.train()), LayerNorm backward
  * (transformer.py:107,130) and the cross-attention core with a dropout mask (transformer.py:29-41,98). */
-IPSB_API int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch /* 128*cols floats */, int64_t rows, int cols,
+IPSB_API int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch /* 512*cols floats */, int64_t rows, int cols,
                       void* stream);   /* biased variance, two-stage deterministic reduction */
 IPSB_API int ipsb_bn_apply_f32(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
                       int64_t rows, int cols, int relu, void* stream);
 /* sums (2*cols) = [dbeta, dgamma]; dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*(y>0) when relu */
 IPSB_API int ipsb_bn_backward_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
-                         const float* gamma, float* sums, float* dx, float* scratch /* 128*cols floats */, int64_t rows, int cols,
+                         const float* gamma, float* sums, float* dx, float* scratch /* 512*cols floats */, int64_t rows, int cols,
                          int relu, void* stream);
 /* dx of y = LayerNorm(x)*gamma+beta (gamma may be NULL); xhat (optional) returns the normalised input for dgamma */
 IPSB_API int ipsb_layernorm_backward_f32(const float* dy, const float* x, const float* gamma, float* dx, float* xhat, int64_t rows,

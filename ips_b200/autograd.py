@@ -114,7 +114,7 @@ class BatchNormTrainFn(torch.autograd.Function):
         rows, cols = x.shape
         mean = torch.empty(cols, dtype=torch.float32, device=x.device)
         var = torch.empty_like(mean)
-        scratch = torch.empty(128 * cols, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(512 * cols, dtype=torch.float32, device=x.device)
         ops._call('ipsb_bn_stats_f32', _p(x), _p(mean), _p(var), _p(scratch), rows, cols, ops._stream())
         with torch.no_grad():
             running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
@@ -134,7 +134,7 @@ class BatchNormTrainFn(torch.autograd.Function):
         dy = dy.contiguous().float()
         sums = torch.empty(2 * cols, dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
-        scratch = torch.empty(128 * cols, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(512 * cols, dtype=torch.float32, device=x.device)
         ops._call('ipsb_bn_backward_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(sums), _p(dx), _p(scratch), rows, cols,
                   int(ctx.relu), ops._stream())
         return dx, sums[cols:], sums[:cols], None, None, None, None, None

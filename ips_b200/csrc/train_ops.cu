@@ -10,6 +10,7 @@ namespace {
 
 // ---- column reductions over rows, two stages (deterministic): grid (cols/32, R row chunks) -> partials -> final ----
 constexpr int kRowChunks = 64;
+constexpr int kRowChunks4 = 256;      // float4 kernels: more, smaller chunks (scratch: 2 * 256 * cols floats)
 
 // partial[(q * R + chunk) * cols + c] for q in {0,1}:
 //   MODE 0: sum x                      MODE 1: sum (x - mean)^2
@@ -47,6 +48,58 @@ __global__ void col_partial_kernel(const float* __restrict__ x, const float* __r
     }
 }
 
+// float4 version for cols in {4 .. 1024} with (cols / 4) dividing 256: a block reads 256 / (cols / 4) whole rows per
+// iteration (fully coalesced 4 KB), every thread owns one group of 4 columns; same partial layout as above.
+template <int MODE>
+__global__ void __launch_bounds__(256) col_partial4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, float* __restrict__ partial,
+                                                           int64_t rows, int cols, int relu) {
+    __shared__ float4 p0[256], p1[256];
+    const int tpr = cols >> 2, rpi = 256 / tpr;                  // threads per row, rows per iteration
+    const int slot = threadIdx.x / tpr, cg = threadIdx.x - slot * tpr;
+    const int R = gridDim.x, chunk = blockIdx.x;
+    const int64_t per = (rows + R - 1) / R, r0 = chunk * per, r1 = min(rows, r0 + per);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    float4 m = a, rs = a;
+    if (MODE >= 1) m = reinterpret_cast<const float4*>(mean)[cg];
+    if (MODE == 2) rs = reinterpret_cast<const float4*>(rstd)[cg];
+    for (int64_t r = r0 + slot; r < r1; r += rpi) {
+        const int64_t i = r * tpr + cg;
+        const float4 xv = reinterpret_cast<const float4*>(x)[i];
+        if (MODE == 0) { a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w; }
+        else if (MODE == 1) {
+            const float dx = xv.x - m.x, dy_ = xv.y - m.y, dz = xv.z - m.z, dw = xv.w - m.w;
+            a.x += dx * dx; a.y += dy_ * dy_; a.z += dz * dz; a.w += dw * dw;
+        } else {
+            float4 g = reinterpret_cast<const float4*>(dy)[i];
+            if (relu) {
+                const float4 yv = reinterpret_cast<const float4*>(y)[i];
+                if (!(yv.x > 0.f)) g.x = 0.f;
+                if (!(yv.y > 0.f)) g.y = 0.f;
+                if (!(yv.z > 0.f)) g.z = 0.f;
+                if (!(yv.w > 0.f)) g.w = 0.f;
+            }
+            a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+            b.x += g.x * (xv.x - m.x) * rs.x; b.y += g.y * (xv.y - m.y) * rs.y;
+            b.z += g.z * (xv.z - m.z) * rs.z; b.w += g.w * (xv.w - m.w) * rs.w;
+        }
+    }
+    p0[threadIdx.x] = a; p1[threadIdx.x] = b;
+    __syncthreads();
+    if (slot == 0) {                                             // fixed order over the row slots: deterministic
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+        for (int k = 0; k < rpi; ++k) {
+            const float4 u = p0[k * tpr + cg], v = p1[k * tpr + cg];
+            t0.x += u.x; t0.y += u.y; t0.z += u.z; t0.w += u.w;
+            t1.x += v.x; t1.y += v.y; t1.z += v.z; t1.w += v.w;
+        }
+        reinterpret_cast<float4*>(partial + (int64_t)chunk * cols)[cg] = t0;
+        if (MODE == 2) reinterpret_cast<float4*>(partial + ((int64_t)R + chunk) * cols)[cg] = t1;
+    }
+}
+
+
 // out[q * cols + c] = scale * sum_chunk partial[(q * R + chunk) * cols + c]
 __global__ void col_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int cols, int R, int nq, float scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,6 +119,44 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
         float v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
         if (relu) v = fmaxf(v, 0.f);
         y[i] = v;
+    }
+}
+
+__global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                 const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ y,
+                                 int64_t n4, int tpr, int relu) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % tpr);
+        const float4 xv = x[i], m = mean[c], r = rstd[c], g = gamma[c], b = beta[c];
+        float4 v = make_float4((xv.x - m.x) * r.x * g.x + b.x, (xv.y - m.y) * r.y * g.y + b.y, (xv.z - m.z) * r.z * g.z + b.z,
+                               (xv.w - m.w) * r.w * g.w + b.w);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        y[i] = v;
+    }
+}
+
+__global__ void bn_bwd_apply4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ y,
+                                     const float4* __restrict__ mean, const float4* __restrict__ rstd, const float4* __restrict__ gamma,
+                                     const float4* __restrict__ sums, float4* __restrict__ dx, int64_t rows, int tpr, int relu) {
+    const int64_t n4 = rows * tpr;
+    const float inv = 1.f / (float)rows;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % tpr);
+        float4 g = dy[i];
+        const float4 xv = x[i], m = mean[c], r = rstd[c], ga = gamma[c], s0 = sums[c], s1 = sums[tpr + c];
+        if (relu) {
+            const float4 yv = y[i];
+            if (!(yv.x > 0.f)) g.x = 0.f;
+            if (!(yv.y > 0.f)) g.y = 0.f;
+            if (!(yv.z > 0.f)) g.z = 0.f;
+            if (!(yv.w > 0.f)) g.w = 0.f;
+        }
+        float4 o;
+        o.x = ga.x * r.x * (g.x - s0.x * inv - (xv.x - m.x) * r.x * s1.x * inv);
+        o.y = ga.y * r.y * (g.y - s0.y * inv - (xv.y - m.y) * r.y * s1.y * inv);
+        o.z = ga.z * r.z * (g.z - s0.z * inv - (xv.z - m.z) * r.z * s1.z * inv);
+        o.w = ga.w * r.w * (g.w - s0.w * inv - (xv.w - m.w) * r.w * s1.w * inv);
+        dx[i] = o;
     }
 }
 
@@ -262,10 +353,22 @@ int grid_for(int64_t n) {
 
 extern "C" {
 
-/* scratch: 2 * 64 * cols floats */
+// float4 kernels need 16-byte aligned rows and a column-group count that divides the block
+static bool fast4(int cols, const void* x) { return cols % 4 == 0 && cols <= 1024 && 256 % (cols / 4) == 0 && ((uintptr_t)x % 16 == 0); }
+
+/* scratch: 2 * 256 * cols floats */
 int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch, int64_t rows, int cols, void* stream) {
     IPSB_REQUIRE(rows > 0 && cols > 0 && scratch != nullptr, "bn_stats: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    if (fast4(cols, x)) {                                         // float4 path: 256 row chunks
+        const int R = (int)(rows < kRowChunks4 ? rows : kRowChunks4);
+        col_partial4_kernel<0><<<R, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, scratch, rows, cols, 0);
+        col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, mean, cols, R, 1, 1.f / (float)rows);
+        col_partial4_kernel<1><<<R, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, scratch, rows, cols, 0);
+        col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, var, cols, R, 1, 1.f / (float)rows);
+        IPSB_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((cols + 31) / 32, kRowChunks);
     col_partial_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, scratch, rows, cols, 0);
     col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, mean, cols, kRowChunks, 1, 1.f / (float)rows);
@@ -277,6 +380,14 @@ int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch, i
 
 int ipsb_bn_apply_f32(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
                       int64_t rows, int cols, int relu, void* stream) {
+    if (cols % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)mean % 16 == 0) &&
+        ((uintptr_t)rstd % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0)) {
+        bn_apply4_kernel<<<grid_for(rows * (cols / 4)), 256, 0, (cudaStream_t)stream>>>(
+            (const float4*)x, (const float4*)mean, (const float4*)rstd, (const float4*)gamma, (const float4*)beta, (float4*)y,
+            rows * (cols / 4), cols / 4, relu);
+        IPSB_LAUNCH_CHECK();
+        return 0;
+    }
     bn_apply_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, gamma, beta, y, rows * cols, cols, relu);
     IPSB_LAUNCH_CHECK();
     return 0;
@@ -286,6 +397,18 @@ int ipsb_bn_apply_f32(const float* x, const float* mean, const float* rstd, cons
 int ipsb_bn_backward_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
                          float* sums, float* dx, float* scratch, int64_t rows, int cols, int relu, void* stream) {
     IPSB_REQUIRE(rows > 0 && cols > 0 && scratch != nullptr, "bn_backward: bad arguments");
+    if (fast4(cols, x) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
+        ((uintptr_t)mean % 16 == 0) && ((uintptr_t)rstd % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)sums % 16 == 0)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int R = (int)(rows < kRowChunks4 ? rows : kRowChunks4);
+        col_partial4_kernel<2><<<R, 256, 0, st>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
+        col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, st>>>(scratch, sums, cols, R, 2, 1.f);
+        bn_bwd_apply4_kernel<<<grid_for(rows * (cols / 4)), 256, 0, st>>>(
+            (const float4*)dy, (const float4*)x, (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
+            (const float4*)sums, (float4*)dx, rows, cols / 4, relu);
+        IPSB_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((cols + 31) / 32, kRowChunks);
     col_partial_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
     col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, sums, cols, kRowChunks, 2, 1.f);
