@@ -39,7 +39,8 @@ class GraphedTrainStep:
               (e.g. `net.ips(x, out=(step.mem_patch, step.mem_pos), row_offset=n_prep)`, `step.labels[k].copy_(...)`)
               and call the object.
     optimizer must be created with `capturable=True` (its step counter lives on the device).
-    grad_hook optional callable run after backward inside the graph (e.g. NCCL all-reduce of the gradients).
+    grad_hook optional callable run after backward (e.g. NCCL all-reduce of the gradients); with a hook the graph covers
+              forward + loss + backward and the hook + optimizer step run eagerly after each replay.
     """
 
     def __init__(self, net, conf, optimizer, batch_size, loss_fn=compute_loss, grad_hook=None, warmup=3, fuse_loss=True):
@@ -68,17 +69,23 @@ class GraphedTrainStep:
     def buffers(self):
         return self.mem_patch, self.mem_pos
 
-    def _step(self):
+    def _fwd_bwd(self):
         self.opt.zero_grad(set_to_none=False)
         if self.fuse_loss:
             loss = fused_loss(self.conf, self.net, self.mem_patch, self.mem_pos, self.labels)
         else:
             loss = self.loss_fn(self.conf, self.net(self.mem_patch, self.mem_pos), self.labels)
         loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _sync_and_update(self):
         if self.grad_hook is not None:
             self.grad_hook([p for p in self.net.parameters() if p.grad is not None])
         self.opt.step()
-        self.loss.copy_(loss.detach())
+
+    def _step(self):
+        self._fwd_bwd()
+        self._sync_and_update()
 
     def capture(self, restore_state=True):
         """Warm up on a side stream (lazy workspaces, kernel attributes, autograd buffers, optimizer state), then
@@ -97,9 +104,14 @@ class GraphedTrainStep:
                 self._step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # with a gradient exchange (NCCL) the graph ends after backward: the collective and the optimizer step run
+        # eagerly between replays (a collective inside a capture must be captured identically on every rank)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._step()
+            if self.grad_hook is None:
+                self._step()
+            else:
+                self._fwd_bwd()
         if snap is not None:
             with torch.no_grad():
                 for p, v in zip(self.net.parameters(), snap[0]):
@@ -117,4 +129,6 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        if self.grad_hook is not None:
+            self._sync_and_update()
         return self.loss
