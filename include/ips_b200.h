@@ -259,12 +259,15 @@ IPSB_API int ipsb_layernorm_backward_f32(const float* dy, const float* x, const 
                                 int D, float eps, void* stream);
 /* q_scaled (T,H*Dk), k (B,M,H*Dk), v (B,M,H*Dv), mask (B,H,T,M) of 0/1 or NULL, keep_scale = 1/(1-p);
  * prob (B,H,T,M) softmax weights (saved for the backward), out (B,T,H*Dv) */
+IPSB_API int64_t ipsb_attention_chunks(int M);   /* chunks of 256 selected patches the attention kernels split M into */
 IPSB_API int ipsb_attention_train_fwd_f32(const float* q_scaled, const float* k, const float* v, const float* mask, float keep_scale,
-                                 float* prob, float* out, int B, int M, int H, int Dk, int Dv, int T, void* stream);
+                                          float* prob, float* out, float* scratch /* B*H*T*chunks*Dv floats */, int B, int M, int H,
+                                          int Dk, int Dv, int T, void* stream);
 /* dq_part (B,T,H*Dk) is per batch element (sum over B = dq); dk (B,M,H*Dk); dv (B,M,H*Dv) */
 IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k, const float* v, const float* mask, float keep_scale,
-                                 const float* prob, const float* dout, float* dq_part, float* dk, float* dv,
-                                 int B, int M, int H, int Dk, int Dv, int T, void* stream);
+                                          const float* prob, const float* out /* forward result */, const float* dout,
+                                          float* dq_part /* (B*chunks, T*H*Dk), summed over rows by the caller */, float* dk, float* dv,
+                                          int B, int M, int H, int Dk, int Dv, int T, void* stream);
 
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the

@@ -84,8 +84,10 @@ SIGNATURES = {
     'ipsb_bn_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_bn_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_layernorm_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
-    'ipsb_attention_train_fwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
-    'ipsb_attention_train_bwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
+    'ipsb_attention_chunks': [_i32],
+    'ipsb_attention_train_fwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
+    'ipsb_attention_train_bwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32,
+                                     _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
     'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64, _i32,
@@ -93,7 +95,7 @@ SIGNATURES = {
     'ipsb_resnet_logits_image': [ctypes.POINTER(ResnetDesc), _ptr, ctypes.POINTER(ImageGeo), _i64, _i64, _i32, _i32, _i32, _i64,
                                  _ptr, _i64, _i32, _ptr, _ptr, _ptr],
 }
-_RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64,
+_RESTYPE = {'ipsb_last_error': ctypes.c_char_p, 'ipsb_resnet_workspace_bytes': ctypes.c_int64, 'ipsb_attention_chunks': ctypes.c_int64,
             'ipsb_pf_rows': ctypes.c_int64, 'ipsb_select_loop_workspace_bytes': ctypes.c_int64,
             'ipsb_gemm_workspace_bytes': ctypes.c_int64}
 

@@ -182,20 +182,23 @@ class CrossAttentionFn(torch.autograd.Function):
         T = q.shape[0]
         prob = torch.empty((B, H, T, M), dtype=torch.float32, device=k.device)
         out = torch.empty((B, T, H * Dv), dtype=torch.float32, device=k.device)
-        ops._call('ipsb_attention_train_fwd_f32', _p(q), _p(k), _p(v), _p(mask), float(keep_scale), _p(prob), _p(out),
+        chunks = (M + 255) // 256                                   # ipsb_attention_chunks(M)
+        scratch = torch.empty(B * H * T * chunks * Dv, dtype=torch.float32, device=k.device)
+        ops._call('ipsb_attention_train_fwd_f32', _p(q), _p(k), _p(v), _p(mask), float(keep_scale), _p(prob), _p(out), _p(scratch),
                   B, M, H, Dk, Dv, T, ops._stream())
-        ctx.save_for_backward(q, k, v, prob, mask)
+        ctx.save_for_backward(q, k, v, prob, mask, out)
         ctx.dims = (B, M, H, Dk, Dv, T, float(keep_scale))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, prob, mask = ctx.saved_tensors
+        q, k, v, prob, mask, out = ctx.saved_tensors
         B, M, H, Dk, Dv, T, keep_scale = ctx.dims
         dout = dout.contiguous().float()
-        dq_part = torch.empty((B, T * H * Dk), dtype=torch.float32, device=k.device)
+        chunks = (M + 255) // 256
+        dq_part = torch.empty((B * chunks, T * H * Dk), dtype=torch.float32, device=k.device)
         dk, dv = torch.empty_like(k), torch.empty_like(v)
-        ops._call('ipsb_attention_train_bwd_f32', _p(q), _p(k), _p(v), _p(mask), keep_scale, _p(prob), _p(dout), _p(dq_part),
+        ops._call('ipsb_attention_train_bwd_f32', _p(q), _p(k), _p(v), _p(mask), keep_scale, _p(prob), _p(out), _p(dout), _p(dq_part),
                   _p(dk), _p(dv), B, M, H, Dk, Dv, T, ops._stream())
         dq = ops.colsum(dq_part).view(T, H * Dk)
         return dq, dk, dv, None, None, None, None, None

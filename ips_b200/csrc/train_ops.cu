@@ -213,133 +213,160 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 }
 
 // ---- cross-attention core, training ------------------------------------------------------------------
-// one CTA per (b, h).  probabilities p (B,H,T,M) are written for the backward; `mask` (same shape, 0/1 floats) and
-// `keep_scale` = 1/(1-p_drop) implement nn.Dropout on the attention weights.
+// softmax(q k^T) (dropout) v per (batch, head, query token), parallel over the M selected patches: a CTA per (b, h, t)
+// owns the softmax statistics, CTAs per (b, h, chunk of 256 patches) do the per-patch work (one warp per patch).
+// probabilities p (B,H,T,M) are kept for the backward; `mask` (same shape, 0/1 floats) and `keep_scale` = 1/(1-p_drop)
+// implement nn.Dropout on the attention weights.  Every reduction has a fixed order (deterministic).
+constexpr int kAttnChunk = 256;
+
+// logits s[b,h,t,m] = q_t . k_m -> prob buffer; grid (B*H, chunks), warp per patch
 __global__ void __launch_bounds__(256)
-attn_train_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                      const float* __restrict__ mask, float keep_scale, float* __restrict__ prob, float* __restrict__ out,
-                      int M, int H, int Dk, int Dv, int T) {
-    extern __shared__ float sm[];
+attn_logits_kernel(const float* __restrict__ q, const float* __restrict__ k, float* __restrict__ prob, int M, int H, int Dk, int T) {
+    extern __shared__ float sm[];                       // [T][Dk]
     const int b = blockIdx.x / H, h = blockIdx.x % H;
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
-    float* qs = sm;                 // [Dk]
-    float* red = qs + Dk;           // [nw]
-    float* accs = red + nw;         // [nw][Dv]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < T * Dk; i += blockDim.x) sm[i] = q[(int64_t)(i / Dk) * H * Dk + h * Dk + (i % Dk)];
+    __syncthreads();
+    const int m0 = blockIdx.y * kAttnChunk;
     const float* kb = k + (int64_t)b * M * H * Dk + h * Dk;
-    const float* vb = v + (int64_t)b * M * H * Dv + h * Dv;
-    for (int t = 0; t < T; ++t) {
-        float* pr = prob + (((int64_t)b * H + h) * T + t) * M;
-        const float* mk = mask ? mask + (((int64_t)b * H + h) * T + t) * M : nullptr;
-        __syncthreads();
-        for (int i = tid; i < Dk; i += nthreads) qs[i] = q[(int64_t)t * H * Dk + h * Dk + i];
-        __syncthreads();
-        // pass 1: logits -> prob buffer, running max
-        float mx = -INFINITY;
-        for (int m = warp; m < M; m += nw) {
-            float s = 0.f;
-            for (int d = lane; d < Dk; d += 32) s = fmaf(qs[d], kb[(int64_t)m * H * Dk + d], s);
+    for (int m = m0 + warp; m < min(M, m0 + kAttnChunk); m += 8) {
+        const float k0 = lane < Dk ? kb[(int64_t)m * H * Dk + lane] : 0.f;
+        const float k1 = lane + 32 < Dk ? kb[(int64_t)m * H * Dk + lane + 32] : 0.f;
+        for (int t = 0; t < T; ++t) {
+            float s = (lane < Dk ? sm[t * Dk + lane] * k0 : 0.f) + (lane + 32 < Dk ? sm[t * Dk + lane + 32] * k1 : 0.f);
             s = ipsb::warp_sum(s);
-            if (lane == 0) pr[m] = s;
-            mx = fmaxf(mx, s);
-        }
-        if (lane == 0) red[warp] = mx;
-        __syncthreads();
-        mx = red[0];
-        for (int w = 1; w < nw; ++w) mx = fmaxf(mx, red[w]);
-        __syncthreads();
-        float den = 0.f;
-        for (int m = tid; m < M; m += nthreads) { const float e = expf(pr[m] - mx); pr[m] = e; den += e; }
-        den = ipsb::warp_sum(den);
-        if (lane == 0) red[warp] = den;
-        __syncthreads();
-        den = 0.f;
-        for (int w = 0; w < nw; ++w) den += red[w];
-        __syncthreads();
-        for (int m = tid; m < M; m += nthreads) pr[m] = pr[m] / den;
-        __syncthreads();
-        // pass 2: out = sum_m p~ v
-        float a0 = 0.f, a1 = 0.f;
-        for (int m = warp; m < M; m += nw) {
-            const float pt = pr[m] * (mk ? mk[m] * keep_scale : 1.f);
-            if (lane < Dv) a0 = fmaf(pt, vb[(int64_t)m * H * Dv + lane], a0);
-            if (lane + 32 < Dv) a1 = fmaf(pt, vb[(int64_t)m * H * Dv + lane + 32], a1);
-        }
-        if (lane < Dv) accs[warp * Dv + lane] = a0;
-        if (lane + 32 < Dv) accs[warp * Dv + lane + 32] = a1;
-        __syncthreads();
-        if (tid < Dv) {
-            float a = 0.f;
-            for (int w = 0; w < nw; ++w) a += accs[w * Dv + tid];
-            out[((int64_t)b * T + t) * H * Dv + h * Dv + tid] = a;
+            if (lane == 0) prob[(((int64_t)b * H + h) * T + t) * M + m] = s;
         }
     }
 }
 
-// backward: dq_part (B,T,H*Dk) per batch element (summed over b by the caller), dk (B,M,H*Dk), dv (B,M,H*Dv)
+// in-place softmax over M of one (b,h,t) row; one CTA per row
+__global__ void __launch_bounds__(256) attn_softmax_kernel(float* __restrict__ prob, int M) {
+    __shared__ float red[8];
+    float* pr = prob + (int64_t)blockIdx.x * M;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = -INFINITY;
+    for (int m = tid; m < M; m += 256) mx = fmaxf(mx, pr[m]);
+    mx = ipsb::warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float den = 0.f;
+    for (int m = tid; m < M; m += 256) { const float e = expf(pr[m] - mx); pr[m] = e; den += e; }
+    den = ipsb::warp_sum(den);
+    if (lane == 0) red[warp] = den;
+    __syncthreads();
+    den = 0.f;
+    for (int w = 0; w < 8; ++w) den += red[w];
+    const float inv = 1.f / den;
+    for (int m = tid; m < M; m += 256) pr[m] *= inv;
+}
+
+// partial out[(b,h,t), chunk, :] = sum_{m in chunk} p~_m v_m; grid (B*H, chunks); part (B*H*T, chunks, Dv)
+__global__ void __launch_bounds__(256)
+attn_pv_kernel(const float* __restrict__ v, const float* __restrict__ mask, float keep_scale, const float* __restrict__ prob,
+               float* __restrict__ part, int M, int H, int Dv, int T, int chunks) {
+    extern __shared__ float sm[];                       // [8][T][Dv] per-warp accumulators
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * kAttnChunk;
+    const float* vb = v + (int64_t)b * M * H * Dv + h * Dv;
+    for (int t = 0; t < T; ++t) {
+        const int64_t row = (((int64_t)b * H + h) * T + t) * M;
+        float a0 = 0.f, a1 = 0.f;
+        for (int m = m0 + warp; m < min(M, m0 + kAttnChunk); m += 8) {
+            const float pt = prob[row + m] * (mask ? mask[row + m] * keep_scale : 1.f);
+            if (lane < Dv) a0 = fmaf(pt, vb[(int64_t)m * H * Dv + lane], a0);
+            if (lane + 32 < Dv) a1 = fmaf(pt, vb[(int64_t)m * H * Dv + lane + 32], a1);
+        }
+        if (lane < Dv) sm[(warp * T + t) * Dv + lane] = a0;
+        if (lane + 32 < Dv) sm[(warp * T + t) * Dv + lane + 32] = a1;
+    }
+    __syncthreads();
+    for (int i = tid; i < T * Dv; i += 256) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += sm[w * T * Dv + i];
+        const int t = i / Dv, d = i - t * Dv;
+        part[((((int64_t)b * H + h) * T + t) * chunks + blockIdx.y) * Dv + d] = a;
+    }
+}
+
+// out[b,t,h*Dv+d] = sum_chunk part; one thread per output element
+__global__ void attn_out_kernel(const float* __restrict__ part, float* __restrict__ out, int B, int H, int Dv, int T, int chunks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H * T * Dv) return;
+    const int d = i % Dv, t = (i / Dv) % T, h = (i / (Dv * T)) % H, b = i / (Dv * T * H);
+    float a = 0.f;
+    for (int c = 0; c < chunks; ++c) a += part[((((int64_t)b * H + h) * T + t) * chunks + c) * Dv + d];
+    out[((int64_t)b * T + t) * H * Dv + h * Dv + d] = a;
+}
+
+// backward: grid (B*H, chunks), warp per patch.  With dp_m = (dout . v_m) mask_m keep_scale the softmax backward needs
+// dot_t = sum_m p_m dp_m = dout_t . out_t (out = the forward result), so no reduction over M precedes the per-patch work.
+// dk (B,M,H*Dk), dv (B,M,H*Dv) are written once per patch; dq partials land in dq_part (B*chunks, T*H*Dk), summed by the caller.
 __global__ void __launch_bounds__(256)
 attn_train_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                       const float* __restrict__ mask, float keep_scale, const float* __restrict__ prob,
-                      const float* __restrict__ dout, float* __restrict__ dq_part, float* __restrict__ dk, float* __restrict__ dv,
-                      int M, int H, int Dk, int Dv, int T) {
+                      const float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ dq_part,
+                      float* __restrict__ dk, float* __restrict__ dv, int M, int H, int Dk, int Dv, int T, int chunks) {
     extern __shared__ float sm[];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
-    float* qs = sm;                 // [Dk]
-    float* dos = qs + Dk;           // [Dv]
-    float* red = dos + Dv;          // [nw]
-    float* accs = red + nw;         // [nw][Dk]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* qs = sm;                      // [T][Dk]
+    float* dos = qs + T * Dk;            // [T][Dv]
+    float* dots = dos + T * Dv;          // [T]
+    float* accs = dots + T;              // [8][T][Dk]
+    for (int i = tid; i < T * Dk; i += 256) qs[i] = q[(int64_t)(i / Dk) * H * Dk + h * Dk + (i % Dk)];
+    for (int i = tid; i < T * Dv; i += 256) dos[i] = dout[((int64_t)b * T + i / Dv) * H * Dv + h * Dv + (i % Dv)];
+    __syncthreads();
+    if (warp < T || T > 8) {
+        for (int t = warp; t < T; t += 8) {
+            float s = 0.f;
+            for (int d = lane; d < Dv; d += 32) s = fmaf(dos[t * Dv + d], out[((int64_t)b * T + t) * H * Dv + h * Dv + d], s);
+            s = ipsb::warp_sum(s);
+            if (lane == 0) dots[t] = s;
+        }
+    }
+    __syncthreads();
+    const int m0 = blockIdx.y * kAttnChunk;
     const float* kb = k + (int64_t)b * M * H * Dk + h * Dk;
     const float* vb = v + (int64_t)b * M * H * Dv + h * Dv;
     float* dkb = dk + (int64_t)b * M * H * Dk + h * Dk;
     float* dvb = dv + (int64_t)b * M * H * Dv + h * Dv;
-    for (int t = 0; t < T; ++t) {
-        const float* pr = prob + (((int64_t)b * H + h) * T + t) * M;
-        const float* mk = mask ? mask + (((int64_t)b * H + h) * T + t) * M : nullptr;
-        __syncthreads();
-        for (int i = tid; i < Dk; i += nthreads) qs[i] = q[(int64_t)t * H * Dk + h * Dk + i];
-        for (int i = tid; i < Dv; i += nthreads) dos[i] = dout[((int64_t)b * T + t) * H * Dv + h * Dv + i];
-        __syncthreads();
-        // pass 1: dot = sum_m p_m dp_m with dp_m = (dout . v_m) * mask_m * keep_scale
-        float dot = 0.f;
-        for (int m = warp; m < M; m += nw) {
-            float s = 0.f;
-            for (int d = lane; d < Dv; d += 32) s = fmaf(dos[d], vb[(int64_t)m * H * Dv + d], s);
+    for (int i = lane; i < T * Dk; i += 32) accs[warp * T * Dk + i] = 0.f;
+    __syncwarp();
+    for (int m = m0 + warp; m < min(M, m0 + kAttnChunk); m += 8) {
+        const float v0 = lane < Dv ? vb[(int64_t)m * H * Dv + lane] : 0.f;
+        const float v1 = lane + 32 < Dv ? vb[(int64_t)m * H * Dv + lane + 32] : 0.f;
+        const float k0 = lane < Dk ? kb[(int64_t)m * H * Dk + lane] : 0.f;
+        const float k1 = lane + 32 < Dk ? kb[(int64_t)m * H * Dk + lane + 32] : 0.f;
+        float dv0 = 0.f, dv1 = 0.f, dk0 = 0.f, dk1 = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const int64_t pi = (((int64_t)b * H + h) * T + t) * M + m;
+            float s = (lane < Dv ? dos[t * Dv + lane] * v0 : 0.f) + (lane + 32 < Dv ? dos[t * Dv + lane + 32] * v1 : 0.f);
             s = ipsb::warp_sum(s);
-            dot += pr[m] * s * (mk ? mk[m] * keep_scale : 1.f);
-        }
-        if (lane == 0) red[warp] = dot;
-        __syncthreads();
-        dot = 0.f;
-        for (int w = 0; w < nw; ++w) dot += red[w];
-        // pass 2: dv, dk, dq
-        float dq0 = 0.f, dq1 = 0.f;
-        for (int m = warp; m < M; m += nw) {
-            float s = 0.f;
-            for (int d = lane; d < Dv; d += 32) s = fmaf(dos[d], vb[(int64_t)m * H * Dv + d], s);
-            s = ipsb::warp_sum(s);
-            const float ms = mk ? mk[m] * keep_scale : 1.f;
-            const float p = pr[m];
-            const float ds = p * (s * ms - dot);
+            const float ms = mask ? mask[pi] * keep_scale : 1.f;
+            const float p = prob[pi];
+            const float ds = p * (s * ms - dots[t]);
             const float pt = p * ms;
-            for (int d = lane; d < Dv; d += 32) {
-                const float add = pt * dos[d];
-                dvb[(int64_t)m * H * Dv + d] = (t == 0 ? 0.f : dvb[(int64_t)m * H * Dv + d]) + add;
-            }
-            for (int d = lane; d < Dk; d += 32) {
-                const float add = ds * qs[d];
-                dkb[(int64_t)m * H * Dk + d] = (t == 0 ? 0.f : dkb[(int64_t)m * H * Dk + d]) + add;
-            }
-            if (lane < Dk) dq0 = fmaf(ds, kb[(int64_t)m * H * Dk + lane], dq0);
-            if (lane + 32 < Dk) dq1 = fmaf(ds, kb[(int64_t)m * H * Dk + lane + 32], dq1);
+            if (lane < Dv) dv0 = fmaf(pt, dos[t * Dv + lane], dv0);
+            if (lane + 32 < Dv) dv1 = fmaf(pt, dos[t * Dv + lane + 32], dv1);
+            if (lane < Dk) { dk0 = fmaf(ds, qs[t * Dk + lane], dk0); accs[(warp * T + t) * Dk + lane] += ds * k0; }
+            if (lane + 32 < Dk) { dk1 = fmaf(ds, qs[t * Dk + lane + 32], dk1); accs[(warp * T + t) * Dk + lane + 32] += ds * k1; }
         }
-        if (lane < Dk) accs[warp * Dk + lane] = dq0;
-        if (lane + 32 < Dk) accs[warp * Dk + lane + 32] = dq1;
-        __syncthreads();
-        if (tid < Dk) {
-            float a = 0.f;
-            for (int w = 0; w < nw; ++w) a += accs[w * Dk + tid];
-            dq_part[((int64_t)b * T + t) * H * Dk + h * Dk + tid] = a;
-        }
+        if (lane < Dv) dvb[(int64_t)m * H * Dv + lane] = dv0;
+        if (lane + 32 < Dv) dvb[(int64_t)m * H * Dv + lane + 32] = dv1;
+        if (lane < Dk) dkb[(int64_t)m * H * Dk + lane] = dk0;
+        if (lane + 32 < Dk) dkb[(int64_t)m * H * Dk + lane + 32] = dk1;
+    }
+    __syncthreads();
+    for (int i = tid; i < T * Dk; i += 256) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += accs[w * T * Dk + i];
+        const int t = i / Dk, d = i - t * Dk;
+        dq_part[((int64_t)b * chunks + blockIdx.y) * T * H * Dk + (int64_t)t * H * Dk + h * Dk + d] = a;
     }
 }
 
@@ -426,22 +453,33 @@ int ipsb_layernorm_backward_f32(const float* dy, const float* x, const float* ga
     return 0;
 }
 
+int64_t ipsb_attention_chunks(int M) { return (M + kAttnChunk - 1) / kAttnChunk; }
+
+/* scratch: B*H*T*chunks*Dv floats (chunks = ipsb_attention_chunks(M)) */
 int ipsb_attention_train_fwd_f32(const float* q_scaled, const float* k, const float* v, const float* mask, float keep_scale,
-                                 float* prob, float* out, int B, int M, int H, int Dk, int Dv, int T, void* stream) {
-    IPSB_REQUIRE(B > 0 && M > 0 && Dk <= 64 && Dv <= 64, "attention_train_fwd: bad shape (Dk, Dv <= 64)");
-    const size_t smem = (size_t)(Dk + 8 + 8 * Dv) * sizeof(float);
-    attn_train_fwd_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>(q_scaled, k, v, mask, keep_scale, prob, out, M, H, Dk, Dv, T);
+                                 float* prob, float* out, float* scratch, int B, int M, int H, int Dk, int Dv, int T, void* stream) {
+    IPSB_REQUIRE(B > 0 && M > 0 && Dk <= 64 && Dv <= 64 && scratch != nullptr, "attention_train_fwd: bad arguments (Dk, Dv <= 64)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = (M + kAttnChunk - 1) / kAttnChunk;
+    dim3 grid(B * H, chunks);
+    attn_logits_kernel<<<grid, 256, (size_t)T * Dk * 4, st>>>(q_scaled, k, prob, M, H, Dk, T);
+    attn_softmax_kernel<<<B * H * T, 256, 0, st>>>(prob, M);
+    attn_pv_kernel<<<grid, 256, (size_t)8 * T * Dv * 4, st>>>(v, mask, keep_scale, prob, scratch, M, H, Dv, T, chunks);
+    attn_out_kernel<<<(B * H * T * Dv + 255) / 256, 256, 0, st>>>(scratch, out, B, H, Dv, T, chunks);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
 
+/* out: the forward result (B,T,H*Dv); dq_part: (B*chunks, T*H*Dk), to be summed over its rows by the caller */
 int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k, const float* v, const float* mask, float keep_scale,
-                                 const float* prob, const float* dout, float* dq_part, float* dk, float* dv,
+                                 const float* prob, const float* out, const float* dout, float* dq_part, float* dk, float* dv,
                                  int B, int M, int H, int Dk, int Dv, int T, void* stream) {
-    IPSB_REQUIRE(B > 0 && M > 0 && Dk <= 64 && Dv <= 64, "attention_train_bwd: bad shape (Dk, Dv <= 64)");
-    const size_t smem = (size_t)(Dk + Dv + 8 + 8 * Dk) * sizeof(float);
-    attn_train_bwd_kernel<<<B * H, 256, smem, (cudaStream_t)stream>>>(q_scaled, k, v, mask, keep_scale, prob, dout, dq_part, dk, dv,
-                                                                     M, H, Dk, Dv, T);
+    IPSB_REQUIRE(B > 0 && M > 0 && Dk <= 64 && Dv <= 64 && out != nullptr, "attention_train_bwd: bad arguments (Dk, Dv <= 64)");
+    const int chunks = (M + kAttnChunk - 1) / kAttnChunk;
+    const size_t smem = (size_t)(T * Dk + T * Dv + T + 8 * T * Dk) * sizeof(float);
+    IPSB_REQUIRE(smem <= 48 * 1024, "attention_train_bwd: T=%d too large", T);
+    attn_train_bwd_kernel<<<dim3(B * H, chunks), 256, smem, (cudaStream_t)stream>>>(q_scaled, k, v, mask, keep_scale, prob, out, dout,
+                                                                                     dq_part, dk, dv, M, H, Dk, Dv, T, chunks);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
