@@ -254,6 +254,13 @@ IPSB_API int ipsb_bn_apply_f32(const float* x, const float* mean, const float* r
 IPSB_API int ipsb_bn_backward_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
                          const float* gamma, float* sums, float* dx, float* scratch /* 512*cols floats */, int64_t rows, int cols,
                          int relu, void* stream);
+/* the two phases of ipsb_bn_backward_f32, for a BatchNorm synchronised over data-parallel ranks: the caller
+ * all-reduces `sums` between them and passes the row count of the whole batch */
+IPSB_API int ipsb_bn_backward_sums_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                                       float* sums, float* scratch /* 512*cols floats */, int64_t rows, int cols, int relu, void* stream);
+IPSB_API int ipsb_bn_backward_apply_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                                        const float* gamma, const float* sums, float* dx, int64_t rows, int cols, int64_t rows_total,
+                                        int relu, void* stream);
 /* dx of y = LayerNorm(x)*gamma+beta (gamma may be NULL); xhat (optional) returns the normalised input for dgamma */
 IPSB_API int ipsb_layernorm_backward_f32(const float* dy, const float* x, const float* gamma, float* dx, float* xhat, int64_t rows,
                                 int D, float eps, void* stream);

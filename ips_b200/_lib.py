@@ -83,6 +83,8 @@ SIGNATURES = {
     'ipsb_bn_stats_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
     'ipsb_bn_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_bn_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
+    'ipsb_bn_backward_sums_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
+    'ipsb_bn_backward_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i64, _i32, _ptr],
     'ipsb_layernorm_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _f32, _ptr],
     'ipsb_attention_chunks': [_i32],
     'ipsb_attention_train_fwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],

@@ -106,25 +106,42 @@ def _p(t):
 
 class BatchNormTrainFn(torch.autograd.Function):
     """BatchNorm over rows in batch-statistics mode with an optional fused ReLU (nn.BatchNorm1d + nn.ReLU under
-    net.train(), architecture/ips_net.py:58-59).  Updates the running statistics like nn.BatchNorm1d."""
+    net.train(), architecture/ips_net.py:58-59; nn.BatchNorm2d on channels-last pixels).  Updates the running
+    statistics like nn.BatchNorm.  `group` (a torch.distributed process group, or True for the default group)
+    synchronises the statistics over data-parallel ranks: means / variances are combined from every rank's
+    (mean, variance, rows) in forward, [sum g, sum g*xhat] are all-reduced in backward, so a batch split over R ranks
+    normalises exactly like the whole batch in one process."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, group=None):
         x = x.contiguous().float()
         rows, cols = x.shape
         mean = torch.empty(cols, dtype=torch.float32, device=x.device)
         var = torch.empty_like(mean)
         scratch = torch.empty(512 * cols, dtype=torch.float32, device=x.device)
         ops._call('ipsb_bn_stats_f32', _p(x), _p(mean), _p(var), _p(scratch), rows, cols, ops._stream())
+        rows_total = rows
+        sync = _dist_group(group)
+        if sync is not None:
+            import torch.distributed as dist
+            R = dist.get_world_size(sync)
+            mine = torch.cat([mean, var, torch.full((1,), float(rows), device=x.device)])
+            parts = [torch.empty_like(mine) for _ in range(R)]
+            dist.all_gather(parts, mine, group=sync)
+            st = torch.stack(parts)                                        # (R, 2*cols + 1)
+            n = st[:, -1:]
+            rows_total = int(round(float(n.sum())))
+            mean = (st[:, :cols] * n).sum(0) / n.sum()
+            var = ((st[:, cols:2 * cols] + (st[:, :cols] - mean) ** 2) * n).sum(0) / n.sum()
         with torch.no_grad():
             running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-            running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows / max(rows - 1, 1))
+            running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows_total / max(rows_total - 1, 1))
         rstd = torch.rsqrt(var + eps)
         y = torch.empty_like(x)
         g, b = gamma.contiguous().float(), beta.contiguous().float()
         ops._call('ipsb_bn_apply_f32', _p(x), _p(mean), _p(rstd), _p(g), _p(b), _p(y), rows, cols, int(relu), ops._stream())
-        ctx.save_for_backward(x, y, mean, rstd, g)
-        ctx.relu = relu
+        ctx.save_for_backward(x, y, mean.contiguous(), rstd, g)
+        ctx.relu, ctx.sync, ctx.rows_total = relu, sync, rows_total
         return y
 
     @staticmethod
@@ -135,9 +152,26 @@ class BatchNormTrainFn(torch.autograd.Function):
         sums = torch.empty(2 * cols, dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         scratch = torch.empty(512 * cols, dtype=torch.float32, device=x.device)
-        ops._call('ipsb_bn_backward_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(sums), _p(dx), _p(scratch), rows, cols,
+        ops._call('ipsb_bn_backward_sums_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(sums), _p(scratch), rows, cols,
                   int(ctx.relu), ops._stream())
-        return dx, sums[cols:], sums[:cols], None, None, None, None, None
+        all_sums = sums
+        if ctx.sync is not None:                                           # dgamma / dbeta stay local (averaged with the other gradients)
+            import torch.distributed as dist
+            all_sums = sums.clone()
+            dist.all_reduce(all_sums, op=dist.ReduceOp.SUM, group=ctx.sync)
+        ops._call('ipsb_bn_backward_apply_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(all_sums), _p(dx), rows, cols,
+                  ctx.rows_total, int(ctx.relu), ops._stream())
+        return dx, sums[cols:], sums[:cols], None, None, None, None, None, None
+
+
+def _dist_group(group):
+    """None (no synchronisation) or the process group to synchronise BatchNorm statistics over."""
+    if group is None or group is False:
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(None if group is True else group) == 1:
+        return None
+    return dist.group.WORLD if group is True else group
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -297,30 +331,30 @@ class StemConvFn(torch.autograd.Function):
         return None, dw
 
 
-def _bn2d_train(x, bn, relu):
+def _bn2d_train(x, bn, relu, group=None):
     """nn.BatchNorm2d in batch-statistics mode on channels-last activations (rows = pixels)."""
     C = x.shape[-1]
-    y = BatchNormTrainFn.apply(x.reshape(-1, C), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+    y = BatchNormTrainFn.apply(x.reshape(-1, C), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, group)
     with torch.no_grad():
         bn.num_batches_tracked += 1
     return y.view(x.shape)
 
 
-def conv_encoder_train(encoder, patches):
+def conv_encoder_train(encoder, patches, bn_group=None):
     """Grad-mode forward of the truncated ResNet-18 (`encoder` = the nn.Sequential of ips_net.py:34-50) on
     (P, C, H, W) patches; every convolution and BatchNorm runs forward and backward on the library's kernels.
     Max-pool, residual add, ReLU and the average pool are PyTorch elementwise / reduction glue."""
     mods = list(encoder.children())
     x = StemConvFn.apply(patches, mods[0].weight)
-    x = _bn2d_train(x, mods[1], True)
+    x = _bn2d_train(x, mods[1], True, bn_group)
     x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
     for layer in mods[4:-1]:
         for blk in layer:
             idt = x
-            y = _bn2d_train(ConvFn.apply(x, blk.conv1.weight, blk.stride, 1), blk.bn1, True)
-            y = _bn2d_train(ConvFn.apply(y, blk.conv2.weight, 1, 1), blk.bn2, False)
+            y = _bn2d_train(ConvFn.apply(x, blk.conv1.weight, blk.stride, 1), blk.bn1, True, bn_group)
+            y = _bn2d_train(ConvFn.apply(y, blk.conv2.weight, 1, 1), blk.bn2, False, bn_group)
             if blk.downsample is not None:
-                idt = _bn2d_train(ConvFn.apply(x, blk.downsample[0].weight, blk.stride, 0), blk.downsample[1], False)
+                idt = _bn2d_train(ConvFn.apply(x, blk.downsample[0].weight, blk.stride, 0), blk.downsample[1], False, bn_group)
             x = torch.relu(y + idt)
     return x.mean(dim=(1, 2))
 

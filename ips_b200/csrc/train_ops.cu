@@ -137,9 +137,10 @@ __global__ void bn_apply4_kernel(const float4* __restrict__ x, const float4* __r
 
 __global__ void bn_bwd_apply4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ y,
                                      const float4* __restrict__ mean, const float4* __restrict__ rstd, const float4* __restrict__ gamma,
-                                     const float4* __restrict__ sums, float4* __restrict__ dx, int64_t rows, int tpr, int relu) {
+                                     const float4* __restrict__ sums, float4* __restrict__ dx, int64_t rows, int tpr, int relu,
+                                     int64_t rows_total) {
     const int64_t n4 = rows * tpr;
-    const float inv = 1.f / (float)rows;
+    const float inv = 1.f / (float)rows_total;      // rows of the whole (possibly multi-rank) batch the sums were taken over
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % tpr);
         float4 g = dy[i];
@@ -163,9 +164,10 @@ __global__ void bn_bwd_apply4_kernel(const float4* __restrict__ dy, const float4
 // dx = gamma * rstd * (g - sum_g / R - xhat * sum_gx / R)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sums, float* __restrict__ dx, int64_t rows, int cols, int relu) {
+                                    const float* __restrict__ sums, float* __restrict__ dx, int64_t rows, int cols, int relu,
+                                    int64_t rows_total) {
     const int64_t n = rows * cols;
-    const float inv = 1.f / (float)rows;
+    const float inv = 1.f / (float)rows_total;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cols);
         const float g = (relu && !(y[i] > 0.f)) ? 0.f : dy[i];
@@ -420,29 +422,46 @@ int ipsb_bn_apply_f32(const float* x, const float* mean, const float* rstd, cons
     return 0;
 }
 
-/* sums (2*cols): [sum g, sum g*xhat]  (= dbeta, dgamma);  dx as in the BatchNorm backward */
-int ipsb_bn_backward_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
-                         float* sums, float* dx, float* scratch, int64_t rows, int cols, int relu, void* stream) {
+/* phase 1: sums (2*cols) = [sum g, sum g*xhat] over this rank's rows (= dbeta, dgamma) */
+int ipsb_bn_backward_sums_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                              float* sums, float* scratch, int64_t rows, int cols, int relu, void* stream) {
     IPSB_REQUIRE(rows > 0 && cols > 0 && scratch != nullptr, "bn_backward: bad arguments");
-    if (fast4(cols, x) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
-        ((uintptr_t)mean % 16 == 0) && ((uintptr_t)rstd % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)sums % 16 == 0)) {
-        cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fast4(cols, x) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)mean % 16 == 0) &&
+        ((uintptr_t)rstd % 16 == 0)) {
         const int R = (int)(rows < kRowChunks4 ? rows : kRowChunks4);
         col_partial4_kernel<2><<<R, 256, 0, st>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
         col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, st>>>(scratch, sums, cols, R, 2, 1.f);
-        bn_bwd_apply4_kernel<<<grid_for(rows * (cols / 4)), 256, 0, st>>>(
-            (const float4*)dy, (const float4*)x, (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
-            (const float4*)sums, (float4*)dx, rows, cols / 4, relu);
-        IPSB_LAUNCH_CHECK();
-        return 0;
+    } else {
+        dim3 grid((cols + 31) / 32, kRowChunks);
+        col_partial_kernel<2><<<grid, 256, 0, st>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
+        col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, st>>>(scratch, sums, cols, kRowChunks, 2, 1.f);
     }
-    dim3 grid((cols + 31) / 32, kRowChunks);
-    col_partial_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
-    col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, sums, cols, kRowChunks, 2, 1.f);
-    IPSB_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(dy, x, y, mean, rstd, gamma, sums, dx, rows, cols, relu);
     IPSB_LAUNCH_CHECK();
     return 0;
+}
+
+/* phase 2: dx from sums taken over rows_total rows (the all-reduced sums of a synchronised BatchNorm, or phase 1's) */
+int ipsb_bn_backward_apply_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
+                               const float* sums, float* dx, int64_t rows, int cols, int64_t rows_total, int relu, void* stream) {
+    IPSB_REQUIRE(rows > 0 && cols > 0 && rows_total >= rows, "bn_backward_apply: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cols % 4 == 0 && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
+        ((uintptr_t)mean % 16 == 0) && ((uintptr_t)rstd % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)sums % 16 == 0))
+        bn_bwd_apply4_kernel<<<grid_for(rows * (cols / 4)), 256, 0, st>>>(
+            (const float4*)dy, (const float4*)x, (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
+            (const float4*)sums, (float4*)dx, rows, cols / 4, relu, rows_total);
+    else
+        bn_bwd_apply_kernel<<<grid_for(rows * cols), 256, 0, st>>>(dy, x, y, mean, rstd, gamma, sums, dx, rows, cols, relu, rows_total);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+/* sums (2*cols): [sum g, sum g*xhat]  (= dbeta, dgamma);  dx as in the BatchNorm backward */
+int ipsb_bn_backward_f32(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
+                         float* sums, float* dx, float* scratch, int64_t rows, int cols, int relu, void* stream) {
+    if (int rc = ipsb_bn_backward_sums_f32(dy, x, y, mean, rstd, sums, scratch, rows, cols, relu, stream)) return rc;
+    return ipsb_bn_backward_apply_f32(dy, x, y, mean, rstd, gamma, sums, dx, rows, cols, rows, relu, stream);
 }
 
 int ipsb_layernorm_backward_f32(const float* dy, const float* x, const float* gamma, float* dx, float* xhat, int64_t rows, int D,

@@ -126,6 +126,9 @@ class IPSNet(nn.Module):
         self.chunk_patches = int(os.environ.get('IPS_B200_CHUNK', getattr(conf, 'chunk_patches', 0)))   # 0 = auto
         # chunks in flight inside the native executor (internal streams); 1 = strictly sequential
         self.lanes = int(os.environ.get('IPS_B200_LANES', getattr(conf, 'lanes', 2)))
+        # data-parallel train step: synchronise BatchNorm statistics over the ranks (True = default process group) so a
+        # batch split over R GPUs normalises like the whole batch in one process; off = per-rank statistics
+        self.sync_bn = getattr(conf, 'sync_bn', False)
         # grad-mode conv encoder: 'native' = library kernels forward and backward (bf16 precision), 'torch' = cuDNN autograd
         self.train_encoder = os.environ.get('IPS_B200_TRAIN_ENCODER', getattr(conf, 'train_encoder', 'native'))
         # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
@@ -548,14 +551,15 @@ class IPSNet(nn.Module):
             ln, lin, bn = self.encoder[0], self.encoder[1], self.encoder[2]
             h = LayerNormFn.apply(mem_patch.reshape(B * M, -1), None, None, ln.eps)
             h = lin(h)
-            mem_emb = BatchNormTrainFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, True)
+            mem_emb = BatchNormTrainFn.apply(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, True,
+                                             self.sync_bn)
             with torch.no_grad():
                 bn.num_batches_tracked += 1
             mem_emb = mem_emb.view(B, M, -1)
         elif (self.is_image and mem_patch.is_cuda and self.training and self.precision == 'bf16'
               and self.train_encoder == 'native' and self.encoder[0].out_channels == 64):
             # conv encoder on the library's kernels, forward and backward (ips_b200/autograd.py::conv_encoder_train)
-            mem_emb = conv_encoder_train(self.encoder, mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
+            mem_emb = conv_encoder_train(self.encoder, mem_patch.reshape(-1, *shape[2:]), self.sync_bn).view(B, M, -1)
         else:
             mem_emb = self.encoder(mem_patch.reshape(-1, *shape[2:])).view(B, M, -1)
         if torch.is_tensor(mem_pos):

@@ -92,6 +92,10 @@ class GraphedTrainStep:
         capture.  The warm-up steps are real steps on whatever the buffers hold; with `restore_state` the parameters,
         BatchNorm statistics and optimizer state are put back in place afterwards (the graph keeps their addresses)."""
         dev = self.net.device
+        from .autograd import _dist_group
+        if _dist_group(getattr(self.net, 'sync_bn', None)) is not None:
+            self.graph = False                       # synchronised BatchNorm puts collectives inside forward/backward: run eagerly
+            return self
         snap = None
         if restore_state:
             snap = ([p.detach().clone() for p in self.net.parameters()], [b.detach().clone() for b in self.net.buffers()],
@@ -128,6 +132,9 @@ class GraphedTrainStep:
     def __call__(self):
         if self.graph is None:
             self.capture()
+        if self.graph is False:
+            self._step()
+            return self.loss
         self.graph.replay()
         if self.grad_hook is not None:
             self._sync_and_update()

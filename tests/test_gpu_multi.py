@@ -110,3 +110,134 @@ def test_sharded_merge_matches_sharded_oracle(pre, B, N, over):
     assert torch.equal(ret['idx0'], ret['idx1'])
     assert torch.equal(ret['idx0'], o_src)
     assert torch.equal(ret['mem_patch'], o_patch)
+
+
+def _worker_syncbn(rank, world, port, name, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        sys.path.insert(0, p)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        import ips_oracle as O
+        from ips_b200 import IPSNet, Struct
+        from ips_b200.distributed import allreduce_gradients
+        from ips_b200.train import compute_loss
+        from golden_util import load_case
+        z, meta, conf, sd, patches = load_case(name)
+        conf = conf.replace(attn_dropout=0.0, dropout=0.0, precision='bf16', sync_bn=True)
+        torch.manual_seed(meta['rng_seed'])
+        mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+        labels = O.make_labels(conf, meta['B'], meta['label_seed'])
+        B = meta['B']
+        lo, hi = rank * B // world, (rank + 1) * B // world        # uneven split when B is odd: the statistics weigh by rows
+        net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+        net.load_state_dict(sd)
+        net.train()
+        preds = net(mem_patch[lo:hi].to(dev), None if mem_pos is None else mem_pos[lo:hi].to(dev))
+        loss = compute_loss(conf, preds, {k: v[lo:hi].to(dev) for k, v in labels.items()})
+        loss.backward()
+        allreduce_gradients(list(net.parameters()))
+        lt = loss.detach().clone()
+        dist.all_reduce(lt)
+        if rank == 0:
+            ret['loss'] = float(lt) / world
+            ret['grads'] = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
+            ret['bn'] = {k: v.cpu() for k, v in net.state_dict().items() if 'running' in k}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('name', ['camelyon_shortcut'])      # even batch: equal shares per rank; fp32-accurate path
+def test_syncbn_data_parallel_equals_single_process(name):
+    """Data-parallel train step with synchronised BatchNorm: batch split over 2 GPUs + gradient all-reduce ==
+    the whole batch on one GPU (loss, every gradient, running statistics), both on the library's kernels."""
+    for p in (os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        sys.path.insert(0, p)
+    import ips_oracle as O
+    from ips_b200 import IPSNet, Struct
+    from ips_b200.train import compute_loss
+    from golden_util import load_case
+    z, meta, conf, sd, patches = load_case(name)
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_syncbn, args=(2, port, name, ret), nprocs=2, join=True)
+    conf = conf.replace(attn_dropout=0.0, dropout=0.0, precision='bf16')
+    torch.manual_seed(meta['rng_seed'])
+    mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+    labels = O.make_labels(conf, meta['B'], meta['label_seed'])
+    dev = torch.device('cuda', 0)
+    net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+    net.load_state_dict(sd)
+    net.train()
+    loss = compute_loss(conf, net(mem_patch.to(dev), None if mem_pos is None else mem_pos.to(dev)), {k: v.to(dev) for k, v in labels.items()})
+    loss.backward()
+    assert abs(ret['loss'] - loss.item()) <= 2e-2 * max(1.0, abs(loss.item()))
+    # both runs compute in bf16: a different fp32 summation order flips bf16 roundings / ReLU gates upstream, so the
+    # comparison is per tensor in the L2 sense (the unsynchronised statistics would be off by tens of percent)
+    scale = max(float(p.grad.norm()) for p in net.parameters() if p.grad is not None)
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        a, b = p.grad.cpu().double(), ret['grads'][k].double()
+        assert float((a - b).norm()) <= 0.15 * float(a.norm()) + 1e-3 * scale, (k, float((a - b).norm()), float(a.norm()))
+    for k, v in net.state_dict().items():
+        if 'running' in k:
+            a, b = v.cpu(), ret['bn'][k]
+            assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max()) + 1e-3, (k, float((a - b).abs().max()))
+
+
+def _worker_bn_unit(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from ips_b200.autograd import BatchNormTrainFn
+        g = torch.Generator().manual_seed(5)
+        rows, cols = 1001, 64                                   # uneven shares: 500 / 501 rows
+        x = torch.randn(rows, cols, generator=g) * 2 + 0.5
+        dy = torch.randn(rows, cols, generator=g)
+        gamma, beta = torch.rand(cols, generator=g) + 0.5, torch.randn(cols, generator=g)
+        lo, hi = rank * rows // world, (rank + 1) * rows // world
+        xs = x[lo:hi].to(dev).requires_grad_(True)
+        gm, bt = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+        rm, rv = torch.zeros(cols, device=dev), torch.ones(cols, device=dev)
+        y = BatchNormTrainFn.apply(xs, gm, bt, rm, rv, 0.1, 1e-5, True, True)
+        y.backward(dy[lo:hi].to(dev))
+        dgm, dbt = gm.grad.clone(), bt.grad.clone()
+        dist.all_reduce(dgm); dist.all_reduce(dbt)              # parameter gradients are summed by the gradient exchange
+        ret[rank] = dict(y=y.detach().cpu(), dx=xs.grad.cpu(), dgamma=dgm.cpu(), dbeta=dbt.cpu(), rm=rm.cpu(), rv=rv.cpu(), lo=lo, hi=hi)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_synchronised_batchnorm_fn_equals_full_batch():
+    """BatchNormTrainFn with a process group on two uneven shares == torch BatchNorm on the whole batch:
+    output, input gradient, parameter gradients (summed over ranks), running statistics."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_bn_unit, args=(2, port, ret), nprocs=2, join=True)
+    g = torch.Generator().manual_seed(5)
+    rows, cols = 1001, 64
+    x = (torch.randn(rows, cols, generator=g) * 2 + 0.5).requires_grad_(True)
+    dy = torch.randn(rows, cols, generator=g)
+    gamma = (torch.rand(cols, generator=g) + 0.5).requires_grad_(True)
+    beta = torch.randn(cols, generator=g).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(cols, eps=1e-5, momentum=0.1)
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    y = torch.relu(bn(x))
+    y.backward(dy)
+    for r in (0, 1):
+        lo, hi = ret[r]['lo'], ret[r]['hi']
+        torch.testing.assert_close(ret[r]['y'], y[lo:hi].detach(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(ret[r]['dx'], x.grad[lo:hi], rtol=1e-3, atol=1e-5)
+        torch.testing.assert_close(ret[r]['rm'], bn.running_mean, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(ret[r]['rv'], bn.running_var, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(ret[0]['dgamma'], bn.weight.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(ret[0]['dbeta'], bn.bias.grad, rtol=1e-3, atol=1e-4)
