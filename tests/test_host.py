@@ -117,3 +117,41 @@ def test_feature_bag_roundtrip(tmp_path):
             want = s if dtype == 'fp32' else s.to(torch.bfloat16)
             assert item['input'].dtype == want.dtype and torch.equal(item['input'], want)
             assert item['metastases'] == i % 2
+
+
+def test_auto_chunk_policy_and_image_geometry():
+    """Host-side planning: rows are split evenly over the lanes under the workspace cap; the patch grid of an image
+    follows the reference's unfold (n = (H - ph) // sh + 1 rows of (W - pw) // sw + 1 patches)."""
+    import torch
+    import ips_oracle as O
+    from ips_b200 import IPSNet, Struct, ops
+    conf = O.preset('traffic')
+    net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    assert net.lanes == 2
+    assert net._auto_chunk((3, 100, 100), 3072) == 1536               # two lanes, one chunk each
+    assert net._auto_chunk((3, 100, 100), 3000) == 1504               # rounded up to a multiple of 8
+    assert net._auto_chunk((3, 100, 100), 20000) <= 2048              # capped by the activation workspace
+    assert net._auto_chunk((3, 100, 100), 10) == 32                   # floor
+    net.chunk_patches = 77
+    assert net._auto_chunk((3, 100, 100), 3072) == 77                 # explicit override
+    img = torch.zeros(2, 3, 1200, 1600)
+    geo, n = ops.image_geo(img, (100, 100), (100, 100))
+    assert n == 192 and geo.n_per_image == 192 and (geo.img_h, geo.img_w, geo.stride_h, geo.stride_w) == (1200, 1600, 100, 100)
+    geo, n = ops.image_geo(torch.zeros(1, 1, 250, 300), (50, 50), (25, 25))
+    assert n == 9 * 11
+
+
+def test_ips_out_buffer_validation():
+    import torch
+    import ips_oracle as O
+    from ips_b200 import IPSNet, Struct
+    conf = O.preset('camelyon', M=8, I=8)
+    net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    good = torch.zeros(4, 8, conf.n_chan_in)
+    a, b = net._out_views((good, None), 1, 2, 8)
+    assert a.shape == (2, 8, conf.n_chan_in) and b is None and a.data_ptr() == good[1].data_ptr()
+    import pytest
+    with pytest.raises(ValueError):
+        net._out_views((good, None), 3, 2, 8)                         # rows 3..4 do not fit 4 rows
+    with pytest.raises(ValueError):
+        net._out_views((torch.zeros(4, 7, conf.n_chan_in), None), 0, 2, 8)
