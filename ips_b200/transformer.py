@@ -17,15 +17,13 @@ from .autograd import Linear, LayerNormFn, CrossAttentionFn
 
 
 def pos_enc_1d(D, len_seq):
-    """Sin/cos table (len_seq, D); same values as transformer.py:6-18."""
+    """Sin/cos table (len_seq, D): even columns sin(n * w_j), odd columns cos(n * w_j), w_j = 10000^(-2j/D); the values
+    of transformer.py:6-18."""
     if D % 2 != 0:
         raise ValueError('Cannot use sin/cos positional encoding with odd dim (got dim={:d})'.format(D))
-    position = torch.arange(0, len_seq).unsqueeze(1).float()
-    div_term = torch.exp(torch.arange(0, D, 2, dtype=torch.float) * -(math.log(10000.0) / D))
-    table = torch.zeros(len_seq, D)
-    table[:, 0::2] = torch.sin(position * div_term)
-    table[:, 1::2] = torch.cos(position * div_term)
-    return table
+    freq = torch.exp(torch.arange(0, D, 2, dtype=torch.float) * -(math.log(10000.0) / D))       # (D/2,)
+    angle = torch.arange(0, len_seq).unsqueeze(1).float() * freq                                  # (len_seq, D/2)
+    return torch.stack((torch.sin(angle), torch.cos(angle)), dim=-1).reshape(len_seq, D)
 
 
 class _Temperature(nn.Module):
@@ -87,11 +85,12 @@ class MultiHeadCrossAttention(nn.Module):
             out = CrossAttentionFn.apply(q, k, v, mask, keep, H, Dk, Dv)                # (B, T, H*Dv)
             out = self.dropout(self.fc(out)) + self.q
             return LayerNormFn.apply(out, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
-        q = self.q_w(self.q).view(1, T, H, Dk).transpose(1, 2)
-        k = self.k_w(x).view(B, L, H, Dk).transpose(1, 2)
-        v = self.v_w(x).view(B, L, H, Dv).transpose(1, 2)
-        attn = self.attention.dropout(torch.softmax(torch.matmul(q / self.attention.temperature, k.transpose(2, 3)), dim=-1))
-        out = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, T, H * Dv)
+        # host path (CPU tensors: golden-vector tests of the module structure)
+        qh = (self.q_w(self.q) / self.attention.temperature).view(T, H, Dk)
+        kh = self.k_w(x).view(B, L, H, Dk)
+        vh = self.v_w(x).view(B, L, H, Dv)
+        attn = self.attention.dropout(torch.softmax(torch.einsum('thd,blhd->bhtl', qh, kh), dim=-1))
+        out = torch.einsum('bhtl,blhd->bthd', attn, vh).reshape(B, T, H * Dv)
         out = self.dropout(self.fc(out)) + self.q
         return self.layer_norm(out)
 
