@@ -545,7 +545,8 @@ def test_stem_pool_fused(dev, C, H, W, P):
 
 
 @pytest.mark.parametrize('case', [(64, 64, 3, 1, 1, 13, 13), (64, 128, 3, 2, 1, 13, 13), (64, 128, 1, 2, 0, 13, 13),
-                                  (128, 256, 3, 2, 1, 7, 7), (256, 256, 3, 1, 1, 4, 4), (256, 512, 1, 2, 0, 7, 7)])
+                                  (128, 256, 3, 2, 1, 7, 7), (256, 256, 3, 1, 1, 4, 4), (256, 512, 1, 2, 0, 7, 7),
+                                  (64, 128, 3, 2, 1, 14, 14), (64, 128, 1, 2, 0, 14, 10)])      # even maps under stride 2
 def test_conv_autograd_fn(dev, case):
     """ConvFn: forward, grad input (same kernel, flipped weights, zero-dilated dy for stride 2) and grad weight
     (im2col x dy, TN GEMM) against torch autograd on the same bf16-rounded operands."""
