@@ -66,7 +66,7 @@ class OracleBackend:
         return torch.stack(rows)
 
 
-def _worker_merge(rank, world, port, case, ret):
+def _worker_merge(rank, world, port, case, ret, M_over=None):
     """north_star schedule: local top-M per rank, all-gather of the candidates, one global re-score."""
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -78,6 +78,8 @@ def _worker_merge(rank, world, port, case, ret):
         from ips_b200.distributed import ips_sharded, shard_bounds
         from golden_util import load_case
         z, meta, conf, sd, patches = load_case(case)
+        if M_over:
+            conf = conf.replace(M=M_over)
         N = patches.shape[1]
         net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
         net.load_state_dict(sd)
@@ -91,16 +93,19 @@ def _worker_merge(rank, world, port, case, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('case', ['camelyon_batch', 'mnist_small'])
-def test_sharded_merge_schedule_world2(case):
+@pytest.mark.parametrize('case,M_over', [('camelyon_batch', None), ('mnist_small', None),
+                                         ('mnist_small', 20)])       # slices (18 patches) not longer than M: keep everything
+def test_sharded_merge_schedule_world2(case, M_over):
     """P5: the local-top-M + merge schedule equals the sharded-schedule oracle run in one process."""
     from golden_util import load_case
     from ips_b200.distributed import shard_bounds
     z, meta, conf, sd, patches = load_case(case)
+    if M_over:
+        conf = conf.replace(M=M_over)
     B, N = patches.shape[:2]
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker_merge, args=(2, port, case, ret), nprocs=2, join=True)
+    mp.spawn(_worker_merge, args=(2, port, case, ret, M_over), nprocs=2, join=True)
     blocks = []
     for r, (lo, hi) in enumerate(shard_bounds(N, 2)):           # the equivalent block-wise permutation
         torch.manual_seed(100 + r)
