@@ -145,7 +145,7 @@ def run_reference(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * B * N / rate, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: IPSNet.ips, B={B} N={N} M={conf.M} I={conf.I}', 'l2': 'n/a (CPU)'},
+        'config': {'workload': f'{args.workload}: IPSNet.ips, B={B} N={N} M={conf.M} I={conf.I} per GPU', 'l2': 'n/a (CPU)'},
         'cpu_baseline': {'value': rate, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': rate, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': time.perf_counter() - t_start,
