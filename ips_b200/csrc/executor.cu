@@ -49,6 +49,9 @@ struct PfPlan {
     int H[4], W[4], C[4];         // geometry of each group's activations
     int64_t rows[4];              // PF rows per buffer for `chunk` patches
     int64_t staged_bytes, stem_bytes, group_bytes[4], total;
+    // groups whose maps do not fill pixel-box tiles (7x7) and are 256 wide can run DENSE through the im2col-mode kernel:
+    // they get their own four (P*H*W, C) buffers (0 bytes when the group is not a candidate), after the PF buffers
+    int64_t dense_bytes[4];
 };
 
 PfPlan make_pf_plan(const ipsb_resnet_desc* net, int64_t chunk, int H, int W) {
@@ -69,7 +72,11 @@ PfPlan make_pf_plan(const ipsb_resnet_desc* net, int64_t chunk, int H, int W) {
         pl.rows[g] = ipsb_pf_rows(chunk, h, w);
         pl.group_bytes[g] = align256(pl.rows[g] * c1.cout * 2);
         pl.total += 4 * pl.group_bytes[g];
+        const int hw = h * w;
+        const bool candidate = g > 0 && c1.cout % 256 == 0 && (hw & (hw - 1)) != 0 && !getenv("IPSB_NO_IM2COL") && !getenv("IPSB_NO_PAIR");
+        pl.dense_bytes[g] = candidate ? align256(chunk * (int64_t)hw * c1.cout * 2) : 0;
     }
+    for (int g = 0; g < pl.n_groups; ++g) pl.total += 4 * pl.dense_bytes[g];      // (after every PF buffer: see resnet_logits_pf)
     return pl;
 }
 
@@ -100,9 +107,9 @@ int lane_streams(LaneStreams** out) {
 }
 
 int run_conv_pf(const ipsb_conv_desc& c, const void* x, const void* res, void* y, int64_t P, int H, int W, int relu,
-                void* stream) {
+                void* stream, int in_pf = 1, int out_pf = 1) {
     return ipsb_conv_bf16_pf(x, c.w, c.scale, c.shift, res, y, P, H, W, c.cin, c.cout, c.kh, c.kw, c.stride, c.pad, relu,
-                             1, 1, stream);
+                             in_pf, out_pf, stream);
 }
 
 }  // namespace
@@ -131,6 +138,14 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
     }
     size_t pf_bytes = 0;
     for (int g = 0; g < pl.n_groups; ++g) pf_bytes += 4 * (size_t)pl.group_bytes[g];
+    // a candidate group runs dense in this call when every chunk has an even number of full 128-pixel tiles
+    bool dense[4] = {false, false, false, false};
+    for (int g = 0; g < pl.n_groups; ++g) {
+        if (pl.dense_bytes[g] == 0) continue;
+        const int64_t hw = (int64_t)pl.H[g] * pl.W[g];
+        const int64_t last = n_rows % chunk;
+        dense[g] = (n_rows >= chunk ? (chunk * hw) % 256 == 0 : true) && (last == 0 || (last * hw) % 256 == 0);
+    }
     if (zero_init)   // pad rows of the padded-flat buffers must be zero; kernels keep them zero afterwards
         for (int l = 0; l < lanes; ++l)
             IPSB_CUDA(cudaMemsetAsync((char*)workspace + l * lane_bytes + pl.staged_bytes + pl.stem_bytes, 0, pf_bytes,
@@ -150,6 +165,9 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         void* gb[4][4];
         for (int g = 0; g < pl.n_groups; ++g)
             for (int i = 0; i < 4; ++i) { gb[g][i] = ws; ws += pl.group_bytes[g]; }
+        void* gd[4][4];
+        for (int g = 0; g < pl.n_groups; ++g)
+            for (int i = 0; i < 4; ++i) { gd[g][i] = ws; ws += pl.dense_bytes[g]; }
         float* emb_ws = (float*)ws;      ws += align256(chunk * net->D * 4);
         int64_t* pos_idx = (int64_t*)ws;
         const int64_t P = (n_rows - lo < chunk) ? n_rows - lo : chunk;
@@ -192,30 +210,34 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         int h = out_dim(hs, 3, 2, 1), w = out_dim(wsz, 3, 2, 1);   // geometry of the current activation
         const void* cur = gb[0][0];
         int cur_slot = 0;
+        bool cur_dense = false;                  // layout of `cur`: padded-flat, or dense (P*H*W, C) rows
         for (int b = 0; b < net->n_blocks; ++b) {
             const ipsb_block_desc& blk = net->blocks[b];
             const int g = b / 2;
+            const bool out_dense = dense[g];
+            void** bufs = out_dense ? gd[g] : gb[g];
             int free_ids[3], nf = 0;
             if (b % 2 == 0 && g > 0) { free_ids[0] = 0; free_ids[1] = 1; free_ids[2] = 2; nf = 3; }   // input lives in the previous group
             else for (int i = 0; i < 4; ++i) if (i != cur_slot) free_ids[nf++] = i;
-            const void* idt = cur;
+            const void* idt = cur;               // (no downsample: same group, same layout as the output)
             if (blk.has_ds) {
-                rc = run_conv_pf(blk.ds, cur, nullptr, gb[g][free_ids[0]], P, h, w, 0, stream);
+                rc = run_conv_pf(blk.ds, cur, nullptr, bufs[free_ids[0]], P, h, w, 0, stream, !cur_dense, !out_dense);
                 if (rc) return rc;
-                idt = gb[g][free_ids[0]];
+                idt = bufs[free_ids[0]];
             }
-            rc = run_conv_pf(blk.c1, cur, nullptr, gb[g][free_ids[1]], P, h, w, 1, stream);
+            rc = run_conv_pf(blk.c1, cur, nullptr, bufs[free_ids[1]], P, h, w, 1, stream, !cur_dense, !out_dense);
             if (rc) return rc;
-            rc = run_conv_pf(blk.c2, gb[g][free_ids[1]], idt, gb[g][free_ids[2]], P, pl.H[g], pl.W[g], 1, stream);
+            rc = run_conv_pf(blk.c2, bufs[free_ids[1]], idt, bufs[free_ids[2]], P, pl.H[g], pl.W[g], 1, stream, !out_dense, !out_dense);
             if (rc) return rc;
-            cur = gb[g][free_ids[2]];
+            cur = bufs[free_ids[2]];
             cur_slot = free_ids[2];
+            cur_dense = out_dense;
             h = pl.H[g]; w = pl.W[g];
         }
         const int gl = pl.n_groups - 1;
         IPSB_REQUIRE(pl.C[gl] == net->D, "resnet_logits: encoder width %d != D %d", pl.C[gl], net->D);
         float* emb = emb_out ? emb_out + lo * net->D : emb_ws;
-        rc = ipsb_avgpool_pf(cur, emb, P, h, w, pl.C[gl], stream);
+        rc = cur_dense ? ipsb_avgpool(cur, emb, P, h * w, pl.C[gl], IPSB_BF16, stream) : ipsb_avgpool_pf(cur, emb, P, h, w, pl.C[gl], stream);
         if (rc) return rc;
         const int64_t* idx = nullptr;
         if (net->add_tab) {

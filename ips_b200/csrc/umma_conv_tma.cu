@@ -244,6 +244,9 @@ int conv_pair_launch(const CUtensorMap& tmA, const CUtensorMap& tmBh, const CUte
                      const float* scale, const float* shift, bool has_res, int P, int Ho, int Wo, int Cout, int kw, int stride, int pad,
                      int relu, int bw, int bh, int bp, int tiles_x, int tiles_y, int n_tiles_n, int m_tiles, int KS, int cblocks,
                      uint32_t a_bytes, cudaStream_t st);
+// dense stride-1 3x3 convolution with im2col-mode TMA (umma_conv_pair.cu); -1 = not eligible
+int conv_pair_im2col(const void* x, const void* w, const float* scale, const float* shift, const void* res, void* y,
+                     int64_t P, int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
 }
 namespace {
 
@@ -354,6 +357,14 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
              int64_t P, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
              bool out_f32, cudaStream_t st, bool in_pf, bool out_pf) {
     IPSB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tma: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+    if (!in_pf && !out_pf && !out_f32 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && Cout % 256 == 0) {
+        // dense 256-wide stride-1 layers: 128 consecutive pixels per tile through im2col-mode TMA (every tile row useful)
+        static const bool im2col_ok = !getenv("IPSB_NO_IM2COL") && !getenv("IPSB_NO_PAIR");
+        if (im2col_ok) {
+            const int rc = conv_pair_im2col(x, w, scale, shift, res, y, P, H, W, Cin, Cout, relu, st);
+            if (rc >= 0) return rc;
+        }
+    }
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     IPSB_REQUIRE(Ho > 0 && Wo > 0, "conv_tma: bad geometry");
     IPSB_REQUIRE(P < (1ll << 31), "conv_tma: too many patches");

@@ -420,3 +420,18 @@ def test_bf16_feature_bag_equals_upcast_fp32():
         got_patch, _ = net.ips(src)
         assert torch.equal(net.last_mem_idx, ref_idx)
         assert got_patch.dtype == torch.float32 and torch.equal(got_patch, ref_patch)
+
+
+def test_native_executor_dense_group_equals_per_layer_calls():
+    """With an even number of full 128-pixel tiles per chunk the native executor runs layer 3 (7x7 maps, 256 channels) on dense
+    activations through the im2col-mode kernel; the logits equal the per-layer padded-flat path bit for bit."""
+    conf = O.preset('traffic', attn_dropout=0.0, dropout=0.0)
+    sd = O.make_state(conf, 81, q_gain=12.0)
+    g = torch.Generator(device=DEV).manual_seed(82)
+    x = torch.randn((2, 256, conf.n_chan_in, *conf.patch_size), generator=g, device=DEV)
+    net = _net(conf.replace(chunk_patches=256, lanes=2, N=256), sd, 'bf16')
+    net.executor = 'native'
+    a = net.patch_logits(x)
+    net.executor = 'python'
+    b = net.patch_logits(x)
+    assert torch.equal(a, b)

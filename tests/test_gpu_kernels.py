@@ -587,3 +587,20 @@ def test_stem_conv_autograd_fn(dev, C, H, W):
     torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-2, atol=1e-2)
     err = (wd.grad.cpu() - wr.grad).abs().max() / wr.grad.abs().max()
     assert err < 1e-2, err
+
+
+@pytest.mark.parametrize('Cin,Cout,H,W,P', [(256, 256, 7, 7, 256), (256, 512, 7, 7, 512), (512, 256, 5, 9, 256)])
+def test_conv_im2col_pair(dev, Cin, Cout, H, W, P):
+    """Dense stride-1 3x3 convolution through the im2col-mode CTA-pair kernel (128 consecutive pixels per tile)."""
+    from ips_b200 import ops
+    x = _rand(P, H, W, Cin, seed=70).to(torch.bfloat16)
+    w = _rand(Cout, Cin, 3, 3, seed=71, scale=math.sqrt(2.0 / (Cin * 9))).to(torch.bfloat16)
+    scale, shift = torch.rand(Cout) + 0.5, _rand(Cout, seed=72, scale=0.1)
+    res = _rand(P, H, W, Cout, seed=73).to(torch.bfloat16)
+    w_nk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().to(dev)
+    assert (P * H * W) % 256 == 0                                   # eligible: an even number of full tiles
+    for use_res, relu in ((False, True), (True, True), (False, False)):
+        ref = _conv_ref(x.float(), w.float(), scale, shift, res.float() if use_res else None, 1, 1, relu)
+        y = ops.conv_bf16_pf(x.to(dev), w_nk, scale.to(dev), shift.to(dev), res.to(dev) if use_res else None, P, H, W, Cout, 3, 3, 1, 1,
+                             relu, False, False)
+        torch.testing.assert_close(y.cpu().float(), ref, rtol=1e-2, atol=1e-2)
