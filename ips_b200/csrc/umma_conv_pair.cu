@@ -12,6 +12,10 @@
 //     warpgroups drain its own 128 TMEM lanes (BN + residual + ReLU -> TMA store) and release the accumulator with a
 //     remote arrive on the leader's barrier.
 // 5 stages of 32 KB per CTA, 2 x 256 TMEM columns (double-buffered accumulators) in each CTA.
+//
+// Two kernels share this pipeline: conv_pair_kernel (pixel-box M tiles, any stride, padded-flat or dense tensors) and
+// conv_pair_im2col_kernel further down (dense stride-1 3x3 layers: 128 consecutive output pixels per tile through
+// im2col-mode TMA, every tile row useful whatever the map size).
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
