@@ -284,6 +284,60 @@ IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k,
 IPSB_API int ipsb_gather_rows(const void* src, int64_t src_batch_stride_rows, const int64_t* idx,
                      int B, int M, int64_t row_bytes, void* dst, void* stream);
 
+/* ---------------------------------------------------------------- sequence-sharded selection over NVLink peer memory
+ * New work (the reference is single-GPU; SURVEY.md 8e, north_star "each rank scans its slice and keeps a local top-M,
+ * the ranks then merge ... M (score, index) candidates plus a global top-M").  One process per GPU; every rank owns an
+ * EXCHANGE BUFFER (allocated by PyTorch, zero-initialised) whose CUDA-IPC handle the host side all-gathers once; after
+ * ipsb_peer_open every rank holds a device address for every peer's buffer and the kernels below move data with plain
+ * stores over NVLink / NVSwitch -- no NCCL call, no host round trip, CUDA-graph capturable.
+ *
+ * Exchange-buffer layout (identical on all ranks): a 4096-byte header (per-phase epoch counters of the owner, block
+ * completion counters, a status word, and flags[phase][rank] written by the peers), then caller-defined sections
+ * addressed by byte offsets.  A push kernel writes its payload into the same section of every destination rank, and
+ * its last block (device-wide completion counter) publishes epoch+1 in flags[phase][own rank] of every peer with a
+ * system-scope release store.  ipsb_peer_wait spins (system-scope acquire loads, bounded: a peer that never arrives
+ * sets status != 0 instead of hanging the GPU) until all ranks' flags of that phase reached the owner's epoch.
+ * Phases: 0 = candidates / logit slices, 1 = winners. */
+#define IPSB_MAX_PEERS 8
+#define IPSB_PEER_HEADER_BYTES 4096
+typedef struct ipsb_peer_ctx {
+    int32_t rank, world;
+    void* base[IPSB_MAX_PEERS];   /* address IN THIS PROCESS of every rank's exchange buffer (base[rank] = own) */
+} ipsb_peer_ctx;
+/* CUDA-IPC export of a device pointer inside a cudaMalloc'ed allocation (PyTorch's caching allocator without
+ * expandable segments): handle of the allocation + byte offset of `ptr` in it. */
+IPSB_API int ipsb_peer_export(const void* ptr, unsigned char handle_out[64], int64_t* offset_out);
+/* Maps a peer's allocation (lazy peer access) and returns the address of its exchange buffer in this process. */
+IPSB_API int ipsb_peer_open(const unsigned char handle[64], int64_t offset, void** ptr_out);
+IPSB_API int ipsb_peer_close(void* ptr, int64_t offset);
+/* status word of the own header (0 = ok, 1 = a wait timed out); synchronises `stream`. */
+IPSB_API int ipsb_peer_status(const ipsb_peer_ctx* ctx, int* status_out, void* stream);
+/* Candidates of this rank -> slot block [slot0, slot0 + m) of EVERY rank's candidate sections:
+ *   cz (B, L, HT) fp32 at byte offset cz_off:  cz[b, slot0 + j, :] = z_local[b, cand[b, j], :]
+ *   ci (B, L) int64   at byte offset ci_off:  ci[b, slot0 + j]    = index_base + cand[b, j]
+ * z_local (B, n_local, HT) is this rank's slice of the logit table, cand (B, m) local indices (best first).
+ * Replaces the two all-gathers (logits, indices) of the candidate merge; signals phase 0. */
+IPSB_API int ipsb_peer_push_candidates(const ipsb_peer_ctx* ctx, const float* z_local, int64_t n_local, const int64_t* cand,
+                                       int B, int m, int HT, int64_t index_base, int64_t L, int64_t slot0,
+                                       int64_t cz_off, int64_t ci_off, void* stream);
+/* This rank's slice (B, n_local, HT) of the logit table -> rows [row0, row0 + n_local) of every rank's full table
+ * (B, N, HT) at byte offset z_off ('exact' mode: the loop is replicated); signals phase 0. */
+IPSB_API int ipsb_peer_push_logits(const ipsb_peer_ctx* ctx, const float* z_local, int B, int64_t n_local, int HT,
+                                   int64_t N, int64_t row0, int64_t z_off, void* stream);
+/* Waits until every rank has signalled `phase` for the current epoch. */
+IPSB_API int ipsb_peer_wait(const ipsb_peer_ctx* ctx, int phase, void* stream);
+/* Winners -> output section (B_out, M, row_bytes) at byte offset out_off of the destination ranks.  win (B, M) holds
+ * either global patch indices (ci == NULL) or positions into ci (B, L) (the merged candidate list); the global index
+ * is also written to idx_out (B, M) on this rank.  A rank copies the rows it owns (row0 <= index < row0 + n_local) out
+ * of local_rows (B, n_local, row_bytes), one 128-bit load and up to `world` 128-bit peer stores per 16 bytes.
+ * slides_per_rank == 0: every rank receives all B slides (replicated, like IPSNet.ips on every rank);
+ * slides_per_rank > 0: slide b goes only to rank b / slides_per_rank, row b % slides_per_rank of its section (the
+ * data-parallel train step that follows needs each slide on one rank only).  Signals phase 1.
+ * Replaces the all-reduce of zero-padded winners of round 1 (reference gather: ips_net.py:244-247). */
+IPSB_API int ipsb_peer_push_winners(const ipsb_peer_ctx* ctx, const void* local_rows, int64_t n_local, int64_t row0,
+                                    const int64_t* win, const int64_t* ci, int64_t L, int B, int M, int64_t row_bytes,
+                                    int slides_per_rank, int64_t out_off, int64_t* idx_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

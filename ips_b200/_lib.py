@@ -38,6 +38,11 @@ class ImageGeo(ctypes.Structure):
                 ('n_per_image', ctypes.c_int32)]
 
 
+class PeerCtx(ctypes.Structure):
+    """ipsb_peer_ctx"""
+    _fields_ = [('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('base', _ptr * 8)]
+
+
 # name -> argtypes (restype is int status unless listed in _RESTYPE)
 SIGNATURES = {
     'ipsb_abi_version': [],
@@ -91,6 +96,14 @@ SIGNATURES = {
     'ipsb_attention_train_bwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32,
                                      _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
+    'ipsb_peer_export': [_ptr, _ptr, ctypes.POINTER(_i64)],
+    'ipsb_peer_open': [_ptr, _i64, ctypes.POINTER(_ptr)],
+    'ipsb_peer_close': [_ptr, _i64],
+    'ipsb_peer_status': [ctypes.POINTER(PeerCtx), ctypes.POINTER(_i32), _ptr],
+    'ipsb_peer_push_candidates': [ctypes.POINTER(PeerCtx), _ptr, _i64, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _ptr],
+    'ipsb_peer_push_logits': [ctypes.POINTER(PeerCtx), _ptr, _i32, _i64, _i32, _i64, _i64, _i64, _ptr],
+    'ipsb_peer_wait': [ctypes.POINTER(PeerCtx), _i32, _ptr],
+    'ipsb_peer_push_winners': [ctypes.POINTER(PeerCtx), _ptr, _i64, _i64, _ptr, _ptr, _i64, _i32, _i32, _i64, _i32, _i64, _ptr, _ptr],
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],
     'ipsb_resnet_logits': [ctypes.POINTER(ResnetDesc), _ptr, _i64, _i64, _i32, _i32, _i32, _i64, _i64, _ptr, _i64, _i32,
                            _ptr, _ptr, _ptr],

@@ -876,6 +876,101 @@ __global__ void __launch_bounds__(1024) topm_kernel(const float* scores, int L, 
     }
 }
 
+// Stable top-M of LONG rows (candidate merge of the sequence-sharded schedule: L = ranks * M): radix select of the
+// rank-M score straight from global memory (coalesced, L2 resident), compaction of the winners (everything above the
+// threshold plus the first-scanned equals), one bitonic sort of the M winners by (score desc, position asc).
+__global__ void __launch_bounds__(1024, 1) topm_big_kernel(const float* scores, int L, int M, int64_t* idx_out, float* val_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = 1024;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Mpad = next_pow2(M);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);      // [Mpad]
+    int* hist = reinterpret_cast<int*>(keys + Mpad);                                   // [256]
+    int* sel = hist + 256;                                                             // [2]
+    int* wsum = sel + 2;                                                               // [64]
+    const float* s = scores + (int64_t)b * L;
+    uint32_t prefix = 0;
+    int remaining = M;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int l0 = 0; l0 < L; l0 += NT) {                  // warp-uniform trip count (hist_add votes)
+            const int l = l0 + tid;
+            const uint32_t k = (l < L) ? order_bits(__ldg(s + l)) : 0u;
+            hist_add(hist, (k >> shift) & 255u, l < L && (pass == 0 || (k >> (shift + 8)) == prefix));
+        }
+        __syncthreads();
+        if (warp == 0) {                                      // lane j owns bins [255-8j-7, 255-8j]: scan from the top
+            int c[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; tot += c[j]; }
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            const int before = inc - tot;
+            if (before < remaining && remaining <= inc) {
+                int run = before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (run < remaining && remaining <= run + c[j]) { sel[0] = 255 - 8 * lane - j; sel[1] = remaining - run; }
+                    run += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | (uint32_t)sel[0];
+        remaining = sel[1];
+        __syncthreads();
+    }
+    const uint32_t thr = prefix;                              // key of rank M; the first `remaining` equals are kept
+    // each warp owns a contiguous range of the row and walks it 32 entries at a time
+    const int per = (((L + 31) / 32) + 31) / 32 * 32;
+    const int lo = warp * per, hi = min(L, lo + per);
+    int ngt = 0, neq = 0;
+    for (int l0 = lo; l0 < hi; l0 += 32) {
+        const int l = l0 + lane;
+        const uint32_t k = (l < hi) ? order_bits(__ldg(s + l)) : 0u;
+        ngt += __popc(__ballot_sync(0xffffffffu, l < hi && k > thr));
+        neq += __popc(__ballot_sync(0xffffffffu, l < hi && k == thr));
+    }
+    if (lane == 0) { wsum[warp] = ngt; wsum[32 + warp] = neq; }
+    __syncthreads();
+    if (warp == 0) {
+        int a = wsum[lane], c2 = wsum[32 + lane];
+        const int a0 = a, c0 = c2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, a, o), v = __shfl_up_sync(0xffffffffu, c2, o);
+            if (lane >= o) { a += u; c2 += v; }
+        }
+        wsum[lane] = a - a0; wsum[32 + lane] = c2 - c0;      // exclusive
+    }
+    for (int r = M + tid; r < Mpad; r += NT) keys[r] = 0ull;
+    __syncthreads();
+    int gt_before = wsum[warp], eq_before = wsum[32 + warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int l0 = lo; l0 < hi; l0 += 32) {
+        const int l = l0 + lane;
+        const float sv = (l < hi) ? __ldg(s + l) : 0.f;
+        const uint32_t k = (l < hi) ? order_bits(sv) : 0u;
+        const bool gt = l < hi && k > thr, eq = l < hi && k == thr;
+        const uint32_t bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+        const int my_gt = gt_before + __popc(bg & lt_mask), my_eq = eq_before + __popc(be & lt_mask);
+        if (gt || (eq && my_eq < remaining))
+            keys[my_gt + min(my_eq, remaining)] = make_key(sv, (uint32_t)l);
+        gt_before += __popc(bg);
+        eq_before += __popc(be);
+    }
+    __syncthreads();
+    bitonic_desc(keys, Mpad);
+    for (int r = tid; r < M; r += NT) {
+        const unsigned long long k = keys[r];
+        idx_out[(int64_t)b * M + r] = key_pos(k);
+        if (val_out) val_out[(int64_t)b * M + r] = order_bits_inv((uint32_t)(k >> 32));
+    }
+}
+
 int host_next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -898,7 +993,14 @@ int ipsb_scores_from_logits(const float* z, float* scores, int B, int L, int H, 
 int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t* idx_out, float* val_out, void* stream) {
     IPSB_REQUIRE(B > 0 && L > 0 && M > 0 && M <= L, "topm: bad shape B=%d L=%d M=%d", B, L, M);
     const int Lpad = host_next_pow2(L);
-    IPSB_REQUIRE(Lpad <= kMaxLpad, "topm: L=%d exceeds the single-CTA limit %d", L, kMaxLpad);
+    if (Lpad > kMaxLpad) {                                    // long rows: radix select from global memory
+        IPSB_REQUIRE(M <= 16384, "topm: M=%d exceeds 16384 for rows longer than %d", M, kMaxLpad);
+        const size_t smem_big = (size_t)host_next_pow2(M) * 8 + (256 + 2 + 64) * 4 + 16;
+        IPSB_CUDA(cudaFuncSetAttribute(topm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        topm_big_kernel<<<B, 1024, smem_big, (cudaStream_t)stream>>>(scores, L, M, idx_out, val_out);
+        IPSB_LAUNCH_CHECK();
+        return 0;
+    }
     const size_t smem = (size_t)Lpad * 8;
     IPSB_CUDA(cudaFuncSetAttribute(topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topm_kernel<<<B, Lpad <= 512 ? 256 : 1024, smem, (cudaStream_t)stream>>>(scores, L, M, idx_out, val_out);

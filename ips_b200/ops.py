@@ -510,6 +510,71 @@ def add(a, b):
     return y
 
 
+# ------------------------------------------------------------------ NVLink peer exchange (sequence-sharded selection)
+
+PEER_HEADER = 4096
+_peer_maps = {}          # (device index, IPC handle bytes) -> base address of the mapping in this process
+
+
+def peer_export(buf):
+    """(handle bytes[64], offset) of a CUDA tensor's storage for ipsb_peer_open in another process."""
+    handle = (ctypes.c_ubyte * 64)()
+    off = ctypes.c_int64(0)
+    _lib.check(_lib.load().ipsb_peer_export(buf.data_ptr(), ctypes.addressof(handle), ctypes.byref(off)))
+    return bytes(handle), off.value
+
+
+def peer_open(handle, offset, device_index):
+    """Address in this process of a peer's exchange buffer; one mapping per peer allocation is kept for the process."""
+    key = (device_index, handle)
+    if key not in _peer_maps:
+        raw = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        out = ctypes.c_void_p(0)
+        _lib.check(_lib.load().ipsb_peer_open(ctypes.addressof(raw), 0, ctypes.byref(out)))
+        _peer_maps[key] = out.value
+    return _peer_maps[key] + offset
+
+
+def peer_ctx(rank, world, bases):
+    c = _lib.PeerCtx()
+    c.rank, c.world = rank, world
+    for q, b in enumerate(bases):
+        c.base[q] = b
+    return c
+
+
+def peer_push_candidates(ctx, z_local, cand, index_base, L, slot0, cz_off, ci_off):
+    _chk(z_local, torch.float32, 'z_local'); _chk(cand, torch.int64, 'cand')
+    B, n_local, HT = z_local.shape
+    _call('ipsb_peer_push_candidates', ctypes.byref(ctx), _p(z_local), n_local, _p(cand), B, cand.shape[1], HT, index_base, L, slot0,
+          cz_off, ci_off, _stream())
+
+
+def peer_push_logits(ctx, z_local, N, row0, z_off):
+    _chk(z_local, torch.float32, 'z_local')
+    B, n_local, HT = z_local.shape
+    _call('ipsb_peer_push_logits', ctypes.byref(ctx), _p(z_local), B, n_local, HT, N, row0, z_off, _stream())
+
+
+def peer_wait(ctx, phase):
+    _call('ipsb_peer_wait', ctypes.byref(ctx), phase, _stream())
+
+
+def peer_push_winners(ctx, local_rows, row0, win, ci, L, row_bytes, slides_per_rank, out_off, idx_out):
+    _chk(win, torch.int64, 'win'); _chk(ci, torch.int64, 'ci'); _chk(idx_out, torch.int64, 'idx_out')
+    if not local_rows.is_cuda or not local_rows.is_contiguous():
+        raise RuntimeError('ips_b200: local patches must be a contiguous CUDA tensor')
+    B, M = win.shape
+    _call('ipsb_peer_push_winners', ctypes.byref(ctx), _p(local_rows), local_rows.shape[1], row0, _p(win), _p(ci), L, B, M, row_bytes,
+          slides_per_rank, out_off, _p(idx_out), _stream())
+
+
+def peer_status(ctx):
+    out = ctypes.c_int32(0)
+    _lib.check(_lib.load().ipsb_peer_status(ctypes.byref(ctx), ctypes.byref(out), _stream()))
+    return out.value
+
+
 # ------------------------------------------------------------------ torch.ops registration
 # Thin public aliases so the kernels are reachable as torch.ops.ips_b200.*; the
 # module code calls the Python functions above directly (lower dispatch overhead).

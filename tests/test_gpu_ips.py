@@ -41,7 +41,9 @@ def test_ips_fp32_matches_golden(name):
     z, meta, conf, sd, patches = load_case(name)
     net = _net(conf, sd, 'fp32')
     torch.manual_seed(meta['rng_seed'])
-    mem_patch, mem_pos = net.ips(patches.to(DEV))
+    # 'instance' shuffling draws torch.rand on the DATA's device (utils/utils.py:48): the golden was produced with the
+    # patches on the host, so the same RNG stream is reached through the lazy (host-resident) input path
+    mem_patch, mem_pos = net.ips(patches if name == 'mnist_instance' else patches.to(DEV))
     assert net.training and net.encoder.training and net.transf.training
     assert list(mem_patch.shape) == list(z['mem_patch_shape'])
     if conf.M >= meta['N']:                                       # shortcut path
@@ -58,8 +60,6 @@ def test_ips_fp32_matches_golden(name):
         assert mem_pos is None
     if 'mem_src' in z and z['mem_src'].size:
         gold = torch.from_numpy(z['mem_src'])
-        if name == 'mnist_instance':
-            pytest.skip("'instance' shuffle draws torch.rand on the data's device: CUDA RNG != CPU RNG stream")
         same_set = all(set(gold[b].tolist()) == set(got[b].tolist()) for b in range(gold.shape[0]))
         assert same_set, f'selection differs from the reference; oracle boundary gap {meta["boundary_gap"]}'
         if 'ties' not in name:
@@ -79,6 +79,71 @@ def test_ips_fp32_tie_fixture(name):
     assert worst < 1e-5, f'picks differ where the oracle boundary gap is {worst}'
 
 
+def _oracle_final_buffer(conf, trace, perm, B):
+    """(original index, oracle score) of every entry of the LAST iteration's buffer, and the rank-M boundary scores."""
+    M, I = conf.M, conf.I
+    n_iter = len(trace)
+    N = perm.shape[1]
+    lo = M + (n_iter - 1) * I
+    hi = min(lo + I, N)
+    prev_mem = trace[-2][1] if n_iter > 1 else torch.arange(M).unsqueeze(0).expand(B, -1)
+    buf_pos = torch.cat((prev_mem, torch.arange(lo, hi).unsqueeze(0).expand(B, -1)), dim=1)
+    return torch.gather(perm, 1, buf_pos), trace[-1][0]
+
+
+@pytest.mark.parametrize('pre,over,B,N', [('camelyon', {}, 1, 50000),          # C4, full size: M = I = 5000, 9 iterations
+                                          ('mnist', {}, 2, 900),               # C1: 8 iterations, pos-enc
+                                          ('traffic', {}, 2, 192),             # C2: 6 iterations, ragged last chunk (22 of 32)
+                                          ('mnist', {'N': 10000}, 1, 10000)])  # C3: 99 iterations
+def test_ips_fp32_matches_oracle_at_baseline_size(pre, over, B, N):
+    """BASELINE.json sizes (per-image shapes exactly as the configs; B reduced so the CPU oracle finishes in seconds):
+    fp32-mode `ips()` against `O.ips` (ips_net.py:169-262) on the same weights, inputs and scan order.  Indices must be
+    identical; where they are not, P3 applies -- a differing pick must sit within fp32 rounding of the
+    oracle's rank-M boundary score -- and the report is printed."""
+    conf = O.preset(pre, attn_dropout=0.0, dropout=0.0, **over)
+    sd = O.make_state(conf, 91, q_gain=12.0)
+    patches = O.make_patches(conf, B, N, 92)
+    net = _net(conf, sd, 'fp32')
+    torch.manual_seed(93)
+    mem_patch, mem_pos = net.ips(patches.to(DEV))
+    got = net.last_mem_idx.cpu()
+    torch.manual_seed(93)
+    perm = torch.randperm(N).unsqueeze(0).expand(B, -1)           # the 'batch' shuffle's draw (utils/utils.py:38)
+    trace = []
+    o_patch, o_pos, o_src = O.ips(sd, conf, patches, perm=perm, tie='stable', trace=trace)
+    assert len(trace) == -(-(N - conf.M) // conf.I)
+    for b in range(B):                                            # the output really is the selected patches, in order
+        assert torch.equal(mem_patch[b].cpu(), patches[b, got[b]])
+    if conf.use_pos:
+        assert torch.equal(mem_pos.cpu(), O.pos_table(conf.D, conf.N)[got])
+    n_diff, worst, outside = 0, 0.0, 0
+    buf_idx, buf_score = _oracle_final_buffer(conf, trace, perm, B)
+    for b in range(B):
+        a, g = set(o_src[b].tolist()), set(got[b].tolist())
+        if a == g:
+            continue
+        srt = buf_score[b].sort(descending=True)[0]
+        boundary = 0.5 * float(srt[conf.M - 1] + srt[conf.M])
+        score_of = dict(zip(buf_idx[b].tolist(), buf_score[b].tolist()))
+        for i in a ^ g:
+            n_diff += 1
+            if i in score_of:
+                worst = max(worst, abs(score_of[i] - boundary) / boundary)
+            else:
+                outside += 1                                      # evicted earlier in the oracle's run (an earlier boundary flip)
+    order_equal = torch.equal(got, o_src)
+    print(f'{pre} B={B} N={N}: identical={order_equal} differing picks={n_diff} (of {B * conf.M}), '
+          f'max |score - boundary| / boundary = {worst:.2e}, not in the oracle\'s last buffer: {outside}')
+    assert n_diff <= 2 * max(1, B * conf.M // 1000), f'{n_diff} differing picks'
+    assert worst < 2e-5, f'a differing pick sits {worst:.2e} (relative) away from the oracle boundary'
+    if n_diff == 0 and not order_equal:                           # same set, different order: only exact-score neighbours may swap
+        sc = {b: dict(zip(buf_idx[b].tolist(), buf_score[b].tolist())) for b in range(B)}
+        for b in range(B):
+            for m in (got[b] != o_src[b]).nonzero().flatten().tolist():
+                x, y = sc[b][int(got[b, m])], sc[b][int(o_src[b, m])]
+                assert abs(x - y) <= 2e-6 * abs(y), (b, m, x, y)
+
+
 @pytest.mark.parametrize('name', ['mnist_small', 'traffic_small', 'camelyon_small', 'camelyon_batch'])
 def test_ips_bf16_close(name):
     """bf16 tensor-core mode: logits within tolerance of the fp32 oracle, selection overlaps."""
@@ -91,8 +156,12 @@ def test_ips_bf16_close(name):
         emb = emb + O.pos_table(conf.D, conf.N)
     ref = O.attn_logits(sd, conf, emb).permute(0, 3, 1, 2).reshape(B, N, -1)
     err = (zt - ref).abs().max().item() / ref.abs().max().item()
-    print(f'{name}: bf16 logit max err / max |logit| = {err:.3e}')
+    big = ref.abs() >= 0.05 * ref.abs().max()                       # element-wise relative error where the logit is not ~0
+    rel = ((zt - ref).abs()[big] / ref.abs()[big])
+    print(f'{name}: bf16 logit max err / max |logit| = {err:.3e}; element-wise relative error (|logit| >= 5% of max): '
+          f'median {rel.median().item():.3e}, p99 {rel.quantile(0.99).item():.3e}, max {rel.max().item():.3e}')
     assert err < 3e-2
+    assert rel.median().item() < 2e-2
     torch.manual_seed(meta['rng_seed'])
     net.ips(patches.to(DEV))
     got = net.last_mem_idx.cpu()

@@ -314,27 +314,23 @@ def test_topm_stable(dev, L, M):
     assert torch.equal(val.cpu(), rv[:, :M])
 
 
-def _loop_reference(z, perm, H, T, M, I):
-    """Python restatement of ips_net.py:213-241 on a logit table.  Tie-break contract of the library:
-    the buffer is kept in scan order, equal scores resolve to the patch scanned first."""
-    B, N, HT = z.shape
-    out_pos, out_src = [], []
-    for b in range(B):
-        order = perm[b] if perm is not None else torch.arange(N)
-        mem = torch.arange(M)
-        for it in range(math.ceil((N - M) / I)):
-            lo = M + it * I
-            hi = min(lo + I, N)
-            cand = torch.cat([mem, torch.arange(lo, hi)])
-            zz = z[b, order[cand]].view(1, -1, H, T).permute(0, 2, 3, 1)
-            sc = torch.softmax(zz, -1).mean(1).transpose(1, 2).mean(-1)[0]
-            top = torch.sort(sc, descending=True, stable=True)[1][:M]
-            final = cand[top]                                    # best first (what the last iteration returns)
-            mem = final.sort()[0]                                # buffer kept in scan order
-        mem = final
-        out_pos.append(mem)
-        out_src.append(order[mem])
-    return torch.stack(out_pos), torch.stack(out_src)
+def _loop_oracle(sd, conf, emb, perm, M, I):
+    """The reference loop (ips_net.py:213-241) composed from the oracle's own `score_and_select` on embeddings, exactly
+    as `O.ips` iterates it: cat(memory, next I) -> score -> top-M.  Returns (positions in scan order, original indices),
+    best first, plus the final iteration's sorted scores (for the boundary report)."""
+    B, N, D = emb.shape
+    order = perm if perm is not None else torch.arange(N).unsqueeze(0).expand(B, -1)
+    px = torch.gather(emb, 1, order.unsqueeze(-1).expand(-1, -1, D))
+    idx = torch.arange(N).unsqueeze(0).expand(B, -1)
+    mem_emb, mem_idx = px[:, :M], idx[:, :M]
+    s = None
+    for it in range(math.ceil((N - M) / I)):
+        lo = M + it * I
+        hi = min(lo + I, N)
+        all_emb = torch.cat((mem_emb, px[:, lo:hi]), dim=1)
+        all_idx = torch.cat((mem_idx, idx[:, lo:hi]), dim=1)
+        mem_emb, mem_idx, s = O.score_and_select(sd, conf, all_emb, None, M, all_idx, tie='stable')
+    return mem_idx, torch.gather(order, 1, mem_idx), s.sort(-1, descending=True)[0]
 
 
 @pytest.mark.parametrize('N,M,I,H,T', [(192, 10, 32, 8, 1), (900, 100, 100, 8, 4), (3000, 500, 500, 8, 1),
@@ -342,9 +338,17 @@ def _loop_reference(z, perm, H, T, M, I):
                                        (12345, 4000, 777, 8, 1)])
 @pytest.mark.parametrize('shuffle', ['none', 'batch', 'instance'])
 def test_select_loop(dev, N, M, I, H, T, shuffle):
+    """The in-kernel loop on the logit table == the oracle's `score_and_select` iterated on the embeddings
+    (ips_net.py:136-155,218-241): same winners in the same order; a differing pick is accepted only when the oracle's
+    own boundary gap is within fp32 rounding (P3)."""
     from ips_b200 import ops
-    B = 2
-    z = _rand(B, N, H * T, seed=25, scale=1.5)
+    B, D, Dk = 2, 64, 8
+    conf = O.preset('camelyon', M=M, I=I, H=H, n_token=T, D=D, D_k=Dk, D_v=Dk, D_inner=64, n_chan_in=16, shuffle=False)
+    if T > 1:
+        conf.tasks = {f'task{t}': {'id': t, 'name': f't{t}', 'act_fn': 'softmax', 'metric': 'accuracy'} for t in range(T)}
+    sd = O.make_state(conf, 27, q_gain=6.0)
+    emb = _rand(B, N, D, seed=25, scale=1.0)
+    z = O.attn_logits(sd, conf, emb).permute(0, 3, 1, 2).reshape(B, N, H * T).contiguous()       # (B,N,HT): h-major, t-minor
     g = torch.Generator().manual_seed(26)
     perm, per_inst = None, False
     if shuffle == 'batch':
@@ -352,16 +356,33 @@ def test_select_loop(dev, N, M, I, H, T, shuffle):
     elif shuffle == 'instance':
         perm, per_inst = torch.stack([torch.randperm(N, generator=g) for _ in range(B)]), True
     pos, src, score = ops.select_loop(z.to(dev), None if perm is None else perm.to(dev), per_inst, H, T, M, I)
-    ref_pos, ref_src = _loop_reference(z, None if perm is None else perm.expand(B, -1), H, T, M, I)
+    ref_pos, ref_src, ref_sorted = _loop_oracle(sd, conf, emb, None if perm is None else perm.expand(B, -1), M, I)
     mism = (src.cpu() != ref_src).sum().item()
-    # fp32 softmax on the GPU vs CPU differs in the last ulp: allow order swaps only between
-    # candidates whose final scores are within 1e-6 relative
     if mism:
-        assert torch.equal(src.cpu().sort(-1)[0], ref_src.sort(-1)[0]), f'{mism} different picks'
+        for b in range(B):
+            a, c = set(src[b].tolist()), set(ref_src[b].tolist())
+            if a != c:                                          # a different SET: only at an fp32-rounding-sized boundary gap
+                gap = float((ref_sorted[b, M - 1] - ref_sorted[b, M]) / ref_sorted[b, M - 1]) if ref_sorted.shape[1] > M else 1.0
+                assert gap < 1e-5, f'image {b}: {len(a ^ c) // 2} different picks at boundary gap {gap:.2e}'
     else:
         assert torch.equal(pos.cpu(), ref_pos)
     sc = score.cpu()
     assert (sc[:, :-1] >= sc[:, 1:]).all()                        # best first
+
+
+@pytest.mark.parametrize('L,M', [(20000, 5000), (40000, 5000), (16385, 1), (33000, 8192)])
+def test_topm_stable_long_rows(dev, L, M):
+    """Rows longer than the single-CTA sort (the candidate merge of the sequence-sharded schedule, L = ranks * M):
+    radix select + compaction + sort of the winners == the first M of a stable descending sort, heavy ties included."""
+    from ips_b200 import ops
+    g = torch.Generator().manual_seed(28)
+    s = torch.rand(3, L, generator=g)
+    s[1] = (s[1] * 8).floor() / 8
+    s[2] = 0.25
+    val, idx = ops.topm_stable(s.to(dev), M)
+    rv, ri = torch.sort(s, dim=-1, descending=True, stable=True)
+    assert torch.equal(idx.cpu(), ri[:, :M])
+    assert torch.equal(val.cpu(), rv[:, :M])
 
 
 # ------------------------------------------------------------------ aggregator + heads (no-grad forward)

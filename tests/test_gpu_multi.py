@@ -21,7 +21,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, pre, B, N, over, ret):
+def _worker(rank, world, port, pre, B, N, over, ret, transport=None, graphed=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     for p in (ROOT, os.path.join(ROOT, 'oracle')):
         sys.path.insert(0, p)
@@ -39,7 +39,18 @@ def _worker(rank, world, port, pre, B, N, over, ret):
         net.load_state_dict(sd)
         lo, hi = shard_bounds(N, world)[rank]
         torch.manual_seed(5)
-        mp_s, pos_s = ips_sharded(net, x[:, lo:hi].contiguous(), N)
+        local = x[:, lo:hi].contiguous()
+        if graphed:                                       # the whole sharded call replayed as ONE CUDA graph
+            from ips_b200.distributed import ShardedIPS
+            sh = ShardedIPS(net, B, N, x.shape[2:], mode='exact').capture(local)
+            torch.manual_seed(5)
+            mp_s, pos_s = sh(local)
+            torch.manual_seed(5)
+            mp_s, pos_s = sh(local)                       # a second replay gives the same answer
+            ret['status%d' % rank] = sh.ex.status()
+        else:
+            mp_s, pos_s = ips_sharded(net, local, N, transport=transport)
+        mp_s = mp_s.clone()
         idx_s = net.last_mem_idx.clone()
         torch.manual_seed(5)
         mp_1, pos_1 = net.ips(x)
@@ -54,14 +65,19 @@ def _worker(rank, world, port, pre, B, N, over, ret):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 @pytest.mark.parametrize('pre,B,N,over', [('camelyon', 1, 20001, dict(M=2000, I=3000)),
                                           ('mnist', 2, 100, dict(N=100, M=16, I=20))])
-def test_sharded_equals_single_gpu(pre, B, N, over):
+@pytest.mark.parametrize('transport,graphed', [('peer', False), ('nccl', False), ('peer', True)])
+def test_sharded_equals_single_gpu(pre, B, N, over, transport, graphed):
+    """'exact' schedule == IPSNet.ips on one GPU, bit for bit: NVLink peer-memory kernels (eager and as one CUDA graph)
+    and the collective baseline transport."""
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, port, pre, B, N, over, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, pre, B, N, over, ret, transport, graphed), nprocs=2, join=True)
     assert ret[0] and ret[1]
+    if graphed:
+        assert ret['status0'] == 0 and ret['status1'] == 0
 
 
-def _worker_merge(rank, world, port, pre, B, N, over, ret):
+def _worker_merge(rank, world, port, pre, B, N, over, ret, transport=None, output='replicated'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     for p in (ROOT, os.path.join(ROOT, 'oracle')):
         sys.path.insert(0, p)
@@ -79,8 +95,9 @@ def _worker_merge(rank, world, port, pre, B, N, over, ret):
         net.load_state_dict(sd)
         lo, hi = shard_bounds(N, world)[rank]
         torch.manual_seed(100 + rank)                       # every rank shuffles its own slice
-        mem_patch, mem_pos = ips_sharded(net, x[:, lo:hi].contiguous().to(dev), N, mode='merge')
+        mem_patch, mem_pos = ips_sharded(net, x[:, lo:hi].contiguous().to(dev), N, mode='merge', transport=transport, output=output)
         ret['idx%d' % rank] = net.last_mem_idx.cpu()
+        ret['mem_patch%d' % rank] = mem_patch.cpu()
         if rank == 0:
             ret['mem_patch'] = mem_patch.cpu()
     finally:
@@ -90,15 +107,17 @@ def _worker_merge(rank, world, port, pre, B, N, over, ret):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 @pytest.mark.parametrize('pre,B,N,over', [('camelyon', 1, 2001, dict(M=200, I=300)),
                                           ('mnist', 2, 100, dict(N=100, M=16, I=20))])
-def test_sharded_merge_matches_sharded_oracle(pre, B, N, over):
-    """P5: local top-M per GPU + all-gather of the candidates + one global re-score == the sharded-schedule oracle
-    (same block-wise scan order) in fp32."""
+@pytest.mark.parametrize('transport,output', [('peer', 'replicated'), ('nccl', 'replicated'), ('peer', 'batch_split')])
+def test_sharded_merge_matches_sharded_oracle(pre, B, N, over, transport, output):
+    """P5: local top-M per GPU + exchange of the candidates + one global re-score == the sharded-schedule oracle
+    (same block-wise scan order) in fp32; peer-memory kernels (winners replicated or delivered per slide) and the
+    collective baseline."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import ips_oracle as O
     from ips_b200.distributed import shard_bounds
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker_merge, args=(2, port, pre, B, N, over, ret), nprocs=2, join=True)
+    mp.spawn(_worker_merge, args=(2, port, pre, B, N, over, ret, transport, output), nprocs=2, join=True)
     conf = O.preset(pre, **over)
     sd = O.make_state(conf, 3, q_gain=12.0)
     x = O.make_patches(conf, B, N, 4)
@@ -107,9 +126,17 @@ def test_sharded_merge_matches_sharded_oracle(pre, B, N, over):
         torch.manual_seed(100 + r)
         blocks.append(O.draw_permutation(conf, B, hi - lo) + lo)
     o_patch, _, o_src = O.ips_sharded(sd, conf, x, R=2, perm=torch.cat(blocks, dim=1), tie='stable')
+    if output == 'batch_split':                          # slide b lives only on rank b // ceil(B / 2)
+        spr = -(-B // 2)
+        got_idx = torch.cat([ret['idx%d' % r] for r in range(2)])[:B]
+        got_patch = torch.cat([ret['mem_patch%d' % r] for r in range(2)])[:B]
+        assert ret['idx0'].shape[0] == min(spr, B)
+        assert torch.equal(got_idx, o_src) and torch.equal(got_patch, o_patch)
+        return
     assert torch.equal(ret['idx0'], ret['idx1'])
     assert torch.equal(ret['idx0'], o_src)
     assert torch.equal(ret['mem_patch'], o_patch)
+    assert torch.equal(ret['mem_patch1'], o_patch)
 
 
 def _worker_syncbn(rank, world, port, name, ret):
