@@ -276,6 +276,16 @@ IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k,
                                           float* dq_part /* (B*chunks, T*H*Dk), summed over rows by the caller */, float* dk, float* dv,
                                           int B, int M, int H, int Dk, int Dv, int T, void* stream);
 
+/* ---------------------------------------------------------------- per-launch timing of the native executor
+ * (measurement only, bench.py's roofline; the reference's counterpart is the track_efficiency bracket,
+ * training/iterative.py:129-132,166-171).  Between begin and end every kernel ipsb_resnet_logits* issues is bracketed by
+ * CUDA events on the internal stream ("lane") it runs on; ipsb_profile_end returns, per launch, the kernel family
+ * (0 stage, 1 stem(+pool), 2 BasicBlock convolution, 3 pooling, 4 logits) and its start / stop time in ms relative to the
+ * event recorded on `stream` by ipsb_profile_begin -- lanes overlap, so a family's busy time is the UNION of its
+ * intervals.  n_out = records written (at most max_records). */
+IPSB_API int ipsb_profile_begin(void* stream);
+IPSB_API int ipsb_profile_end(int max_records, int* kinds, float* start_ms, float* stop_ms, int* n_out);
+
 /* ---------------------------------------------------------------- gathers
  * Replaces torch.gather(patches, 1, mem_idx expanded) (ips_net.py:244-247) and the
  * pos-enc gather (:249-250): dst[b,m,:] = src[b*src_batch_stride + idx[b,m], :],

@@ -6,7 +6,35 @@
 #include "pf.cuh"
 #include "../../include/ips_b200.h"
 
+#include <vector>
+
 namespace {
+
+// ---- per-launch timing of the executor's kernels (bench.py roofline): CUDA events around every library call on the
+//      lane it is issued on, all measured against one base event, so the host can take the union of the intervals of
+//      a kernel family across the concurrently running lanes.  Off (zero cost) unless ipsb_profile_begin was called.
+struct ProfRec { int kind; cudaEvent_t a, b; };
+struct Profiler {
+    bool on = false;
+    cudaEvent_t base = nullptr;
+    std::vector<ProfRec> recs;
+};
+Profiler& profiler() { static Profiler p; return p; }
+template <class F>
+int timed_call(int kind, void* stream, const F& f) {
+    Profiler& pr = profiler();
+    if (!pr.on) return f();
+    ProfRec r{kind, nullptr, nullptr};
+    IPSB_CUDA(cudaEventCreate(&r.a));
+    IPSB_CUDA(cudaEventCreate(&r.b));
+    IPSB_CUDA(cudaEventRecord(r.a, (cudaStream_t)stream));
+    const int rc = f();
+    IPSB_CUDA(cudaEventRecord(r.b, (cudaStream_t)stream));
+    pr.recs.push_back(r);
+    return rc;
+}
+#define PROF(kind, stream, call) timed_call(kind, stream, [&]() -> int { return (call); })
+enum { K_STAGE = 0, K_STEM = 1, K_CONV = 2, K_POOL = 3, K_LOGITS = 4 };
 
 struct Geo { int H, W, C; };
 
@@ -90,10 +118,13 @@ struct LaneStreams {
     cudaEvent_t done[MAX_LANES] = {};
     cudaEvent_t fork = nullptr;
 };
+constexpr int MAX_DEVICES = 16;
 int lane_streams(LaneStreams** out) {
-    static thread_local LaneStreams ls;
+    static thread_local LaneStreams per_device[MAX_DEVICES];      // one set per device: nothing leaks when the caller switches
     int dev = 0;
     IPSB_CUDA(cudaGetDevice(&dev));
+    IPSB_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "resnet_logits: device index %d", dev);
+    LaneStreams& ls = per_device[dev];
     if (ls.device != dev) {
         for (int i = 0; i < MAX_LANES; ++i) {
             IPSB_CUDA(cudaStreamCreateWithFlags(&ls.s[i], cudaStreamNonBlocking));
@@ -115,6 +146,37 @@ int run_conv_pf(const ipsb_conv_desc& c, const void* x, const void* res, void* y
 }  // namespace
 
 extern "C" {
+
+int ipsb_profile_begin(void* stream) {
+    Profiler& pr = profiler();
+    for (ProfRec& r : pr.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    pr.recs.clear();
+    if (!pr.base) IPSB_CUDA(cudaEventCreate(&pr.base));
+    IPSB_CUDA(cudaEventRecord(pr.base, (cudaStream_t)stream));
+    pr.on = true;
+    return 0;
+}
+
+int ipsb_profile_end(int max_records, int* kinds, float* start_ms, float* stop_ms, int* n_out) {
+    Profiler& pr = profiler();
+    pr.on = false;
+    IPSB_REQUIRE(n_out != nullptr, "profile_end: null output");
+    int n = 0;
+    for (ProfRec& r : pr.recs) {
+        if (n < max_records && kinds && start_ms && stop_ms) {
+            IPSB_CUDA(cudaEventSynchronize(r.b));
+            kinds[n] = r.kind;
+            IPSB_CUDA(cudaEventElapsedTime(&start_ms[n], pr.base, r.a));
+            IPSB_CUDA(cudaEventElapsedTime(&stop_ms[n], pr.base, r.b));
+            ++n;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    pr.recs.clear();
+    *n_out = n;
+    return 0;
+}
 
 int64_t ipsb_resnet_workspace_bytes(const ipsb_resnet_desc* net, int64_t chunk, int C, int H, int W) {
     (void)C;
@@ -155,8 +217,7 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         for (int l = 0; l < lanes; ++l) IPSB_CUDA(cudaStreamWaitEvent(ls->s[l], ls->fork, 0));
     }
 
-    int64_t ci = 0;
-    for (int64_t lo = 0; lo < n_rows; lo += chunk, ++ci) {
+    auto run_chunk = [&](int64_t lo, int64_t ci) -> int {
         const int lane = (int)(ci % lanes);
         void* stream = lanes > 1 ? (void*)ls->s[lane] : caller_stream;
         char* ws = (char*)workspace + lane * lane_bytes;
@@ -181,30 +242,30 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         for (int64_t s0 = 0; s0 < P; s0 += sub) {
             const int64_t Ps = (P - s0 < sub) ? P - s0 : sub;
             if (st.mode == 4) {               // space-to-depth frame -> shifted-window stem -> strided max-pool
-                rc = img_geo ? ipsb_stage_image_s2d(patches, img_geo, first_row + lo + s0, Ps, C, H, W, staged, stream)
-                             : ipsb_stage_patches_s2d(patches, nullptr, first_row + lo + s0, Ps, C, H, W, staged, stream);
+                rc = PROF(K_STAGE, stream, img_geo ? ipsb_stage_image_s2d(patches, img_geo, first_row + lo + s0, Ps, C, H, W, staged, stream)
+                                                   : ipsb_stage_patches_s2d(patches, nullptr, first_row + lo + s0, Ps, C, H, W, staged, stream));
                 if (rc) return rc;
                 if (st.cout == 64 && !getenv("IPSB_STEM_UNFUSED")) {   // stem + pool fused: the stem output stays on chip
-                    rc = ipsb_stem_pool_s2d(staged, st.w, st.scale, st.shift, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, H, W,
-                                            1, stream);
+                    rc = PROF(K_STEM, stream, ipsb_stem_pool_s2d(staged, st.w, st.scale, st.shift, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, H, W,
+                                                                  1, stream));
                     if (rc) return rc;
                     continue;
                 }
-                rc = ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H, W, 16, st.cout, 7, 7, 2, 3, 1, 4,
-                                         stream);
+                rc = PROF(K_STEM, stream, ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H, W, 16, st.cout, 7, 7, 2, 3, 1, 4,
+                                                               stream));
                 if (rc) return rc;
-                rc = ipsb_maxpool3x3s2_pf_strided(stem_out, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, hs, wsz, st.cout,
-                                                  wsz + 3, (hs + 3) * (wsz + 3), stream);
+                rc = PROF(K_POOL, stream, ipsb_maxpool3x3s2_pf_strided(stem_out, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, hs, wsz, st.cout,
+                                                                        wsz + 3, (hs + 3) * (wsz + 3), stream));
                 if (rc) return rc;
                 continue;
             }
-            rc = ipsb_stage_patches_padded(patches, nullptr, first_row + lo + s0, Ps, C, H, W, 3, 4, H + 6, W + 6, staged, stream);
+            rc = PROF(K_STAGE, stream, ipsb_stage_patches_padded(patches, nullptr, first_row + lo + s0, Ps, C, H, W, 3, 4, H + 6, W + 6, staged, stream));
             if (rc) return rc;
-            rc = ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H + 6, W + 6, 4, st.cout, 7, 7, 2, 3,
-                                     1, 3, stream);
+            rc = PROF(K_STEM, stream, ipsb_conv_bf16_umma(staged, st.w, st.scale, st.shift, nullptr, stem_out, Ps, H + 6, W + 6, 4, st.cout, 7, 7, 2, 3,
+                                                           1, 3, stream));
             if (rc) return rc;
             // patch s0 of the chunk starts s0*Sp rows into the padded-flat buffer (same lead-in G0)
-            rc = ipsb_maxpool3x3s2_pf(stem_out, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, hs, wsz, st.cout, stream);
+            rc = PROF(K_POOL, stream, ipsb_maxpool3x3s2_pf(stem_out, (char*)gb[0][0] + (size_t)s0 * gq.Sp * st.cout * 2, Ps, hs, wsz, st.cout, stream));
             if (rc) return rc;
         }
         int h = out_dim(hs, 3, 2, 1), w = out_dim(wsz, 3, 2, 1);   // geometry of the current activation
@@ -221,13 +282,13 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
             else for (int i = 0; i < 4; ++i) if (i != cur_slot) free_ids[nf++] = i;
             const void* idt = cur;               // (no downsample: same group, same layout as the output)
             if (blk.has_ds) {
-                rc = run_conv_pf(blk.ds, cur, nullptr, bufs[free_ids[0]], P, h, w, 0, stream, !cur_dense, !out_dense);
+                rc = PROF(K_CONV, stream, run_conv_pf(blk.ds, cur, nullptr, bufs[free_ids[0]], P, h, w, 0, stream, !cur_dense, !out_dense));
                 if (rc) return rc;
                 idt = bufs[free_ids[0]];
             }
-            rc = run_conv_pf(blk.c1, cur, nullptr, bufs[free_ids[1]], P, h, w, 1, stream, !cur_dense, !out_dense);
+            rc = PROF(K_CONV, stream, run_conv_pf(blk.c1, cur, nullptr, bufs[free_ids[1]], P, h, w, 1, stream, !cur_dense, !out_dense));
             if (rc) return rc;
-            rc = run_conv_pf(blk.c2, bufs[free_ids[1]], idt, bufs[free_ids[2]], P, pl.H[g], pl.W[g], 1, stream, !out_dense, !out_dense);
+            rc = PROF(K_CONV, stream, run_conv_pf(blk.c2, bufs[free_ids[1]], idt, bufs[free_ids[2]], P, pl.H[g], pl.W[g], 1, stream, !out_dense, !out_dense));
             if (rc) return rc;
             cur = bufs[free_ids[2]];
             cur_slot = free_ids[2];
@@ -237,7 +298,7 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
         const int gl = pl.n_groups - 1;
         IPSB_REQUIRE(pl.C[gl] == net->D, "resnet_logits: encoder width %d != D %d", pl.C[gl], net->D);
         float* emb = emb_out ? emb_out + lo * net->D : emb_ws;
-        rc = cur_dense ? ipsb_avgpool(cur, emb, P, h * w, pl.C[gl], IPSB_BF16, stream) : ipsb_avgpool_pf(cur, emb, P, h, w, pl.C[gl], stream);
+        rc = PROF(K_POOL, stream, cur_dense ? ipsb_avgpool(cur, emb, P, h * w, pl.C[gl], IPSB_BF16, stream) : ipsb_avgpool_pf(cur, emb, P, h, w, pl.C[gl], stream));
         if (rc) return rc;
         const int64_t* idx = nullptr;
         if (net->add_tab) {
@@ -245,15 +306,21 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
             IPSB_LAUNCH_CHECK();
             idx = pos_idx;
         }
-        rc = ipsb_logits(emb, net->U, net->add_tab, idx, z_out + lo * net->HT, P, net->D, net->HT, stream);
-        if (rc) return rc;
-    }
+        rc = PROF(K_LOGITS, stream, ipsb_logits(emb, net->U, net->add_tab, idx, z_out + lo * net->HT, P, net->D, net->HT, stream));
+        return rc;
+    };
+    int status = 0;
+    int64_t ci = 0;
+    for (int64_t lo = 0; lo < n_rows && status == 0; lo += chunk, ++ci) status = run_chunk(lo, ci);
+    // every exit joins the lanes back into the caller's stream: after an error the caller's stream must still be ordered
+    // behind the kernels already enqueued on the lanes (they write `workspace` and `z_out`)
     if (lanes > 1)
         for (int l = 0; l < lanes; ++l) {
-            IPSB_CUDA(cudaEventRecord(ls->done[l], ls->s[l]));
-            IPSB_CUDA(cudaStreamWaitEvent((cudaStream_t)caller_stream, ls->done[l], 0));
+            const cudaError_t e1 = cudaEventRecord(ls->done[l], ls->s[l]);
+            const cudaError_t e2 = (e1 == cudaSuccess) ? cudaStreamWaitEvent((cudaStream_t)caller_stream, ls->done[l], 0) : e1;
+            if (e2 != cudaSuccess && status == 0) status = ipsb::fail("resnet_logits: lane join -> %s", cudaGetErrorString(e2));
         }
-    return 0;
+    return status;
 }
 
 int ipsb_resnet_logits_image(const ipsb_resnet_desc* net, const float* images, const ipsb_image_geo* geo, int64_t first_row,

@@ -26,6 +26,21 @@ from .utils import scan_order
 _BN_EPS = 1e-5
 
 
+def _on_device(fn):
+    """Run a method with the module's CUDA device current: the library launches on the CURRENT device's stream and keeps
+    per-device internal streams, so `IPSNet(device='cuda:1')` must work without `torch.cuda.set_device(1)`."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        dev = torch.device(self.device)
+        if dev.type != 'cuda' or (dev.index is not None and dev.index == torch.cuda.current_device()):
+            return fn(self, *a, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 # ----------------------------------------------------------------------------------------
 # parameter containers (state_dict compatible with the truncated torchvision ResNet)
 # ----------------------------------------------------------------------------------------
@@ -49,7 +64,21 @@ class _BasicBlock(nn.Module):
         return self.relu(self.bn2(self.conv2(y)) + idt)
 
 
-def _conv_patch_encoder(enc_type, n_chan_in, n_res_blocks):
+def _imagenet_resnet18_state():
+    """ImageNet weights of torchvision's resnet18 (`ResNet18_Weights.IMAGENET1K_V1`, ips_net.py:19-27), renamed to the
+    children of the truncated trunk.  Raises -- never continues with random weights -- when they cannot be had."""
+    try:
+        from torchvision.models import resnet18, ResNet18_Weights
+        sd = resnet18(weights=ResNet18_Weights.IMAGENET1K_V1).state_dict()
+    except Exception as e:
+        raise RuntimeError('ips_b200: conf.pretrained is set but the ImageNet ResNet-18 weights are not available '
+                           '(torchvision missing, or no cached checkpoint and no network): %s.  Set `pretrained: False` '
+                           'to train the patch encoder from random initialisation.' % (e,)) from e
+    ren = {'conv1': '0', 'bn1': '1', 'layer1': '4', 'layer2': '5', 'layer3': '6', 'layer4': '7'}
+    return {ren[k.split('.', 1)[0]] + '.' + k.split('.', 1)[1]: v for k, v in sd.items() if k.split('.', 1)[0] in ren}
+
+
+def _conv_patch_encoder(enc_type, n_chan_in, n_res_blocks, pretrained=False):
     """Children 0,1,2,3,4,5[,6,7],avgpool exactly as ips_net.py:34-50 composes them."""
     if enc_type != 'resnet18':
         raise NotImplementedError("only enc_type 'resnet18' is built (resnet50 is unused by the shipped configs)")
@@ -65,6 +94,9 @@ def _conv_patch_encoder(enc_type, n_chan_in, n_res_blocks):
     for m in enc.modules():                    # torchvision's ResNet initialisation
         if isinstance(m, nn.Conv2d):
             nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+    if pretrained:                             # ImageNet weights for every child that is kept (:19-27)
+        have = enc.state_dict()
+        enc.load_state_dict({k: v for k, v in _imagenet_resnet18_state().items() if k in have}, strict=True)
     if n_chan_in == 1:                         # the reference swaps in a default-initialised stem (:29-31)
         enc[0].reset_parameters()
     return enc
@@ -109,7 +141,7 @@ class IPSNet(nn.Module):
             raise ValueError(f'unknown precision {self.precision!r}')
 
         if self.is_image:
-            self.encoder = _conv_patch_encoder(conf.enc_type, conf.n_chan_in, conf.n_res_blocks)
+            self.encoder = _conv_patch_encoder(conf.enc_type, conf.n_chan_in, conf.n_res_blocks, bool(getattr(conf, 'pretrained', False)))
         else:
             self.encoder = _projector(conf.n_chan_in, self.D)
         self.transf = Transformer(conf.n_token, conf.H, conf.D, conf.D_k, conf.D_v, conf.D_inner,
@@ -134,6 +166,9 @@ class IPSNet(nn.Module):
         # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
         self.executor = os.environ.get('IPS_B200_EXECUTOR', 'native')
         self._ws_cache = {}
+        # lazy loading (`eager: False`): host inputs up to this size also keep a device copy for the final gather; larger
+        # ones stream through a three-chunk ring so device memory stays O(chunk), independent of N
+        self.lazy_resident_bytes = int(os.environ.get('IPS_B200_LAZY_RESIDENT_BYTES', getattr(conf, 'lazy_resident_bytes', 8 << 30)))
         # bf16 stem: 4 = shifted-window kernel on the space-to-depth frame, 3 = TMA-fed im2col rows (both need even
         # patch sizes), 1 = cp.async gather
         ps = getattr(conf, 'patch_size', [0, 0])
@@ -211,6 +246,13 @@ class IPSNet(nn.Module):
             plan['p_w'] = w.to(torch.bfloat16).contiguous() if self.precision == 'bf16' else w
         return plan
 
+    def invalidate_plan(self):
+        """Drop the folded-parameter plan.  `ips()` notices in-place parameter updates through the tensors' version
+        counters; updates that bypass them -- a CUDA-graph replay of the optimizer step (`GraphedTrainStep`), writes
+        through `.data` -- must call this, or the next `ips()` would select with stale weights."""
+        self._plan = None
+        self._plan_key = None
+
     def _get_plan(self):
         key = self._state_versions()
         if self._plan is None or key != self._plan_key:
@@ -225,6 +267,7 @@ class IPSNet(nn.Module):
             return f(x, e['w'], e['scale'], e['shift'], res, e['cout'], e['kh'], e['kw'], e['stride'], e['pad'], relu, e['mode'])
         return f(x, e['w'], e['scale'], e['shift'], res, e['cout'], e['kh'], e['kw'], e['stride'], e['pad'], relu)
 
+    @_on_device
     @torch.no_grad()
     def embed(self, flat, row_idx=None, first_row=0, n_rows=None):
         """Eval-mode patch embeddings (rows, D) fp32 of `flat` = (rows, C, ph, pw) or (rows, F) on the GPU.
@@ -300,6 +343,7 @@ class IPSNet(nn.Module):
         n = -(-per_lane // cap)                                        # chunks per lane
         return max(32, -(-(-(-per_lane // n)) // 8) * 8)
 
+    @_on_device
     @torch.no_grad()
     def patch_logits(self, patches, pos_offset=0):
         """(B,N,...) -> (B,N,H*T) fp32 logit table on `self.device`, original patch order.
@@ -332,8 +376,13 @@ class IPSNet(nn.Module):
     @torch.no_grad()
     def _stream_in(self, patches):
         """Host-resident patches (lazy loading, `conf.eager: False`): copy them to the device chunk by chunk on a
-        side stream while the encoder already works on the chunks that have arrived.  Returns the device copy and
-        the logit table.  (The reference moves each chunk with `.to(device)` inside its loop, ips_net.py:206,223.)"""
+        side stream while the encoder already works on the chunks that have arrived.  (The reference moves each chunk
+        with `.to(device)` inside its loop, ips_net.py:206,223.)  Returns (device copy or None, logit table).
+
+        Memory: IPS's guarantee is O(M + I) device memory whatever N.  A whole-tensor device copy is
+        kept only when it fits `lazy_resident_bytes` (the final gather then runs on the device); larger inputs stream
+        through a ring of three chunk buffers, only the logit table (N * H*T * 4 bytes) survives, and the M winners are
+        gathered from the host tensor afterwards like the reference does (:244-247)."""
         plan = self._get_plan()
         B, N = patches.shape[:2]
         rows = B * N
@@ -346,35 +395,56 @@ class IPSNet(nn.Module):
         # last chunk's compute is exposed after the copy (traffic, 369 MB over PCIe: raw copy 6.7 ms, ips() 8.0 ms)
         chunk = self.chunk_patches or (max(32, min(4096, (512 * 10000) // max(patches.shape[-1] * patches.shape[-2], 1)))
                                        if self.is_image else 16384)
+        chunk = min(chunk, rows)
         main = torch.cuda.current_stream(self.device)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         cs = self._copy_stream
-        dev = torch.empty(flat_h.shape, dtype=flat_h.dtype, device=self.device)
+        resident = flat_h.numel() * flat_h.element_size() <= self.lazy_resident_bytes
+        n_chunks = -(-rows // chunk)
+        ring = 1 if resident else min(3, n_chunks)
+        dev = torch.empty((rows if resident else ring * chunk, *flat_h.shape[1:]), dtype=flat_h.dtype, device=self.device)
         dev.record_stream(cs)
         cs.wait_stream(main)
-        events = []
-        with torch.cuda.stream(cs):
-            for lo in range(0, rows, chunk):
-                n = min(chunk, rows - lo)
-                dev[lo:lo + n].copy_(flat_h[lo:lo + n], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-                events.append(ev)
         z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
         native = self.is_image and self.executor == 'native'
         if native and 'desc' not in plan:
             plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
         pos_idx = (torch.arange(rows, device=self.device) % N).contiguous() if self.use_pos else None
-        for ci, lo in enumerate(range(0, rows, chunk)):
+        arrived, consumed = [], []
+
+        def issue_copy(ci):
+            lo = ci * chunk
             n = min(chunk, rows - lo)
-            main.wait_event(events[ci])
+            slot = lo if resident else (ci % ring) * chunk
+            with torch.cuda.stream(cs):
+                if not resident and ci >= ring:
+                    cs.wait_event(consumed[ci - ring])        # the encoder is done with this slot's previous chunk
+                dev[slot:slot + n].copy_(flat_h[lo:lo + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                arrived.append(ev)
+
+        ahead = n_chunks if resident else ring
+        for ci in range(min(ahead, n_chunks)):
+            issue_copy(ci)
+        for ci in range(n_chunks):
+            lo = ci * chunk
+            n = min(chunk, rows - lo)
+            slot = lo if resident else (ci % ring) * chunk
+            main.wait_event(arrived[ci])
             if native:
-                ops.resnet_logits(plan['desc'], dev, N, chunk, self._ws_cache, first_row=lo, n_rows=n, z=z)
+                ops.resnet_logits(plan['desc'], dev, N, chunk, self._ws_cache, first_row=lo, n_rows=n, z=z, src_first_row=lo - slot)
             else:
-                emb = self.embed(dev, first_row=lo, n_rows=n)
+                emb = self.embed(dev, first_row=slot, n_rows=n)
                 z[lo:lo + n] = ops.logits(emb, plan['U'], plan['posU'], None if pos_idx is None else pos_idx[lo:lo + n].contiguous())
-        return dev.view(patches.shape), z.view(B, N, HT)
+            if not resident:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                consumed.append(ev)
+                if ci + ring < n_chunks:
+                    issue_copy(ci + ring)
+        return (dev.view(patches.shape) if resident else None), z.view(B, N, HT)
 
     # ------------------------------------------------------------------ reference API
     def do_shuffle(self, patches, pos_enc):
@@ -391,6 +461,7 @@ class IPSNet(nn.Module):
             pos_enc = torch.stack([pos_enc[b, idx[b].to(pos_enc.device)] for b in range(B)])
         return patches, pos_enc
 
+    @_on_device
     @torch.no_grad()
     def score_and_select(self, emb, emb_pos, M, idx):
         """Scores embeddings and keeps the top M (ips_net.py:136-155); stable tie-break."""
@@ -408,6 +479,7 @@ class IPSNet(nn.Module):
             preds[task['name']] = self.output_layers[task['name']](embeddings[:, task['id']])
         return preds
 
+    @_on_device
     @torch.no_grad()
     def ips(self, patches, out=None, row_offset=0):
         """Iterative Patch Selection (ips_net.py:169-262): returns (mem_patch, mem_pos).
@@ -438,7 +510,9 @@ class IPSNet(nn.Module):
 
         ca = self.transf.crs_attn
         if not patches.is_cuda:                                   # lazy loading: overlap H2D with the encoder
-            patches, z = self._stream_in(patches)
+            dev_copy, z = self._stream_in(patches)
+            if dev_copy is not None:
+                patches = dev_copy
         else:
             z = self.patch_logits(patches)                        # encode + project every patch once
         _, mem_src, _ = ops.select_loop(z, perm, per_inst, ca.H, ca.n_token, M, I)
@@ -454,7 +528,7 @@ class IPSNet(nn.Module):
             mem_patch = ops.gather_rows(patches.contiguous(), mem_src, N, out=o_patch)
         else:                                                    # lazy loading: gather on the host, :244-247
             host_idx = mem_src.cpu()
-            mem_patch = torch.stack([patches[b, host_idx[b]] for b in range(B)]).to(device)
+            mem_patch = torch.stack([patches[b, host_idx[b]] for b in range(B)]).to(device).float()
             if o_patch is not None:
                 o_patch.copy_(mem_patch)
                 mem_patch = o_patch
@@ -472,6 +546,7 @@ class IPSNet(nn.Module):
         o_pos = buf_pos[row_offset:row_offset + B] if (self.use_pos and buf_pos is not None) else None
         return buf_patch[row_offset:row_offset + B], o_pos
 
+    @_on_device
     @torch.no_grad()
     def ips_image(self, images, patch_size=None, patch_stride=None, out=None, row_offset=0):
         """`ips` on whole images (B, C, Himg, Wimg): the patch grid the reference's data loaders cut on the CPU
@@ -538,6 +613,7 @@ class IPSNet(nn.Module):
             preds[task['name']] = ops.head_activation(zl, task['act_fn'])
         return preds
 
+    @_on_device
     def forward(self, mem_patch, mem_pos=None, tokens_only=False):
         """Encode + aggregate the selected patches (ips_net.py:264-283).  Inference (eval mode, no grad) runs on
         the library's kernels; the grad-mode train step uses PyTorch autograd on the same parameters."""
@@ -567,6 +643,7 @@ class IPSNet(nn.Module):
         tok = self.transf(mem_emb)
         return tok if tokens_only else self.get_preds(tok)
 
+    @_on_device
     def loss(self, mem_patch, mem_pos, labels, eps=1e-6):
         """`compute_loss(net, mem_patch, mem_pos, criterions, labels, conf)` of training/iterative.py:65-100 with the
         head activations, the losses and their gradients fused into one kernel per task: mean over

@@ -330,10 +330,12 @@ def gather_patches_image(images, geo, idx, patch_size, out=None):
 
 
 def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=False, first_row=0, n_rows=None, z=None, lanes=1,
-                  geo=None, patch_size=None):
+                  geo=None, patch_size=None, src_first_row=0):
     """Whole eval-mode encoder + logit projection of (rows,C,H,W) fp32 patches in ONE library call.
     `first_row` / `n_rows` restrict the call to a row range (its logits land in z[first_row : first_row+n_rows]).
-    `lanes` > 1 sizes the workspace for that many chunks in flight on the library's internal streams."""
+    `lanes` > 1 sizes the workspace for that many chunks in flight on the library's internal streams.
+    `src_first_row`: logical row index of patches[0] (a ring buffer that holds only rows [src_first_row, ...) of the
+    sequence; the kernels touch rows [first_row, first_row + n_rows) only)."""
     global LAUNCHES
     _chk(patches, torch.float32, 'patches')
     if geo is None:
@@ -360,7 +362,12 @@ def resnet_logits(desc, patches, n_per_image, chunk, workspace_cache, want_emb=F
     z_ptr = z.data_ptr() + first_row * desc.HT * 4
     e_ptr = 0 if emb is None else emb.data_ptr() + first_row * desc.D * 4
     if geo is None:
-        _lib.check(lib.ipsb_resnet_logits(desc, _p(patches), first_row, rows, C, H, W, n_per_image, chunk, _p(ws), need,
+        src_ptr = _p(patches) - src_first_row * C * H * W * 4
+        if src_first_row:
+            if not (src_first_row <= first_row and first_row + rows <= src_first_row + patches.shape[0]):
+                raise RuntimeError('ips_b200: rows [%d, %d) are not inside the staged window' % (first_row, first_row + rows))
+            total_rows = first_row + rows
+        _lib.check(lib.ipsb_resnet_logits(desc, src_ptr, first_row, rows, C, H, W, n_per_image, chunk, _p(ws), need,
                                           int(fresh), e_ptr, z_ptr, _stream()))
     else:
         _lib.check(lib.ipsb_resnet_logits_image(desc, _p(patches), ctypes.byref(geo), first_row, rows, C, H, W, chunk, _p(ws), need,
@@ -508,6 +515,42 @@ def add(a, b):
     y = torch.empty_like(a)
     _call('ipsb_add_f32', _p(a), _p(b), _p(y), a.numel(), _stream())
     return y
+
+
+# ------------------------------------------------------------------ per-launch timing of the native executor
+
+PROFILE_KINDS = ('stage', 'stem', 'conv', 'pool', 'logits')
+
+
+def profile_begin():
+    """Start bracketing every kernel the native executor issues with CUDA events (measurement only)."""
+    _lib.check(_lib.load().ipsb_profile_begin(_stream()))
+
+
+def profile_end(max_records=1 << 16):
+    """Stop; returns [(family, start_ms, stop_ms)] relative to profile_begin, after synchronising the events."""
+    kinds = (ctypes.c_int32 * max_records)()
+    t0 = (ctypes.c_float * max_records)()
+    t1 = (ctypes.c_float * max_records)()
+    n = ctypes.c_int32(0)
+    _lib.check(_lib.load().ipsb_profile_end(max_records, ctypes.addressof(kinds), ctypes.addressof(t0), ctypes.addressof(t1),
+                                            ctypes.byref(n)))
+    return [(PROFILE_KINDS[kinds[i]], t0[i], t1[i]) for i in range(n.value)]
+
+
+def busy_ms(intervals):
+    """Length of the union of (start, stop) intervals."""
+    total, cur_a, cur_b = 0.0, None, None
+    for a, b in sorted(intervals):
+        if cur_b is None or a > cur_b:
+            if cur_b is not None:
+                total += cur_b - cur_a
+            cur_a, cur_b = a, b
+        else:
+            cur_b = max(cur_b, b)
+    if cur_b is not None:
+        total += cur_b - cur_a
+    return total
 
 
 # ------------------------------------------------------------------ NVLink peer exchange (sequence-sharded selection)

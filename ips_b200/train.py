@@ -116,6 +116,7 @@ class GraphedTrainStep:
                 self._step()
             else:
                 self._fwd_bwd()
+        self.net.invalidate_plan()           # warm-up steps and the restore below move the parameters
         if snap is not None:
             with torch.no_grad():
                 for p, v in zip(self.net.parameters(), snap[0]):
@@ -134,8 +135,10 @@ class GraphedTrainStep:
             self.capture()
         if self.graph is False:
             self._step()
+            self.net.invalidate_plan()
             return self.loss
         self.graph.replay()
         if self.grad_hook is not None:
             self._sync_and_update()
+        self.net.invalidate_plan()           # the replay changed parameters / BatchNorm statistics behind the version counters
         return self.loss
