@@ -276,6 +276,18 @@ IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k,
                                           float* dq_part /* (B*chunks, T*H*Dk), summed over rows by the caller */, float* dk, float* dv,
                                           int B, int M, int H, int Dk, int Dv, int T, void* stream);
 
+/* ---------------------------------------------------------------- feature projector + score projection, fused
+ * Replaces, in the no-grad pass of ips() on feature bags: LayerNorm(no affine) -> Linear -> BatchNorm1d(eval) -> ReLU
+ * (ips_net.py:54-60) followed by the key projection + query dot product (transformer.py:71-83, folded into U):
+ *     z[r, :] = ReLU(rstd_r * (a_n * (x_r . W_n) - mean_r * b_n) + shift_n) @ U
+ * x (rows, K) fp32 or bf16 (x_is_bf16), rounded to bf16 on chip; mean_r / rstd_r are the LayerNorm statistics of the
+ * rounded row (fp32, eps); w_bf16 (N, K) bf16 K-major; table (N, 12) fp32 per output column n:
+ *     [a_n = BN scale, b_n = a_n * sum_k w_bf16[n, k], shift_n = bias_n * a_n + BN shift, 0, U[n, 0..7]]  (U zero-padded to 8);
+ * z (rows, HT) fp32, HT <= 8.  N in {256, 512} (the 128 x N fp32 tile fills tensor memory), K % 64 == 0, K >= 256.
+ * Only the features (once) and 4*HT bytes per row of logits touch HBM. */
+IPSB_API int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
+                                   int64_t rows, int K, int N, int HT, float eps, void* stream);
+
 /* ---------------------------------------------------------------- per-launch timing of the native executor
  * (measurement only, bench.py's roofline; the reference's counterpart is the track_efficiency bracket,
  * training/iterative.py:129-132,166-171).  Between begin and end every kernel ipsb_resnet_logits* issues is bracketed by

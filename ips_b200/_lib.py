@@ -96,6 +96,7 @@ SIGNATURES = {
     'ipsb_attention_train_bwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32,
                                      _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
+    'ipsb_projector_logits': [_ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],
     'ipsb_profile_begin': [_ptr],
     'ipsb_profile_end': [_i32, _ptr, _ptr, _ptr, ctypes.POINTER(_i32)],
     'ipsb_peer_export': [_ptr, _ptr, ctypes.POINTER(_i64)],

@@ -286,12 +286,17 @@ class ShardedIPS:
         perm, per_inst = self._draw_order()
         if self.graph is None:
             return self._result(self._run(local_patches, perm, per_inst))
-        if local_patches.data_ptr() != self._g_in.data_ptr():
+        if local_patches.data_ptr() != self._g_in.data_ptr():     # (fill `static_input` in place to avoid this copy)
             self._g_in.copy_(local_patches, non_blocking=True)
         if perm is not None:
             self._g_perm.copy_(perm, non_blocking=True)
         self.graph.replay()
         return self._result(self._g_pos)
+
+    @property
+    def static_input(self):
+        """The graph's input buffer (after `capture`): write the next slice into it and call the object with it."""
+        return self._g_in
 
     @torch.no_grad()
     def capture(self, local_patches):

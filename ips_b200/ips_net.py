@@ -244,6 +244,11 @@ class IPSNet(nn.Module):
             plan['p_shift'] = (lin.bias.detach().float() * scale + bshift).contiguous()
             w = lin.weight.detach().float().contiguous()
             plan['p_w'] = w.to(torch.bfloat16).contiguous() if self.precision == 'bf16' else w
+            K, HT = w.shape[1], plan['U'].shape[1]
+            plan['p_table'] = None                        # one-kernel path: features -> logits (csrc/umma_projector.cu)
+            if (self.precision == 'bf16' and self.D in (256, 512) and HT <= 8 and K % 64 == 0 and K >= 256 and not self.use_pos
+                    and not os.environ.get('IPSB_NO_FUSED_PROJECTOR')):
+                plan['p_table'] = ops.projector_table(scale, plan['p_shift'], plan['p_w'], plan['U'])
         return plan
 
     def invalidate_plan(self):
@@ -360,6 +365,8 @@ class IPSNet(nn.Module):
                 plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
             z, _ = ops.resnet_logits(plan['desc'], flat.contiguous(), N, chunk, self._ws_cache, lanes=self.lanes)
             return z.view(B, N, HT)
+        if not self.is_image and flat.is_cuda and plan.get('p_table') is not None and flat.dtype in (torch.float32, torch.bfloat16):
+            return ops.projector_logits(flat.contiguous(), plan['p_w'], plan['p_table'], HT, 1e-5).view(B, N, HT)
         z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
         pos_idx = None
         if self.use_pos:
@@ -435,6 +442,8 @@ class IPSNet(nn.Module):
             main.wait_event(arrived[ci])
             if native:
                 ops.resnet_logits(plan['desc'], dev, N, chunk, self._ws_cache, first_row=lo, n_rows=n, z=z, src_first_row=lo - slot)
+            elif not self.is_image and plan.get('p_table') is not None:
+                z[lo:lo + n] = ops.projector_logits(dev[slot:slot + n], plan['p_w'], plan['p_table'], HT, 1e-5)
             else:
                 emb = self.embed(dev, first_row=slot, n_rows=n)
                 z[lo:lo + n] = ops.logits(emb, plan['U'], plan['posU'], None if pos_idx is None else pos_idx[lo:lo + n].contiguous())

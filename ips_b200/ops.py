@@ -293,6 +293,30 @@ def linear_bf16(a, w, scale=None, shift=None, relu=False):
     return y
 
 
+def projector_table(scale, shift, w_bf16, U):
+    """(N, 12) fp32 column table of ipsb_projector_logits: a_n, b_n = a_n * colsum(w_bf16)_n, shift_n, 0, U[n, 0..7]."""
+    N, HT = U.shape
+    a = scale.float()
+    cs = w_bf16.float().sum(dim=1)
+    tab = torch.zeros((N, 12), dtype=torch.float32, device=U.device)
+    tab[:, 0], tab[:, 1], tab[:, 2] = a, a * cs, shift.float()
+    tab[:, 4:4 + HT] = U
+    return tab.contiguous()
+
+
+def projector_logits(x, w_bf16, table, HT, eps=1e-5):
+    """Feature rows (rows, K) fp32 or bf16 -> logits (rows, HT) fp32 in ONE kernel: LayerNorm (algebraic) + Linear on the
+    tensor cores + BatchNorm(eval) + ReLU + score projection (ips_net.py:54-60, transformer.py:71-83)."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError('ips_b200: features must be fp32 or bf16')
+    _chk(x, x.dtype, 'x'); _chk(w_bf16, torch.bfloat16, 'w'); _chk(table, torch.float32, 'table')
+    rows, K = x.shape
+    N = w_bf16.shape[0]
+    z = torch.empty((rows, HT), dtype=torch.float32, device=x.device)
+    _call('ipsb_projector_logits', _p(x), int(x.dtype == torch.bfloat16), _p(w_bf16), _p(table), _p(z), rows, K, N, HT, eps, _stream())
+    return z
+
+
 def make_resnet_desc(plan, dt, D, HT):
     """Pack the folded-parameter plan of IPSNet into the ipsb_resnet_desc the native executor reads."""
     def conv(e):

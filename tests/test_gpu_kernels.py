@@ -385,6 +385,35 @@ def test_topm_stable_long_rows(dev, L, M):
     assert torch.equal(val.cpu(), rv[:, :M])
 
 
+@pytest.mark.parametrize('rows,K,N,HT,in_bf16', [(333, 2048, 512, 8, False), (128, 256, 512, 8, False), (5000, 2048, 512, 8, True),
+                                                  (1000, 512, 256, 4, False), (40000, 2048, 512, 8, False), (129, 1024, 512, 1, True)])
+def test_projector_logits_fused(dev, rows, K, N, HT, in_bf16):
+    """One kernel from features to logits (csrc/umma_projector.cu) against the fp32 definition of the same chain
+    (ips_net.py:54-60 + transformer.py:71-83) evaluated on the bf16-rounded operands: LayerNorm applied algebraically in
+    the epilogue, BatchNorm + ReLU, score projection; ragged last tile, fp32 and bf16 features, 256- and 512-wide."""
+    from ips_b200 import ops
+    x = _rand(rows, K, seed=60) * 1.5 + 0.3
+    w = _rand(N, K, seed=61) * (1.0 / math.sqrt(K))
+    scale, shift = torch.rand(N, generator=torch.Generator().manual_seed(62)) + 0.5, _rand(N, seed=63) * 0.2
+    U = _rand(N, HT, seed=64) * 0.1
+    wb = w.to(torch.bfloat16)
+    xin = x.to(torch.bfloat16) if in_bf16 else x
+    tab = ops.projector_table(scale.to(dev), shift.to(dev), wb.to(dev), U.to(dev))
+    z = ops.projector_logits(xin.to(dev), wb.to(dev), tab, HT, 1e-5).cpu()
+    xr = x.to(torch.bfloat16).double()                                  # what the tensor cores see
+    mean, var = xr.mean(1, keepdim=True), xr.var(1, unbiased=False, keepdim=True)
+    y = ((xr - mean) / torch.sqrt(var + 1e-5)) @ wb.double().t()
+    emb = torch.relu(y * scale.double() + shift.double())
+    ref = (emb @ U.double()).float()
+    err = (z - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err                                              # fp32 accumulation of exact bf16 products
+    # and against the unfused chain of round 1 (LayerNorm -> bf16 -> GEMM -> logits): same result within bf16 rounding of LN(x)
+    a = ops.rows_to_bf16(xin.to(dev), layernorm=True, eps=1e-5)
+    emb2 = ops.linear_bf16(a, wb.to(dev), scale.to(dev), shift.to(dev), relu=True)
+    z2 = ops.logits(emb2, U.to(dev).contiguous()).cpu()
+    assert (z - z2).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
 # ------------------------------------------------------------------ aggregator + heads (no-grad forward)
 
 @pytest.mark.parametrize('B,M,H,Dk,Dv,T', [(2, 100, 8, 16, 16, 4), (3, 10, 8, 64, 64, 1), (1, 5000, 8, 64, 64, 1), (2, 7, 3, 8, 24, 2)])
