@@ -18,6 +18,7 @@
 //
 // HBM traffic = the features once (8 192 B / patch fp32) + 32 B / patch of logits; W (2 MB) is re-streamed from L2 per tile.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/ips_b200.h"
@@ -43,6 +44,7 @@ struct ProjParams {
     int K, N, HT, KS, halves; // KS = K / 64, halves = N / 256
     int tiles;
     float eps;
+    int prefetch;             // k blocks the converters' L2 prefetch runs ahead of their register loads (0 = off)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -185,7 +187,24 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                 }
             }
         };
+        // one k block of register loads in flight (32 KB per CTA) does not cover the HBM latency: an L2 prefetch of the
+        // same 256-byte row segments runs `prefetch` k blocks ahead, so the register loads hit L2
+        auto prefetch = [&](uint32_t it) {
+            if (chunk != 0) return;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(it / (uint32_t)p.KS) * gridDim.x;
+            const int kb = (int)(it % (uint32_t)p.KS);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = tile * TILE_M + cw * 16 + i * 4 + sub;
+                if (row < p.rows) {
+                    const char* ptr = reinterpret_cast<const char*>(p.x) + (row * p.K + kb * BK) * (IN_BF16 ? 2 : 4);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "n"(IN_BF16 ? 128 : 256) : "memory");
+                }
+            }
+        };
         float s1[4], s2[4];
+        if (p.prefetch > 0)
+            for (uint32_t j = 1; j < (uint32_t)p.prefetch && j < total; ++j) prefetch(j);
         if (total > 0) load(0, nxt);
         for (uint32_t it = 0; it < total; ++it) {
 #pragma unroll
@@ -193,6 +212,7 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
 #pragma unroll
                 for (int j = 0; j < 8; ++j) cur[i][j] = nxt[i][j];
             if (it + 1 < total) load(it + 1, nxt);
+            if (p.prefetch > 0 && it + (uint32_t)p.prefetch < total) prefetch(it + (uint32_t)p.prefetch);
             const int kb = (int)(it % (uint32_t)p.KS);
             const uint32_t tcount = it / (uint32_t)p.KS;
             if (kb == 0) {
@@ -356,6 +376,11 @@ int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, cons
     p.x = x; p.table = table; p.z = z; p.rows = rows; p.K = K; p.N = N; p.HT = HT; p.KS = K / BK; p.halves = N / 256;
     p.tiles = (int)((rows + TILE_M - 1) / TILE_M);
     p.eps = eps;
+    {
+        const char* e = getenv("IPSB_PROJ_PREFETCH");
+        p.prefetch = e ? atoi(e) : 6;
+        if (p.prefetch < 0 || p.prefetch > 64) p.prefetch = 6;
+    }
     const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + 2 * TILE_M * 8 + 2 * TILE_M * HTP * 4 +
                         8 * (2 * SW + 2 * SA + 4) + 64;
     IPSB_REQUIRE(smem <= 227 * 1024, "projector_logits: %zu bytes of shared memory", smem);
