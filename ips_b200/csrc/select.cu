@@ -497,8 +497,18 @@ __device__ __forceinline__ void hist_add(int* hist, uint32_t bin, bool active) {
     if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
 }
 
+// (m, s) <- merge of two online-softmax partials; an empty partial is (-inf, 0)
+__device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
+    const float M = fmaxf(m, m2);
+    const float a = (m == -INFINITY) ? 0.f : s * expf(m - M);
+    const float b = (m2 == -INFINITY) ? 0.f : s2 * expf(m2 - M);
+    m = M;
+    s = a + b;
+}
+
 struct ClusterScratch {
-    float part_max[kMaxHT], part_sum[kMaxHT];   // this CTA's partials (read remotely)
+    float part_max[kMaxHT], part_sum[kMaxHT];   // this CTA's (max, sum of exp relative to it) partials (read remotely)
+    float wpart[16][kMaxHT][2];                 // per-warp partials
     float gmax[kMaxHT], gsum[kMaxHT];           // cluster-wide results
     int hist[4][256];                           // this CTA's radix histograms (read remotely)
     int tot[256];
@@ -613,34 +623,48 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
         }
         if (tid < 256) { cs->hist[0][tid] = 0; cs->hist[1][tid] = 0; cs->hist[2][tid] = 0; cs->hist[3][tid] = 0; }
         __syncthreads();
-        // ---- per-(h,t) max over the whole buffer
-        const int ht = tid % HT;
-        float v = -INFINITY;
-        if (tid < nt_eff)
-            for (int e = tid; e < n_own * HT; e += nt_eff) v = fmaxf(v, zl[e]);
-        reduce_classes<true>(v, HT, pow2, nt_eff, &cs->red, cs->part_max);
-        csync();
-        if (tid < HT) {
-            float m = cs->part_max[tid];
-            if (NC > 1) for (int r = 0; r < NC; ++r) m = fmaxf(m, cluster.map_shared_rank(cs->part_max, r)[tid]);
-            cs->gmax[tid] = m;
+        // ---- per-(h,t) max and sum of exp over the whole buffer in ONE exchange: every thread keeps an online
+        //      (max, sum relative to that max) pair, merged through shuffles, shared memory and DSMEM in a fixed order
+        {
+            float m = -INFINITY, sm = 0.f;
+            if (tid < nt_eff) {
+                for (int e = tid; e < n_own * HT; e += nt_eff) m = fmaxf(m, zl[e]);
+                for (int e = tid; e < n_own * HT; e += nt_eff) sm += expf(zl[e] - m);
+            }
+            if (pow2) {
+                for (int o = 16; o >= HT; o >>= 1) {
+                    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
+                    merge_ms(m, sm, m2, s2);
+                }
+                if (lane < HT) { cs->wpart[warp][lane][0] = m; cs->wpart[warp][lane][1] = sm; }
+                __syncthreads();
+                if (tid < HT) {
+                    float mm = cs->wpart[0][tid][0], ss = cs->wpart[0][tid][1];
+                    for (int w = 1; w < NT / 32; ++w) merge_ms(mm, ss, cs->wpart[w][tid][0], cs->wpart[w][tid][1]);
+                    cs->part_max[tid] = mm; cs->part_sum[tid] = ss;
+                }
+            } else {                                          // generic H*T: one pair per thread through shared memory
+                cs->red.slow[tid] = m;
+                cs->red.slow[NT + tid] = sm;
+                __syncthreads();
+                if (tid < HT) {
+                    float mm = -INFINITY, ss = 0.f;
+                    for (int i = tid; i < nt_eff; i += HT) merge_ms(mm, ss, cs->red.slow[i], cs->red.slow[NT + i]);
+                    cs->part_max[tid] = mm; cs->part_sum[tid] = ss;
+                }
+            }
+            csync();
+            if (tid < HT) {
+                float mm = -INFINITY, ss = 0.f;
+                for (int r = 0; r < NC; ++r) {
+                    const float m2 = (NC > 1) ? cluster.map_shared_rank(cs->part_max, r)[tid] : cs->part_max[tid];
+                    const float s2 = (NC > 1) ? cluster.map_shared_rank(cs->part_sum, r)[tid] : cs->part_sum[tid];
+                    merge_ms(mm, ss, m2, s2);
+                }
+                cs->gmax[tid] = mm; cs->gsum[tid] = ss;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- per-(h,t) sum of exp
-        v = 0.f;
-        if (tid < nt_eff) {
-            const float m = cs->gmax[ht];
-            for (int e = tid; e < n_own * HT; e += nt_eff) v += expf(zl[e] - m);
-        }
-        reduce_classes<false>(v, HT, pow2, nt_eff, &cs->red, cs->part_sum);
-        csync();
-        if (tid < HT) {
-            float sm = 0.f;
-            if (NC > 1) { for (int r = 0; r < NC; ++r) sm += cluster.map_shared_rank(cs->part_sum, r)[tid]; }
-            else sm = cs->part_sum[tid];
-            cs->gsum[tid] = sm;
-        }
-        __syncthreads();
         // ---- scores -> order bits; first radix histogram on the fly
         for (int i0 = 0; i0 < n_own; i0 += NT) {             // warp-uniform trip count (hist_add uses warp votes)
             const int i = i0 + tid;
@@ -815,314 +839,6 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
     }
 }
 
-// ---- cluster-parallel variant, version 2: THREE cluster barriers per iteration -------------------------------------
-// Same data layout and semantics as select_loop_cluster_kernel.  What changed is the number of cluster-wide exchanges on
-// the per-iteration dependency chain (each costs a cluster barrier):
-//   1. softmax statistics: every thread keeps an online (max, sum) pair, merged through shuffles / shared memory / DSMEM
-//      in a fixed order -- one exchange instead of two (max, then sum);
-//   2. keys: every CTA stores the order bits of its slice's scores into ALL CTAs' key arrays (DSMEM stores), so each CTA
-//      runs the 4-pass radix select of the rank-M key redundantly on the whole buffer (keys in registers, block barriers
-//      only) and derives its own compaction offsets from the same scan -- no histogram reduction across the cluster,
-//      no broadcast of the threshold;
-//   3. the compacted memory buffer becomes visible.
-struct V2Scratch {
-    float part_m[kMaxHT], part_s[kMaxHT];       // this CTA's (max, sum) partials (read remotely)
-    float gmax[kMaxHT], gsum[kMaxHT];           // cluster-wide results
-    float wpart[16][kMaxHT][2];                 // per-warp partials
-    int hist[4][256];
-    int sel[2];
-    int wsum[64];
-};
-
-// (m, s) <- merge of two online-softmax partials; an empty partial is (-inf, 0)
-__device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
-    const float M = fmaxf(m, m2);
-    const float a = (m == -INFINITY) ? 0.f : s * expf(m - M);
-    const float b = (m2 == -INFINITY) ? 0.f : s2 * expf(m2 - M);
-    m = M;
-    s = a + b;
-}
-
-template <int NC>
-__global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(512, 1)
-select_loop_v2_kernel(LoopParams p, ClusterArgs a, int key_slots) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cg::cluster_group cluster = cg::this_cluster();
-    constexpr int NT = 512, TPS = NT / NC, E0MAX = 32;
-    const int cr = (NC == 1) ? 0 : (int)cluster.block_rank();
-    const int b = blockIdx.x / NC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HT = p.H * p.T, M = p.M, cap = a.slice_cap;
-    float* zl = reinterpret_cast<float*>(smem_raw);                     // [cap][HT] logits of this slice
-    uint32_t* key = reinterpret_cast<uint32_t*>(zl + (size_t)cap * HT); // [cap]
-    int* cand = reinterpret_cast<int*>(key + cap);                      // [cap] table rows
-    int* posl = cand + cap;                                             // [cap] scan positions
-    size_t front = (size_t)cap * (HT + 3) * 4;
-    { const size_t fs = (size_t)next_pow2((M + NC - 1) / NC) * 8; if (front < fs) front = fs; front = (front + 15) / 16 * 16; }
-    V2Scratch* cs = reinterpret_cast<V2Scratch*>(smem_raw + front);
-    uint32_t* allkeys = reinterpret_cast<uint32_t*>(cs + 1);            // [key_slots] the whole buffer's keys; later the final runs
-
-    const float* zs = a.zs + (int64_t)b * p.N * HT;
-    const int* srcs = a.srcs + (int64_t)b * p.N;
-    float* z_buf[2] = {a.m_z + (int64_t)b * 2 * M * HT, a.m_z + (int64_t)b * 2 * M * HT + (int64_t)M * HT};
-    int* pos_buf[2] = {a.m_pos + (int64_t)b * 2 * M, a.m_pos + (int64_t)b * 2 * M + M};
-    int* src_buf[2] = {a.m_src + (int64_t)b * 2 * M, a.m_src + (int64_t)b * 2 * M + M};
-    uint32_t* key_buf = a.m_key + (int64_t)b * M;
-    auto csync = [&]() { if (NC == 1) __syncthreads(); else cluster.sync(); };
-
-    for (int i = cr * NT + tid; i < M * HT; i += NC * NT) z_buf[0][i] = zs[i];
-    for (int r = cr * NT + tid; r < M; r += NC * NT) { pos_buf[0][r] = r; src_buf[0][r] = srcs[r]; }
-    __threadfence();
-    csync();
-
-    const int n_iter = (p.N - M + p.I - 1) / p.I;
-    const int ht = tid % HT;                                  // HT is a power of two <= 32: NT % HT == 0
-    int cur = 0;
-    for (int it = 0; it < n_iter; ++it) {
-        const int lo = M + it * p.I;
-        const int hi = min(lo + p.I, p.N);
-        const int L = M + (hi - lo);
-        const int S = (L + NC - 1) / NC;                     // slice length
-        const int l0 = cr * S;
-        const int n_own = max(0, min(S, L - l0));
-        const int E0 = (S + TPS - 1) / TPS;                  // keys per thread in the select; slice r owns slots [r*TPS*E0, +TPS*E0)
-        // ---- (a) this slice's logits / positions / rows -> shared memory
-        {
-            const int hv = HT >> 2;
-            if (hv > 0) {
-                const int total4 = n_own * hv;
-                float4* zl4 = reinterpret_cast<float4*>(zl);
-                for (int e0 = tid; e0 < total4; e0 += 4 * NT) {
-                    float4 v4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int e = e0 + u * NT;
-                        if (e < total4) {
-                            const int i = e / hv, c4 = e - i * hv, l = l0 + i;
-                            const float* src_row = (l < M) ? z_buf[cur] + (int64_t)l * HT : zs + (int64_t)(lo + l - M) * HT;
-                            v4[u] = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);   // L2: the memory rows were written by other SMs
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int e = e0 + u * NT;
-                        if (e < total4) zl4[e] = v4[u];
-                    }
-                }
-            } else {
-                for (int e = tid; e < n_own * HT; e += NT) {
-                    const int i = e / HT, c = e - i * HT, l = l0 + i;
-                    zl[e] = (l < M) ? z_buf[cur][(int64_t)l * HT + c] : zs[(int64_t)(lo + l - M) * HT + c];
-                }
-            }
-        }
-        for (int i = tid; i < n_own; i += NT) {
-            const int l = l0 + i;
-            if (l < M) { posl[i] = pos_buf[cur][l]; cand[i] = src_buf[cur][l]; }
-            else { posl[i] = lo + (l - M); cand[i] = srcs[lo + (l - M)]; }
-        }
-        for (int i = tid; i < 4 * 256; i += NT) (&cs->hist[0][0])[i] = 0;
-        __syncthreads();
-        // ---- (b) per-(h,t) max and sum of exp over the whole buffer: one online (max, sum) pair per thread
-        {
-            float m = -INFINITY, sm = 0.f;
-            for (int e = tid; e < n_own * HT; e += NT) m = fmaxf(m, zl[e]);
-            for (int e = tid; e < n_own * HT; e += NT) sm += expf(zl[e] - m);
-            for (int o = 16; o >= HT; o >>= 1) {
-                const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
-                merge_ms(m, sm, m2, s2);
-            }
-            if (lane < HT) { cs->wpart[warp][lane][0] = m; cs->wpart[warp][lane][1] = sm; }
-            __syncthreads();
-            if (tid < HT) {
-                float mm = cs->wpart[0][tid][0], ss = cs->wpart[0][tid][1];
-                for (int w = 1; w < NT / 32; ++w) merge_ms(mm, ss, cs->wpart[w][tid][0], cs->wpart[w][tid][1]);
-                cs->part_m[tid] = mm; cs->part_s[tid] = ss;
-            }
-            csync();                                         // #1
-            if (tid < HT) {
-                float mm = -INFINITY, ss = 0.f;
-                for (int r = 0; r < NC; ++r) {
-                    const float m2 = (NC > 1) ? cluster.map_shared_rank(cs->part_m, r)[tid] : cs->part_m[tid];
-                    const float s2 = (NC > 1) ? cluster.map_shared_rank(cs->part_s, r)[tid] : cs->part_s[tid];
-                    merge_ms(mm, ss, m2, s2);
-                }
-                cs->gmax[tid] = mm; cs->gsum[tid] = ss;
-            }
-            __syncthreads();
-        }
-        // ---- (c) scores -> order bits, stored into every CTA's key array (slot = position in scan order, padded per slice)
-        {
-            const int slots = TPS * E0;
-            for (int i = tid; i < slots; i += NT) {
-                uint32_t k = 0u;                             // 0 = padding (valid keys have the top bit set)
-                if (i < n_own) {
-                    const float* zr = zl + (size_t)i * HT;
-                    float tok = 0.f;
-                    for (int t = 0; t < p.T; ++t) {
-                        float hs = 0.f;
-                        for (int h = 0; h < p.H; ++h) {
-                            const int c = h * p.T + t;
-                            hs += expf(zr[c] - cs->gmax[c]) / cs->gsum[c];
-                        }
-                        tok += hs / (float)p.H;
-                    }
-                    k = order_bits(tok / (float)p.T);
-                    key[i] = k;
-                }
-                if (NC > 1) {
-#pragma unroll
-                    for (int r = 0; r < NC; ++r) cluster.map_shared_rank(allkeys, r)[cr * slots + i] = k;
-                } else {
-                    allkeys[i] = k;
-                }
-            }
-            csync();                                         // #2
-        }
-        // ---- (d) radix select of the rank-M key on the whole buffer, redundantly in every CTA: keys in registers
-        uint32_t kreg[E0MAX];
-#pragma unroll
-        for (int e = 0; e < E0MAX; ++e) kreg[e] = (e < E0) ? allkeys[tid * E0 + e] : 0u;
-        uint32_t prefix = 0;
-        int remaining = M;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-#pragma unroll
-            for (int e = 0; e < E0MAX; ++e) {
-                if (e < E0) {                                // warp-uniform
-                    const uint32_t k = kreg[e];
-                    hist_add(cs->hist[pass], (k >> shift) & 255u, k != 0u && (pass == 0 || (k >> (shift + 8)) == prefix));
-                }
-            }
-            __syncthreads();
-            if (warp == 0) {
-                int c[8], tot = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { c[j] = cs->hist[pass][255 - 8 * lane - j]; tot += c[j]; }
-                int inc = tot;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-                const int before = inc - tot;
-                if (before < remaining && remaining <= inc) {
-                    int run = before;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (run < remaining && remaining <= run + c[j]) { cs->sel[0] = 255 - 8 * lane - j; cs->sel[1] = remaining - run; }
-                        run += c[j];
-                    }
-                }
-            }
-            __syncthreads();
-            prefix = (prefix << 8) | (uint32_t)cs->sel[0];
-            remaining = cs->sel[1];
-            // (sel is rewritten only after the next pass's barrier)
-        }
-        const uint32_t thr = prefix;
-        // ---- (e) stable compaction in scan order: exclusive scan of (above, equal) counts over the threads' slot ranges
-        int ngt = 0, neq = 0;
-#pragma unroll
-        for (int e = 0; e < E0MAX; ++e) {
-            if (e < E0) { ngt += (kreg[e] > thr); neq += (kreg[e] == thr); }
-        }
-        int inc_gt = ngt, inc_eq = neq;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, inc_gt, o), w = __shfl_up_sync(0xffffffffu, inc_eq, o);
-            if (lane >= o) { inc_gt += u; inc_eq += w; }
-        }
-        if (lane == 31) { cs->wsum[warp] = inc_gt; cs->wsum[32 + warp] = inc_eq; }
-        __syncthreads();
-        if (warp == 0) {
-            int g1 = lane < NT / 32 ? cs->wsum[lane] : 0, c2 = lane < NT / 32 ? cs->wsum[32 + lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, g1, o), w = __shfl_up_sync(0xffffffffu, c2, o);
-                if (lane >= o) { g1 += u; c2 += w; }
-            }
-            cs->wsum[lane] = g1; cs->wsum[32 + lane] = c2;
-        }
-        __syncthreads();
-        int gt_before = (inc_gt - ngt) + (warp ? cs->wsum[warp - 1] : 0);
-        int eq_before = (inc_eq - neq) + (warp ? cs->wsum[32 + warp - 1] : 0);
-        const int nxt = cur ^ 1;
-        if (tid / TPS == cr) {                               // the threads whose slots are this CTA's slice write its survivors
-            const int i0 = (tid - cr * TPS) * E0;
-#pragma unroll
-            for (int e = 0; e < E0MAX; ++e) {
-                if (e < E0) {
-                    const int i = i0 + e;
-                    const uint32_t k = kreg[e];
-                    if (i < n_own) {
-                        if ((k > thr) || (k == thr && eq_before < remaining)) {
-                            const int dst = gt_before + (eq_before < remaining ? eq_before : remaining);
-                            pos_buf[nxt][dst] = posl[i];
-                            src_buf[nxt][dst] = cand[i];
-                            key_buf[dst] = k;
-                            posl[i] = dst;                   // remembered for the cooperative logit copy below
-                        } else {
-                            posl[i] = -1;
-                        }
-                    }
-                    gt_before += (k > thr);
-                    eq_before += (k == thr);
-                }
-            }
-        }
-        __syncthreads();
-        for (int e = tid; e < n_own * HT; e += NT) {         // survivors' logits -> next buffer, coalesced per row
-            const int i = e / HT, dst = posl[i];
-            if (dst >= 0) z_buf[nxt][(int64_t)dst * HT + (e - i * HT)] = zl[e];
-        }
-        __threadfence();
-        csync();                                             // #3: new buffer visible to the whole cluster
-        cur = nxt;
-    }
-    // ---- final ordering (score descending, ties -> scanned first), as in version 1
-    {
-        const int Sm = (M + NC - 1) / NC;
-        const int j0 = cr * Sm;
-        const int n_mine = max(0, min(Sm, M - j0));
-        const int pad = next_pow2(Sm);
-        unsigned long long* run = reinterpret_cast<unsigned long long*>(smem_raw);
-        for (int r = tid; r < pad; r += NT)
-            run[r] = (r < n_mine) ? (((unsigned long long)key_buf[j0 + r] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(j0 + r))) : 0ull;
-        __syncthreads();
-        bitonic_desc(run, pad);
-        unsigned long long* g_runs = a.m_runs + (int64_t)b * NC * Sm;
-        for (int r = tid; r < n_mine; r += NT) g_runs[(int64_t)cr * Sm + r] = run[r];
-        __threadfence();
-        csync();
-        unsigned long long* all = reinterpret_cast<unsigned long long*>(allkeys);            // [NC][Sm]
-        if (NC > 1) {
-            for (int r = tid; r < NC * Sm; r += NT) {
-                const int rr = r / Sm, k = r - rr * Sm;
-                all[r] = (k < max(0, min(Sm, M - rr * Sm))) ? g_runs[r] : 0ull;
-            }
-            __syncthreads();
-        }
-        for (int r = tid; r < n_mine; r += NT) {
-            const unsigned long long K = run[r];
-            int rank = r;
-            if (NC > 1) {
-                for (int rr = 0; rr < NC; ++rr) {
-                    if (rr == cr) continue;
-                    const unsigned long long* o = all + rr * Sm;
-                    const int n_o = max(0, min(Sm, M - rr * Sm));
-                    int lo_ = 0, hi_ = n_o;
-                    while (lo_ < hi_) {
-                        const int mid = (lo_ + hi_) >> 1;
-                        if (o[mid] > K) lo_ = mid + 1; else hi_ = mid;
-                    }
-                    rank += lo_;
-                }
-            }
-            const int j = (int)key_pos(K);
-            p.out_pos[(int64_t)b * M + rank] = pos_buf[cur][j];
-            p.out_src[(int64_t)b * M + rank] = src_buf[cur][j];
-            if (p.out_score) p.out_score[(int64_t)b * M + rank] = order_bits_inv((uint32_t)(K >> 32));
-        }
-    }
-}
-
 template <int NC>
 int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     const int HT = p.H * p.T, M = p.M, N = p.N;
@@ -1131,11 +847,7 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     size_t front = (size_t)cap * (HT + 3) * 4;
     if (front < (size_t)host_next_pow2(Sm) * 8) front = (size_t)host_next_pow2(Sm) * 8;     // final sort aliases the slice arrays
     front = (front + 15) / 16 * 16;
-    const bool v2 = getenv("IPSB_SELECT_V1") == nullptr;
-    const int key_slots = 512 * (int)((cap + 512 / NC - 1) / (512 / NC));          // version 2: 512 threads x keys per thread
-    size_t tail_bytes = (size_t)NC * Sm * 8;                                        // final runs; version 2 aliases its key array
-    if (v2 && tail_bytes < (size_t)key_slots * 4) tail_bytes = (size_t)key_slots * 4;
-    const size_t smem = front + (v2 ? sizeof(V2Scratch) : sizeof(ClusterScratch)) + tail_bytes + 64;
+    const size_t smem = front + sizeof(ClusterScratch) + (size_t)NC * Sm * 8 + 64;
     if (smem > 200 * 1024) return -1;                        // caller falls back
     const int64_t need = ipsb_select_loop_workspace_bytes(B, N, HT, M);
     IPSB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "select_loop: workspace of %lld bytes required", (long long)need);
@@ -1155,15 +867,9 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     if (g > (int64_t)ipsb::sm_count() * 8) g = (int64_t)ipsb::sm_count() * 8;
     permute_logits_kernel<<<(unsigned)g, 256, 0, st>>>(p.z, p.perm, p.perm_stride, N, HT, zs, srcs, total);
     IPSB_LAUNCH_CHECK();
-    if (v2) {
-        auto kern = select_loop_v2_kernel<NC>;
-        IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<B * NC, 512, smem, st>>>(p, a, key_slots);
-    } else {
-        auto kern = select_loop_cluster_kernel<NC>;
-        IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<B * NC, 512, smem, st>>>(p, a);
-    }
+    auto kern = select_loop_cluster_kernel<NC>;
+    IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * NC, 512, smem, st>>>(p, a);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

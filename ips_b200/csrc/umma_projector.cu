@@ -6,15 +6,17 @@
 // Round 1 ran four passes over HBM for this (LayerNorm + cast, GEMM, logits; 205 MB bf16 copy + 102 MB embeddings written
 // and re-read per 50 k-patch slide).  Here a CTA owns 128 rows at a time:
 //
-//   converter warps   stream the fp32 (or bf16) rows from HBM with 256-bit loads, round to bf16 straight into the
-//                     128B-swizzled K-major A stage in shared memory, and accumulate each row's sum / sum of squares of the
-//                     ROUNDED values: LayerNorm is applied algebraically in the epilogue,
+//   16 worker warps   K loop: stream the fp32 (or bf16) rows from HBM with 256-bit loads -- three k blocks (96 KB per CTA) in
+//                     flight in registers --, round to bf16 straight into the 128B-swizzled K-major A stage in shared memory
+//                     and accumulate each row's sum / sum of squares of the ROUNDED values: LayerNorm is applied
+//                     algebraically in the epilogue,
 //                         LN(x) W^T = rstd * (x W^T - mean * colsum(W))
 //                     so the tensor cores consume the raw features and no normalised copy exists anywhere;
+//                     tile end: the same warps drain the accumulator: tcgen05.ld -> rstd * (a_n * acc - mean * b_n) + shift_n
+//                     -> ReLU -> 8 running dot products with U in registers (fp32) -> 32 bytes of logits per row to HBM
+//                     (their loads for the next tile are already in flight);
 //   TMA warp          streams W (N, K) bf16 in (256 x 64) boxes;
-//   MMA warp          tcgen05.mma 128 x 256 x 16, two accumulators side by side: all 512 TMEM columns hold the 128 x N tile;
-//   epilogue warps    tcgen05.ld -> rstd * (a_n * acc - mean * b_n) + shift_n -> ReLU -> 8 running dot products with U in
-//                     registers (fp32) -> 32 bytes of logits per row to HBM.
+//   MMA warp          tcgen05.mma 128 x 256 x 16, two accumulators side by side: all 512 TMEM columns hold the 128 x N tile.
 //
 // HBM traffic = the features once (8 192 B / patch fp32) + 32 B / patch of logits; W (2 MB) is re-streamed from L2 per tile.
 #include <cuda.h>
@@ -33,8 +35,9 @@ constexpr int SW = 4;                         // W stages (256 rows x 64 bf16 = 
 constexpr int A_BYTES = TILE_M * 128;
 constexpr int W_BYTES = 256 * 128;
 constexpr int HTP = 8;                        // logit columns kept per row (H*T <= 8)
-constexpr int N_CONV_WARPS = 8, N_EPI_WARPS = 8;
-constexpr int THREADS = 32 * (2 + N_CONV_WARPS + N_EPI_WARPS);
+constexpr int N_WORK_WARPS = 16;               // converters during the K loop, epilogue at the end of a tile
+constexpr int N_WORKERS = 32 * N_WORK_WARPS;
+constexpr int THREADS = 32 * (2 + N_WORK_WARPS);
 
 struct ProjParams {
     const void* x;            // (rows, K) fp32 or bf16
@@ -44,7 +47,6 @@ struct ProjParams {
     int K, N, HT, KS, halves; // KS = K / 64, halves = N / 256
     int tiles;
     float eps;
-    int prefetch;             // k blocks the converters' L2 prefetch runs ahead of their register loads (0 = off)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -71,17 +73,16 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
     const uint32_t a0 = smem0;                                   // SA x 16 KB
     const uint32_t w0 = a0 + SA * A_BYTES;                       // SW x 32 KB
     const uint32_t tab0 = w0 + SW * W_BYTES;                     // N x 48 B
-    const uint32_t stat0 = tab0 + (uint32_t)p.N * 48u;           // 2 x 128 x (mean, rstd)
-    const uint32_t zb0 = stat0 + 2u * TILE_M * 8u;               // 2 x 128 x 8 floats
-    const uint32_t bar0 = zb0 + 2u * TILE_M * HTP * 4u;
+    const uint32_t stat0 = tab0 + (uint32_t)p.N * 48u;           // 128 x (mean, rstd)
+    const uint32_t zb0 = stat0 + TILE_M * 8u;                    // 2 (tile parity) x 3 (column groups 1..3) x 128 x 8 floats
+    const uint32_t bar0 = zb0 + 2u * 3u * TILE_M * HTP * 4u;
     auto w_full = [&](int s) { return bar0 + 8u * s; };
     auto w_empty = [&](int s) { return bar0 + 8u * (SW + s); };
     auto a_full = [&](int s) { return bar0 + 8u * (2 * SW + s); };
     auto a_empty = [&](int s) { return bar0 + 8u * (2 * SW + SA + s); };
     const uint32_t t_full = bar0 + 8u * (2 * SW + 2 * SA);
     const uint32_t t_empty = t_full + 8u;
-    auto s_full = [&](int b) { return t_full + 16u + 8u * b; };
-    const uint32_t tmem_slot = t_full + 32u;
+    const uint32_t tmem_slot = t_full + 16u;
     auto gptr = [&](uint32_t saddr) { return smem_raw + (saddr - raw0); };
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gptr(tmem_slot));
 
@@ -89,11 +90,9 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
 
     if (tid == 0) {
         for (int s = 0; s < SW; ++s) { umma::mbar_init(w_full(s), 1); umma::mbar_init(w_empty(s), 1); }
-        for (int s = 0; s < SA; ++s) { umma::mbar_init(a_full(s), N_CONV_WARPS); umma::mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < SA; ++s) { umma::mbar_init(a_full(s), N_WORK_WARPS); umma::mbar_init(a_empty(s), 1); }
         umma::mbar_init(t_full, 1);
-        umma::mbar_init(t_empty, 32 * N_EPI_WARPS);
-        umma::mbar_init(s_full(0), N_CONV_WARPS);
-        umma::mbar_init(s_full(1), N_CONV_WARPS);
+        umma::mbar_init(t_empty, N_WORKERS);
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
@@ -157,22 +156,29 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
             if (kb == p.KS - 1) umma::mma_commit_w(t_full, leader);
         }
         __syncwarp();
-    } else if (warp < 2 + N_CONV_WARPS) {
-        // ---------------- converters: HBM -> registers -> bf16 -> swizzled A stage; row statistics of the rounded values
-        const int cw = warp - 2;
+    } else {
+        // ---------------- workers: K loop = HBM -> registers -> bf16 -> swizzled A stage (+ row statistics of the rounded
+        //                  values); tile end = epilogue on the accumulator
+        const int cw = warp - 2;                                 // 0..15: rows [8 cw, 8 cw + 8) of the tile in the K loop
         const int sub = lane >> 3, chunk = lane & 7;             // 8 lanes cover one row's 64-element k block
-        float nxt[4][8], cur[4][8];
-        auto load = [&](uint32_t it, float (&buf)[4][8]) {
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        const int grp = cw >> 2;                                 // epilogue: column group [grp * N/4, +N/4)
+        const int erow = q * 32 + lane;                          // epilogue: accumulator row of this thread
+        const int cols_per_grp = p.N / 4;
+        const int col0 = grp * cols_per_grp;
+        const float4* tab = reinterpret_cast<const float4*>(gptr(tab0));
+        float2* stats = reinterpret_cast<float2*>(gptr(stat0));
+        auto load = [&](uint32_t it, float (&buf)[2][8]) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)(it / (uint32_t)p.KS) * gridDim.x;
             const int kb = (int)(it % (uint32_t)p.KS);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t row = tile * TILE_M + cw * 16 + i * 4 + sub;
+            for (int i = 0; i < 2; ++i) {
+                const int64_t row = tile * TILE_M + cw * 8 + i * 4 + sub;
                 if (row < p.rows) {
                     const int64_t off = row * p.K + kb * BK + chunk * 8;
                     if (IN_BF16) {
-                        const int4 q = ipsb::ld_stream16(reinterpret_cast<const bf16*>(p.x) + off);
-                        const uint32_t u[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+                        const int4 qv = ipsb::ld_stream16(reinterpret_cast<const bf16*>(p.x) + off);
+                        const uint32_t u[4] = {(uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             buf[i][2 * j] = __uint_as_float(u[j] << 16);
@@ -187,44 +193,18 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                 }
             }
         };
-        // one k block of register loads in flight (32 KB per CTA) does not cover the HBM latency: an L2 prefetch of the
-        // same 256-byte row segments runs `prefetch` k blocks ahead, so the register loads hit L2
-        auto prefetch = [&](uint32_t it) {
-            if (chunk != 0) return;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(it / (uint32_t)p.KS) * gridDim.x;
-            const int kb = (int)(it % (uint32_t)p.KS);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t row = tile * TILE_M + cw * 16 + i * 4 + sub;
-                if (row < p.rows) {
-                    const char* ptr = reinterpret_cast<const char*>(p.x) + (row * p.K + kb * BK) * (IN_BF16 ? 2 : 4);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "n"(IN_BF16 ? 128 : 256) : "memory");
-                }
-            }
-        };
-        float s1[4], s2[4];
-        if (p.prefetch > 0)
-            for (uint32_t j = 1; j < (uint32_t)p.prefetch && j < total; ++j) prefetch(j);
-        if (total > 0) load(0, nxt);
-        for (uint32_t it = 0; it < total; ++it) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) cur[i][j] = nxt[i][j];
-            if (it + 1 < total) load(it + 1, nxt);
-            if (p.prefetch > 0 && it + (uint32_t)p.prefetch < total) prefetch(it + (uint32_t)p.prefetch);
+        float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+        // one k block: three further k blocks stay in flight in `fut` and the two other buffers while `cur` is converted
+        auto step = [&](uint32_t it, float (&cur)[2][8], float (&fut)[2][8]) {
+            if (it + 3 < total) load(it + 3, fut);
             const int kb = (int)(it % (uint32_t)p.KS);
             const uint32_t tcount = it / (uint32_t)p.KS;
-            if (kb == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-            }
             const int sa = it % SA;
             umma::mbar_wait(a_empty(sa), ((it / SA) & 1) ^ 1);
             const uint32_t a_addr = a0 + sa * A_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rl = cw * 16 + i * 4 + sub;
+            for (int i = 0; i < 2; ++i) {
+                const int rl = cw * 8 + i * 4 + sub;
                 uint32_t w[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -239,54 +219,40 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
             umma::fence_proxy_async();                           // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(a_full(sa));
-            if (kb == p.KS - 1) {                                // row complete: mean / rstd for the epilogue
-                const int b = (int)(tcount & 1);
-                float2* stats = reinterpret_cast<float2*>(gptr(stat0)) + b * TILE_M;
+            if (kb != p.KS - 1) return;
+            // ================= end of a tile: row statistics, then the epilogue =================
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)tcount * gridDim.x;
+            const int par = (int)(tcount & 1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float a = s1[i], c = s2[i];
+            for (int i = 0; i < 2; ++i) {
+                float a = s1[i], c = s2[i];
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        c += __shfl_xor_sync(0xffffffffu, c, o);
-                    }
-                    if (chunk == 0) {
-                        const float mean = a / (float)p.K;
-                        const float var = fmaxf(c / (float)p.K - mean * mean, 0.f);
-                        stats[cw * 16 + i * 4 + sub] = make_float2(mean, rsqrtf(var + p.eps));
-                    }
+                for (int o = 1; o < 8; o <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
                 }
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(s_full(b));
+                if (chunk == 0) {
+                    const float mean = a / (float)p.K;
+                    const float var = fmaxf(c / (float)p.K - mean * mean, 0.f);
+                    stats[cw * 8 + i * 4 + sub] = make_float2(mean, rsqrtf(var + p.eps));
+                }
+                s1[i] = 0.f; s2[i] = 0.f;
             }
-        }
-    } else {
-        // ---------------- epilogue: two warpgroups, each owns half of the columns of every row
-        const int ew = warp - (2 + N_CONV_WARPS);
-        const int wg = ew >> 2;
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;
-        const int cols_per_wg = p.N / 2;
-        const int col0 = wg * cols_per_wg;
-        const float4* tab = reinterpret_cast<const float4*>(gptr(tab0));
-        for (int t = 0; t < n_my; ++t) {
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
-            const int b = t & 1;
-            umma::mbar_wait(s_full(b), (t >> 1) & 1);
-            const float2 st = reinterpret_cast<const float2*>(gptr(stat0))[b * TILE_M + row];
-            const float nmean = -st.x, rstd = st.y;
-            umma::mbar_wait(t_full, t & 1);
+            umma::named_bar_sync(1, N_WORKERS);                  // statistics of all 128 rows are in shared memory
+            const float2 st = stats[erow];
+            const float k_mu = -st.x * st.y, rstd = st.y;        // e = relu(acc * (rstd a_n) + (shift_n - rstd mean b_n))
+            umma::mbar_wait(t_full, tcount & 1);
             umma::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
             float zacc[HTP];
 #pragma unroll
             for (int j = 0; j < HTP; ++j) zacc[j] = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < cols_per_wg; c0 += 32) {
+            for (int c0 = 0; c0 < cols_per_grp; c0 += 32) {
                 uint32_t v[32];
                 umma::tmem_ld32(t_row + (uint32_t)c0, v);
                 umma::tmem_ld_wait();
-                if (c0 + 32 >= cols_per_wg) {                    // accumulator fully read by this thread
+                if (c0 + 32 >= cols_per_grp) {                   // accumulator fully read by this thread
                     umma::tc_fence_before();
                     umma::mbar_arrive(t_empty);
                 }
@@ -294,36 +260,55 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                 for (int c = 0; c < 32; ++c) {
                     const int n = col0 + c0 + c;
                     const float4 pr = tab[3 * n], u0 = tab[3 * n + 1], u1 = tab[3 * n + 2];
-                    const float tt = fmaf(__uint_as_float(v[c]), pr.x, nmean * pr.y);
-                    const float e = fmaxf(fmaf(rstd, tt, pr.z), 0.f);
+                    const float e = fmaxf(fmaf(__uint_as_float(v[c]), rstd * pr.x, fmaf(k_mu, pr.y, pr.z)), 0.f);
                     zacc[0] = fmaf(e, u0.x, zacc[0]); zacc[1] = fmaf(e, u0.y, zacc[1]);
                     zacc[2] = fmaf(e, u0.z, zacc[2]); zacc[3] = fmaf(e, u0.w, zacc[3]);
                     zacc[4] = fmaf(e, u1.x, zacc[4]); zacc[5] = fmaf(e, u1.y, zacc[5]);
                     zacc[6] = fmaf(e, u1.z, zacc[6]); zacc[7] = fmaf(e, u1.w, zacc[7]);
                 }
             }
-            // combine the two column halves (fixed order: deterministic) and store the row's logits
-            float* zb = reinterpret_cast<float*>(gptr(zb0)) + (b * TILE_M + row) * HTP;
-            if (wg == 1) {
-                reinterpret_cast<float4*>(zb)[0] = make_float4(zacc[0], zacc[1], zacc[2], zacc[3]);
-                reinterpret_cast<float4*>(zb)[1] = make_float4(zacc[4], zacc[5], zacc[6], zacc[7]);
+            // combine the four column groups in a fixed order (deterministic) and store the row's logits
+            float* zb = reinterpret_cast<float*>(gptr(zb0)) + (size_t)par * 3 * TILE_M * HTP;
+            if (grp > 0) {
+                float4* d = reinterpret_cast<float4*>(zb + ((size_t)(grp - 1) * TILE_M + erow) * HTP);
+                d[0] = make_float4(zacc[0], zacc[1], zacc[2], zacc[3]);
+                d[1] = make_float4(zacc[4], zacc[5], zacc[6], zacc[7]);
             }
-            umma::named_bar_sync(1, 32 * N_EPI_WARPS);
-            if (wg == 0) {
-                const float4 o0 = reinterpret_cast<const float4*>(zb)[0], o1 = reinterpret_cast<const float4*>(zb)[1];
-                const float r[HTP] = {zacc[0] + o0.x, zacc[1] + o0.y, zacc[2] + o0.z, zacc[3] + o0.w,
-                                      zacc[4] + o1.x, zacc[5] + o1.y, zacc[6] + o1.z, zacc[7] + o1.w};
-                const int64_t grow = tile * TILE_M + row;
+            umma::named_bar_sync(1, N_WORKERS);
+            if (grp == 0) {
+                float r[HTP];
+#pragma unroll
+                for (int j = 0; j < HTP; ++j) r[j] = zacc[j];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    const float4* o = reinterpret_cast<const float4*>(zb + ((size_t)g * TILE_M + erow) * HTP);
+                    const float4 o0 = o[0], o1 = o[1];
+                    r[0] += o0.x; r[1] += o0.y; r[2] += o0.z; r[3] += o0.w;
+                    r[4] += o1.x; r[5] += o1.y; r[6] += o1.z; r[7] += o1.w;
+                }
+                const int64_t grow = tile * TILE_M + erow;
                 if (grow < p.rows) {
                     float* dst = p.z + grow * p.HT;
                     if (p.HT == HTP) {
                         reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
                         reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
                     } else {
-                        for (int j = 0; j < p.HT; ++j) dst[j] = r[j];
+#pragma unroll
+                        for (int j = 0; j < HTP; ++j)
+                            if (j < p.HT) dst[j] = r[j];
                     }
                 }
             }
+        };
+        float b0[2][8], b1[2][8], b2[2][8], b3[2][8];
+        if (total > 0) load(0, b0);
+        if (total > 1) load(1, b1);
+        if (total > 2) load(2, b2);
+        for (uint32_t it = 0; it < total; it += 4) {
+            step(it, b0, b3);
+            if (it + 1 < total) step(it + 1, b1, b0);
+            if (it + 2 < total) step(it + 2, b2, b1);
+            if (it + 3 < total) step(it + 3, b3, b2);
         }
     }
 
@@ -376,13 +361,8 @@ int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, cons
     p.x = x; p.table = table; p.z = z; p.rows = rows; p.K = K; p.N = N; p.HT = HT; p.KS = K / BK; p.halves = N / 256;
     p.tiles = (int)((rows + TILE_M - 1) / TILE_M);
     p.eps = eps;
-    {
-        const char* e = getenv("IPSB_PROJ_PREFETCH");
-        p.prefetch = e ? atoi(e) : 6;
-        if (p.prefetch < 0 || p.prefetch > 64) p.prefetch = 6;
-    }
-    const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + 2 * TILE_M * 8 + 2 * TILE_M * HTP * 4 +
-                        8 * (2 * SW + 2 * SA + 4) + 64;
+    const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + TILE_M * 8 + 2 * 3 * TILE_M * HTP * 4 +
+                        8 * (2 * SW + 2 * SA + 2) + 64;
     IPSB_REQUIRE(smem <= 227 * 1024, "projector_logits: %zu bytes of shared memory", smem);
     const int grid = p.tiles < ipsb::sm_count() ? p.tiles : ipsb::sm_count();
     if (x_is_bf16) {
