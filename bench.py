@@ -427,11 +427,7 @@ class Bench:
         labels_t = {k: (v.repeat(n_calls, *([1] * (v.dim() - 1)))) for k, v in labels.items()}
         from ips_b200.train import GraphedTrainStep
         opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=conf.wd, capturable=True)
-        hook = None
-        if self.world > 1:
-            from ips_b200.distributed import allreduce_gradients
-            hook = allreduce_gradients
-        gstep = GraphedTrainStep(net, conf, opt, B_train, grad_hook=hook)
+        gstep = GraphedTrainStep(net, conf, opt, B_train, data_parallel=True if self.world > 1 else None)
         for k, v in labels_t.items():
             gstep.labels[k].copy_(v)
         for i in range(n_calls):
@@ -452,7 +448,8 @@ class Bench:
                 'note': 'ips() (plan re-folded from the updated weights every step) + forward + loss + backward + AdamW; '
                         + ('grad-mode half replayed as one CUDA graph' if graphed else 'grad-mode half eager (synchronised BatchNorm '
                            'puts collectives inside forward/backward)')
-                        + ('; gradient all-reduce (NCCL) + optimizer step after the replay' if self.world > 1 else '')}
+                        + ('; data parallel: ONE NCCL all-reduce of the flat gradient buffer between the [forward+backward] graph and the '
+                           '[1/R scaling + AdamW] graph' if self.world > 1 and graphed else '')}
 
     # ---- north_star's multi-GPU mode: one sequence sharded over the ranks ----------------------------------------
     def seq_sharded(self, steps):

@@ -497,18 +497,8 @@ __device__ __forceinline__ void hist_add(int* hist, uint32_t bin, bool active) {
     if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
 }
 
-// (m, s) <- merge of two online-softmax partials; an empty partial is (-inf, 0)
-__device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
-    const float M = fmaxf(m, m2);
-    const float a = (m == -INFINITY) ? 0.f : s * expf(m - M);
-    const float b = (m2 == -INFINITY) ? 0.f : s2 * expf(m2 - M);
-    m = M;
-    s = a + b;
-}
-
 struct ClusterScratch {
-    float part_max[kMaxHT], part_sum[kMaxHT];   // this CTA's (max, sum of exp relative to it) partials (read remotely)
-    float wpart[16][kMaxHT][2];                 // per-warp partials
+    float part_max[kMaxHT], part_sum[kMaxHT];   // this CTA's partials (read remotely)
     float gmax[kMaxHT], gsum[kMaxHT];           // cluster-wide results
     int hist[4][256];                           // this CTA's radix histograms (read remotely)
     int tot[256];
@@ -623,48 +613,34 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
         }
         if (tid < 256) { cs->hist[0][tid] = 0; cs->hist[1][tid] = 0; cs->hist[2][tid] = 0; cs->hist[3][tid] = 0; }
         __syncthreads();
-        // ---- per-(h,t) max and sum of exp over the whole buffer in ONE exchange: every thread keeps an online
-        //      (max, sum relative to that max) pair, merged through shuffles, shared memory and DSMEM in a fixed order
-        {
-            float m = -INFINITY, sm = 0.f;
-            if (tid < nt_eff) {
-                for (int e = tid; e < n_own * HT; e += nt_eff) m = fmaxf(m, zl[e]);
-                for (int e = tid; e < n_own * HT; e += nt_eff) sm += expf(zl[e] - m);
-            }
-            if (pow2) {
-                for (int o = 16; o >= HT; o >>= 1) {
-                    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
-                    merge_ms(m, sm, m2, s2);
-                }
-                if (lane < HT) { cs->wpart[warp][lane][0] = m; cs->wpart[warp][lane][1] = sm; }
-                __syncthreads();
-                if (tid < HT) {
-                    float mm = cs->wpart[0][tid][0], ss = cs->wpart[0][tid][1];
-                    for (int w = 1; w < NT / 32; ++w) merge_ms(mm, ss, cs->wpart[w][tid][0], cs->wpart[w][tid][1]);
-                    cs->part_max[tid] = mm; cs->part_sum[tid] = ss;
-                }
-            } else {                                          // generic H*T: one pair per thread through shared memory
-                cs->red.slow[tid] = m;
-                cs->red.slow[NT + tid] = sm;
-                __syncthreads();
-                if (tid < HT) {
-                    float mm = -INFINITY, ss = 0.f;
-                    for (int i = tid; i < nt_eff; i += HT) merge_ms(mm, ss, cs->red.slow[i], cs->red.slow[NT + i]);
-                    cs->part_max[tid] = mm; cs->part_sum[tid] = ss;
-                }
-            }
-            csync();
-            if (tid < HT) {
-                float mm = -INFINITY, ss = 0.f;
-                for (int r = 0; r < NC; ++r) {
-                    const float m2 = (NC > 1) ? cluster.map_shared_rank(cs->part_max, r)[tid] : cs->part_max[tid];
-                    const float s2 = (NC > 1) ? cluster.map_shared_rank(cs->part_sum, r)[tid] : cs->part_sum[tid];
-                    merge_ms(mm, ss, m2, s2);
-                }
-                cs->gmax[tid] = mm; cs->gsum[tid] = ss;
-            }
-            __syncthreads();
+        // ---- per-(h,t) max over the whole buffer
+        const int ht = tid % HT;
+        float v = -INFINITY;
+        if (tid < nt_eff)
+            for (int e = tid; e < n_own * HT; e += nt_eff) v = fmaxf(v, zl[e]);
+        reduce_classes<true>(v, HT, pow2, nt_eff, &cs->red, cs->part_max);
+        csync();
+        if (tid < HT) {
+            float m = cs->part_max[tid];
+            if (NC > 1) for (int r = 0; r < NC; ++r) m = fmaxf(m, cluster.map_shared_rank(cs->part_max, r)[tid]);
+            cs->gmax[tid] = m;
         }
+        __syncthreads();
+        // ---- per-(h,t) sum of exp
+        v = 0.f;
+        if (tid < nt_eff) {
+            const float m = cs->gmax[ht];
+            for (int e = tid; e < n_own * HT; e += nt_eff) v += expf(zl[e] - m);
+        }
+        reduce_classes<false>(v, HT, pow2, nt_eff, &cs->red, cs->part_sum);
+        csync();
+        if (tid < HT) {
+            float sm = 0.f;
+            if (NC > 1) { for (int r = 0; r < NC; ++r) sm += cluster.map_shared_rank(cs->part_sum, r)[tid]; }
+            else sm = cs->part_sum[tid];
+            cs->gsum[tid] = sm;
+        }
+        __syncthreads();
         // ---- scores -> order bits; first radix histogram on the fly
         for (int i0 = 0; i0 < n_own; i0 += NT) {             // warp-uniform trip count (hist_add uses warp votes)
             const int i = i0 + tid;

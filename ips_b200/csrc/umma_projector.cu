@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <bool IN_BF16>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __maxnreg__(112)
 projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw0 = umma::smem_u32(smem_raw);
@@ -197,8 +197,6 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
         // one k block: three further k blocks stay in flight in `fut` and the two other buffers while `cur` is converted
         auto step = [&](uint32_t it, float (&cur)[2][8], float (&fut)[2][8]) {
             if (it + 3 < total) load(it + 3, fut);
-            const int kb = (int)(it % (uint32_t)p.KS);
-            const uint32_t tcount = it / (uint32_t)p.KS;
             const int sa = it % SA;
             umma::mbar_wait(a_empty(sa), ((it / SA) & 1) ^ 1);
             const uint32_t a_addr = a0 + sa * A_BYTES;
@@ -219,8 +217,9 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
             umma::fence_proxy_async();                           // generic-proxy stores -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(a_full(sa));
-            if (kb != p.KS - 1) return;
-            // ================= end of a tile: row statistics, then the epilogue =================
+        };
+        // ================= end of a tile: row statistics, then the epilogue =================
+        auto epilogue = [&](uint32_t tcount) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)tcount * gridDim.x;
             const int par = (int)(tcount & 1);
 #pragma unroll
@@ -304,11 +303,15 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
         if (total > 0) load(0, b0);
         if (total > 1) load(1, b1);
         if (total > 2) load(2, b2);
-        for (uint32_t it = 0; it < total; it += 4) {
-            step(it, b0, b3);
-            if (it + 1 < total) step(it + 1, b1, b0);
-            if (it + 2 < total) step(it + 2, b2, b1);
-            if (it + 3 < total) step(it + 3, b3, b2);
+        uint32_t it = 0;
+        for (int t = 0; t < n_my; ++t) {                         // KS % 4 == 0: the buffer rotation lines up with the tiles
+            for (int kb = 0; kb < p.KS; kb += 4, it += 4) {
+                step(it, b0, b3);
+                step(it + 1, b1, b0);
+                step(it + 2, b2, b1);
+                step(it + 3, b3, b2);
+            }
+            epilogue((uint32_t)t);
         }
     }
 
@@ -339,7 +342,7 @@ extern "C" {
 int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
                           int64_t rows, int K, int N, int HT, float eps, void* stream) {
     IPSB_REQUIRE(x && w_bf16 && table && z && rows > 0, "projector_logits: null argument");
-    IPSB_REQUIRE(K % BK == 0 && K >= BK * (SA + 1), "projector_logits: K=%d must be a multiple of 64, at least %d", K, BK * (SA + 1));
+    IPSB_REQUIRE(K % (4 * BK) == 0 && K >= 4 * BK, "projector_logits: K=%d must be a multiple of %d", K, 4 * BK);
     IPSB_REQUIRE(N == 256 || N == 512, "projector_logits: N=%d (256 or 512 supported: the 128 x N tile lives in TMEM)", N);
     IPSB_REQUIRE(HT >= 1 && HT <= HTP, "projector_logits: H*T=%d exceeds %d", HT, HTP);
     IPSB_REQUIRE(((uintptr_t)x % 32) == 0 && ((uintptr_t)w_bf16 % 16) == 0 && ((uintptr_t)table % 16) == 0 && ((uintptr_t)z % 16) == 0,

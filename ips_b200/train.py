@@ -41,11 +41,25 @@ class GraphedTrainStep:
     optimizer must be created with `capturable=True` (its step counter lives on the device).
     grad_hook optional callable run after backward (e.g. NCCL all-reduce of the gradients); with a hook the graph covers
               forward + loss + backward and the hook + optimizer step run eagerly after each replay.
+    data_parallel  True / a process group: the data-parallel step of north_star.  Every gradient lives in ONE flat fp32
+              buffer (`p.grad` are views of it), so the exchange is a single NCCL all-reduce with no flatten / unflatten
+              copies, issued between two graphs: [forward + loss + backward] -> all-reduce(flat) -> [1/R scaling +
+              optimizer step].  Nothing of the step runs as eager per-tensor kernels.
     """
 
-    def __init__(self, net, conf, optimizer, batch_size, loss_fn=compute_loss, grad_hook=None, warmup=3, fuse_loss=True):
+    def __init__(self, net, conf, optimizer, batch_size, loss_fn=compute_loss, grad_hook=None, warmup=3, fuse_loss=True,
+                 data_parallel=None):
         dev = net.device
         self.net, self.conf, self.opt, self.loss_fn, self.grad_hook = net, conf, optimizer, loss_fn, grad_hook
+        self.dp_group, self.flat_grad, self.graph_update = None, None, None
+        if data_parallel is not None and data_parallel is not False:
+            import torch.distributed as dist
+            self.dp_group = None if data_parallel is True else data_parallel
+            self.dp_world = dist.get_world_size(self.dp_group)
+            if grad_hook is not None:
+                raise ValueError('give either grad_hook or data_parallel')
+            from .distributed import allreduce_gradients
+            self.grad_hook = lambda params: allreduce_gradients(params, self.dp_group)      # warm-up steps and the eager fallback
         M = min(net.M, getattr(conf, 'N', net.M)) if getattr(conf, 'N', None) else net.M
         if conf.is_image:
             self.mem_patch = torch.zeros((batch_size, M, conf.n_chan_in, *conf.patch_size), device=dev)
@@ -70,7 +84,10 @@ class GraphedTrainStep:
         return self.mem_patch, self.mem_pos
 
     def _fwd_bwd(self):
-        self.opt.zero_grad(set_to_none=False)
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()
+        else:
+            self.opt.zero_grad(set_to_none=False)
         if self.fuse_loss:
             loss = fused_loss(self.conf, self.net, self.mem_patch, self.mem_pos, self.labels)
         else:
@@ -110,12 +127,30 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         # with a gradient exchange (NCCL) the graph ends after backward: the collective and the optimizer step run
         # eagerly between replays (a collective inside a capture must be captured identically on every rank)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            if self.grad_hook is None:
-                self._step()
-            else:
+        if self.dp_group is not None or getattr(self, 'dp_world', None):
+            # one flat buffer behind every gradient the warm-up produced (parameters without a gradient stay untouched, as
+            # with the reference's optimizer, which skips `grad is None`)
+            with_grad = [p for p in self.net.parameters() if p.grad is not None]
+            self.flat_grad = torch.zeros(sum(p.numel() for p in with_grad), dtype=torch.float32, device=dev)
+            off = 0
+            for p in with_grad:
+                n = p.numel()
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                off += n
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
                 self._fwd_bwd()
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update):
+                self.flat_grad.mul_(1.0 / self.dp_world)
+                self.opt.step()
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                if self.grad_hook is None:
+                    self._step()
+                else:
+                    self._fwd_bwd()
         self.net.invalidate_plan()           # warm-up steps and the restore below move the parameters
         if snap is not None:
             with torch.no_grad():
@@ -138,7 +173,11 @@ class GraphedTrainStep:
             self.net.invalidate_plan()
             return self.loss
         self.graph.replay()
-        if self.grad_hook is not None:
+        if self.graph_update is not None:            # data parallel: ONE all-reduce of the flat gradient between the two graphs
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.dp_group)
+            self.graph_update.replay()
+        elif self.grad_hook is not None:
             self._sync_and_update()
         self.net.invalidate_plan()           # the replay changed parameters / BatchNorm statistics behind the version counters
         return self.loss

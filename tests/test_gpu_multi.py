@@ -268,3 +268,65 @@ def test_synchronised_batchnorm_fn_equals_full_batch():
         torch.testing.assert_close(ret[r]['rv'], bn.running_var, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(ret[0]['dgamma'], bn.weight.grad, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(ret[0]['dbeta'], bn.bias.grad, rtol=1e-3, atol=1e-4)
+
+
+def _worker_dp_step(rank, world, port, name, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+        sys.path.insert(0, p)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        import ips_oracle as O
+        from ips_b200 import IPSNet, Struct
+        from ips_b200.distributed import allreduce_gradients
+        from ips_b200.train import GraphedTrainStep
+        from golden_util import load_case
+        z, meta, conf, sd, patches = load_case(name)
+        conf = conf.replace(attn_dropout=0.0, dropout=0.0, precision='bf16')
+        B = meta['B']
+        torch.manual_seed(meta['rng_seed'])
+        mem_patch, mem_pos, _ = O.ips(sd, conf, patches, perm='draw', tie='topk')
+        labels = O.make_labels(conf, B, meta['label_seed'])
+        mem_patch = (mem_patch + 0.01 * rank).to(dev)                     # different data on each rank
+        out = {}
+        for mode in ('hook', 'flat'):
+            net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+            net.load_state_dict(sd)
+            net.train()
+            opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=conf.wd, capturable=True)
+            kw = dict(grad_hook=allreduce_gradients) if mode == 'hook' else dict(data_parallel=True)
+            step = GraphedTrainStep(net, conf, opt, B, **kw)
+            step.mem_patch.copy_(mem_patch)
+            if mem_pos is not None:
+                step.mem_pos.copy_(mem_pos.to(dev))
+            for k, v in labels.items():
+                step.labels[k].copy_(v.to(dev))
+            step.capture()
+            losses = [float(step()) for _ in range(3)]
+            out[mode] = (losses, {k: v.detach().float().cpu() for k, v in net.state_dict().items()})
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('name', ['traffic_small', 'camelyon_batch'])
+def test_data_parallel_step_flat_gradient_buffer_equals_bucketed_hook(name):
+    """The data-parallel train step with ONE all-reduce of a flat gradient buffer between two CUDA graphs takes the same
+    optimizer steps as the bucketed all-reduce hook + eager AdamW of round 1, and leaves both ranks with equal weights."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_dp_step, args=(2, port, name, ret), nprocs=2, join=True)
+    for r in (0, 1):
+        (l_hook, sd_hook), (l_flat, sd_flat) = ret[r]['hook'], ret[r]['flat']
+        assert all(abs(a - b) <= 2e-3 * max(1.0, abs(a)) for a, b in zip(l_hook, l_flat)), (l_hook, l_flat)
+        for k, v in sd_hook.items():
+            if 'running' in k or 'num_batches' in k:
+                continue
+            assert float((v - sd_flat[k]).abs().max()) <= 2e-3 * (1.0 + float(v.abs().max())), k
+    for k, v in ret[0]['flat'][1].items():
+        if 'running' in k or 'num_batches' in k:
+            continue                                              # per-rank BatchNorm statistics (sync_bn off)
+        assert torch.equal(v, ret[1]['flat'][1][k]), k
