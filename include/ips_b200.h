@@ -283,7 +283,7 @@ IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k,
  * x (rows, K) fp32 or bf16 (x_is_bf16), rounded to bf16 on chip; mean_r / rstd_r are the LayerNorm statistics of the
  * rounded row (fp32, eps); w_bf16 (N, K) bf16 K-major; table (N, 12) fp32 per output column n:
  *     [a_n = BN scale, b_n = a_n * sum_k w_bf16[n, k], shift_n = bias_n * a_n + BN shift, 0, U[n, 0..7]]  (U zero-padded to 8);
- * z (rows, HT) fp32, HT <= 8.  N in {256, 512} (the 128 x N fp32 tile fills tensor memory), K % 64 == 0, K >= 256.
+ * z (rows, HT) fp32, HT <= 8.  N in {256, 512} (the 128 x N fp32 tile fills tensor memory), K % 128 == 0, K >= 256.
  * Only the features (once) and 4*HT bytes per row of logits touch HBM. */
 IPSB_API int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
                                    int64_t rows, int K, int N, int HT, float eps, void* stream);

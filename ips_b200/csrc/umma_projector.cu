@@ -6,10 +6,10 @@
 // Round 1 ran four passes over HBM for this (LayerNorm + cast, GEMM, logits; 205 MB bf16 copy + 102 MB embeddings written
 // and re-read per 50 k-patch slide).  Here a CTA owns 128 rows at a time:
 //
-//   16 worker warps   K loop: stream the fp32 (or bf16) rows from HBM with 256-bit loads -- three k blocks (96 KB per CTA) in
-//                     flight in registers --, round to bf16 straight into the 128B-swizzled K-major A stage in shared memory
-//                     and accumulate each row's sum / sum of squares of the ROUNDED values: LayerNorm is applied
-//                     algebraically in the epilogue,
+//   8 worker warps    K loop: stream the fp32 (or bf16) rows from HBM with 256-bit loads -- a ring of eight register buffers
+//                     per thread keeps seven loads (57 KB per CTA) in flight --, round to bf16 straight into the
+//                     128B-swizzled K-major A stage in shared memory and accumulate each row's sum / sum of squares of the
+//                     ROUNDED values: LayerNorm is applied algebraically in the epilogue,
 //                         LN(x) W^T = rstd * (x W^T - mean * colsum(W))
 //                     so the tensor cores consume the raw features and no normalised copy exists anywhere;
 //                     tile end: the same warps drain the accumulator: tcgen05.ld -> rstd * (a_n * acc - mean * b_n) + shift_n
@@ -35,7 +35,8 @@ constexpr int SW = 4;                         // W stages (256 rows x 64 bf16 = 
 constexpr int A_BYTES = TILE_M * 128;
 constexpr int W_BYTES = 256 * 128;
 constexpr int HTP = 8;                        // logit columns kept per row (H*T <= 8)
-constexpr int N_WORK_WARPS = 16;               // converters during the K loop, epilogue at the end of a tile
+constexpr int N_WORK_WARPS = 8;                // converters during the K loop, epilogue at the end of a tile
+                                              // (10 warps: the register file leaves ~168 registers per thread for the load pipeline)
 constexpr int N_WORKERS = 32 * N_WORK_WARPS;
 constexpr int THREADS = 32 * (2 + N_WORK_WARPS);
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <bool IN_BF16>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(THREADS, 1)
 projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw0 = umma::smem_u32(smem_raw);
@@ -74,8 +75,8 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
     const uint32_t w0 = a0 + SA * A_BYTES;                       // SW x 32 KB
     const uint32_t tab0 = w0 + SW * W_BYTES;                     // N x 48 B
     const uint32_t stat0 = tab0 + (uint32_t)p.N * 48u;           // 128 x (mean, rstd)
-    const uint32_t zb0 = stat0 + TILE_M * 8u;                    // 2 (tile parity) x 3 (column groups 1..3) x 128 x 8 floats
-    const uint32_t bar0 = zb0 + 2u * 3u * TILE_M * HTP * 4u;
+    const uint32_t zb0 = stat0 + TILE_M * 8u;                    // 2 (tile parity) x 128 x 8 floats
+    const uint32_t bar0 = zb0 + 2u * TILE_M * HTP * 4u;
     auto w_full = [&](int s) { return bar0 + 8u * s; };
     auto w_empty = [&](int s) { return bar0 + 8u * (SW + s); };
     auto a_full = [&](int s) { return bar0 + 8u * (2 * SW + s); };
@@ -159,71 +160,70 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
     } else {
         // ---------------- workers: K loop = HBM -> registers -> bf16 -> swizzled A stage (+ row statistics of the rounded
         //                  values); tile end = epilogue on the accumulator
-        const int cw = warp - 2;                                 // 0..15: rows [8 cw, 8 cw + 8) of the tile in the K loop
+        const int cw = warp - 2;                                 // 0..7: rows [16 cw, 16 cw + 16) of the tile in the K loop
         const int sub = lane >> 3, chunk = lane & 7;             // 8 lanes cover one row's 64-element k block
         const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-        const int grp = cw >> 2;                                 // epilogue: column group [grp * N/4, +N/4)
+        const int grp = cw >> 2;                                 // epilogue: column half [grp * N/2, +N/2)
         const int erow = q * 32 + lane;                          // epilogue: accumulator row of this thread
-        const int cols_per_grp = p.N / 4;
+        const int cols_per_grp = p.N / 2;
         const int col0 = grp * cols_per_grp;
         const float4* tab = reinterpret_cast<const float4*>(gptr(tab0));
         float2* stats = reinterpret_cast<float2*>(gptr(stat0));
-        auto load = [&](uint32_t it, float (&buf)[2][8]) {
+        const uint32_t total_q = total * 4u;                     // one "quarter" = one row of this thread's four per k block
+        // quarter qi = (k block it = qi / 4, row j = qi % 4 of the thread): one 256-bit load
+        auto load = [&](uint32_t qi, float (&buf)[8]) {
+            const uint32_t it = qi >> 2;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)(it / (uint32_t)p.KS) * gridDim.x;
             const int kb = (int)(it % (uint32_t)p.KS);
+            const int64_t row = tile * TILE_M + cw * 16 + (int)(qi & 3u) * 4 + sub;
+            if (row < p.rows) {
+                const int64_t off = row * p.K + kb * BK + chunk * 8;
+                if (IN_BF16) {
+                    const int4 qv = ipsb::ld_stream16(reinterpret_cast<const bf16*>(p.x) + off);
+                    const uint32_t u[4] = {(uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int64_t row = tile * TILE_M + cw * 8 + i * 4 + sub;
-                if (row < p.rows) {
-                    const int64_t off = row * p.K + kb * BK + chunk * 8;
-                    if (IN_BF16) {
-                        const int4 qv = ipsb::ld_stream16(reinterpret_cast<const bf16*>(p.x) + off);
-                        const uint32_t u[4] = {(uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            buf[i][2 * j] = __uint_as_float(u[j] << 16);
-                            buf[i][2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
-                        }
-                    } else {
-                        ldg256(reinterpret_cast<const float*>(p.x) + off, buf[i]);
+                    for (int j = 0; j < 4; ++j) {
+                        buf[2 * j] = __uint_as_float(u[j] << 16);
+                        buf[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
                     }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) buf[i][j] = 0.f;
+                    ldg256(reinterpret_cast<const float*>(p.x) + off, buf);
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) buf[j] = 0.f;
             }
         };
-        float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-        // one k block: three further k blocks stay in flight in `fut` and the two other buffers while `cur` is converted
-        auto step = [&](uint32_t it, float (&cur)[2][8], float (&fut)[2][8]) {
-            if (it + 3 < total) load(it + 3, fut);
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        // convert quarter qi (row J of the thread, known at compile time) while seven later quarters stay in flight
+        auto conv = [&](uint32_t qi, const int J, float (&cur)[8], float (&fut)[8]) {
+            if (qi + 7 < total_q) load(qi + 7, fut);
+            const uint32_t it = qi >> 2;
             const int sa = it % SA;
-            umma::mbar_wait(a_empty(sa), ((it / SA) & 1) ^ 1);
-            const uint32_t a_addr = a0 + sa * A_BYTES;
+            if (J == 0) umma::mbar_wait(a_empty(sa), ((it / SA) & 1) ^ 1);
+            const int rl = cw * 16 + J * 4 + sub;
+            uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int rl = cw * 8 + i * 4 + sub;
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    w[j] = pack_bf16x2(cur[i][2 * j], cur[i][2 * j + 1]);
-                    const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
-                    s1[i] += lo + hi;
-                    s2[i] = fmaf(lo, lo, fmaf(hi, hi, s2[i]));
-                }
-                const uint32_t dst = a_addr + (uint32_t)rl * 128u + (((uint32_t)chunk ^ (uint32_t)(rl & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            for (int j = 0; j < 4; ++j) {
+                w[j] = pack_bf16x2(cur[2 * j], cur[2 * j + 1]);
+                const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+                s1[J] += lo + hi;
+                s2[J] = fmaf(lo, lo, fmaf(hi, hi, s2[J]));
             }
-            umma::fence_proxy_async();                           // generic-proxy stores -> visible to tcgen05.mma
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(a_full(sa));
+            const uint32_t dst = a0 + sa * A_BYTES + (uint32_t)rl * 128u + (((uint32_t)chunk ^ (uint32_t)(rl & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            if (J == 3) {                                        // the warp's 16 rows of this k block are in the stage
+                umma::fence_proxy_async();                       // generic-proxy stores -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(a_full(sa));
+            }
         };
         // ================= end of a tile: row statistics, then the epilogue =================
         auto epilogue = [&](uint32_t tcount) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)tcount * gridDim.x;
             const int par = (int)(tcount & 1);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 float a = s1[i], c = s2[i];
 #pragma unroll
                 for (int o = 1; o < 8; o <<= 1) {
@@ -233,7 +233,7 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                 if (chunk == 0) {
                     const float mean = a / (float)p.K;
                     const float var = fmaxf(c / (float)p.K - mean * mean, 0.f);
-                    stats[cw * 8 + i * 4 + sub] = make_float2(mean, rsqrtf(var + p.eps));
+                    stats[cw * 16 + i * 4 + sub] = make_float2(mean, rsqrtf(var + p.eps));
                 }
                 s1[i] = 0.f; s2[i] = 0.f;
             }
@@ -266,25 +266,17 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                     zacc[6] = fmaf(e, u1.z, zacc[6]); zacc[7] = fmaf(e, u1.w, zacc[7]);
                 }
             }
-            // combine the four column groups in a fixed order (deterministic) and store the row's logits
-            float* zb = reinterpret_cast<float*>(gptr(zb0)) + (size_t)par * 3 * TILE_M * HTP;
-            if (grp > 0) {
-                float4* d = reinterpret_cast<float4*>(zb + ((size_t)(grp - 1) * TILE_M + erow) * HTP);
-                d[0] = make_float4(zacc[0], zacc[1], zacc[2], zacc[3]);
-                d[1] = make_float4(zacc[4], zacc[5], zacc[6], zacc[7]);
+            // combine the two column halves in a fixed order (deterministic) and store the row's logits
+            float* zb = reinterpret_cast<float*>(gptr(zb0)) + ((size_t)par * TILE_M + erow) * HTP;
+            if (grp == 1) {
+                reinterpret_cast<float4*>(zb)[0] = make_float4(zacc[0], zacc[1], zacc[2], zacc[3]);
+                reinterpret_cast<float4*>(zb)[1] = make_float4(zacc[4], zacc[5], zacc[6], zacc[7]);
             }
             umma::named_bar_sync(1, N_WORKERS);
             if (grp == 0) {
-                float r[HTP];
-#pragma unroll
-                for (int j = 0; j < HTP; ++j) r[j] = zacc[j];
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    const float4* o = reinterpret_cast<const float4*>(zb + ((size_t)g * TILE_M + erow) * HTP);
-                    const float4 o0 = o[0], o1 = o[1];
-                    r[0] += o0.x; r[1] += o0.y; r[2] += o0.z; r[3] += o0.w;
-                    r[4] += o1.x; r[5] += o1.y; r[6] += o1.z; r[7] += o1.w;
-                }
+                const float4 o0 = reinterpret_cast<const float4*>(zb)[0], o1 = reinterpret_cast<const float4*>(zb)[1];
+                const float r[HTP] = {zacc[0] + o0.x, zacc[1] + o0.y, zacc[2] + o0.z, zacc[3] + o0.w,
+                                      zacc[4] + o1.x, zacc[5] + o1.y, zacc[6] + o1.z, zacc[7] + o1.w};
                 const int64_t grow = tile * TILE_M + erow;
                 if (grow < p.rows) {
                     float* dst = p.z + grow * p.HT;
@@ -299,17 +291,25 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                 }
             }
         };
-        float b0[2][8], b1[2][8], b2[2][8], b3[2][8];
-        if (total > 0) load(0, b0);
-        if (total > 1) load(1, b1);
-        if (total > 2) load(2, b2);
-        uint32_t it = 0;
-        for (int t = 0; t < n_my; ++t) {                         // KS % 4 == 0: the buffer rotation lines up with the tiles
-            for (int kb = 0; kb < p.KS; kb += 4, it += 4) {
-                step(it, b0, b3);
-                step(it + 1, b1, b0);
-                step(it + 2, b2, b1);
-                step(it + 3, b3, b2);
+        float b0[8], b1[8], b2[8], b3[8], b4[8], b5[8], b6[8], b7[8];
+        if (total_q > 0) load(0, b0);
+        if (total_q > 1) load(1, b1);
+        if (total_q > 2) load(2, b2);
+        if (total_q > 3) load(3, b3);
+        if (total_q > 4) load(4, b4);
+        if (total_q > 5) load(5, b5);
+        if (total_q > 6) load(6, b6);
+        uint32_t qi = 0;
+        for (int t = 0; t < n_my; ++t) {                         // KS is even: the ring of eight buffers lines up with the tiles
+            for (int kb = 0; kb < p.KS; kb += 2, qi += 8) {
+                conv(qi, 0, b0, b7);
+                conv(qi + 1, 1, b1, b0);
+                conv(qi + 2, 2, b2, b1);
+                conv(qi + 3, 3, b3, b2);
+                conv(qi + 4, 0, b4, b3);
+                conv(qi + 5, 1, b5, b4);
+                conv(qi + 6, 2, b6, b5);
+                conv(qi + 7, 3, b7, b6);
             }
             epilogue((uint32_t)t);
         }
@@ -342,7 +342,7 @@ extern "C" {
 int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
                           int64_t rows, int K, int N, int HT, float eps, void* stream) {
     IPSB_REQUIRE(x && w_bf16 && table && z && rows > 0, "projector_logits: null argument");
-    IPSB_REQUIRE(K % (4 * BK) == 0 && K >= 4 * BK, "projector_logits: K=%d must be a multiple of %d", K, 4 * BK);
+    IPSB_REQUIRE(K % (2 * BK) == 0 && K >= 4 * BK, "projector_logits: K=%d must be a multiple of %d, at least %d", K, 2 * BK, 4 * BK);
     IPSB_REQUIRE(N == 256 || N == 512, "projector_logits: N=%d (256 or 512 supported: the 128 x N tile lives in TMEM)", N);
     IPSB_REQUIRE(HT >= 1 && HT <= HTP, "projector_logits: H*T=%d exceeds %d", HT, HTP);
     IPSB_REQUIRE(((uintptr_t)x % 32) == 0 && ((uintptr_t)w_bf16 % 16) == 0 && ((uintptr_t)table % 16) == 0 && ((uintptr_t)z % 16) == 0,
@@ -364,7 +364,7 @@ int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, cons
     p.x = x; p.table = table; p.z = z; p.rows = rows; p.K = K; p.N = N; p.HT = HT; p.KS = K / BK; p.halves = N / 256;
     p.tiles = (int)((rows + TILE_M - 1) / TILE_M);
     p.eps = eps;
-    const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + TILE_M * 8 + 2 * 3 * TILE_M * HTP * 4 +
+    const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + TILE_M * 8 + 2 * TILE_M * HTP * 4 +
                         8 * (2 * SW + 2 * SA + 2) + 64;
     IPSB_REQUIRE(smem <= 227 * 1024, "projector_logits: %zu bytes of shared memory", smem);
     const int grid = p.tiles < ipsb::sm_count() ? p.tiles : ipsb::sm_count();

@@ -246,7 +246,7 @@ class IPSNet(nn.Module):
             plan['p_w'] = w.to(torch.bfloat16).contiguous() if self.precision == 'bf16' else w
             K, HT = w.shape[1], plan['U'].shape[1]
             plan['p_table'] = None                        # one-kernel path: features -> logits (csrc/umma_projector.cu)
-            if (self.precision == 'bf16' and self.D in (256, 512) and HT <= 8 and K % 64 == 0 and K >= 256 and not self.use_pos
+            if (self.precision == 'bf16' and self.D in (256, 512) and HT <= 8 and K % 128 == 0 and K >= 256 and not self.use_pos
                     and not os.environ.get('IPSB_NO_FUSED_PROJECTOR')):
                 plan['p_table'] = ops.projector_table(scale, plan['p_shift'], plan['p_w'], plan['U'])
         return plan
