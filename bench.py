@@ -412,6 +412,7 @@ class Bench:
         torch = self.torch
         net, conf, B, N, x = m['net'], m['conf'], m['B'], m['N'], m['x']
         net.sync_bn = bool(sync_bn)
+        net.sync_bn_equal_shares = True                       # every rank trains on B_train images: no row counts to exchange
         labels = {}
         for task in conf.tasks.values():
             if task['metric'] == 'multilabel_accuracy':
@@ -432,7 +433,15 @@ class Bench:
             gstep.labels[k].copy_(v)
         for i in range(n_calls):
             net.ips(x, out=gstep.buffers, row_offset=i * B)
-        gstep.capture()
+        try:
+            gstep.capture()
+        except Exception as e:                                # e.g. a collective that cannot be captured here: eager step
+            sys.stderr.write('train step: CUDA-graph capture failed (%s); running eagerly\n' % (str(e)[:200],))
+            net.sync_bn_equal_shares = False
+            gstep = GraphedTrainStep(net, conf, opt, B_train, data_parallel=True if self.world > 1 else None)
+            for k, v in labels_t.items():
+                gstep.labels[k].copy_(v)
+            gstep.capture()
         graphed = gstep.graph is not False and gstep.graph is not None
 
         def train_step():

@@ -122,7 +122,18 @@ class BatchNormTrainFn(torch.autograd.Function):
         ops._call('ipsb_bn_stats_f32', _p(x), _p(mean), _p(var), _p(scratch), rows, cols, ops._stream())
         rows_total = rows
         sync = _dist_group(group)
-        if sync is not None:
+        if sync is not None and SYNC_BN_EQUAL_SHARES:
+            # every rank holds the same number of rows (fixed per-rank batch): no row counts to exchange, no host read --
+            # the collectives can be captured in the train step's CUDA graph
+            import torch.distributed as dist
+            R = dist.get_world_size(sync)
+            mine = torch.cat([mean, var])
+            st = torch.empty((R, 2 * cols), dtype=torch.float32, device=x.device)
+            dist.all_gather_into_tensor(st, mine, group=sync)
+            rows_total = rows * R
+            mean = st[:, :cols].mean(0)
+            var = (st[:, cols:] + (st[:, :cols] - mean) ** 2).mean(0)
+        elif sync is not None:
             import torch.distributed as dist
             R = dist.get_world_size(sync)
             mine = torch.cat([mean, var, torch.full((1,), float(rows), device=x.device)])
@@ -162,6 +173,10 @@ class BatchNormTrainFn(torch.autograd.Function):
         ops._call('ipsb_bn_backward_apply_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(all_sums), _p(dx), rows, cols,
                   ctx.rows_total, int(ctx.relu), ops._stream())
         return dx, sums[cols:], sums[:cols], None, None, None, None, None, None
+
+
+# Set by the data-parallel train step when every rank feeds the same number of rows to each BatchNorm (see above).
+SYNC_BN_EQUAL_SHARES = False
 
 
 def _dist_group(group):

@@ -170,37 +170,57 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
         const float4* tab = reinterpret_cast<const float4*>(gptr(tab0));
         float2* stats = reinterpret_cast<float2*>(gptr(stat0));
         const uint32_t total_q = total * 4u;                     // one "quarter" = one row of this thread's four per k block
-        // quarter qi = (k block it = qi / 4, row j = qi % 4 of the thread): one 256-bit load
-        auto load = [&](uint32_t qi, float (&buf)[8]) {
-            const uint32_t it = qi >> 2;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(it / (uint32_t)p.KS) * gridDim.x;
-            const int kb = (int)(it % (uint32_t)p.KS);
-            const int64_t row = tile * TILE_M + cw * 16 + (int)(qi & 3u) * 4 + sub;
-            if (row < p.rows) {
-                const int64_t off = row * p.K + kb * BK + chunk * 8;
-                if (IN_BF16) {
-                    const int4 qv = ipsb::ld_stream16(reinterpret_cast<const bf16*>(p.x) + off);
-                    const uint32_t u[4] = {(uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
+        // The load stream runs seven quarters ahead of the conversion.  Its position is kept incrementally (no integer
+        // divisions in the loop): pointer to this thread's chunk of row (16 cw + sub) of the stream's tile at its k block,
+        // the k block index inside the tile, and which of the thread's four rows exist (ragged last tile).
+        const int esz = IN_BF16 ? 2 : 4;
+        const int64_t row_step = 4 * (int64_t)p.K * esz;         // bytes between the thread's consecutive rows (4 rows apart)
+        int ld_t = 0, ld_kb = 0;
+        uint32_t ld_issued = 0;
+        const char* ld_ptr = nullptr;
+        int ld_rows = 0;                                         // number of this thread's rows (0..4) inside the tensor
+        auto ld_enter_tile = [&]() {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)ld_t * gridDim.x;
+            const int64_t row0 = tile * TILE_M + cw * 16 + sub;
+            ld_ptr = reinterpret_cast<const char*>(p.x) + (row0 * p.K + chunk * 8) * esz;
+            const int64_t left = p.rows - row0;                  // rows row0, row0 + 4, row0 + 8, row0 + 12
+            ld_rows = left <= 0 ? 0 : (left > 12 ? 4 : (int)((left + 3) / 4));
+        };
+        ld_enter_tile();
+        // quarter J of the stream's current k block: one 256-bit (fp32) / 128-bit (bf16) load
+        auto load = [&](const int J, float (&buf)[8]) {
+            if (ld_issued < total_q) {
+                if (J < ld_rows) {
+                    const char* src = ld_ptr + J * row_step;
+                    if (IN_BF16) {
+                        const int4 qv = ipsb::ld_stream16(src);
+                        const uint32_t u[4] = {(uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        buf[2 * j] = __uint_as_float(u[j] << 16);
-                        buf[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+                        for (int j = 0; j < 4; ++j) {
+                            buf[2 * j] = __uint_as_float(u[j] << 16);
+                            buf[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+                        }
+                    } else {
+                        ldg256(reinterpret_cast<const float*>(src), buf);
                     }
                 } else {
-                    ldg256(reinterpret_cast<const float*>(p.x) + off, buf);
-                }
-            } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) buf[j] = 0.f;
+                    for (int j = 0; j < 8; ++j) buf[j] = 0.f;
+                }
+                ++ld_issued;
+                if (J == 3) {                                    // next k block of the stream
+                    ld_ptr += BK * esz;
+                    if (++ld_kb == p.KS) { ld_kb = 0; ++ld_t; ld_enter_tile(); }
+                }
             }
         };
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         // convert quarter qi (row J of the thread, known at compile time) while seven later quarters stay in flight
-        auto conv = [&](uint32_t qi, const int J, float (&cur)[8], float (&fut)[8]) {
-            if (qi + 7 < total_q) load(qi + 7, fut);
-            const uint32_t it = qi >> 2;
-            const int sa = it % SA;
-            if (J == 0) umma::mbar_wait(a_empty(sa), ((it / SA) & 1) ^ 1);
+        uint32_t cv_sa = 0, cv_ph = 1;                           // A stage of the k block being converted, parity to wait for
+        auto conv = [&](const int J, float (&cur)[8], float (&fut)[8]) {
+            load((J + 3) & 3, fut);                              // quarter (qi + 7): row (J + 7) % 4
+            const uint32_t sa = cv_sa;
+            if (J == 0) umma::mbar_wait(a_empty(sa), cv_ph);
             const int rl = cw * 16 + J * 4 + sub;
             uint32_t w[4];
 #pragma unroll
@@ -216,6 +236,7 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                 umma::fence_proxy_async();                       // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(a_full(sa));
+                if (++cv_sa == SA) { cv_sa = 0; cv_ph ^= 1u; }
             }
         };
         // ================= end of a tile: row statistics, then the epilogue =================
@@ -292,24 +313,17 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
             }
         };
         float b0[8], b1[8], b2[8], b3[8], b4[8], b5[8], b6[8], b7[8];
-        if (total_q > 0) load(0, b0);
-        if (total_q > 1) load(1, b1);
-        if (total_q > 2) load(2, b2);
-        if (total_q > 3) load(3, b3);
-        if (total_q > 4) load(4, b4);
-        if (total_q > 5) load(5, b5);
-        if (total_q > 6) load(6, b6);
-        uint32_t qi = 0;
+        load(0, b0); load(1, b1); load(2, b2); load(3, b3); load(0, b4); load(1, b5); load(2, b6);
         for (int t = 0; t < n_my; ++t) {                         // KS is even: the ring of eight buffers lines up with the tiles
-            for (int kb = 0; kb < p.KS; kb += 2, qi += 8) {
-                conv(qi, 0, b0, b7);
-                conv(qi + 1, 1, b1, b0);
-                conv(qi + 2, 2, b2, b1);
-                conv(qi + 3, 3, b3, b2);
-                conv(qi + 4, 0, b4, b3);
-                conv(qi + 5, 1, b5, b4);
-                conv(qi + 6, 2, b6, b5);
-                conv(qi + 7, 3, b7, b6);
+            for (int kb = 0; kb < p.KS; kb += 2) {
+                conv(0, b0, b7);
+                conv(1, b1, b0);
+                conv(2, b2, b1);
+                conv(3, b3, b2);
+                conv(0, b4, b3);
+                conv(1, b5, b4);
+                conv(2, b6, b5);
+                conv(3, b7, b6);
             }
             epilogue((uint32_t)t);
         }

@@ -109,10 +109,15 @@ class GraphedTrainStep:
         capture.  The warm-up steps are real steps on whatever the buffers hold; with `restore_state` the parameters,
         BatchNorm statistics and optimizer state are put back in place afterwards (the graph keeps their addresses)."""
         dev = self.net.device
-        from .autograd import _dist_group
-        if _dist_group(getattr(self.net, 'sync_bn', None)) is not None:
-            self.graph = False                       # synchronised BatchNorm puts collectives inside forward/backward: run eagerly
-            return self
+        from . import autograd
+        if autograd._dist_group(getattr(self.net, 'sync_bn', None)) is not None:
+            # synchronised BatchNorm puts collectives inside forward/backward.  With equal shares per rank (fixed per-rank
+            # batch: `net.sync_bn_equal_shares = True`) they need no host read and are captured with the rest of the
+            # step (NCCL supports stream capture); otherwise the step runs eagerly.
+            if not getattr(self.net, 'sync_bn_equal_shares', False):
+                self.graph = False
+                return self
+            autograd.SYNC_BN_EQUAL_SHARES = True
         snap = None
         if restore_state:
             snap = ([p.detach().clone() for p in self.net.parameters()], [b.detach().clone() for b in self.net.buffers()],

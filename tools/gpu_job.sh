@@ -21,14 +21,3 @@ ncu -i /tmp/proj.ncu-rep --page details > $OUT/j_proj_details.txt 2>/dev/null
 ncu -i /tmp/proj.ncu-rep --page source --csv > $OUT/j_proj_source.csv 2>/dev/null
 grep -E "Duration|SM Frequency|DRAM Throughput|L2 Cache Throughput|SM Active Cycles|Elapsed Cycles" $OUT/j_proj_details.txt | head
 echo "=== done"
-for cfg in "2 0" "3 0" "4 0" "2 1024" "3 512"; do
-  set -- $cfg
-  IPS_B200_LANES=$1 IPS_B200_CHUNK=$2 python bench.py --steps 20 --skip train,library,cpu,workloads,exact,sustained,seq > $OUT/j_lanes.log 2>&1
-  python - <<PY
-import json
-for l in open('$OUT/j_lanes.log'):
-    if l.startswith('{'):
-        d = json.loads(l); r = d['roofline']; print('lanes $1 chunk $2', round(d['ms_per_step'], 4), 'busy', round(r['family_busy_ms_per_step'],4), 'frac', round(r['frac'],4))
-PY
-done
-echo "=== done2"
