@@ -18,6 +18,8 @@
 //   TMA warp          streams W (N, K) bf16 in (256 x 64) boxes;
 //   MMA warp          tcgen05.mma 128 x 256 x 16, two accumulators side by side: all 512 TMEM columns hold the 128 x N tile.
 //
+// (Measured and dropped: L2 prefetches ahead of the register loads -- per k block or row-contiguous a quarter tile ahead --
+// made the kernel 20-35 % slower.)
 // HBM traffic = the features once (8 192 B / patch fp32) + 32 B / patch of logits; W (2 MB) is re-streamed from L2 per tile.
 #include <cuda.h>
 #include <stdlib.h>
@@ -48,7 +50,6 @@ struct ProjParams {
     int K, N, HT, KS, halves; // KS = K / 64, halves = N / 256
     int tiles;
     float eps;
-    int prefetch;             // row-contiguous L2 prefetch ahead of the register loads (IPSB_PROJ_PREFETCH=0 switches it off)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -314,27 +315,9 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
             }
         };
         float b0[8], b1[8], b2[8], b3[8], b4[8], b5[8], b6[8], b7[8];
-        // DRAM locality: the register loads touch 256-byte pieces of 128 rows that lie K*4 bytes apart.  An L2 prefetch runs a
-        // quarter of a tile ahead in pieces that are contiguous per row (K/4 elements = 2 KB of one row per request, one
-        // request per row), so DRAM sees long bursts and the register loads hit L2.
-        const int wt = cw * 32 + lane;                           // worker thread index 0..255; threads 0..127 own one row each
-        const int pf_elems = (p.KS / 4) * BK;                    // elements per row and prefetch round (0: K too short, off)
-        auto prefetch_round = [&](int t, int r) {                // round r (0..3) of this CTA's tile number t
-            if (wt >= TILE_M || pf_elems == 0 || t >= n_my || !p.prefetch) return;
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE_M + wt;
-            if (row >= p.rows) return;
-            const char* ptr = reinterpret_cast<const char*>(p.x) + (row * p.K + (int64_t)r * pf_elems) * esz;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(pf_elems * esz) : "memory");
-        };
-        prefetch_round(0, 1);
         load(0, b0); load(1, b1); load(2, b2); load(3, b3); load(0, b4); load(1, b5); load(2, b6);
-        const int kq = p.KS / 4;
         for (int t = 0; t < n_my; ++t) {                         // KS is even: the ring of eight buffers lines up with the tiles
             for (int kb = 0; kb < p.KS; kb += 2) {
-                if (kq >= 2 && kb % kq == 0) {                   // entering quarter kb / kq: fetch the quarter after next
-                    const int r = kb / kq + 2;
-                    if (r < 4) prefetch_round(t, r); else prefetch_round(t + 1, r - 4);
-                }
                 conv(0, b0, b7);
                 conv(1, b1, b0);
                 conv(2, b2, b1);
@@ -397,7 +380,6 @@ int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, cons
     p.x = x; p.table = table; p.z = z; p.rows = rows; p.K = K; p.N = N; p.HT = HT; p.KS = K / BK; p.halves = N / 256;
     p.tiles = (int)((rows + TILE_M - 1) / TILE_M);
     p.eps = eps;
-    { const char* e = getenv("IPSB_PROJ_PREFETCH"); p.prefetch = (e && e[0] == '0') ? 0 : 1; }
     const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + TILE_M * 8 + 2 * TILE_M * HTP * 4 +
                         8 * (2 * SW + 2 * SA + 2) + 64;
     IPSB_REQUIRE(smem <= 227 * 1024, "projector_logits: %zu bytes of shared memory", smem);
