@@ -487,8 +487,13 @@ class Bench:
                 continue
             lo, hi = shard_bounds(N, R)[rank]
             local = x[:, lo:hi].contiguous()
-            for mode in ('merge', 'exact'):
-                sh = ShardedIPS(net, B, N, (F,), mode=mode)
+            variants = [('merge', 'replicated'), ('exact', 'replicated')]
+            if B >= R:
+                variants.append(('merge', 'batch_split'))      # slide b delivered only to the rank whose train step consumes it
+            for mode, output in variants:
+                sh = ShardedIPS(net, B, N, (F,), mode=mode, output=output)
+                spr = sh.spr
+                my_b = list(range(rank * spr, min(B, (rank + 1) * spr))) if spr else list(range(B))
                 for _ in range(3):
                     sh(local)
                 ms_eager = self.timed(lambda: sh(local), steps) / steps
@@ -497,11 +502,11 @@ class Bench:
                 mem_patch, _ = sh(local)
                 got_idx = net.last_mem_idx.clone()
                 got_sum = mem_patch.double().sum().item()
-                rows_ok = all(bool(torch.equal(mem_patch[b], x[b, got_idx[b]])) for b in range(B))
+                rows_ok = all(bool(torch.equal(mem_patch[j], x[b, got_idx[j]])) for j, b in enumerate(my_b))
                 if mode == 'exact':
                     torch.manual_seed(7)
                     ref_patch, _ = net.ips(x)                                     # the same call on ONE GPU
-                    same = bool(torch.equal(net.last_mem_idx, got_idx)) and bool(torch.equal(ref_patch, mem_patch))
+                    same = bool(torch.equal(net.last_mem_idx[my_b], got_idx)) and bool(torch.equal(ref_patch[my_b], mem_patch))
                     parity = {'exact_equals_single_gpu_bit_for_bit': same}
                 else:
                     # the same schedule composed in ONE process from the product kernels: per-slice loop, candidates in rank
@@ -519,14 +524,20 @@ class Bench:
                     cz, ci = torch.cat(cz, 1).contiguous(), torch.cat(ci, 1)
                     pos = ops.topm_stable(ops.scores_from_logits(cz, ca.H, ca.n_token), M)[1]
                     ref_idx = torch.gather(ci, 1, pos)
-                    parity = {'merge_equals_single_process_schedule': bool(torch.equal(ref_idx, got_idx))}
+                    parity = {'merge_equals_single_process_schedule': bool(torch.equal(ref_idx[my_b], got_idx))}
                 parity['rows_are_the_selected_patches'] = rows_ok
                 flag = torch.tensor([int(all(parity.values()))], device=self.dev)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 parity['all_ranks'] = bool(flag.item())
                 parity['exchange_status'] = sh.ex.status()
-                owned = int(((got_idx >= lo) & (got_idx < hi)).sum().item())
-                pushed = (R - 1) * ((B * M * (HT * 4 + 8) if mode == 'merge' else B * (hi - lo) * HT * 4) + owned * F * 4)
+                all_idx = sh.mem_src                                              # (B, M) on every rank
+                owned = ((all_idx >= lo) & (all_idx < hi))
+                if spr:                                                         # rows this rank sends to OTHER ranks
+                    dest = torch.arange(B, device=self.dev).unsqueeze(1) // spr
+                    sent_rows = int((owned & (dest != rank)).sum().item())
+                else:
+                    sent_rows = int(owned.sum().item()) * (R - 1)
+                pushed = (R - 1) * (B * M * (HT * 4 + 8) if mode == 'merge' else B * (hi - lo) * HT * 4) + sent_rows * F * 4
                 # the whole call as ONE CUDA graph
                 ms_graph, graph_err = None, None
                 try:
@@ -542,7 +553,7 @@ class Bench:
                     graph_err = str(e)[:200]
                 best = min(v for v in (ms_eager, ms_graph) if v is not None)
                 r2 = dict(rec)
-                r2.update(mode=mode, transport='nvlink peer memory (CUDA IPC exchange buffers, push + flag kernels; no NCCL on the data path)',
+                r2.update(mode=mode, output=output, transport='nvlink peer memory (CUDA IPC exchange buffers, push + flag kernels; no NCCL on the data path)',
                           ms_eager=ms_eager, ms_graph=ms_graph, ms=best, patches_per_s=B * N / (best / 1e3),
                           bytes_pushed_to_peers_per_rank=pushed, parity_check=parity)
                 if graph_err:

@@ -815,6 +815,170 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
     }
 }
 
+// ---- short buffers (M + I <= 1024): one CTA per image, the whole loop in shared memory ------------------------------
+// The megapixel-MNIST configurations run 8 - 99 iterations on a 200-entry buffer: the loop is a pure latency chain, and
+// the radix select (4 histogram passes with shared-memory atomics, ~12 block barriers) and the round trip of the survivors
+// through global memory dominate it.  Here
+//   * the memory rows (logits, position, table row) stay in shared memory, double buffered across iterations;
+//   * the softmax statistics are one online (max, sum) pair per thread, merged through shuffles and one shared-memory step;
+//   * the top-M is found by RANK COUNTING: rank_i = #{j : key_j > key_i} + #{j < i : key_j == key_i} (keys read as 128-bit
+//     broadcasts) -- no histogram, no atomics, and the rank IS the position in the final best-first order, so the last
+//     iteration needs no sort;
+//   * survivors are compacted in scan order (the library's tie-break contract) with one block scan.
+// 8 block barriers per iteration, no global-memory dependency between iterations (the next chunk is read from the
+// scan-ordered logit table).
+__device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
+    const float M = fmaxf(m, m2);
+    const float a = (m == -INFINITY) ? 0.f : s * expf(m - M);
+    const float b = (m2 == -INFINITY) ? 0.f : s2 * expf(m2 - M);
+    m = M;
+    s = a + b;
+}
+
+struct SmallScratch {
+    float wpart[16][kMaxHT][2];
+    float gmax[kMaxHT], gsum[kMaxHT];
+    int wsum[32];
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) select_loop_small_kernel(LoopParams p, const float* __restrict__ zs_all,
+                                                                  const int* __restrict__ srcs_all, int Lcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HT = p.H * p.T, M = p.M;
+    float* zl[2];
+    zl[0] = reinterpret_cast<float*>(smem_raw);                          // [Lcap][HT]
+    zl[1] = zl[0] + (size_t)Lcap * HT;
+    int* posb[2]; int* srcb[2];
+    posb[0] = reinterpret_cast<int*>(zl[1] + (size_t)Lcap * HT);         // [Lcap] scan positions
+    posb[1] = posb[0] + Lcap;
+    srcb[0] = posb[1] + Lcap;                                            // [Lcap] table rows
+    srcb[1] = srcb[0] + Lcap;
+    uint32_t* key = reinterpret_cast<uint32_t*>(srcb[1] + Lcap);         // [Lcap + 4] order bits of the scores (padded to x4)
+    int* dstmap = reinterpret_cast<int*>(key + Lcap + 4);                // [Lcap] survivor's row in the next buffer, or -1
+    SmallScratch* sc = reinterpret_cast<SmallScratch*>(dstmap + Lcap);
+
+    const float* zs = zs_all + (int64_t)b * p.N * HT;
+    const int* srcs = srcs_all + (int64_t)b * p.N;
+    // initial memory buffer: the first M scan positions
+    for (int e = tid; e < M * HT; e += NT) zl[0][e] = zs[e];
+    for (int r = tid; r < M; r += NT) { posb[0][r] = r; srcb[0][r] = srcs[r]; }
+
+    const int n_iter = (p.N - M + p.I - 1) / p.I;
+    int cur = 0;
+    for (int it = 0; it < n_iter; ++it) {
+        const int lo = M + it * p.I;
+        const int hi = min(lo + p.I, p.N);
+        const int n_new = hi - lo, L = M + n_new;
+        const bool last = (it == n_iter - 1);
+        float* z = zl[cur];
+        // ---- (a) the next chunk: contiguous rows of the scan-ordered table
+        for (int e = tid; e < n_new * HT; e += NT) z[M * HT + e] = __ldg(zs + (int64_t)lo * HT + e);
+        for (int r = tid; r < n_new; r += NT) { posb[cur][M + r] = lo + r; srcb[cur][M + r] = __ldg(srcs + lo + r); }
+        __syncthreads();
+        // ---- (b) per-(h,t) max and sum of exp over the buffer: online (max, sum) pairs, fixed merge order
+        {
+            float m = -INFINITY, sm = 0.f;
+            for (int e = tid; e < L * HT; e += NT) m = fmaxf(m, z[e]);   // NT % HT == 0: a thread stays in one class
+            for (int e = tid; e < L * HT; e += NT) sm += expf(z[e] - m);
+            for (int o = 16; o >= HT; o >>= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
+                merge_ms(m, sm, m2, s2);
+            }
+            if (lane < HT) { sc->wpart[warp][lane][0] = m; sc->wpart[warp][lane][1] = sm; }
+            __syncthreads();
+            if (tid < HT) {
+                float mm = sc->wpart[0][tid][0], ss = sc->wpart[0][tid][1];
+                for (int w = 1; w < NT / 32; ++w) merge_ms(mm, ss, sc->wpart[w][tid][0], sc->wpart[w][tid][1]);
+                sc->gmax[tid] = mm; sc->gsum[tid] = ss;
+            }
+            __syncthreads();
+        }
+        // ---- (c) scores -> order bits (thread t owns the contiguous candidates [t*E, t*E + E))
+        const int E = (L + NT - 1) / NT;
+        const int i0 = tid * E;
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i < L) {
+                const float* zr = z + (size_t)i * HT;
+                float tok = 0.f;
+                for (int t = 0; t < p.T; ++t) {
+                    float hs = 0.f;
+                    for (int h = 0; h < p.H; ++h) {
+                        const int c = h * p.T + t;
+                        hs += expf(zr[c] - sc->gmax[c]) / sc->gsum[c];
+                    }
+                    tok += hs / (float)p.H;
+                }
+                key[i] = order_bits(tok / (float)p.T);
+            }
+        }
+        if (tid < 4) key[L + tid] = 0u;                                  // padding read by the 128-bit rank loop (never larger)
+        __syncthreads();
+        // ---- (d) rank counting + compaction offsets
+        int kept = 0;
+        int rank_e[2] = {M, M};                                          // E <= 2: L <= 1024 with 512 threads, L <= 128 with 128
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i < L) {
+                const uint32_t k = key[i];
+                int gt = 0, eqb = 0;
+                const uint4* k4 = reinterpret_cast<const uint4*>(key);
+                for (int j4 = 0; j4 * 4 < L; ++j4) {
+                    const uint4 q = k4[j4];
+                    const int j = j4 * 4;
+                    gt += (q.x > k) + (q.y > k) + (q.z > k) + (q.w > k);
+                    eqb += (q.x == k && j < i) + (q.y == k && j + 1 < i) + (q.z == k && j + 2 < i) + (q.w == k && j + 3 < i);
+                }
+                rank_e[e] = gt + eqb;
+                kept += (rank_e[e] < M);
+            }
+        }
+        int inc = kept;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) sc->wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int v = lane < NT / 32 ? sc->wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            sc->wsum[lane] = v;
+        }
+        __syncthreads();
+        int dst = (inc - kept) + (warp ? sc->wsum[warp - 1] : 0);        // survivors scanned before this thread's first candidate
+        const int nxt = cur ^ 1;
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i >= L) break;
+            const int rank = rank_e[e];
+            if (rank < M) {
+                if (last) {                                              // best first: the rank is the output slot
+                    p.out_pos[(int64_t)b * M + rank] = posb[cur][i];
+                    p.out_src[(int64_t)b * M + rank] = srcb[cur][i];
+                    if (p.out_score) p.out_score[(int64_t)b * M + rank] = order_bits_inv(key[i]);
+                }
+                posb[nxt][dst] = posb[cur][i];
+                srcb[nxt][dst] = srcb[cur][i];
+                dstmap[i] = dst++;
+            } else {
+                dstmap[i] = -1;
+            }
+        }
+        if (last) break;
+        __syncthreads();
+        // ---- (e) survivors' logits -> the other buffer, rows in scan order (coalesced, conflict free)
+        float* zn = zl[nxt];
+        for (int e = tid; e < L * HT; e += NT) {
+            const int i = e / HT, d = dstmap[i];
+            if (d >= 0) zn[d * HT + (e - i * HT)] = z[e];
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+}
+
 template <int NC>
 int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     const int HT = p.H * p.T, M = p.M, N = p.N;
@@ -843,6 +1007,24 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     if (g > (int64_t)ipsb::sm_count() * 8) g = (int64_t)ipsb::sm_count() * 8;
     permute_logits_kernel<<<(unsigned)g, 256, 0, st>>>(p.z, p.perm, p.perm_stride, N, HT, zs, srcs, total);
     IPSB_LAUNCH_CHECK();
+    if (NC == 1 && Lmax <= 1024 && getenv("IPSB_SELECT_NO_SMALL") == nullptr) {      // short buffers: shared-memory resident loop
+        const int Lcap = (Lmax + 3) / 4 * 4;
+        const size_t sm_small = (size_t)Lcap * HT * 8 + (size_t)Lcap * 4 * 4 + ((size_t)Lcap + 4) * 4 + (size_t)Lcap * 4 +
+                                sizeof(SmallScratch) + 64;
+        if (sm_small <= 200 * 1024) {
+            if (Lmax <= 128) {
+                auto ks = select_loop_small_kernel<128>;
+                IPSB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
+                ks<<<B, 128, sm_small, st>>>(p, zs, srcs, Lcap);
+            } else {
+                auto ks = select_loop_small_kernel<512>;
+                IPSB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
+                ks<<<B, 512, sm_small, st>>>(p, zs, srcs, Lcap);
+            }
+            IPSB_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     auto kern = select_loop_cluster_kernel<NC>;
     IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B * NC, 512, smem, st>>>(p, a);
@@ -993,8 +1175,8 @@ int ipsb_scores_from_logits(const float* z, float* scores, int B, int L, int H, 
 int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t* idx_out, float* val_out, void* stream) {
     IPSB_REQUIRE(B > 0 && L > 0 && M > 0 && M <= L, "topm: bad shape B=%d L=%d M=%d", B, L, M);
     const int Lpad = host_next_pow2(L);
-    if (Lpad > kMaxLpad) {                                    // long rows: radix select from global memory
-        IPSB_REQUIRE(M <= 16384, "topm: M=%d exceeds 16384 for rows longer than %d", M, kMaxLpad);
+    if (Lpad > 2048 && M <= 16384) {                          // long rows: radix select from global memory (a single-CTA bitonic
+                                                              // sort of 16 384 keys costs > 100 us; this is ~3x faster at L = 10 000)
         const size_t smem_big = (size_t)host_next_pow2(M) * 8 + (256 + 2 + 64) * 4 + 16;
         IPSB_CUDA(cudaFuncSetAttribute(topm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         topm_big_kernel<<<B, 1024, smem_big, (cudaStream_t)stream>>>(scores, L, M, idx_out, val_out);

@@ -4,14 +4,16 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 OUT=gpurun_out
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:select_loop_cluster --launch-skip 3 --launch-count 1 -o /tmp/sel -f \
-    python bench.py --workload camelyon --steps 2 --skip train,library,cpu,workloads,exact,sustained,seq,roofline > $OUT/j_ncu.log 2>&1
-ncu -i /tmp/sel.ncu-rep --page details > $OUT/j_sel_details.txt 2>/dev/null
-ncu -i /tmp/sel.ncu-rep --page source --csv > $OUT/j_sel_source.csv 2>/dev/null
-grep -E "Duration|SM Frequency|Elapsed Cycles" $OUT/j_sel_details.txt | head
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:select_loop_cluster --launch-skip 3 --launch-count 1 -o /tmp/sel2 -f \
-    python bench.py --workload mnist5000 --steps 2 --skip train,library,cpu,workloads,exact,sustained,seq,roofline > $OUT/j_ncu2.log 2>&1
-ncu -i /tmp/sel2.ncu-rep --page details > $OUT/j_sel2_details.txt 2>/dev/null
-ncu -i /tmp/sel2.ncu-rep --page source --csv > $OUT/j_sel2_source.csv 2>/dev/null
-grep -E "Duration|SM Frequency|Elapsed Cycles" $OUT/j_sel2_details.txt | head
+python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider -k "select_loop or topm or golden or baseline_size or full_size or lazy or callsite or training_loop" > $OUT/j_tests.log 2>&1
+tail -6 $OUT/j_tests.log
+for w in mnist5000 mnist traffic; do
+    python bench.py --workload $w --steps 10 --skip train,library,cpu,workloads,exact,sustained,seq > $OUT/j_bench_${w}.log 2>&1
+    python - <<PY
+import json
+for l in open('$OUT/j_bench_${w}.log'):
+    if l.startswith('{'):
+        d = json.loads(l); print('$w', round(d['ms_per_step'], 4), d['value'])
+PY
+done
+python tools/select_sweep.py > $OUT/j_select_sweep.txt 2>&1; tail -30 $OUT/j_select_sweep.txt
 echo "=== done"
