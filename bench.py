@@ -671,9 +671,17 @@ def run_ours(args):
                 k = 20 if w != 'mnist5000' else 10
                 mw = bench.measure(w, args.precision, k, 3, e2e=True)
                 r = bench.roofline(mw, w, mw['ms_per_step'] * k)
-                return {'value': mw['value'], 'unit': 'patches/s', 'ms_per_step': mw['ms_per_step'], 'steps': k, 'warmup': 3,
-                        'e2e': mw['e2e'], 'gpu_launches': mw['gpu_launches'], 'clocks': mw['clocks'],
-                        'config': f"{w}: IPSNet.ips, B={mw['B']} N={mw['N']} M={mw['conf'].M} I={mw['conf'].I}", 'roofline': r}
+                rec = {'value': mw['value'], 'unit': 'patches/s', 'ms_per_step': mw['ms_per_step'], 'steps': k, 'warmup': 3,
+                       'e2e': mw['e2e'], 'gpu_launches': mw['gpu_launches'], 'clocks': mw['clocks'],
+                       'config': f"{w}: IPSNet.ips, B={mw['B']} N={mw['N']} M={mw['conf'].M} I={mw['conf'].I}", 'roofline': r}
+                del mw
+                torch.cuda.empty_cache()
+                if 'library' not in skip:
+                    try:
+                        rec['gpu_library_baseline'] = bench.gpu_library_baseline(w, calls=3)
+                    except Exception as e:
+                        rec['gpu_library_baseline'] = {'error': str(e)[:200]}
+                return rec
             workloads[w] = guarded('workloads', run_w)
             torch.cuda.empty_cache()
 

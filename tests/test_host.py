@@ -2,6 +2,7 @@
 module keeps the reference's surface, and the grad-mode forward reproduces the golden
 train step.  No kernel is launched here."""
 import os
+import sys
 import re
 
 import numpy as np
@@ -155,3 +156,54 @@ def test_ips_out_buffer_validation():
         net._out_views((good, None), 3, 2, 8)                         # rows 3..4 do not fit 4 rows
     with pytest.raises(ValueError):
         net._out_views((torch.zeros(4, 7, conf.n_chan_in), None), 0, 2, 8)
+
+
+def test_interval_union_of_overlapping_lanes():
+    """bench.py's roofline takes the UNION of a kernel family's launch intervals over the concurrent lanes."""
+    from ips_b200 import ops
+    assert ops.busy_ms([]) == 0.0
+    assert ops.busy_ms([(0.0, 1.0), (0.5, 2.0), (3.0, 4.0)]) == pytest.approx(3.0)
+    assert ops.busy_ms([(2.0, 3.0), (0.0, 5.0)]) == pytest.approx(5.0)
+    assert ops.busy_ms([(0.0, 1.0), (1.0, 2.0)]) == pytest.approx(2.0)
+
+
+def test_reference_copy_is_the_unmodified_reference():
+    """baseline/_ref (what `bench.py --impl reference` and the call-site tests import) is a byte-for-byte copy."""
+    import filecmp
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import install_ref
+    import ref_harness
+    if install_ref.ref_path() is None:
+        pytest.skip('baseline/_ref not installed (run baseline/install_ref.py where /root/reference exists)')
+    if os.path.isdir(install_ref.SRC):
+        for rel in ('architecture/ips_net.py', 'architecture/transformer.py', 'utils/utils.py', 'training/iterative.py'):
+            assert filecmp.cmp(os.path.join(install_ref.SRC, rel), os.path.join(install_ref.DST, rel), shallow=False), rel
+    IPSNet, Struct, iterative = ref_harness.load_reference()
+    conf = ref_harness.reference_conf('camelyon', M=4, I=4)
+    net = IPSNet(torch.device('cpu'), conf)
+    assert os.path.abspath(sys.modules[IPSNet.__module__].__file__).startswith(os.path.abspath(install_ref.DST))
+    mp_, pos = net.ips(torch.randn(1, 16, 2048))
+    assert mp_.shape == (1, 4, 2048) and pos is None and hasattr(iterative, 'train_one_epoch')
+
+
+def test_pretrained_is_honoured_or_raises():
+    """conf.pretrained must not be dropped silently (ips_net.py:19-27): either the ImageNet weights load or the constructor raises."""
+    from ips_b200 import IPSNet, Struct
+    conf = O.preset('traffic', pretrained=True)
+    try:
+        net = IPSNet(torch.device('cpu'), Struct(**conf.__dict__))
+    except RuntimeError as e:
+        assert 'pretrained' in str(e)
+        return
+    ref = IPSNet(torch.device('cpu'), Struct(**O.preset('traffic').__dict__))
+    assert not torch.equal(net.encoder[0].weight, ref.encoder[0].weight)      # not a random init
+
+
+def test_sharded_exchange_layout_is_identical_on_all_ranks():
+    """Section offsets of the peer exchange buffer depend only on the global shapes, never on the rank."""
+    from ips_b200.distributed import _align, shard_bounds
+    assert _align(1) == 256 and _align(256) == 256 and _align(257) == 512
+    for N, R in ((50000, 8), (200000, 8), (20001, 2), (7, 3)):
+        b = shard_bounds(N, R)
+        assert b[0][0] == 0 and b[-1][1] == N and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
