@@ -815,18 +815,20 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
     }
 }
 
-// ---- short buffers (M + I <= 1024): one CTA per image, the whole loop in shared memory ------------------------------
-// The megapixel-MNIST configurations run 8 - 99 iterations on a 200-entry buffer: the loop is a pure latency chain, and
-// the radix select (4 histogram passes with shared-memory atomics, ~12 block barriers) and the round trip of the survivors
-// through global memory dominate it.  Here
+// ---- tiny buffers (M + I <= 128): one CTA of 128 threads per image, the whole loop in shared memory -------------------
+// The traffic configuration (M = 10, I = 32) and the small-M corner of the selection sweep run hundreds to thousands of
+// iterations on a buffer of a few dozen entries: a pure latency chain in which the radix select (4 histogram passes with
+// shared-memory atomics, ~12 block barriers) and the round trip of the survivors through global memory dominate.  Here
 //   * the memory rows (logits, position, table row) stay in shared memory, double buffered across iterations;
 //   * the softmax statistics are one online (max, sum) pair per thread, merged through shuffles and one shared-memory step;
 //   * the top-M is found by RANK COUNTING: rank_i = #{j : key_j > key_i} + #{j < i : key_j == key_i} (keys read as 128-bit
 //     broadcasts) -- no histogram, no atomics, and the rank IS the position in the final best-first order, so the last
 //     iteration needs no sort;
 //   * survivors are compacted in scan order (the library's tie-break contract) with one block scan.
-// 8 block barriers per iteration, no global-memory dependency between iterations (the next chunk is read from the
-// scan-ordered logit table).
+// 8 block barriers per iteration, no global-memory dependency between iterations.  Measured (B200, H*T = 8): 3.3 us per
+// iteration at M = I = 10 (cluster<1> kernel: 5.9), 3.7 at M = 10 / I = 32 (6.0), 4.7 at M = I = 50 (6.3).  The pair
+// count grows with L^2: at L = 200 it only ties the radix kernel (7.7 vs 7.2 us) and at L = 1000 it is 4x slower (57 vs
+// 14 us), so longer buffers stay on select_loop_cluster_kernel<1>.
 __device__ __forceinline__ void merge_ms(float& m, float& s, float m2, float s2) {
     const float M = fmaxf(m, m2);
     const float a = (m == -INFINITY) ? 0.f : s * expf(m - M);
@@ -918,7 +920,7 @@ __global__ void __launch_bounds__(NT, 1) select_loop_small_kernel(LoopParams p, 
         __syncthreads();
         // ---- (d) rank counting + compaction offsets
         int kept = 0;
-        int rank_e[2] = {M, M};                                          // E <= 2: L <= 1024 with 512 threads, L <= 128 with 128
+        int rank_e[2] = {M, M};                                          // E = 1 (L <= 128 with 128 threads); generic up to 2
         for (int e = 0; e < E; ++e) {
             const int i = i0 + e;
             if (i < L) {
@@ -1007,23 +1009,15 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     if (g > (int64_t)ipsb::sm_count() * 8) g = (int64_t)ipsb::sm_count() * 8;
     permute_logits_kernel<<<(unsigned)g, 256, 0, st>>>(p.z, p.perm, p.perm_stride, N, HT, zs, srcs, total);
     IPSB_LAUNCH_CHECK();
-    if (NC == 1 && Lmax <= 1024 && getenv("IPSB_SELECT_NO_SMALL") == nullptr) {      // short buffers: shared-memory resident loop
+    if (NC == 1 && Lmax <= 128 && getenv("IPSB_SELECT_NO_SMALL") == nullptr) {       // tiny buffers: shared-memory resident loop
         const int Lcap = (Lmax + 3) / 4 * 4;
         const size_t sm_small = (size_t)Lcap * HT * 8 + (size_t)Lcap * 4 * 4 + ((size_t)Lcap + 4) * 4 + (size_t)Lcap * 4 +
                                 sizeof(SmallScratch) + 64;
-        if (sm_small <= 200 * 1024) {
-            if (Lmax <= 128) {
-                auto ks = select_loop_small_kernel<128>;
-                IPSB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
-                ks<<<B, 128, sm_small, st>>>(p, zs, srcs, Lcap);
-            } else {
-                auto ks = select_loop_small_kernel<512>;
-                IPSB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
-                ks<<<B, 512, sm_small, st>>>(p, zs, srcs, Lcap);
-            }
-            IPSB_LAUNCH_CHECK();
-            return 0;
-        }
+        auto ks = select_loop_small_kernel<128>;
+        IPSB_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
+        ks<<<B, 128, sm_small, st>>>(p, zs, srcs, Lcap);
+        IPSB_LAUNCH_CHECK();
+        return 0;
     }
     auto kern = select_loop_cluster_kernel<NC>;
     IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
