@@ -276,6 +276,28 @@ IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k,
                                           float* dq_part /* (B*chunks, T*H*Dk), summed over rows by the caller */, float* dk, float* dv,
                                           int B, int M, int H, int Dk, int Dv, int T, void* stream);
 
+/* ---------------------------------------------------------------- plan folding (one launch per weight update)
+ * Replaces what eval-mode `conv -> bn` costs the reference implicitly on every ips() call (ips_net.py:191-193,209,227):
+ * here the convolution weights are re-laid out for the kernels and BatchNorm(eval) is folded into per-channel scale /
+ * shift ONCE per weight version.  `items_dev` is a DEVICE array of n_items descriptors (all pointers device pointers):
+ * w_src (Cout, cin, kh, kw) fp32 -> w_dst in `layout` (element type bf16 if dst_bf16 else fp32), channels zero-padded to
+ * cin_pad; scale_dst = bn_weight * rsqrt(bn_var + eps), shift_dst = bn_bias - bn_mean * scale_dst (skipped when
+ * scale_dst is NULL; the weight part is skipped when w_dst is NULL). */
+#define IPSB_FOLD_KMAJOR 0    /* (Cout, kh*kw*cin_pad), k = (r*kw+s)*cin_pad + c : tcgen05 kernels            */
+#define IPSB_FOLD_KN 1        /* (kh*kw*cin_pad, Cout)                            : fp32 SIMT kernels         */
+#define IPSB_FOLD_STEM_S2D 2  /* (Cout, 256), k = (a*4+b)*16 + (dy*2+dx)*4 + c = w[2a+dy-1, 2b+dx-1, c]        */
+#define IPSB_FOLD_STEM_8X8 3  /* (Cout, 256), k = r*32 + (s+1)*4 + c                                           */
+typedef struct ipsb_fold_item {
+    const float* w_src;
+    void* w_dst;
+    const float* bn_weight; const float* bn_bias; const float* bn_mean; const float* bn_var;
+    float* scale_dst; float* shift_dst;
+    int64_t dst_elems;
+    int32_t cout, cin, kh, kw, cin_pad, layout, dst_bf16;
+    float eps;
+} ipsb_fold_item;
+IPSB_API int ipsb_fold_plan(const ipsb_fold_item* items_dev, int n_items, int blocks_per_item, void* stream);
+
 /* ---------------------------------------------------------------- feature projector + score projection, fused
  * Replaces, in the no-grad pass of ips() on feature bags: LayerNorm(no affine) -> Linear -> BatchNorm1d(eval) -> ReLU
  * (ips_net.py:54-60) followed by the key projection + query dot product (transformer.py:71-83, folded into U):

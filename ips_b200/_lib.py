@@ -38,6 +38,17 @@ class ImageGeo(ctypes.Structure):
                 ('n_per_image', ctypes.c_int32)]
 
 
+class FoldItem(ctypes.Structure):
+    """ipsb_fold_item"""
+    _fields_ = [('w_src', _ptr), ('w_dst', _ptr), ('bn_weight', _ptr), ('bn_bias', _ptr), ('bn_mean', _ptr), ('bn_var', _ptr),
+                ('scale_dst', _ptr), ('shift_dst', _ptr), ('dst_elems', ctypes.c_int64),
+                ('cout', ctypes.c_int32), ('cin', ctypes.c_int32), ('kh', ctypes.c_int32), ('kw', ctypes.c_int32),
+                ('cin_pad', ctypes.c_int32), ('layout', ctypes.c_int32), ('dst_bf16', ctypes.c_int32), ('eps', ctypes.c_float)]
+
+
+FOLD_KMAJOR, FOLD_KN, FOLD_STEM_S2D, FOLD_STEM_8X8 = 0, 1, 2, 3
+
+
 class PeerCtx(ctypes.Structure):
     """ipsb_peer_ctx"""
     _fields_ = [('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('base', _ptr * 8)]
@@ -96,6 +107,7 @@ SIGNATURES = {
     'ipsb_attention_train_bwd_f32': [_ptr, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32,
                                      _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
+    'ipsb_fold_plan': [_ptr, _i32, _i32, _ptr],
     'ipsb_projector_logits': [_ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],
     'ipsb_profile_begin': [_ptr],
     'ipsb_profile_end': [_i32, _ptr, _ptr, _ptr, ctypes.POINTER(_i32)],

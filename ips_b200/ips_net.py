@@ -193,31 +193,70 @@ class IPSNet(nn.Module):
         return tuple(vs)
 
     def _conv_entry(self, conv, bn, stem=False):
-        w = conv.weight.detach().float()
+        """Geometry + destination buffers of one folded convolution and its `ipsb_fold_item` (filled by `ipsb_fold_plan`)."""
+        from . import _lib
+        w = conv.weight
         cout, cin, kh, kw = w.shape
+        dev, bf16 = w.device, self.precision == 'bf16'
         e = dict(cin=4 if stem else cin, cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0],
-                 mode=(self.stem_mode if self.precision == 'bf16' else 1) if stem else 0)
-        e['scale'], e['shift'] = _fold_bn(bn)
-        if stem:                                                  # channels padded to 4
-            w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
-            w4[:, :cin] = w
-            if self.precision == 'bf16' and e['mode'] == 4:       # k = (a*4+b)*16 + (dy*2+dx)*4 + c = w[2a+dy-1, 2b+dx-1, c]
-                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
-                wp[:, 1:kh + 1, 1:kw + 1] = w4.permute(0, 2, 3, 1)
-                wp = wp.view(cout, 4, 2, 4, 2, 4).permute(0, 1, 3, 2, 4, 5)
-                e['w'] = wp.reshape(cout, 256).to(torch.bfloat16).contiguous()
+                 mode=(self.stem_mode if bf16 else 1) if stem else 0)
+        e['scale'] = torch.empty(cout, dtype=torch.float32, device=dev)
+        e['shift'] = torch.empty(cout, dtype=torch.float32, device=dev)
+        if stem and bf16:                                         # channels padded to 4; 8 x 8 taps
+            layout = _lib.FOLD_STEM_S2D if e['mode'] == 4 else _lib.FOLD_STEM_8X8
+            e['w'] = torch.empty((cout, 256), dtype=torch.bfloat16, device=dev)
+            cin_pad = 4
+            if e['mode'] == 4:
                 e['cin'] = 16
-            elif self.precision == 'bf16':                        # k = r*32 + (s+1)*4 + c, 8x8 taps
-                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
-                wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
-                e['w'] = wp.reshape(cout, 256).to(torch.bfloat16).contiguous()
-            else:
-                e['w'] = w4.permute(2, 3, 1, 0).reshape(kh * kw * 4, cout).contiguous()
-        elif self.precision == 'bf16':
-            e['w'] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(torch.bfloat16).contiguous()
+        elif bf16:
+            layout, cin_pad = _lib.FOLD_KMAJOR, cin
+            e['w'] = torch.empty((cout, kh * kw * cin), dtype=torch.bfloat16, device=dev)
         else:
-            e['w'] = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+            layout, cin_pad = _lib.FOLD_KN, (4 if stem else cin)
+            e['w'] = torch.empty((kh * kw * cin_pad, cout), dtype=torch.float32, device=dev)
+        e['item'] = _lib.FoldItem(w.data_ptr(), e['w'].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                  bn.running_mean.data_ptr(), bn.running_var.data_ptr(), e['scale'].data_ptr(), e['shift'].data_ptr(),
+                                  e['w'].numel(), cout, cin, kh, kw, cin_pad, layout, int(bf16), float(bn.eps))
+        e['src'] = (w, bn.weight, bn.bias, bn.running_mean, bn.running_var)
         return e
+
+    def _fold_static(self):
+        """Destination buffers and the device-resident item table of the conv encoder's folded parameters: built once per
+        set of parameter storages (keyed on data pointers), refilled by ONE kernel launch whenever the values change."""
+        enc = self.encoder
+        convs = [(enc[0], enc[1], True)]
+        for child in list(enc.children())[4:-1]:
+            for blk in child:
+                convs.append((blk.conv1, blk.bn1, False))
+                convs.append((blk.conv2, blk.bn2, False))
+                if blk.downsample is not None:
+                    convs.append((blk.downsample[0], blk.downsample[1], False))
+        key = (self.precision, self.stem_mode) + tuple(t.data_ptr() for c, b, _ in convs
+                                                       for t in (c.weight, b.weight, b.bias, b.running_mean, b.running_var))
+        st = getattr(self, '_fold_cache', None)
+        if st is not None and st['key'] == key:
+            return st
+        for c, b, _ in convs:
+            for t in (c.weight, b.weight, b.bias, b.running_mean, b.running_var):
+                if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                    raise RuntimeError('ips_b200: encoder parameters must be contiguous fp32 CUDA tensors')
+        entries = [self._conv_entry(c, b, stem) for c, b, stem in convs]
+        import ctypes
+        arr = (type(entries[0]['item']) * len(entries))(*[e['item'] for e in entries])
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        it = iter(entries)
+        stem = next(it)
+        blocks = []
+        for child in list(enc.children())[4:-1]:
+            for blk in child:
+                b = dict(c1=next(it), c2=next(it), ds=None)
+                if blk.downsample is not None:
+                    b['ds'] = next(it)
+                blocks.append(b)
+        st = dict(key=key, items=host.to(entries[0]['w'].device), n=len(entries), stem=stem, blocks=blocks,
+                  blocks_per_item=max(1, min(64, max(e['w'].numel() for e in entries) // 4096)))
+        self._fold_cache = st
+        return st
 
     def _build_plan(self):
         plan = {}
@@ -227,16 +266,9 @@ class IPSNet(nn.Module):
         if self.use_pos:
             plan['posU'] = ops.logits(self.pos_enc[0].contiguous().float(), plan['U'])      # (N, HT)
         if self.is_image:
-            enc = self.encoder
-            plan['stem'] = self._conv_entry(enc[0], enc[1], stem=True)
-            blocks = []
-            for child in list(enc.children())[4:-1]:
-                for blk in child:
-                    b = dict(c1=self._conv_entry(blk.conv1, blk.bn1), c2=self._conv_entry(blk.conv2, blk.bn2), ds=None)
-                    if blk.downsample is not None:
-                        b['ds'] = self._conv_entry(blk.downsample[0], blk.downsample[1])
-                    blocks.append(b)
-            plan['blocks'] = blocks
+            st = self._fold_static()
+            ops.fold_plan(st['items'], st['n'], st['blocks_per_item'])      # every layer's weights + BatchNorm in one launch
+            plan['stem'], plan['blocks'] = st['stem'], st['blocks']
         else:
             lin, bn = self.encoder[1], self.encoder[2]
             scale, bshift = _fold_bn(bn)

@@ -293,6 +293,12 @@ def linear_bf16(a, w, scale=None, shift=None, relu=False):
     return y
 
 
+def fold_plan(items_dev, n_items, blocks_per_item):
+    """Refill every folded convolution weight / BatchNorm scale+shift described by the device item table in ONE launch."""
+    _chk(items_dev, torch.uint8, 'items')
+    _call('ipsb_fold_plan', _p(items_dev), n_items, blocks_per_item, _stream())
+
+
 def projector_table(scale, shift, w_bf16, U):
     """(N, 12) fp32 column table of ipsb_projector_logits: a_n, b_n = a_n * colsum(w_bf16)_n, shift_n, 0, U[n, 0..7]."""
     N, HT = U.shape

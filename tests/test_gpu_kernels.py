@@ -414,6 +414,65 @@ def test_projector_logits_fused(dev, rows, K, N, HT, in_bf16):
     assert (z - z2).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize('pre,precision,stem_env', [('traffic', 'bf16', None), ('mnist', 'bf16', None), ('traffic', 'fp32', None),
+                                                    ('mnist', 'bf16', 'tma')])
+def test_fold_plan_one_launch(dev, pre, precision, stem_env, monkeypatch):
+    """ipsb_fold_plan (every conv weight re-laid out + BatchNorm(eval) folded, ONE launch) against the per-layer torch
+    formulas it replaces: K-major / (K, N) layouts, the space-to-depth and 8x8 stem packings, scale / shift."""
+    from ips_b200 import IPSNet, Struct
+    if stem_env:
+        monkeypatch.setenv('IPS_B200_STEM', stem_env)
+    conf = O.preset(pre, precision=precision)
+    net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+    net.load_state_dict(O.make_state(conf, 5, q_gain=3.0))
+    plan = net._build_plan()
+
+    def expect(conv, bn, e, stem):
+        w = conv.weight.detach().float()
+        cout, cin, kh, kw = w.shape
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var.detach() + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean.detach() * scale
+        if stem:
+            w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
+            w4[:, :cin] = w
+            if precision == 'bf16' and e['mode'] == 4:
+                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
+                wp[:, 1:kh + 1, 1:kw + 1] = w4.permute(0, 2, 3, 1)
+                ww = wp.view(cout, 4, 2, 4, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(cout, 256).to(torch.bfloat16)
+            elif precision == 'bf16':
+                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
+                wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
+                ww = wp.reshape(cout, 256).to(torch.bfloat16)
+            else:
+                ww = w4.permute(2, 3, 1, 0).reshape(kh * kw * 4, cout)
+        elif precision == 'bf16':
+            ww = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(torch.bfloat16)
+        else:
+            ww = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout)
+        assert e['w'].shape == ww.shape and e['w'].dtype == ww.dtype
+        assert torch.equal(e['w'], ww.contiguous())
+        torch.testing.assert_close(e['scale'], scale, rtol=2e-6, atol=0)
+        torch.testing.assert_close(e['shift'], shift, rtol=1e-5, atol=1e-7)
+
+    enc = net.encoder
+    expect(enc[0], enc[1], plan['stem'], True)
+    blocks = [blk for child in list(enc.children())[4:-1] for blk in child]
+    assert len(blocks) == len(plan['blocks'])
+    for blk, b in zip(blocks, plan['blocks']):
+        expect(blk.conv1, blk.bn1, b['c1'], False)
+        expect(blk.conv2, blk.bn2, b['c2'], False)
+        assert (blk.downsample is None) == (b['ds'] is None)
+        if blk.downsample is not None:
+            expect(blk.downsample[0], blk.downsample[1], b['ds'], False)
+    # a second build after an in-place update refills the SAME buffers
+    ptr = plan['stem']['w'].data_ptr()
+    with torch.no_grad():
+        enc[0].weight.mul_(2.0)
+    plan2 = net._get_plan()
+    assert plan2['stem']['w'].data_ptr() == ptr
+    expect(enc[0], enc[1], plan2['stem'], True)
+
+
 # ------------------------------------------------------------------ aggregator + heads (no-grad forward)
 
 @pytest.mark.parametrize('B,M,H,Dk,Dv,T', [(2, 100, 8, 16, 16, 4), (3, 10, 8, 64, 64, 1), (1, 5000, 8, 64, 64, 1), (2, 7, 3, 8, 24, 2)])
