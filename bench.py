@@ -522,7 +522,7 @@ class Bench:
                         cz.append(torch.gather(zl, 1, cand.unsqueeze(-1).expand(-1, -1, HT)))
                         ci.append(cand + a)
                     cz, ci = torch.cat(cz, 1).contiguous(), torch.cat(ci, 1)
-                    pos = ops.topm_stable(ops.scores_from_logits(cz, ca.H, ca.n_token), M)[1]
+                    pos = ops.merge_candidates(cz, ca.H, ca.n_token, M)
                     ref_idx = torch.gather(ci, 1, pos)
                     parity = {'merge_equals_single_process_schedule': bool(torch.equal(ref_idx[my_b], got_idx))}
                 parity['rows_are_the_selected_patches'] = rows_ok

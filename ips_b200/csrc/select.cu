@@ -1002,7 +1002,7 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     a.m_pos = (int*)take((size_t)B * 2 * M * 4);
     a.m_src = (int*)take((size_t)B * 2 * M * 4);
     a.m_key = (uint32_t*)take((size_t)B * M * 4);
-    a.m_runs = (unsigned long long*)take((size_t)B * (M + 8) * 8);
+    a.m_runs = (unsigned long long*)take((size_t)B * (M + 16) * 8);
     a.zs = zs; a.srcs = srcs; a.slice_cap = cap;
     const int64_t total = (int64_t)B * N * HT;
     int64_t g = (total + 255) / 256;
@@ -1021,6 +1021,20 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     }
     auto kern = select_loop_cluster_kernel<NC>;
     IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NC > 8) {                                            // 16 CTAs per cluster: beyond the portable size, one cluster per GPC
+        IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * NC)); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess || n_clusters < 1) {
+            (void)cudaGetLastError();
+            return -1;                                       // caller falls back
+        }
+    }
     kern<<<B * NC, 512, smem, st>>>(p, a);
     IPSB_LAUNCH_CHECK();
     return 0;
@@ -1185,7 +1199,7 @@ int ipsb_topm_stable(const float* scores, int B, int L, int M, int64_t* idx_out,
 }
 
 int64_t ipsb_select_loop_workspace_bytes(int B, int N, int HT, int M) {
-    return (int64_t)B * ((int64_t)N * (HT + 1) + 2ll * M * (HT + 2) + M) * 4 + (int64_t)B * (M + 8) * 8 + 7 * 256;
+    return (int64_t)B * ((int64_t)N * (HT + 1) + 2ll * M * (HT + 2) + M) * 4 + (int64_t)B * (M + 16) * 8 + 7 * 256;
 }
 
 int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_stride,
@@ -1200,9 +1214,13 @@ int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_str
     // shared-memory-resident loop: one CTA per image, or a cluster of 8 CTAs per image for long buffers
     const bool ht_pow2 = ((H * T) & (H * T - 1)) == 0;
     if (ht_pow2 && workspace != nullptr && getenv("IPSB_SELECT_SINGLE_CTA") == nullptr) {
-        const int rc = (Lmax >= 2048) ? launch_cluster<8>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream)
-                                      : launch_cluster<1>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream);
+        int rc = (Lmax >= 2048) ? launch_cluster<8>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream)
+                                : launch_cluster<1>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc >= 0) return rc;
+        if (Lmax >= 2048) {      // slices too long for 8 CTAs' shared memory (candidate merge of 8 ranks: 40 000 entries; H*T = 32)
+            rc = launch_cluster<16>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream);
+            if (rc >= 0) return rc;
+        }
     }
     // single-CTA long-buffer variant (kept as a cross-check, IPSB_SELECT_SINGLE_CTA=1)
     if (H * T == 8 && Lmax > 2048 && M <= 8192 && N < 65536 * 1024) {

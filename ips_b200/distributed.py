@@ -66,7 +66,7 @@ class _CudaBackend:
         """(B, L, HT) candidate logits -> positions (B, M) of the stable top-M of their scores in ONE buffer."""
         from . import ops
         ca = self.net.transf.crs_attn
-        return ops.topm_stable(ops.scores_from_logits(zc.contiguous(), ca.H, ca.n_token), M)[1]
+        return ops.merge_candidates(zc.contiguous(), ca.H, ca.n_token, M)
 
 
 def gather_logit_table(z_local, N, group=None):
@@ -251,7 +251,7 @@ class ShardedIPS:
             cand = ops.select_loop(z_local.contiguous(), perm, per_inst, ca.H, ca.n_token, M, net.I)[1]   # local, best first
             ops.peer_push_candidates(ctx, z_local, cand, self.lo, self.L, self.rank * M, self.cz_off, self.ci_off)
             ops.peer_wait(ctx, 0)
-            win = ops.topm_stable(ops.scores_from_logits(self.cz, ca.H, ca.n_token), M)[1]   # positions in the candidate list
+            win = ops.merge_candidates(self.cz, ca.H, ca.n_token, M)                          # positions in the candidate list
             ci = self.ci
         else:
             ops.peer_push_logits(ctx, z_local, self.N, self.lo, self.z_off)

@@ -461,6 +461,17 @@ def select_loop(z, perm, per_instance, H, T, M, I):
     return mem_pos, mem_src, score
 
 
+def merge_candidates(cz, H, T, M):
+    """Global re-score of a candidate list cz (B, L, H*T) and stable top-M: positions (B, M) into the list, best first,
+    equal scores -> lowest position (score_and_select, ips_net.py:136-155, on the merged buffer).  Long lists run as ONE
+    iteration of the cluster selection loop (memory = the first M candidates, chunk = the rest: the same softmax over all
+    L entries, the same tie-break), short ones through the single-CTA scores + top-M kernels."""
+    B, L = cz.shape[:2]
+    if L >= 2048 and ((H * T) & (H * T - 1)) == 0 and L - M >= 1:
+        return select_loop(cz, None, False, H, T, M, L - M)[1]
+    return topm_stable(scores_from_logits(cz, H, T), M)[1]
+
+
 def gemm_bf16(mode, a, b, scale=None, shift=None, relu=False, out_dtype=torch.float32):
     """Tensor-core GEMM, bf16 operands, fp32 accumulate.  mode 'nt': a (M,K) b (N,K) -> a b^T;
     'nn': a (M,K) b (K,N) -> a b;  'tn': a (K,M) b (K,N) -> a^T b (split-K, deterministic)."""

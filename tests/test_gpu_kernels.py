@@ -335,7 +335,9 @@ def _loop_oracle(sd, conf, emb, perm, M, I):
 
 @pytest.mark.parametrize('N,M,I,H,T', [(192, 10, 32, 8, 1), (900, 100, 100, 8, 4), (3000, 500, 500, 8, 1),
                                        (50, 49, 7, 2, 2), (23000, 5000, 5000, 8, 1), (9000, 1500, 1500, 8, 1),
-                                       (12345, 4000, 777, 8, 1)])
+                                       (12345, 4000, 777, 8, 1),
+                                       (45000, 5000, 35000, 8, 1),       # 40 000-entry buffer: cluster of 16 CTAs
+                                       (30000, 5000, 5000, 8, 4)])       # H*T = 32 on a long buffer: cluster of 16 CTAs
 @pytest.mark.parametrize('shuffle', ['none', 'batch', 'instance'])
 def test_select_loop(dev, N, M, I, H, T, shuffle):
     """The in-kernel loop on the logit table == the oracle's `score_and_select` iterated on the embeddings
@@ -368,6 +370,23 @@ def test_select_loop(dev, N, M, I, H, T, shuffle):
         assert torch.equal(pos.cpu(), ref_pos)
     sc = score.cpu()
     assert (sc[:, :-1] >= sc[:, 1:]).all()                        # best first
+
+
+@pytest.mark.parametrize('B,L,M', [(2, 40000, 5000), (1, 10000, 5000), (3, 20000, 5000), (2, 300, 100)])
+def test_merge_candidates(dev, B, L, M):
+    """The candidate merge of the sequence-sharded schedule (global re-score + stable top-M of R*M candidates): one
+    iteration of the cluster loop on long lists == scores_from_logits + topm_stable (order swaps only between
+    candidates whose scores agree to fp32 rounding)."""
+    from ips_b200 import ops
+    H, T = 8, 1
+    cz = _rand(B, L, H * T, seed=29, scale=1.5).to(dev)
+    got = ops.merge_candidates(cz, H, T, M)
+    sc = ops.scores_from_logits(cz, H, T)
+    ref = ops.topm_stable(sc, M)[1]
+    assert torch.equal(got.sort(-1)[0], ref.sort(-1)[0])
+    a, b = torch.gather(sc, 1, got), torch.gather(sc, 1, ref)
+    assert float(((a - b).abs() / b).max()) <= 2e-6
+    assert bool((a[:, :-1] >= a[:, 1:] * (1 - 2e-6)).all())
 
 
 @pytest.mark.parametrize('L,M', [(20000, 5000), (40000, 5000), (16385, 1), (33000, 8192)])
