@@ -368,6 +368,13 @@ IPSB_API int ipsb_peer_push_candidates(const ipsb_peer_ctx* ctx, const float* z_
  * (B, N, HT) at byte offset z_off ('exact' mode: the loop is replicated); signals phase 0. */
 IPSB_API int ipsb_peer_push_logits(const ipsb_peer_ctx* ctx, const float* z_local, int B, int64_t n_local, int HT,
                                    int64_t N, int64_t row0, int64_t z_off, void* stream);
+/* Small all-gather over peer memory (synchronised BatchNorm statistics of the data-parallel train step; the
+ * reference is single-process): `bytes` (16-byte multiple) of `src` -> every rank; dst (world x bytes, local) receives all
+ * ranks' data in rank order.  The section at sec_off holds two slots of slot_stride >= world * bytes that alternate with the
+ * device-side epoch of `phase` (safe under CUDA-graph replay).  A tens-of-microseconds NCCL collective becomes two small
+ * kernels (push + flag, wait + copy). */
+IPSB_API int ipsb_peer_allgather_small(const ipsb_peer_ctx* ctx, const void* src, int64_t bytes, int64_t sec_off, int64_t slot_stride,
+                                       int phase, void* dst, void* stream);
 /* Waits until every rank has signalled `phase` for the current epoch. */
 IPSB_API int ipsb_peer_wait(const ipsb_peer_ctx* ctx, int phase, void* stream);
 /* Winners -> output section (B_out, M, row_bytes) at byte offset out_off of the destination ranks.  win (B, M) holds

@@ -117,6 +117,7 @@ SIGNATURES = {
     'ipsb_peer_status': [ctypes.POINTER(PeerCtx), ctypes.POINTER(_i32), _ptr],
     'ipsb_peer_push_candidates': [ctypes.POINTER(PeerCtx), _ptr, _i64, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _ptr],
     'ipsb_peer_push_logits': [ctypes.POINTER(PeerCtx), _ptr, _i32, _i64, _i32, _i64, _i64, _i64, _ptr],
+    'ipsb_peer_allgather_small': [ctypes.POINTER(PeerCtx), _ptr, _i64, _i64, _i64, _i32, _ptr, _ptr],
     'ipsb_peer_wait': [ctypes.POINTER(PeerCtx), _i32, _ptr],
     'ipsb_peer_push_winners': [ctypes.POINTER(PeerCtx), _ptr, _i64, _i64, _ptr, _ptr, _i64, _i32, _i32, _i64, _i32, _i64, _ptr, _ptr],
     'ipsb_resnet_workspace_bytes': [ctypes.POINTER(ResnetDesc), _i64, _i32, _i32, _i32],

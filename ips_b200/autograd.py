@@ -128,8 +128,11 @@ class BatchNormTrainFn(torch.autograd.Function):
             import torch.distributed as dist
             R = dist.get_world_size(sync)
             mine = torch.cat([mean, var])
-            st = torch.empty((R, 2 * cols), dtype=torch.float32, device=x.device)
-            dist.all_gather_into_tensor(st, mine, group=sync)
+            if SYNC_BN_PEER is not None and cols % 2 == 0:                 # NVLink peer-memory exchange (no NCCL call)
+                st = SYNC_BN_PEER.all_gather(mine)
+            else:
+                st = torch.empty((R, 2 * cols), dtype=torch.float32, device=x.device)
+                dist.all_gather_into_tensor(st, mine, group=sync)
             rows_total = rows * R
             mean = st[:, :cols].mean(0)
             var = (st[:, cols:] + (st[:, :cols] - mean) ** 2).mean(0)
@@ -168,8 +171,11 @@ class BatchNormTrainFn(torch.autograd.Function):
         all_sums = sums
         if ctx.sync is not None:                                           # dgamma / dbeta stay local (averaged with the other gradients)
             import torch.distributed as dist
-            all_sums = sums.clone()
-            dist.all_reduce(all_sums, op=dist.ReduceOp.SUM, group=ctx.sync)
+            if SYNC_BN_PEER is not None and SYNC_BN_EQUAL_SHARES and cols % 2 == 0:
+                all_sums = SYNC_BN_PEER.all_gather(sums).sum(0)            # same order on every rank: identical results
+            else:
+                all_sums = sums.clone()
+                dist.all_reduce(all_sums, op=dist.ReduceOp.SUM, group=ctx.sync)
         ops._call('ipsb_bn_backward_apply_f32', _p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g), _p(all_sums), _p(dx), rows, cols,
                   ctx.rows_total, int(ctx.relu), ops._stream())
         return dx, sums[cols:], sums[:cols], None, None, None, None, None, None
@@ -177,6 +183,8 @@ class BatchNormTrainFn(torch.autograd.Function):
 
 # Set by the data-parallel train step when every rank feeds the same number of rows to each BatchNorm (see above).
 SYNC_BN_EQUAL_SHARES = False
+# `distributed.PeerStatExchange` of the data-parallel group, or None (NCCL collectives)
+SYNC_BN_PEER = None
 
 
 def _dist_group(group):

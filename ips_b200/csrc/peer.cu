@@ -158,6 +158,37 @@ __global__ void __launch_bounds__(256) push_winners_kernel(ipsb_peer_ctx c, WinP
     signal_peers(c, 1);
 }
 
+// Small all-gather (synchronised BatchNorm statistics: a few KB per rank).  Two slots alternate with the parity of the
+// owner's epoch (identical on all ranks, advanced on the device: correct under CUDA-graph replay): every rank stores its
+// `n16` 16-byte words into [slot][rank] of the section of every peer, then signals `phase`.
+__global__ void __launch_bounds__(256) allgather_small_kernel(ipsb_peer_ctx c, const int4* __restrict__ src, int n16, int64_t sec_off,
+                                                              int64_t slot_stride, int phase) {
+    const unsigned int e = reinterpret_cast<const PeerHdr*>(c.base[c.rank])->epoch[phase];   // bumped only after every block signalled
+    const int64_t off = sec_off + (int64_t)(e & 1u) * slot_stride + (int64_t)c.rank * n16 * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+        const int4 v = src[i];
+        for (int q = 0; q < c.world; ++q) st_peer16(reinterpret_cast<char*>(c.base[q]) + off + (int64_t)i * 16, v);
+    }
+    signal_peers(c, phase);
+}
+
+// Waits for `phase`, then copies the (world x n16) words of the slot just filled into dst (a fixed local address).
+__global__ void __launch_bounds__(256) wait_gather_kernel(ipsb_peer_ctx c, int phase, long long budget_clocks, int64_t sec_off,
+                                                          int64_t slot_stride, int4* __restrict__ dst, int n16_total) {
+    PeerHdr* me = reinterpret_cast<PeerHdr*>(c.base[c.rank]);
+    const unsigned int e = me->epoch[phase];                       // own push of this exchange already ran: epoch = exchange number
+    if ((int)threadIdx.x < c.world) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(&me->flags[phase][threadIdx.x]) - e) < 0) {
+            if (clock64() - t0 > budget_clocks) { me->status = 1u; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const char*>(c.base[c.rank]) + sec_off + (int64_t)((e - 1u) & 1u) * slot_stride);
+    for (int i = threadIdx.x; i < n16_total; i += blockDim.x) dst[i] = __ldcg(src + i);
+}
+
 __global__ void read_status_kernel(ipsb_peer_ctx c, int* out) { *out = (int)reinterpret_cast<PeerHdr*>(c.base[c.rank])->status; }
 
 int check_ctx(const ipsb_peer_ctx* ctx) {
@@ -261,6 +292,23 @@ int ipsb_peer_push_logits(const ipsb_peer_ctx* ctx, const float* z_local, int B,
     IPSB_REQUIRE(z_off >= IPSB_PEER_HEADER_BYTES && z_off % 16 == 0, "peer_push_logits: section must lie behind the header, 16-byte aligned");
     LogitParams p{z_local, B, HT, n_local, N, row0, z_off};
     push_logits_kernel<<<grid_for((int64_t)B * n_local * HT / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(*ctx, p);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_peer_allgather_small(const ipsb_peer_ctx* ctx, const void* src, int64_t bytes, int64_t sec_off, int64_t slot_stride,
+                              int phase, void* dst, void* stream) {
+    if (int rc = check_ctx(ctx)) return rc;
+    IPSB_REQUIRE(src && dst && bytes > 0 && bytes % 16 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0 && bytes <= (1 << 20),
+                 "peer_allgather_small: %lld bytes (16-byte multiples up to 1 MiB, aligned buffers)", (long long)bytes);
+    IPSB_REQUIRE(sec_off >= IPSB_PEER_HEADER_BYTES && sec_off % 16 == 0 && slot_stride >= bytes * ctx->world && slot_stride % 16 == 0 &&
+                 phase >= 0 && phase < 4, "peer_allgather_small: bad section / phase");
+    const int n16 = (int)(bytes / 16);
+    int grid = (n16 + 255) / 256;
+    if (grid > 8) grid = 8;
+    allgather_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*ctx, (const int4*)src, n16, sec_off, slot_stride, phase);
+    IPSB_LAUNCH_CHECK();
+    wait_gather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*ctx, phase, 8000000000ll, sec_off, slot_stride, (int4*)dst, n16 * ctx->world);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -176,6 +176,25 @@ class PeerExchange:
         return ops.peer_status(self.ctx)
 
 
+class PeerStatExchange:
+    """All-gathers of a few KB over NVLink peer memory: the statistic exchanges of synchronised BatchNorm in the
+    data-parallel train step (forward: every rank's mean / variance; backward: [sum g, sum g*xhat]).  Two kernels per
+    exchange (push + flag, wait + copy) instead of an NCCL collective; capturable in the step's CUDA graph."""
+
+    def __init__(self, device, max_floats=4096, group=None):
+        self.R = dist.get_world_size(group)
+        self.stride = _align(self.R * max_floats * 4, 16)
+        self.max_floats = max_floats
+        self.ex = PeerExchange(4096 + 2 * self.stride, device, group)
+
+    def all_gather(self, v):
+        """v: contiguous fp32 vector (length a multiple of 4, at most max_floats) -> (R, len) in rank order."""
+        from . import ops
+        if v.numel() % 4 or v.numel() > self.max_floats:
+            raise ValueError('PeerStatExchange: vector of %d floats' % v.numel())
+        return ops.peer_allgather_small(self.ex.ctx, v.contiguous(), 4096, self.stride, 2, self.R)
+
+
 class ShardedIPS:
     """Sequence-sharded `IPSNet.ips` over NVLink peer memory for fixed shapes: this rank's slice is
     (B, n_local, *row_shape) fp32 of a sequence of N patches (`shard_bounds(N, world)[rank]`).

@@ -640,6 +640,14 @@ def peer_push_logits(ctx, z_local, N, row0, z_off):
     _call('ipsb_peer_push_logits', ctypes.byref(ctx), _p(z_local), B, n_local, HT, N, row0, z_off, _stream())
 
 
+def peer_allgather_small(ctx, src, sec_off, slot_stride, phase, world):
+    """src (contiguous fp32 CUDA vector, length a multiple of 4) -> (world, len) tensor with every rank's vector."""
+    _chk(src, torch.float32, 'src')
+    out = torch.empty((world, src.numel()), dtype=torch.float32, device=src.device)
+    _call('ipsb_peer_allgather_small', ctypes.byref(ctx), _p(src), src.numel() * 4, sec_off, slot_stride, phase, _p(out), _stream())
+    return out
+
+
 def peer_wait(ctx, phase):
     _call('ipsb_peer_wait', ctypes.byref(ctx), phase, _stream())
 

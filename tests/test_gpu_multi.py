@@ -216,16 +216,21 @@ def test_syncbn_data_parallel_equals_single_process(name):
             assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max()) + 1e-3, (k, float((a - b).abs().max()))
 
 
-def _worker_bn_unit(rank, world, port, ret):
+def _worker_bn_unit(rank, world, port, ret, rows=1001, peer=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
+        from ips_b200 import autograd
         from ips_b200.autograd import BatchNormTrainFn
+        if peer:                                                # equal shares: statistics over NVLink peer memory, no NCCL call
+            from ips_b200.distributed import PeerStatExchange
+            autograd.SYNC_BN_EQUAL_SHARES = True
+            autograd.SYNC_BN_PEER = PeerStatExchange(dev)
         g = torch.Generator().manual_seed(5)
-        rows, cols = 1001, 64                                   # uneven shares: 500 / 501 rows
+        cols = 64                                               # rows = 1001: uneven shares (500 / 501)
         x = torch.randn(rows, cols, generator=g) * 2 + 0.5
         dy = torch.randn(rows, cols, generator=g)
         gamma, beta = torch.rand(cols, generator=g) + 0.5, torch.randn(cols, generator=g)
@@ -233,8 +238,14 @@ def _worker_bn_unit(rank, world, port, ret):
         xs = x[lo:hi].to(dev).requires_grad_(True)
         gm, bt = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
         rm, rv = torch.zeros(cols, device=dev), torch.ones(cols, device=dev)
-        y = BatchNormTrainFn.apply(xs, gm, bt, rm, rv, 0.1, 1e-5, True, True)
-        y.backward(dy[lo:hi].to(dev))
+        for _ in range(3 if peer else 1):                       # repeated exchanges alternate the two slots
+            if xs.grad is not None:
+                xs.grad = None; gm.grad = None; bt.grad = None
+                rm.zero_(); rv.fill_(1.0)
+            y = BatchNormTrainFn.apply(xs, gm, bt, rm, rv, 0.1, 1e-5, True, True)
+            y.backward(dy[lo:hi].to(dev))
+        if peer:
+            ret['status%d' % rank] = autograd.SYNC_BN_PEER.ex.status()
         dgm, dbt = gm.grad.clone(), bt.grad.clone()
         dist.all_reduce(dgm); dist.all_reduce(dbt)              # parameter gradients are summed by the gradient exchange
         ret[rank] = dict(y=y.detach().cpu(), dx=xs.grad.cpu(), dgamma=dgm.cpu(), dbeta=dbt.cpu(), rm=rm.cpu(), rv=rv.cpu(), lo=lo, hi=hi)
@@ -243,14 +254,18 @@ def _worker_bn_unit(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_synchronised_batchnorm_fn_equals_full_batch():
-    """BatchNormTrainFn with a process group on two uneven shares == torch BatchNorm on the whole batch:
-    output, input gradient, parameter gradients (summed over ranks), running statistics."""
+@pytest.mark.parametrize('rows,peer', [(1001, False), (1000, True)])
+def test_synchronised_batchnorm_fn_equals_full_batch(rows, peer):
+    """BatchNormTrainFn with a process group on two shares == torch BatchNorm on the whole batch: output, input gradient,
+    parameter gradients (summed over ranks), running statistics.  Uneven shares through NCCL collectives; equal shares
+    through the peer-memory statistic exchange (the form captured in the data-parallel train step's CUDA graph)."""
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker_bn_unit, args=(2, port, ret), nprocs=2, join=True)
+    mp.spawn(_worker_bn_unit, args=(2, port, ret, rows, peer), nprocs=2, join=True)
+    if peer:
+        assert ret['status0'] == 0 and ret['status1'] == 0
     g = torch.Generator().manual_seed(5)
-    rows, cols = 1001, 64
+    cols = 64
     x = (torch.randn(rows, cols, generator=g) * 2 + 0.5).requires_grad_(True)
     dy = torch.randn(rows, cols, generator=g)
     gamma = (torch.rand(cols, generator=g) + 0.5).requires_grad_(True)
