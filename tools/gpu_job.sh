@@ -1,23 +1,11 @@
 #!/bin/bash
-# round-2 final single-GPU session: all tests, smoke, both bench arms, ncu launch list (+DRAM bytes) of the bench command,
-# ncu --set full tables, selection sweep with the CPU column.  Output -> gpurun_out/.
+# ncu --set full of the projector kernel (final state) -> gpurun_out/p_proj_details.txt
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 OUT=gpurun_out
-run() { name=$1; shift; echo "=== $name"; timeout "${TMO:-300}" "$@" > $OUT/f_$name.log 2>&1; echo "exit $?" | tee -a $OUT/f_$name.log; tail -n "${TAIL:-4}" $OUT/f_$name.log | cut -c1-400; }
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/f_gpu.txt 2>&1
-python -c "import os; print('cpus', os.cpu_count())" >> $OUT/f_gpu.txt
-TAIL=12 TMO=900 run t_gpu python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider
-TMO=300 run smoke python __graft_entry__.py smoke
-TAIL=1 TMO=600 run bench python bench.py
-TAIL=1 TMO=300 run bench_ref python bench.py --impl reference --steps 20 --warmup 5
-TAIL=1 TMO=500 run ncu_launches ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -c 400 --csv --log-file $OUT/f_launches.csv python bench.py --steps 2 --warmup 1 --skip train,library,cpu,workloads,exact,sustained,seq,roofline
-TAIL=1 TMO=500 run ncu_full ncu --set full --clock-control none --import-source off \
-    -k regex:'stem_pool|conv_pair|conv_halo|conv_tma|stage_s2d|select_loop|gather_rows16' --launch-skip 120 --launch-count 16 \
-    -o /tmp/full -f python bench.py --steps 1 --warmup 3 --skip train,library,cpu,workloads,exact,sustained,seq,roofline
-ncu -i /tmp/full.ncu-rep --page raw --csv > $OUT/f_full_raw.csv 2>/dev/null
-TAIL=3 TMO=500 run sweep python tools/select_sweep.py 1 --cpu
-TAIL=3 TMO=300 run sweep16 python tools/select_sweep.py 16
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:projector_logits --launch-skip 3 --launch-count 1 -o /tmp/proj -f \
+    python bench.py --workload camelyon --steps 2 --skip train,library,cpu,workloads,exact,sustained,seq,roofline > $OUT/p_ncu.log 2>&1
+ncu -i /tmp/proj.ncu-rep --page details > $OUT/p_proj_details.txt 2>/dev/null
+grep -E "Duration|SM Frequency|DRAM Throughput|L2 Cache Throughput|TC is|SM Active Cycles|Elapsed Cycles" $OUT/p_proj_details.txt | head
 echo "=== done"
