@@ -117,6 +117,10 @@ struct LaneStreams {
     cudaStream_t s[MAX_LANES] = {};
     cudaEvent_t done[MAX_LANES] = {};
     cudaEvent_t fork = nullptr;
+    // per lane: a side stream for the 1x1 downsample convolution of a stride-2 BasicBlock, which reads the same input as
+    // the block's first 3x3 convolution and is needed only by the second one
+    cudaStream_t aux[MAX_LANES] = {};
+    cudaEvent_t aux_fork[MAX_LANES] = {}, aux_join[MAX_LANES] = {};
 };
 constexpr int MAX_DEVICES = 16;
 int lane_streams(LaneStreams** out) {
@@ -129,6 +133,9 @@ int lane_streams(LaneStreams** out) {
         for (int i = 0; i < MAX_LANES; ++i) {
             IPSB_CUDA(cudaStreamCreateWithFlags(&ls.s[i], cudaStreamNonBlocking));
             IPSB_CUDA(cudaEventCreateWithFlags(&ls.done[i], cudaEventDisableTiming));
+            IPSB_CUDA(cudaStreamCreateWithFlags(&ls.aux[i], cudaStreamNonBlocking));
+            IPSB_CUDA(cudaEventCreateWithFlags(&ls.aux_fork[i], cudaEventDisableTiming));
+            IPSB_CUDA(cudaEventCreateWithFlags(&ls.aux_join[i], cudaEventDisableTiming));
         }
         IPSB_CUDA(cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming));
         ls.device = dev;
@@ -195,7 +202,8 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
     const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
     if (lanes > n_chunks) lanes = (int)n_chunks;
     LaneStreams* ls = nullptr;
-    if (lanes > 1) {
+    const bool ds_side = getenv("IPSB_DS_INLINE") == nullptr;     // downsample convolutions on the lane's side stream
+    if (lanes > 1 || ds_side) {
         if (int rc = lane_streams(&ls)) return rc;
     }
     size_t pf_bytes = 0;
@@ -281,12 +289,25 @@ static int resnet_logits_pf(const ipsb_resnet_desc* net, const float* patches, i
             if (b % 2 == 0 && g > 0) { free_ids[0] = 0; free_ids[1] = 1; free_ids[2] = 2; nf = 3; }   // input lives in the previous group
             else for (int i = 0; i < 4; ++i) if (i != cur_slot) free_ids[nf++] = i;
             const void* idt = cur;               // (no downsample: same group, same layout as the output)
-            if (blk.has_ds) {
+            bool join_pending = false;
+            if (blk.has_ds && ds_side) {
+                // the 1x1 stride-2 downsample is a short, latency-bound launch (1 % of the FLOPs, 22-43 us): it runs next to the
+                // block's first convolution on the lane's side stream and is joined before the second one, which adds it in
+                cudaStream_t aux = ls->aux[lane];
+                IPSB_CUDA(cudaEventRecord(ls->aux_fork[lane], (cudaStream_t)stream));
+                IPSB_CUDA(cudaStreamWaitEvent(aux, ls->aux_fork[lane], 0));
+                rc = PROF(K_CONV, aux, run_conv_pf(blk.ds, cur, nullptr, bufs[free_ids[0]], P, h, w, 0, aux, !cur_dense, !out_dense));
+                IPSB_CUDA(cudaEventRecord(ls->aux_join[lane], aux));
+                join_pending = true;
+                if (rc) { cudaStreamWaitEvent((cudaStream_t)stream, ls->aux_join[lane], 0); return rc; }
+                idt = bufs[free_ids[0]];
+            } else if (blk.has_ds) {
                 rc = PROF(K_CONV, stream, run_conv_pf(blk.ds, cur, nullptr, bufs[free_ids[0]], P, h, w, 0, stream, !cur_dense, !out_dense));
                 if (rc) return rc;
                 idt = bufs[free_ids[0]];
             }
             rc = PROF(K_CONV, stream, run_conv_pf(blk.c1, cur, nullptr, bufs[free_ids[1]], P, h, w, 1, stream, !cur_dense, !out_dense));
+            if (join_pending) IPSB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ls->aux_join[lane], 0));
             if (rc) return rc;
             rc = PROF(K_CONV, stream, run_conv_pf(blk.c2, bufs[free_ids[1]], idt, bufs[free_ids[2]], P, pl.H[g], pl.W[g], 1, stream, !out_dense, !out_dense));
             if (rc) return rc;

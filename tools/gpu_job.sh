@@ -1,11 +1,21 @@
 #!/bin/bash
-# ncu --set full of the projector kernel (final state) -> gpurun_out/p_proj_details.txt
+# A/B: downsample convolutions on the lane's side stream vs inline
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 OUT=gpurun_out
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:projector_logits --launch-skip 3 --launch-count 1 -o /tmp/proj -f \
-    python bench.py --workload camelyon --steps 2 --skip train,library,cpu,workloads,exact,sustained,seq,roofline > $OUT/p_ncu.log 2>&1
-ncu -i /tmp/proj.ncu-rep --page details > $OUT/p_proj_details.txt 2>/dev/null
-grep -E "Duration|SM Frequency|DRAM Throughput|L2 Cache Throughput|TC is|SM Active Cycles|Elapsed Cycles" $OUT/p_proj_details.txt | head
+python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider -k "executor or lanes or image_equals or golden or bf16_close or full_size" > $OUT/j_tests.log 2>&1
+tail -4 $OUT/j_tests.log
+for mode in side inline side inline; do
+  if [ $mode = inline ]; then export IPSB_DS_INLINE=1; else unset IPSB_DS_INLINE; fi
+  for w in traffic mnist; do
+    python bench.py --workload $w --steps 20 --skip train,library,cpu,workloads,exact,sustained,seq > $OUT/j_ds.log 2>&1
+    python - <<PY
+import json
+for l in open('$OUT/j_ds.log'):
+    if l.startswith('{'):
+        d = json.loads(l); r = d['roofline']; print('$mode $w', round(d['ms_per_step'], 4), round(d['value']), 'busy', round(r['family_busy_ms_per_step'],4), 'frac', round(r['frac'],4))
+PY
+  done
+done
 echo "=== done"
