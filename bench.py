@@ -660,6 +660,16 @@ def run_ours(args):
                                  'reference\'s, tests/test_gpu_ips.py)', 'value': me['value'], 'ms_per_step': me['ms_per_step'], 'steps': 3}
         exact = guarded('exact', run_exact)
 
+        def run_x3():
+            me = bench.measure(args.workload, 'bf16x3', 5, 2, e2e=False)
+            return {'precision': "bf16x3 (near-fp32 on the tensor cores: operands as hi + lo bf16 pairs, three tcgen05 products per "
+                                 "multiply, fp32 accumulation and fp32 between layers; same winners as the fp32 reference on the parity "
+                                 "fixtures and at the BASELINE sizes, tests/test_gpu_ips.py)",
+                    'value': me['value'], 'ms_per_step': me['ms_per_step'], 'steps': 5}
+        exact_tc = guarded('exact', run_x3)
+        if isinstance(exact, dict) and exact_tc is not None:
+            exact['tensor_core_near_fp32'] = exact_tc
+
     workloads = None
     if extras_ok and 'workloads' not in skip:
         workloads = {}
@@ -726,7 +736,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='traffic', choices=sorted(WORKLOADS))
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32', 'bf16x3'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--skip', default='', help='comma list of auxiliary records to skip: roofline,sustained,train,exact,workloads,'
                                                'library,cpu,seq,oracle')

@@ -51,7 +51,7 @@ int conv3x3_halo(const void* x, const void* w, const float* scale, const float* 
 int conv_stem_s2d(const void* x, const void* w, const float* scale, const float* shift, void* y, int64_t P, int H, int W,
                   int Cout, int relu, cudaStream_t st);
 int conv_stem_tma(const void* x, const void* w, const float* scale, const float* shift, void* y,
-                  int64_t P, int H, int W, int Cout, int relu, cudaStream_t st);
+                  int64_t P, int H, int W, int Cout, int relu, cudaStream_t st, bool out_f32 = false);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -300,6 +300,18 @@ int ipsb_conv_bf16_pf(const void* x, const void* w, const float* scale, const fl
                           (cudaStream_t)stream, in_pf != 0, out_pf != 0);
 }
 
+// fp32-output convolution on dense bf16 activations: one of the three partial products of the bf16x3 precision (split3.cu)
+int ipsb_conv_bf16_f32out(const void* x, const void* w, const float* scale, const float* shift, float* y, int64_t P, int H, int W,
+                          int Cin, int Cout, int kh, int kw, int stride, int pad, int mode, void* stream) {
+    IPSB_REQUIRE(x && w && y && P > 0, "conv_bf16_f32out: null argument");
+    if (mode == 3) {    // TMA-fed stem on the zero-bordered (P, H, W, 4) frame, image = (H-6) x (W-6)
+        IPSB_REQUIRE(Cin == 4 && kh == 7 && kw == 7 && stride == 2, "conv_bf16_f32out mode 3 is the 7x7/2 stem");
+        return ipsb::conv_stem_tma(x, w, scale, shift, y, P, H - 6, W - 6, Cout, 0, (cudaStream_t)stream, true);
+    }
+    IPSB_REQUIRE(mode == 0, "conv_bf16_f32out: mode %d", mode);
+    return ipsb::conv_tma(x, w, scale, shift, nullptr, y, P, H, W, Cin, Cout, kh, kw, stride, pad, 0, true, (cudaStream_t)stream);
+}
+
 int ipsb_linear_bf16_umma(const void* a, const void* w, const float* scale, const float* shift,
                           float* y, int64_t M, int N, int K, int relu, void* stream) {
     IPSB_REQUIRE(M > 0 && K % 64 == 0 && N % 64 == 0, "linear_umma: K=%d, N=%d must be multiples of 64", K, N);

@@ -427,7 +427,7 @@ int conv_tma(const void* x, const void* w, const float* scale, const float* shif
 // 7x7 stride-2 pad-3 stem.  x: (P, H+6, W+6, 4) bf16 with a zero border (3 rows above, 4 columns left);
 // w: (Cout, 256) bf16 with k = r*32 + t*4 + c, t = s + 1.
 int conv_stem_tma(const void* x, const void* w, const float* scale, const float* shift, void* y,
-                  int64_t P, int H, int W, int Cout, int relu, cudaStream_t st) {
+                  int64_t P, int H, int W, int Cout, int relu, cudaStream_t st, bool out_f32) {
     IPSB_REQUIRE(Cout == 64 && W % 2 == 0 && H % 2 == 0, "conv_stem_tma: needs Cout=64 and even H, W");
     const int Hp = H + 6, Wp = W + 6;
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
@@ -457,6 +457,10 @@ int conv_stem_tma(const void* x, const void* w, const float* scale, const float*
     }
     if (int rc = encode_weights(enc, &tmB, w, 256, Cout, 64)) return rc;
     alignas(64) CUtensorMap tmC;
+    if (out_f32) {
+        if (int rc = encode_output<float>(enc, &tmC, y, p, false)) return rc;
+        return dispatch<true, float>(tmA, tmB, tmC, tmC, p, 64, true, st);
+    }
     if (int rc = encode_output<bf16>(enc, &tmC, y, p, false)) return rc;
     return dispatch<true, bf16>(tmA, tmB, tmC, tmC, p, 64, true, st);
 }

@@ -135,9 +135,10 @@ class IPSNet(nn.Module):
         self.shuffle = conf.shuffle
         self.shuffle_style = conf.shuffle_style
         self.is_image = conf.is_image
-        # optional, not a reference key: 'bf16' (tcgen05, default) or 'fp32' (CUDA-core exact mode)
+        # optional, not a reference key: 'bf16' (tcgen05, default), 'fp32' (CUDA-core exact mode) or 'bf16x3' (near-fp32 on
+        # the tensor cores: operands as hi + lo bf16 pairs, three MMAs per product, fp32 between layers; csrc/split3.cu)
         self.precision = os.environ.get('IPS_B200_PRECISION', getattr(conf, 'precision', 'bf16'))
-        if self.precision not in ('bf16', 'fp32'):
+        if self.precision not in ('bf16', 'fp32', 'bf16x3'):
             raise ValueError(f'unknown precision {self.precision!r}')
 
         if self.is_image:
@@ -151,7 +152,7 @@ class IPSNet(nn.Module):
 
         for m in self.modules():                     # train-step GEMMs follow the same precision switch as ips()
             if isinstance(m, Linear):
-                m.precision = self.precision
+                m.precision = 'bf16' if self.precision == 'bf16' else 'fp32'      # (grad-mode GEMMs: bf16x3 trains in fp32)
         self._plan = None
         self._plan_key = None
         self.last_mem_idx = None      # (B,M) original-order indices of the last ips() call (notebook cell 9)
@@ -265,7 +266,9 @@ class IPSNet(nn.Module):
         plan['posU'] = None
         if self.use_pos:
             plan['posU'] = ops.logits(self.pos_enc[0].contiguous().float(), plan['U'])      # (N, HT)
-        if self.is_image:
+        if self.precision == 'bf16x3':
+            self._build_plan_x3(plan)
+        elif self.is_image:
             st = self._fold_static()
             ops.fold_plan(st['items'], st['n'], st['blocks_per_item'])      # every layer's weights + BatchNorm in one launch
             plan['stem'], plan['blocks'] = st['stem'], st['blocks']
@@ -282,6 +285,88 @@ class IPSNet(nn.Module):
                     and not os.environ.get('IPSB_NO_FUSED_PROJECTOR')):
                 plan['p_table'] = ops.projector_table(scale, plan['p_shift'], plan['p_w'], plan['U'])
         return plan
+
+    # ------------------------------------------------------------------ bf16x3: near-fp32 on the tensor cores
+    @staticmethod
+    def _split_w(w):
+        hi = w.to(torch.bfloat16)
+        return hi.contiguous(), (w - hi.float()).to(torch.bfloat16).contiguous()
+
+    def _build_plan_x3(self, plan):
+        """Weights as (hi, lo) bf16 pairs in the tcgen05 K-major layouts; BatchNorm(eval) as fp32 scale / shift."""
+        def entry(conv, bn, stem=False):
+            w = conv.weight.detach().float()
+            cout, cin, kh, kw = w.shape
+            e = dict(cin=cin, cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0], mode=3 if stem else 0)
+            e['scale'], e['shift'] = _fold_bn(bn)
+            e['zero'] = torch.zeros_like(e['shift'])
+            if stem:                                              # (cout, 256): k = r*32 + (s+1)*4 + c on the zero-bordered frame
+                w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
+                w4[:, :cin] = w
+                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
+                wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
+                wk = wp.reshape(cout, 256)
+                e['cin'] = 4
+            else:
+                wk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+            e['wh'], e['wl'] = self._split_w(wk.contiguous())
+            return e
+        if self.is_image:
+            enc = self.encoder
+            ps = self.patch_size
+            if enc[0].out_channels != 64 or ps[0] % 2 or ps[1] % 2 or max(ps) > 480:
+                raise NotImplementedError("precision 'bf16x3' needs even patch sizes up to 480 and the 64-channel stem")
+            plan['stem'] = entry(enc[0], enc[1], stem=True)
+            blocks = []
+            for child in list(enc.children())[4:-1]:
+                for blk in child:
+                    b = dict(c1=entry(blk.conv1, blk.bn1), c2=entry(blk.conv2, blk.bn2), ds=None)
+                    if blk.downsample is not None:
+                        b['ds'] = entry(blk.downsample[0], blk.downsample[1])
+                    blocks.append(b)
+            plan['blocks'] = blocks
+        else:
+            lin, bn = self.encoder[1], self.encoder[2]
+            scale, bshift = _fold_bn(bn)
+            plan['p_scale'] = scale
+            plan['p_shift'] = (lin.bias.detach().float() * scale + bshift).contiguous()
+            plan['p_zero'] = torch.zeros_like(scale)
+            plan['p_wh'], plan['p_wl'] = self._split_w(lin.weight.detach().float().contiguous())
+            plan['p_table'] = None
+
+    def _embed_x3(self, plan, flat, first_row, n_rows):
+        """Eval-mode embeddings (rows, D) fp32 in the bf16x3 precision: every convolution / the projector GEMM as three
+        fp32-output tensor-core launches on (hi, lo) operands, sums / residual / ReLU / pooling in fp32."""
+        P = n_rows
+        if not self.is_image:
+            rows = flat[first_row:first_row + n_rows].contiguous().float()
+            K = rows.shape[1]
+            if K % 64 or self.D % 64:
+                raise NotImplementedError("precision 'bf16x3' needs feature and embedding widths that are multiples of 64")
+            a = ops.layernorm_rows(rows, 1e-5)
+            ah, al = ops.split_f32(a)
+            parts = ops.conv_x3(ah.view(P, 1, 1, K), al.view(P, 1, 1, K), plan['p_wh'], plan['p_wl'], plan['p_scale'], plan['p_shift'],
+                                plan['p_zero'], self.D, 1, 1, 1, 0)
+            return ops.sum3_split(parts, relu=True, want_f32=True, want_pair=False)[2].view(P, self.D)
+        _, C, H, W = flat.shape
+        e = plan['stem']
+        fh, fl = ops.stage_patches_padded_split(flat, P, C, H, W, first_row=first_row)
+        parts = ops.conv_x3(fh, fl, e['wh'], e['wl'], e['scale'], e['shift'], e['zero'], e['cout'], 7, 7, 2, 3, mode=3)
+        xh, xl = ops.sum3_maxpool_split(parts, relu=True)                       # conv1 + bn1 + relu + maxpool
+        out = None
+        for bi, b in enumerate(plan['blocks']):
+            last = bi == len(plan['blocks']) - 1
+            idt_pair, idt_f32 = (xh, xl), None
+            if b['ds'] is not None:
+                d = b['ds']
+                parts = ops.conv_x3(xh, xl, d['wh'], d['wl'], d['scale'], d['shift'], d['zero'], d['cout'], d['kh'], d['kw'], d['stride'], d['pad'])
+                idt_pair, idt_f32 = None, ops.sum3_split(parts, relu=False, want_f32=True, want_pair=False)[2]
+            c1, c2 = b['c1'], b['c2']
+            parts = ops.conv_x3(xh, xl, c1['wh'], c1['wl'], c1['scale'], c1['shift'], c1['zero'], c1['cout'], c1['kh'], c1['kw'], c1['stride'], c1['pad'])
+            yh, yl, _ = ops.sum3_split(parts, relu=True)
+            parts = ops.conv_x3(yh, yl, c2['wh'], c2['wl'], c2['scale'], c2['shift'], c2['zero'], c2['cout'], c2['kh'], c2['kw'], c2['stride'], c2['pad'])
+            xh, xl, out = ops.sum3_split(parts, relu=True, res_f32=idt_f32, res_pair=idt_pair, want_f32=last, want_pair=not last)
+        return ops.avgpool(out, ops.F32)
 
     def invalidate_plan(self):
         """Drop the folded-parameter plan.  `ips()` notices in-place parameter updates through the tensors' version
@@ -313,6 +398,10 @@ class IPSNet(nn.Module):
         dt = ops.BF16 if self.precision == 'bf16' else ops.F32
         if n_rows is None:
             n_rows = flat.shape[0] - first_row if row_idx is None else row_idx.numel()
+        if self.precision == 'bf16x3':
+            if row_idx is not None:
+                flat, first_row = flat[row_idx].contiguous(), 0
+            return self._embed_x3(plan, flat.contiguous(), first_row, n_rows)
         if self.is_image:
             _, C, H, W = flat.shape
             if plan['stem']['mode'] >= 3:
@@ -392,7 +481,7 @@ class IPSNet(nn.Module):
         flat = patches.reshape(rows, *patches.shape[2:])
         HT = plan['U'].shape[1]
         chunk = self._auto_chunk(patches.shape, rows)
-        if self.is_image and flat.is_cuda and self.executor == 'native' and pos_offset == 0:
+        if self.is_image and flat.is_cuda and self.executor == 'native' and pos_offset == 0 and self.precision != 'bf16x3':
             if 'desc' not in plan:
                 plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
             z, _ = ops.resnet_logits(plan['desc'], flat.contiguous(), N, chunk, self._ws_cache, lanes=self.lanes)
@@ -446,7 +535,7 @@ class IPSNet(nn.Module):
         dev.record_stream(cs)
         cs.wait_stream(main)
         z = torch.empty((rows, HT), dtype=torch.float32, device=self.device)
-        native = self.is_image and self.executor == 'native'
+        native = self.is_image and self.executor == 'native' and self.precision != 'bf16x3'
         if native and 'desc' not in plan:
             plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
         pos_idx = (torch.arange(rows, device=self.device) % N).contiguous() if self.use_pos else None

@@ -293,6 +293,67 @@ def linear_bf16(a, w, scale=None, shift=None, relu=False):
     return y
 
 
+# ---- "bf16x3": fp32 values as (hi, lo) pairs of bf16 tensors, products as three bf16 MMAs (csrc/split3.cu) ----------------
+
+def split_f32(x):
+    """fp32 tensor -> (hi, lo) bf16 tensors with hi + lo = x to ~17 significant bits (numel a multiple of 4)."""
+    _chk(x, torch.float32, 'x')
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    _call('ipsb_sum3_split', _p(x), 0, 0, 0, 0, 0, 0, _p(hi), _p(lo), 0, x.numel(), _stream())
+    return hi, lo
+
+
+def conv_x3(xh, xl, wh, wl, scale, shift, zero_shift, Cout, kh, kw, stride, pad, mode=0):
+    """The three partial products xh*wh + xh*wl + xl*wh of one convolution as fp32 tensors (P, Ho, Wo, Cout); BatchNorm
+    scale on each, shift on the first."""
+    P, H, W, Cin = xh.shape
+    if mode == 3:
+        Ho, Wo = (H - kh) // stride + 1, (W - kw) // stride + 1
+    else:
+        Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    outs = []
+    for x, w, sh in ((xh, wh, shift), (xh, wl, zero_shift), (xl, wh, zero_shift)):
+        _chk(x, torch.bfloat16, 'x'); _chk(w, torch.bfloat16, 'w')
+        y = torch.empty((P, Ho, Wo, Cout), dtype=torch.float32, device=xh.device)
+        _call('ipsb_conv_bf16_f32out', _p(x), _p(w), _p(scale), _p(sh), _p(y), P, H, W, Cin, Cout, kh, kw, stride, pad, mode, _stream())
+        outs.append(y)
+    return outs
+
+
+def sum3_split(parts, relu, res_f32=None, res_pair=None, want_f32=False, want_pair=True):
+    """a + b + c (+ residual) (+ ReLU) -> (hi, lo) and / or the fp32 sum."""
+    a, b, c = parts
+    hi = lo = out = None
+    if want_pair:
+        hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+        lo = torch.empty_like(hi)
+    if want_f32:
+        out = torch.empty_like(a)
+    _call('ipsb_sum3_split', _p(a), _p(b), _p(c), _p(res_f32), _p(res_pair[0]) if res_pair else 0, _p(res_pair[1]) if res_pair else 0,
+          int(relu), _p(hi), _p(lo), _p(out), a.numel(), _stream())
+    return hi, lo, out
+
+
+def sum3_maxpool_split(parts, relu=True):
+    a, b, c = parts
+    P, H, W, C = a.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    hi = torch.empty((P, Ho, Wo, C), dtype=torch.bfloat16, device=a.device)
+    lo = torch.empty_like(hi)
+    _call('ipsb_sum3_maxpool_split', _p(a), _p(b), _p(c), P, H, W, C, int(relu), _p(hi), _p(lo), _stream())
+    return hi, lo
+
+
+def stage_patches_padded_split(src, n_rows, C, H, W, first_row=0):
+    """(rows,C,H,W) fp32 -> hi / lo zero-bordered (n_rows,H+6,W+6,4) bf16 frames for the TMA stem."""
+    _chk(src, torch.float32, 'src')
+    hi = torch.empty((n_rows, H + 6, W + 6, 4), dtype=torch.bfloat16, device=src.device)
+    lo = torch.empty_like(hi)
+    _call('ipsb_stage_patches_padded_split', _p(src), first_row, n_rows, C, H, W, _p(hi), _p(lo), _stream())
+    return hi, lo
+
+
 def fold_plan(items_dev, n_items, blocks_per_item):
     """Refill every folded convolution weight / BatchNorm scale+shift described by the device item table in ONE launch."""
     _chk(items_dev, torch.uint8, 'items')

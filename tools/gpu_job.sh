@@ -1,21 +1,26 @@
 #!/bin/bash
-# A/B: downsample convolutions on the lane's side stream vs inline
+# bf16x3 precision: parity report + per-call timing
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 OUT=gpurun_out
-python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider -k "executor or lanes or image_equals or golden or bf16_close or full_size" > $OUT/j_tests.log 2>&1
-tail -4 $OUT/j_tests.log
-for mode in side inline side inline; do
-  if [ $mode = inline ]; then export IPSB_DS_INLINE=1; else unset IPSB_DS_INLINE; fi
-  for w in traffic mnist; do
-    python bench.py --workload $w --steps 20 --skip train,library,cpu,workloads,exact,sustained,seq > $OUT/j_ds.log 2>&1
-    python - <<PY
-import json
-for l in open('$OUT/j_ds.log'):
-    if l.startswith('{'):
-        d = json.loads(l); r = d['roofline']; print('$mode $w', round(d['ms_per_step'], 4), round(d['value']), 'busy', round(r['family_busy_ms_per_step'],4), 'frac', round(r['frac'],4))
+python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider -s -k "bf16x3" 2>&1 | grep -E "bf16x3|passed|failed" > $OUT/j_tests.log
+cat $OUT/j_tests.log | cut -c1-220
+python - <<'PY'
+import sys, torch
+sys.path.insert(0, '.')
+import bench
+from ips_b200 import ops
+class A: pass
+b = bench.Bench(type('X', (), {'skip': '', 'features': 'fp32'})())
+m = b.measure('traffic', 'bf16x3', 3, 2, e2e=False)
+ops.TIMER = {}
+m['net'].ips(m['x']); torch.cuda.synchronize()
+per = {k: (sum(a.elapsed_time(bb) for a, bb, _ in v), len(v)) for k, v in ops.TIMER.items()}
+ops.TIMER = None
+for k, (ms, n) in sorted(per.items(), key=lambda kv: -kv[1][0]): print(f'{k:36s} {ms:8.3f} ms  {n:4d} launches')
+for w in ('mnist', 'camelyon'):
+    mm = b.measure(w, 'bf16x3', 3, 2, e2e=False)
+    print(w, 'bf16x3', round(mm['value']), round(mm['ms_per_step'], 3))
 PY
-  done
-done
 echo "=== done"
