@@ -278,18 +278,20 @@ IPSB_API int ipsb_attention_train_bwd_f32(const float* q_scaled, const float* k,
 
 /* ---------------------------------------------------------------- "bf16x3": near-fp32 arithmetic on the bf16 tensor cores
  * Same reference arithmetic as the fp32 SIMT kernels (fp32 conv2d / linear + eval BatchNorm, ips_net.py:17-60).  Every fp32
- * operand is a pair of bf16 tensors v = hi + lo (hi = bf16(v), lo = bf16(v - hi)); x*w = xh*wh + xh*wl + xl*wh as three
- * launches of ipsb_conv_bf16_f32out (exact bf16 products, fp32 accumulation; y = conv * scale + shift, no activation, dense
- * (P,H,W,Cin) bf16 in, dense fp32 out; mode 0 = generic, mode 3 = the 7x7/2 stem on the zero-bordered 4-channel frame);
- * ipsb_sum3_split adds the partial results (+ a residual given as fp32 or as a hi / lo pair), applies ReLU and splits the
- * result again (and / or stores it as fp32); ipsb_sum3_maxpool_split is the stem's tail (sum, ReLU, max_pool2d(3, 2, 1));
- * ipsb_stage_patches_padded_split stages fp32 patches as the hi / lo frames of the stem. */
+ * operand is a pair of bf16 values v = hi + lo (hi = bf16(v), lo = bf16(v - hi)); x*w = xh*wh + xh*wl + xl*wh.  Activations
+ * are stored "tri": (pixels, 3C) bf16 = [hi | hi | lo], weights as [wh | wl | wh] along the input channels, so ONE launch of
+ * ipsb_conv_bf16_f32out with Cin' = 3C accumulates the three products in tensor memory (exact bf16 products, fp32
+ * accumulation; y = conv * scale + shift, no activation, dense bf16 in, dense fp32 out; mode 0 = generic, mode 3 = the 7x7/2
+ * stem on the zero-bordered 4-channel frame, run three times on hi / lo frames).  ipsb_sum3_split adds up to three partial
+ * results (+ a residual given as fp32, as a hi / lo pair, or as a tri tensor when tri_C > 0), applies ReLU and splits the
+ * result again (pair, or tri tensor in out_hi when tri_C > 0; and / or stores it as fp32); ipsb_sum3_maxpool_split is the
+ * stem's tail (sum, ReLU, max_pool2d(3, 2, 1)); ipsb_stage_patches_padded_split stages fp32 patches as the stem's frames. */
 IPSB_API int ipsb_conv_bf16_f32out(const void* x, const void* w, const float* scale, const float* shift, float* y, int64_t P, int H, int W,
                                    int Cin, int Cout, int kh, int kw, int stride, int pad, int mode, void* stream);
 IPSB_API int ipsb_sum3_split(const float* a, const float* b, const float* c, const float* res_f32, const void* res_hi, const void* res_lo,
-                             int relu, void* out_hi, void* out_lo, float* out_f32, int64_t n, void* stream);
+                             int relu, void* out_hi, void* out_lo, float* out_f32, int64_t n, int tri_C, void* stream);
 IPSB_API int ipsb_sum3_maxpool_split(const float* a, const float* b, const float* c, int64_t P, int H, int W, int C, int relu,
-                                     void* out_hi, void* out_lo, void* stream);
+                                     void* out_hi, void* out_lo, int tri, void* stream);
 IPSB_API int ipsb_stage_patches_padded_split(const float* src, int64_t first_row, int64_t n_rows, int C, int H, int W,
                                              void* dst_hi, void* dst_lo, void* stream);
 

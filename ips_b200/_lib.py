@@ -108,8 +108,8 @@ SIGNATURES = {
                                      _ptr],
     'ipsb_gather_rows': [_ptr, _i64, _ptr, _i32, _i32, _i64, _ptr, _ptr],
     'ipsb_conv_bf16_f32out': [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
-    'ipsb_sum3_split': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i64, _ptr],
-    'ipsb_sum3_maxpool_split': [_ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr],
+    'ipsb_sum3_split': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
+    'ipsb_sum3_maxpool_split': [_ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _ptr, _i32, _ptr],
     'ipsb_stage_patches_padded_split': [_ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr],
     'ipsb_fold_plan': [_ptr, _i32, _i32, _ptr],
     'ipsb_projector_logits': [_ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],

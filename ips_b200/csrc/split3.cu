@@ -2,9 +2,11 @@
 //
 // Every fp32 operand is split into two bf16 values, v = hi + lo with hi = bf16(v), lo = bf16(v - hi) (16-17 significant
 // bits together), and a product x*w is evaluated as xh*wh + xh*wl + xl*wh: three bf16 MMAs whose products are exact and are
-// accumulated in fp32 (the dropped xl*wl term is below 2^-17 of |x||w|).  Activations live in HBM as (hi, lo) pairs of bf16
-// tensors; a convolution is three launches of the fp32-output tcgen05 kernel (umma_conv_tma.cu) and the kernels below add
-// the three partial results, apply the residual / ReLU / max-pool in fp32 and split the result again.
+// accumulated in fp32 (the dropped xl*wl term is below 2^-17 of |x||w|).  Activations live in HBM in a "tri" layout: per
+// pixel 3C bf16 channels [hi | hi | lo]; with the weights laid out as [wh | wl | wh] along the input channels ONE launch of the
+// fp32-output tcgen05 kernel (umma_conv_tma.cu) with Cin' = 3C accumulates all three products in tensor memory.  The stem
+// (4 input channels, special frame layout) runs as three launches on (hi, lo) frames.  The kernels below add partial
+// results, apply the residual / ReLU / max-pool in fp32 and split the result again.
 // Used for index-stable selection at tensor-core speed; reference arithmetic: fp32 conv2d / linear of
 // architecture/ips_net.py:17-60.
 #include "common.cuh"
@@ -47,7 +49,14 @@ struct Sum3Params {
     bf16* out_hi; bf16* out_lo; float* out_f32;
     int64_t n4;                                            // float4 groups
     int relu;
+    int tri_C;                                             // > 0: out_hi / res_hi are tri tensors (pixels, 3C) = [hi | hi | lo]
 };
+
+// offset (in elements) of the hi copy of float4 group i in a tri tensor with C channels (lo at + 2C, second hi at + C)
+__device__ __forceinline__ int64_t tri_off(int64_t i, int C) {
+    const int64_t e = i * 4, px = e / C;
+    return px * 3 * C + (e - px * C);
+}
 
 __global__ void __launch_bounds__(256) sum3_split_kernel(Sum3Params p) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < p.n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -56,7 +65,9 @@ __global__ void __launch_bounds__(256) sum3_split_kernel(Sum3Params p) {
         if (p.c) { const float4 u = reinterpret_cast<const float4*>(p.c)[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
         if (p.res_f32) { const float4 u = reinterpret_cast<const float4*>(p.res_f32)[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
         if (p.res_hi) {
-            const uint2 hh = reinterpret_cast<const uint2*>(p.res_hi)[i], ll = reinterpret_cast<const uint2*>(p.res_lo)[i];
+            const int64_t ro = p.tri_C ? tri_off(i, p.tri_C) : i * 4;
+            const uint2 hh = *reinterpret_cast<const uint2*>(p.res_hi + ro);
+            const uint2 ll = *reinterpret_cast<const uint2*>((p.tri_C ? p.res_hi + 2 * p.tri_C : p.res_lo) + ro);
             v.x += __uint_as_float(hh.x << 16) + __uint_as_float(ll.x << 16);
             v.y += __uint_as_float(hh.x & 0xffff0000u) + __uint_as_float(ll.x & 0xffff0000u);
             v.z += __uint_as_float(hh.y << 16) + __uint_as_float(ll.y << 16);
@@ -67,8 +78,15 @@ __global__ void __launch_bounds__(256) sum3_split_kernel(Sum3Params p) {
         if (p.out_hi) {
             __align__(8) bf16 h[4], l[4];
             split(v.x, h[0], l[0]); split(v.y, h[1], l[1]); split(v.z, h[2], l[2]); split(v.w, h[3], l[3]);
-            reinterpret_cast<uint2*>(p.out_hi)[i] = *reinterpret_cast<const uint2*>(h);
-            reinterpret_cast<uint2*>(p.out_lo)[i] = *reinterpret_cast<const uint2*>(l);
+            if (p.tri_C) {
+                bf16* d = p.out_hi + tri_off(i, p.tri_C);
+                *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(d + p.tri_C) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(d + 2 * p.tri_C) = *reinterpret_cast<const uint2*>(l);
+            } else {
+                reinterpret_cast<uint2*>(p.out_hi)[i] = *reinterpret_cast<const uint2*>(h);
+                reinterpret_cast<uint2*>(p.out_lo)[i] = *reinterpret_cast<const uint2*>(l);
+            }
         }
     }
 }
@@ -76,7 +94,7 @@ __global__ void __launch_bounds__(256) sum3_split_kernel(Sum3Params p) {
 // (P, H, W, C) fp32 partial sums a + b + c -> ReLU -> max_pool2d(3, 2, 1) -> (P, Ho, Wo, C) hi / lo; 4 channels per thread
 __global__ void __launch_bounds__(256) sum3_maxpool_split_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                  const float* __restrict__ c, int64_t P, int H, int W, int C, int Ho, int Wo,
-                                                                 int relu, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                                                                 int relu, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int tri) {
     const int C4 = C >> 2;
     const int64_t total = P * Ho * Wo * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -102,8 +120,15 @@ __global__ void __launch_bounds__(256) sum3_maxpool_split_kernel(const float* __
         if (relu) { m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); m.z = fmaxf(m.z, 0.f); m.w = fmaxf(m.w, 0.f); }
         __align__(8) bf16 h[4], l[4];
         split(m.x, h[0], l[0]); split(m.y, h[1], l[1]); split(m.z, h[2], l[2]); split(m.w, h[3], l[3]);
-        reinterpret_cast<uint2*>(out_hi)[i] = *reinterpret_cast<const uint2*>(h);
-        reinterpret_cast<uint2*>(out_lo)[i] = *reinterpret_cast<const uint2*>(l);
+        if (tri) {                                            // (pixels, 3C) = [hi | hi | lo]
+            bf16* d = out_hi + tri_off(i, C);
+            *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(d + C) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(d + 2 * C) = *reinterpret_cast<const uint2*>(l);
+        } else {
+            reinterpret_cast<uint2*>(out_hi)[i] = *reinterpret_cast<const uint2*>(h);
+            reinterpret_cast<uint2*>(out_lo)[i] = *reinterpret_cast<const uint2*>(l);
+        }
     }
 }
 
@@ -130,23 +155,25 @@ int ipsb_stage_patches_padded_split(const float* src, int64_t first_row, int64_t
 }
 
 int ipsb_sum3_split(const float* a, const float* b, const float* c, const float* res_f32, const void* res_hi, const void* res_lo,
-                    int relu, void* out_hi, void* out_lo, float* out_f32, int64_t n, void* stream) {
+                    int relu, void* out_hi, void* out_lo, float* out_f32, int64_t n, int tri_C, void* stream) {
     IPSB_REQUIRE(a && n > 0 && n % 4 == 0, "sum3_split: n=%lld must be a positive multiple of 4", (long long)n);
-    IPSB_REQUIRE((res_hi == nullptr) == (res_lo == nullptr) && (out_hi == nullptr) == (out_lo == nullptr) && (out_hi || out_f32),
-                 "sum3_split: hi / lo buffers come in pairs and an output is required");
-    Sum3Params p{a, b, c, res_f32, (const bf16*)res_hi, (const bf16*)res_lo, (bf16*)out_hi, (bf16*)out_lo, out_f32, n / 4, relu};
+    IPSB_REQUIRE(tri_C >= 0 && tri_C % 4 == 0 && (tri_C == 0 || n % tri_C == 0), "sum3_split: tri layout with C=%d", tri_C);
+    IPSB_REQUIRE(tri_C > 0 || ((res_hi == nullptr) == (res_lo == nullptr) && (out_hi == nullptr) == (out_lo == nullptr)),
+                 "sum3_split: hi / lo buffers come in pairs");
+    IPSB_REQUIRE(out_hi || out_f32, "sum3_split: an output is required");
+    Sum3Params p{a, b, c, res_f32, (const bf16*)res_hi, (const bf16*)res_lo, (bf16*)out_hi, (bf16*)out_lo, out_f32, n / 4, relu, tri_C};
     sum3_split_kernel<<<grid_for(p.n4, 256), 256, 0, (cudaStream_t)stream>>>(p);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
 
 int ipsb_sum3_maxpool_split(const float* a, const float* b, const float* c, int64_t P, int H, int W, int C, int relu,
-                            void* out_hi, void* out_lo, void* stream) {
-    IPSB_REQUIRE(a && b && c && out_hi && out_lo && P > 0 && C % 4 == 0, "sum3_maxpool_split: bad arguments");
+                            void* out_hi, void* out_lo, int tri, void* stream) {
+    IPSB_REQUIRE(a && b && c && out_hi && (out_lo || tri) && P > 0 && C % 4 == 0, "sum3_maxpool_split: bad arguments");
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int64_t total = P * Ho * Wo * (C / 4);
     sum3_maxpool_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, P, H, W, C, Ho, Wo, relu,
-                                                                                      (bf16*)out_hi, (bf16*)out_lo);
+                                                                                      (bf16*)out_hi, (bf16*)out_lo, tri);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -293,30 +293,34 @@ class IPSNet(nn.Module):
         return hi.contiguous(), (w - hi.float()).to(torch.bfloat16).contiguous()
 
     def _build_plan_x3(self, plan):
-        """Weights as (hi, lo) bf16 pairs in the tcgen05 K-major layouts; BatchNorm(eval) as fp32 scale / shift."""
-        def entry(conv, bn, stem=False):
+        """Weights as hi / lo bf16 in the tcgen05 K-major layouts, arranged [wh | wl | wh] along the input channels (the
+        partner of the activations' [hi | hi | lo] layout); BatchNorm(eval) as fp32 scale / shift."""
+        def entry(conv, bn):
             w = conv.weight.detach().float()
             cout, cin, kh, kw = w.shape
-            e = dict(cin=cin, cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0], mode=3 if stem else 0)
+            e = dict(cin=cin, cout=cout, kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0])
             e['scale'], e['shift'] = _fold_bn(bn)
-            e['zero'] = torch.zeros_like(e['shift'])
-            if stem:                                              # (cout, 256): k = r*32 + (s+1)*4 + c on the zero-bordered frame
-                w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
-                w4[:, :cin] = w
-                wp = torch.zeros((cout, 8, 8, 4), device=w.device)
-                wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
-                wk = wp.reshape(cout, 256)
-                e['cin'] = 4
-            else:
-                wk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
-            e['wh'], e['wl'] = self._split_w(wk.contiguous())
+            wt = w.permute(0, 2, 3, 1).contiguous()                          # (cout, kh, kw, cin)
+            wh, wl = self._split_w(wt)
+            e['w3'] = torch.cat([wh, wl, wh], dim=3).reshape(cout, kh * kw * 3 * cin).contiguous()
             return e
         if self.is_image:
             enc = self.encoder
             ps = self.patch_size
             if enc[0].out_channels != 64 or ps[0] % 2 or ps[1] % 2 or max(ps) > 480:
                 raise NotImplementedError("precision 'bf16x3' needs even patch sizes up to 480 and the 64-channel stem")
-            plan['stem'] = entry(enc[0], enc[1], stem=True)
+            conv, bn = enc[0], enc[1]                                         # stem: (cout, 256), k = r*32 + (s+1)*4 + c, as hi and lo
+            w = conv.weight.detach().float()
+            cout, cin, kh, kw = w.shape
+            st = dict(cout=cout)
+            st['scale'], st['shift'] = _fold_bn(bn)
+            st['zero'] = torch.zeros_like(st['shift'])
+            w4 = torch.zeros((cout, 4, kh, kw), device=w.device)
+            w4[:, :cin] = w
+            wp = torch.zeros((cout, 8, 8, 4), device=w.device)
+            wp[:, :kh, 1:kw + 1] = w4.permute(0, 2, 3, 1)
+            st['wh'], st['wl'] = self._split_w(wp.reshape(cout, 256).contiguous())
+            plan['stem'] = st
             blocks = []
             for child in list(enc.children())[4:-1]:
                 for blk in child:
@@ -330,42 +334,41 @@ class IPSNet(nn.Module):
             scale, bshift = _fold_bn(bn)
             plan['p_scale'] = scale
             plan['p_shift'] = (lin.bias.detach().float() * scale + bshift).contiguous()
-            plan['p_zero'] = torch.zeros_like(scale)
-            plan['p_wh'], plan['p_wl'] = self._split_w(lin.weight.detach().float().contiguous())
+            wh, wl = self._split_w(lin.weight.detach().float().contiguous())
+            plan['p_w3'] = torch.cat([wh, wl, wh], dim=1).contiguous()        # (D, 3K)
             plan['p_table'] = None
 
     def _embed_x3(self, plan, flat, first_row, n_rows):
-        """Eval-mode embeddings (rows, D) fp32 in the bf16x3 precision: every convolution / the projector GEMM as three
-        fp32-output tensor-core launches on (hi, lo) operands, sums / residual / ReLU / pooling in fp32."""
+        """Eval-mode embeddings (rows, D) fp32 in the bf16x3 precision: every convolution / the projector GEMM as ONE
+        fp32-output tensor-core launch over the tripled input channels, sums / residual / ReLU / pooling in fp32."""
         P = n_rows
         if not self.is_image:
             rows = flat[first_row:first_row + n_rows].contiguous().float()
             K = rows.shape[1]
             if K % 64 or self.D % 64:
                 raise NotImplementedError("precision 'bf16x3' needs feature and embedding widths that are multiples of 64")
-            a = ops.layernorm_rows(rows, 1e-5)
-            ah, al = ops.split_f32(a)
-            parts = ops.conv_x3(ah.view(P, 1, 1, K), al.view(P, 1, 1, K), plan['p_wh'], plan['p_wl'], plan['p_scale'], plan['p_shift'],
-                                plan['p_zero'], self.D, 1, 1, 1, 0)
-            return ops.sum3_split(parts, relu=True, want_f32=True, want_pair=False)[2].view(P, self.D)
+            a3 = ops.tri_from_f32(ops.layernorm_rows(rows, 1e-5))                                  # (P, 3K)
+            y = ops.conv_f32out(a3.view(P, 1, 1, 3 * K), plan['p_w3'], plan['p_scale'], plan['p_shift'], self.D, 1, 1, 1, 0)
+            return ops.sum_split_tri([y], relu=True, C=self.D, want_f32=True, want_tri=False)[1].view(P, self.D)
         _, C, H, W = flat.shape
         e = plan['stem']
         fh, fl = ops.stage_patches_padded_split(flat, P, C, H, W, first_row=first_row)
-        parts = ops.conv_x3(fh, fl, e['wh'], e['wl'], e['scale'], e['shift'], e['zero'], e['cout'], 7, 7, 2, 3, mode=3)
-        xh, xl = ops.sum3_maxpool_split(parts, relu=True)                       # conv1 + bn1 + relu + maxpool
+        parts = [ops.conv_f32out(f, w, e['scale'], sh, e['cout'], 7, 7, 2, 3, mode=3)
+                 for f, w, sh in ((fh, e['wh'], e['shift']), (fh, e['wl'], e['zero']), (fl, e['wh'], e['zero']))]
+        x3 = ops.sum3_maxpool_tri(parts, relu=True)                           # conv1 + bn1 + relu + maxpool -> (P, h, w, 192)
+        del parts, fh, fl
         out = None
+
+        def conv(x3, c):
+            return ops.conv_f32out(x3, c['w3'], c['scale'], c['shift'], c['cout'], c['kh'], c['kw'], c['stride'], c['pad'])
         for bi, b in enumerate(plan['blocks']):
             last = bi == len(plan['blocks']) - 1
-            idt_pair, idt_f32 = (xh, xl), None
+            idt_tri, idt_f32 = x3, None
             if b['ds'] is not None:
-                d = b['ds']
-                parts = ops.conv_x3(xh, xl, d['wh'], d['wl'], d['scale'], d['shift'], d['zero'], d['cout'], d['kh'], d['kw'], d['stride'], d['pad'])
-                idt_pair, idt_f32 = None, ops.sum3_split(parts, relu=False, want_f32=True, want_pair=False)[2]
-            c1, c2 = b['c1'], b['c2']
-            parts = ops.conv_x3(xh, xl, c1['wh'], c1['wl'], c1['scale'], c1['shift'], c1['zero'], c1['cout'], c1['kh'], c1['kw'], c1['stride'], c1['pad'])
-            yh, yl, _ = ops.sum3_split(parts, relu=True)
-            parts = ops.conv_x3(yh, yl, c2['wh'], c2['wl'], c2['scale'], c2['shift'], c2['zero'], c2['cout'], c2['kh'], c2['kw'], c2['stride'], c2['pad'])
-            xh, xl, out = ops.sum3_split(parts, relu=True, res_f32=idt_f32, res_pair=idt_pair, want_f32=last, want_pair=not last)
+                idt_tri, idt_f32 = None, conv(x3, b['ds'])                    # downsample branch stays fp32
+            y3, _ = ops.sum_split_tri([conv(x3, b['c1'])], relu=True, C=b['c1']['cout'])
+            x3, out = ops.sum_split_tri([conv(y3, b['c2'])], relu=True, C=b['c2']['cout'], res_f32=idt_f32, res_tri=idt_tri,
+                                        want_f32=last, want_tri=not last)
         return ops.avgpool(out, ops.F32)
 
     def invalidate_plan(self):

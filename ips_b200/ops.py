@@ -293,56 +293,50 @@ def linear_bf16(a, w, scale=None, shift=None, relu=False):
     return y
 
 
-# ---- "bf16x3": fp32 values as (hi, lo) pairs of bf16 tensors, products as three bf16 MMAs (csrc/split3.cu) ----------------
+# ---- "bf16x3": fp32 values as hi + lo bf16, products as three bf16 MMAs accumulated in fp32 (csrc/split3.cu) -------------
+# Activations in the "tri" layout (pixels, 3C) = [hi | hi | lo]; weights [wh | wl | wh] along the input channels.
 
-def split_f32(x):
-    """fp32 tensor -> (hi, lo) bf16 tensors with hi + lo = x to ~17 significant bits (numel a multiple of 4)."""
+def tri_from_f32(x):
+    """fp32 (rows..., C) -> tri bf16 (rows..., 3C) = [hi | hi | lo] with hi + lo = x to ~17 significant bits."""
     _chk(x, torch.float32, 'x')
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty_like(hi)
-    _call('ipsb_sum3_split', _p(x), 0, 0, 0, 0, 0, 0, _p(hi), _p(lo), 0, x.numel(), _stream())
-    return hi, lo
+    C = x.shape[-1]
+    tri = torch.empty((*x.shape[:-1], 3 * C), dtype=torch.bfloat16, device=x.device)
+    _call('ipsb_sum3_split', _p(x), 0, 0, 0, 0, 0, 0, _p(tri), 0, 0, x.numel(), C, _stream())
+    return tri
 
 
-def conv_x3(xh, xl, wh, wl, scale, shift, zero_shift, Cout, kh, kw, stride, pad, mode=0):
-    """The three partial products xh*wh + xh*wl + xl*wh of one convolution as fp32 tensors (P, Ho, Wo, Cout); BatchNorm
-    scale on each, shift on the first."""
-    P, H, W, Cin = xh.shape
+def conv_f32out(x, w, scale, shift, Cout, kh, kw, stride, pad, mode=0):
+    """bf16 (P,H,W,Cin) x bf16 (Cout, K) -> fp32 (P,Ho,Wo,Cout) = conv * scale + shift (no activation); fp32 accumulation."""
+    _chk(x, torch.bfloat16, 'x'); _chk(w, torch.bfloat16, 'w')
+    P, H, W, Cin = x.shape
     if mode == 3:
         Ho, Wo = (H - kh) // stride + 1, (W - kw) // stride + 1
     else:
         Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
-    outs = []
-    for x, w, sh in ((xh, wh, shift), (xh, wl, zero_shift), (xl, wh, zero_shift)):
-        _chk(x, torch.bfloat16, 'x'); _chk(w, torch.bfloat16, 'w')
-        y = torch.empty((P, Ho, Wo, Cout), dtype=torch.float32, device=xh.device)
-        _call('ipsb_conv_bf16_f32out', _p(x), _p(w), _p(scale), _p(sh), _p(y), P, H, W, Cin, Cout, kh, kw, stride, pad, mode, _stream())
-        outs.append(y)
-    return outs
+    y = torch.empty((P, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    _call('ipsb_conv_bf16_f32out', _p(x), _p(w), _p(scale), _p(shift), _p(y), P, H, W, Cin, Cout, kh, kw, stride, pad, mode, _stream())
+    return y
 
 
-def sum3_split(parts, relu, res_f32=None, res_pair=None, want_f32=False, want_pair=True):
-    """a + b + c (+ residual) (+ ReLU) -> (hi, lo) and / or the fp32 sum."""
-    a, b, c = parts
-    hi = lo = out = None
-    if want_pair:
-        hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
-        lo = torch.empty_like(hi)
-    if want_f32:
-        out = torch.empty_like(a)
-    _call('ipsb_sum3_split', _p(a), _p(b), _p(c), _p(res_f32), _p(res_pair[0]) if res_pair else 0, _p(res_pair[1]) if res_pair else 0,
-          int(relu), _p(hi), _p(lo), _p(out), a.numel(), _stream())
-    return hi, lo, out
+def sum_split_tri(parts, relu, C, res_f32=None, res_tri=None, want_f32=False, want_tri=True):
+    """a (+ b + c) (+ residual: fp32 or tri) (+ ReLU) -> tri tensor (..., 3C) and / or the fp32 sum."""
+    a = parts[0]
+    b = parts[1] if len(parts) > 1 else None
+    c = parts[2] if len(parts) > 2 else None
+    tri = torch.empty((*a.shape[:-1], 3 * C), dtype=torch.bfloat16, device=a.device) if want_tri else None
+    out = torch.empty_like(a) if want_f32 else None
+    _call('ipsb_sum3_split', _p(a), _p(b), _p(c), _p(res_f32), _p(res_tri), 0, int(relu), _p(tri), 0, _p(out), a.numel(), C, _stream())
+    return tri, out
 
 
-def sum3_maxpool_split(parts, relu=True):
+def sum3_maxpool_tri(parts, relu=True):
+    """stem tail: a + b + c -> ReLU -> max_pool2d(3, 2, 1) -> tri (P, Ho, Wo, 3C)."""
     a, b, c = parts
     P, H, W, C = a.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    hi = torch.empty((P, Ho, Wo, C), dtype=torch.bfloat16, device=a.device)
-    lo = torch.empty_like(hi)
-    _call('ipsb_sum3_maxpool_split', _p(a), _p(b), _p(c), P, H, W, C, int(relu), _p(hi), _p(lo), _stream())
-    return hi, lo
+    tri = torch.empty((P, Ho, Wo, 3 * C), dtype=torch.bfloat16, device=a.device)
+    _call('ipsb_sum3_maxpool_split', _p(a), _p(b), _p(c), P, H, W, C, int(relu), _p(tri), 0, 1, _stream())
+    return tri
 
 
 def stage_patches_padded_split(src, n_rows, C, H, W, first_row=0):
