@@ -367,7 +367,7 @@ class Bench:
         counts = {k: len(v) // reps for k, v in ops.TIMER.items()}
         ops.TIMER = None
         family = ('ipsb_conv_bf16_pf', 'ipsb_conv_bf16_umma', 'ipsb_stem_pool_s2d', 'ipsb_linear_bf16_umma', 'ipsb_conv_f32',
-                  'ipsb_linear_f32', 'ipsb_projector_logits')
+                  'ipsb_linear_f32', 'ipsb_projector_logits', 'ipsb_projector_logits_scan')
         fam_ms = sum(v for k, v in per.items() if k in family)
         if fam_ms <= 0:
             return None
@@ -464,7 +464,8 @@ class Bench:
     def seq_sharded(self, steps):
         torch, dist = self.torch, self.dist
         from ips_b200 import ops
-        from ips_b200.distributed import ShardedIPS, shard_bounds, local_scan_order
+        from ips_b200.distributed import ShardedIPS, shard_bounds
+        from ips_b200.utils import scan_order
         R, rank = self.world, self.rank
         net, conf, _, _ = self.make_net('camelyon', 'bf16', seed=4321)           # identical weights on every rank
         ca = net.transf.crs_attn
@@ -478,11 +479,15 @@ class Bench:
             rec = {'case': name, 'B': B, 'N': N, 'M': M, 'I': conf.I, 'n_gpus': R, 'scaling': 'strong'}
             if R == 1:
                 step = lambda: net.ips(x)
-                for _ in range(3):
-                    step()
-                ms = self.timed(step, steps) / steps
-                rec.update(mode='single GPU IPSNet.ips', ms=ms, patches_per_s=B * N / (ms / 1e3))
-                records.append(rec)
+                for rng in ('reference', 'device'):
+                    net.scan_order_rng = rng
+                    for _ in range(3):
+                        step()
+                    ms = self.timed(step, steps) / steps
+                    r1 = dict(rec)
+                    r1.update(mode='single GPU IPSNet.ips', scan_order_rng=rng, ms=ms, patches_per_s=B * N / (ms / 1e3))
+                    records.append(r1)
+                net.scan_order_rng = 'reference'
                 del x
                 continue
             lo, hi = shard_bounds(N, R)[rank]
@@ -490,76 +495,81 @@ class Bench:
             variants = [('merge', 'replicated'), ('exact', 'replicated')]
             if B >= R:
                 variants.append(('merge', 'batch_split'))      # slide b delivered only to the rank whose train step consumes it
-            for mode, output in variants:
-                sh = ShardedIPS(net, B, N, (F,), mode=mode, output=output)
-                spr = sh.spr
-                my_b = list(range(rank * spr, min(B, (rank + 1) * spr))) if spr else list(range(B))
-                for _ in range(3):
-                    sh(local)
-                ms_eager = self.timed(lambda: sh(local), steps) / steps
-                # parity self-check (eager call, known seeds)
-                torch.manual_seed(100 + rank if mode == 'merge' else 7)
-                mem_patch, _ = sh(local)
-                got_idx = net.last_mem_idx.clone()
-                got_sum = mem_patch.double().sum().item()
-                rows_ok = all(bool(torch.equal(mem_patch[j], x[b, got_idx[j]])) for j, b in enumerate(my_b))
-                if mode == 'exact':
-                    torch.manual_seed(7)
-                    ref_patch, _ = net.ips(x)                                     # the same call on ONE GPU
-                    same = bool(torch.equal(net.last_mem_idx[my_b], got_idx)) and bool(torch.equal(ref_patch[my_b], mem_patch))
-                    parity = {'exact_equals_single_gpu_bit_for_bit': same}
-                else:
-                    # the same schedule composed in ONE process from the product kernels: per-slice loop, candidates in rank
-                    # order, one global re-score
-                    z = net.patch_logits(x)
-                    cz, ci = [], []
-                    for r, (a, b_) in enumerate(shard_bounds(N, R)):
-                        torch.manual_seed(100 + r)
-                        perm, per_inst = local_scan_order(net, B, b_ - a, torch.device('cpu'))
-                        perm = None if perm is None else perm.to(self.dev)
-                        zl = z[:, a:b_].contiguous()
-                        cand = ops.select_loop(zl, perm, per_inst, ca.H, ca.n_token, M, conf.I)[1]
-                        cz.append(torch.gather(zl, 1, cand.unsqueeze(-1).expand(-1, -1, HT)))
-                        ci.append(cand + a)
-                    cz, ci = torch.cat(cz, 1).contiguous(), torch.cat(ci, 1)
-                    pos = ops.merge_candidates(cz, ca.H, ca.n_token, M)
-                    ref_idx = torch.gather(ci, 1, pos)
-                    parity = {'merge_equals_single_process_schedule': bool(torch.equal(ref_idx[my_b], got_idx))}
-                parity['rows_are_the_selected_patches'] = rows_ok
-                flag = torch.tensor([int(all(parity.values()))], device=self.dev)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                parity['all_ranks'] = bool(flag.item())
-                parity['exchange_status'] = sh.ex.status()
-                all_idx = sh.mem_src                                              # (B, M) on every rank
-                owned = ((all_idx >= lo) & (all_idx < hi))
-                if spr:                                                         # rows this rank sends to OTHER ranks
-                    dest = torch.arange(B, device=self.dev).unsqueeze(1) // spr
-                    sent_rows = int((owned & (dest != rank)).sum().item())
-                else:
-                    sent_rows = int(owned.sum().item()) * (R - 1)
-                pushed = (R - 1) * (B * M * (HT * 4 + 8) if mode == 'merge' else B * (hi - lo) * HT * 4) + sent_rows * F * 4
-                # the whole call as ONE CUDA graph
-                ms_graph, graph_err = None, None
-                try:
-                    sh.capture(local)
-                    gin = sh.static_input                                        # the slice lives in the graph's input buffer
+            for rng in ('reference', 'device'):          # scan order: the reference's host RNG calls / drawn on the device
+                net.scan_order_rng = rng
+                for mode, output in variants:
+                    if rng == 'device' and mode == 'exact':
+                        continue
+                    sh = ShardedIPS(net, B, N, (F,), mode=mode, output=output)
+                    spr = sh.spr
+                    my_b = list(range(rank * spr, min(B, (rank + 1) * spr))) if spr else list(range(B))
                     for _ in range(3):
-                        sh(gin)
-                    ms_graph = self.timed(lambda: sh(gin), steps) / steps
+                        sh(local)
+                    ms_eager = self.timed(lambda: sh(local), steps) / steps
+                    # parity self-check (eager call, known seeds)
                     torch.manual_seed(100 + rank if mode == 'merge' else 7)
-                    sh(gin)
-                    parity['graph_replay_equals_eager'] = bool(torch.equal(net.last_mem_idx, got_idx))
-                except Exception as e:                                           # keep the eager record
-                    graph_err = str(e)[:200]
-                best = min(v for v in (ms_eager, ms_graph) if v is not None)
-                r2 = dict(rec)
-                r2.update(mode=mode, output=output, transport='nvlink peer memory (CUDA IPC exchange buffers, push + flag kernels; no NCCL on the data path)',
-                          ms_eager=ms_eager, ms_graph=ms_graph, ms=best, patches_per_s=B * N / (best / 1e3),
-                          bytes_pushed_to_peers_per_rank=pushed, parity_check=parity)
-                if graph_err:
-                    r2['graph_error'] = graph_err
-                records.append(r2)
-                del sh
+                    mem_patch, _ = sh(local)
+                    got_idx = net.last_mem_idx.clone()
+                    got_sum = mem_patch.double().sum().item()
+                    rows_ok = all(bool(torch.equal(mem_patch[j], x[b, got_idx[j]])) for j, b in enumerate(my_b))
+                    if mode == 'exact':
+                        torch.manual_seed(7)
+                        ref_patch, _ = net.ips(x)                                     # the same call on ONE GPU
+                        same = bool(torch.equal(net.last_mem_idx[my_b], got_idx)) and bool(torch.equal(ref_patch[my_b], mem_patch))
+                        parity = {'exact_equals_single_gpu_bit_for_bit': same}
+                    else:
+                        # the same schedule composed in ONE process from the product kernels: per-slice loop, candidates in rank
+                        # order, one global re-score
+                        z = net.patch_logits(x)
+                        cz, ci = [], []
+                        for r, (a, b_) in enumerate(shard_bounds(N, R)):
+                            torch.manual_seed(100 + r)
+                            perm, per_inst = scan_order(net.shuffle, net.shuffle_style, B, b_ - a, torch.device('cpu'), rng, self.dev)
+                            perm = None if perm is None else perm.to(self.dev)
+                            zl = z[:, a:b_].contiguous()
+                            cand = ops.select_loop(zl, perm, per_inst, ca.H, ca.n_token, M, conf.I)[1]
+                            cz.append(torch.gather(zl, 1, cand.unsqueeze(-1).expand(-1, -1, HT)))
+                            ci.append(cand + a)
+                        cz, ci = torch.cat(cz, 1).contiguous(), torch.cat(ci, 1)
+                        pos = ops.merge_candidates(cz, ca.H, ca.n_token, M)
+                        ref_idx = torch.gather(ci, 1, pos)
+                        parity = {'merge_equals_single_process_schedule': bool(torch.equal(ref_idx[my_b], got_idx))}
+                    parity['rows_are_the_selected_patches'] = rows_ok
+                    flag = torch.tensor([int(all(parity.values()))], device=self.dev)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                    parity['all_ranks'] = bool(flag.item())
+                    parity['exchange_status'] = sh.ex.status()
+                    all_idx = sh.mem_src                                              # (B, M) on every rank
+                    owned = ((all_idx >= lo) & (all_idx < hi))
+                    if spr:                                                         # rows this rank sends to OTHER ranks
+                        dest = torch.arange(B, device=self.dev).unsqueeze(1) // spr
+                        sent_rows = int((owned & (dest != rank)).sum().item())
+                    else:
+                        sent_rows = int(owned.sum().item()) * (R - 1)
+                    pushed = (R - 1) * (B * M * (HT * 4 + 8) if mode == 'merge' else B * (hi - lo) * HT * 4) + sent_rows * F * 4
+                    # the whole call as ONE CUDA graph
+                    ms_graph, graph_err = None, None
+                    try:
+                        sh.capture(local)
+                        gin = sh.static_input                                        # the slice lives in the graph's input buffer
+                        for _ in range(3):
+                            sh(gin)
+                        ms_graph = self.timed(lambda: sh(gin), steps) / steps
+                        torch.manual_seed(100 + rank if mode == 'merge' else 7)
+                        sh(gin)
+                        parity['graph_replay_equals_eager'] = bool(torch.equal(net.last_mem_idx, got_idx))
+                    except Exception as e:                                           # keep the eager record
+                        graph_err = str(e)[:200]
+                    best = min(v for v in (ms_eager, ms_graph) if v is not None)
+                    r2 = dict(rec)
+                    r2.update(mode=mode, output=output, scan_order_rng=rng, transport='nvlink peer memory (CUDA IPC exchange buffers, push + flag kernels; no NCCL on the data path)',
+                              ms_eager=ms_eager, ms_graph=ms_graph, ms=best, patches_per_s=B * N / (best / 1e3),
+                              bytes_pushed_to_peers_per_rank=pushed, parity_check=parity)
+                    if graph_err:
+                        r2['graph_error'] = graph_err
+                    records.append(r2)
+                    del sh
+            net.scan_order_rng = 'reference'
             # the collective baseline transport (one packed all-gather + all-reduce of the winners), eager
             from ips_b200.distributed import ips_sharded
             if name != 'slides_16x50k':
@@ -684,6 +694,23 @@ def run_ours(args):
                 rec = {'value': mw['value'], 'unit': 'patches/s', 'ms_per_step': mw['ms_per_step'], 'steps': k, 'warmup': 3,
                        'e2e': mw['e2e'], 'gpu_launches': mw['gpu_launches'], 'clocks': mw['clocks'],
                        'config': f"{w}: IPSNet.ips, B={mw['B']} N={mw['N']} M={mw['conf'].M} I={mw['conf'].I}", 'roofline': r}
+                if mw['N'] >= 5000:
+                    # long sequences: the reference's host-side randperm (0.4 ms for 50 000 patches) is longer than the
+                    # GPU work of the call, so the default configuration above is HOST bound; the same call with the scan
+                    # order drawn on the device (conf.scan_order_rng='device': a shuffle, but not the reference's random stream)
+                    net_w, x_w = mw['net'], mw['x']
+                    sub = {}
+                    for label, shuffle, rng in (('device_scan_order', True, 'device'), ('no_shuffle', False, 'reference')):
+                        net_w.shuffle, net_w.scan_order_rng = shuffle, rng
+                        for _ in range(3):
+                            net_w.ips(x_w)
+                        ms_d = bench.timed(lambda: net_w.ips(x_w), k) / k
+                        sub[label] = {'value': bench.world * mw['B'] * mw['N'] / (ms_d / 1e3), 'ms_per_step': ms_d}
+                    net_w.shuffle, net_w.scan_order_rng = True, 'reference'
+                    sub['note'] = ('value / ms_per_step above: default configuration = scan order drawn with the reference\'s host RNG calls '
+                                   '(torch.randperm on the CPU, then copied), which bounds the call; device_scan_order: conf.scan_order_rng='
+                                   '"device" (keyed bijection drawn on the GPU); no_shuffle: conf.shuffle=False')
+                    rec['scan_order_variants'] = sub
                 del mw
                 torch.cuda.empty_cache()
                 if 'library' not in skip:

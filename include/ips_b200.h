@@ -181,6 +181,29 @@ IPSB_API int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_
                      int B, int N, int H, int T, int M, int I,
                      int64_t* mem_pos, int64_t* mem_src, float* mem_score,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* Streamed form: zs (B,N,H*T) is already in SCAN order (ipsb_projector_logits_scan) -- no permuted copy -- and may still be
+ * being written on another stream: the loop waits (bounded) on tile_flags[(b N + pos) / tile_rows] before it reads a chunk.
+ * perm gives mem_src = perm[pos] (NULL: pos).  sync_words (2 ints, zeroed by the caller, or NULL): [0] is set when the
+ * loop's kernel is resident (gate the producer's launch on it with ipsb_wait_word so the producer does not take the SMs
+ * first), [1] != 0 afterwards means a wait ran out (producer missing).  Returns -2 without launching when the shape is
+ * outside the 8-CTA cluster kernel (M + I < 2048, H*T not a power of two, slices beyond shared memory): use
+ * ipsb_select_loop.  Same results as ipsb_select_loop on the same scan order, bit for bit. */
+IPSB_API int ipsb_select_loop_scan(const float* zs, const int64_t* perm, int64_t perm_batch_stride,
+                     int B, int N, int H, int T, int M, int I,
+                     int64_t* mem_pos, int64_t* mem_src, float* mem_score,
+                     void* workspace, int64_t workspace_bytes,
+                     const int* tile_flags, int tile_rows, int* sync_words, void* stream);
+IPSB_API int ipsb_wait_word(const int* word, void* stream);
+/* Scan order drawn on the device (the reference draws it on the host: randperm / rand().argsort, utils/utils.py:33-58; 0.4 ms
+ * of host time for 50 000 patches).  perm (rows, N) int64: row r = a keyed bijection of [0, N) -- eight rounds of xor /
+ * odd multiply mod 2^k / xor-shift on k = ceil(log2 N) bits with cycle walking -- for the key (key[0], key[1], r); key = two
+ * int64 in DEVICE memory (drawn from the CUDA generator by the caller).  Same distribution family as a shuffle, not the
+ * reference's random stream; oracle: ips_oracle.keyed_scan_order. */
+IPSB_API int ipsb_keyed_scan_order(const int64_t* key, int rows, int N, int64_t* perm, void* stream);
+/* Load the kernels of the streamed pair (loop, gate, projector) now: CUDA's lazy first-use loading of the producer could
+ * otherwise wait for the consumer that is already spinning on its flags.  Call once before the first streamed selection. */
+IPSB_API int ipsb_streamed_preload(void);
+IPSB_API int ipsb_projector_preload(void);
 
 /* ---------------------------------------------------------------- native encoder executor
  * One call = the whole eval-mode patch encoder + logit projection for `n_rows` patches
@@ -328,6 +351,17 @@ IPSB_API int ipsb_fold_plan(const ipsb_fold_item* items_dev, int n_items, int bl
  * Only the features (once) and 4*HT bytes per row of logits touch HBM. */
 IPSB_API int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
                                    int64_t rows, int K, int N, int HT, float eps, void* stream);
+/* Scan-order form, the producer half of the streamed selection (ips_net.py:200-241: the reference shuffles the bag, then
+ * embeds chunk after chunk inside the loop -- here the rows are READ through the shuffle and the loop runs beside the
+ * projector).  Row g of z is the logits of feature row (g / rows_per_batch) * rows_per_batch + perm[(g / rows_per_batch) *
+ * perm_batch_stride + g % rows_per_batch] (perm int64, NULL = identity; perm_batch_stride = rows_per_batch for
+ * per-instance orders, 0 for a shared one).  tile_flags (ceil(rows / 128) ints, zeroed by the caller, or NULL): flag t is
+ * set (release, device scope) once rows [128 t, 128 t + 128) of z are written; tiles are handed to the CTAs in rounds, so
+ * with all CTAs co-resident they complete in order.  max_ctas > 0 caps the grid (leaves SMs to the loop's cluster). */
+IPSB_API int ipsb_projector_logits_scan(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
+                                        int64_t rows, int K, int N, int HT, float eps,
+                                        const int64_t* perm, int64_t perm_batch_stride, int64_t rows_per_batch,
+                                        int* tile_flags, int max_ctas, void* stream);
 
 /* ---------------------------------------------------------------- per-launch timing of the native executor
  * (measurement only, bench.py's roofline; the reference's counterpart is the track_efficiency bracket,
@@ -383,6 +417,11 @@ IPSB_API int ipsb_peer_status(const ipsb_peer_ctx* ctx, int* status_out, void* s
 IPSB_API int ipsb_peer_push_candidates(const ipsb_peer_ctx* ctx, const float* z_local, int64_t n_local, const int64_t* cand,
                                        int B, int m, int HT, int64_t index_base, int64_t L, int64_t slot0,
                                        int64_t cz_off, int64_t ci_off, void* stream);
+/* Same, with the logits of candidate (b, j) read from row rows[b, j] of z_local instead of row cand[b, j] (a table kept in
+ * scan order by the streamed selection: rows = the winners' scan positions, cand = their original indices). */
+IPSB_API int ipsb_peer_push_candidates_rows(const ipsb_peer_ctx* ctx, const float* z_local, int64_t n_local, const int64_t* cand,
+                                            const int64_t* rows, int B, int m, int HT, int64_t index_base, int64_t L,
+                                            int64_t slot0, int64_t cz_off, int64_t ci_off, void* stream);
 /* This rank's slice (B, n_local, HT) of the logit table -> rows [row0, row0 + n_local) of every rank's full table
  * (B, N, HT) at byte offset z_off ('exact' mode: the loop is replicated); signals phase 0. */
 IPSB_API int ipsb_peer_push_logits(const ipsb_peer_ctx* ctx, const float* z_local, int B, int64_t n_local, int HT,

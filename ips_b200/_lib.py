@@ -113,12 +113,19 @@ SIGNATURES = {
     'ipsb_stage_patches_padded_split': [_ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr],
     'ipsb_fold_plan': [_ptr, _i32, _i32, _ptr],
     'ipsb_projector_logits': [_ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr],
+    'ipsb_projector_logits_scan': [_ptr, _i32, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr, _i64, _i64, _ptr, _i32, _ptr],
+    'ipsb_select_loop_scan': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i32, _ptr, _ptr],
+    'ipsb_wait_word': [_ptr, _ptr],
+    'ipsb_keyed_scan_order': [_ptr, _i32, _i32, _ptr, _ptr],
+    'ipsb_streamed_preload': [],
+    'ipsb_projector_preload': [],
     'ipsb_profile_begin': [_ptr],
     'ipsb_profile_end': [_i32, _ptr, _ptr, _ptr, ctypes.POINTER(_i32)],
     'ipsb_peer_export': [_ptr, _ptr, ctypes.POINTER(_i64)],
     'ipsb_peer_open': [_ptr, _i64, ctypes.POINTER(_ptr)],
     'ipsb_peer_close': [_ptr, _i64],
     'ipsb_peer_status': [ctypes.POINTER(PeerCtx), ctypes.POINTER(_i32), _ptr],
+    'ipsb_peer_push_candidates_rows': [ctypes.POINTER(PeerCtx), _ptr, _i64, _ptr, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _ptr],
     'ipsb_peer_push_candidates': [ctypes.POINTER(PeerCtx), _ptr, _i64, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _ptr],
     'ipsb_peer_push_logits': [ctypes.POINTER(PeerCtx), _ptr, _i32, _i64, _i32, _i64, _i64, _i64, _ptr],
     'ipsb_peer_allgather_small': [ctypes.POINTER(PeerCtx), _ptr, _i64, _i64, _i64, _i32, _ptr, _ptr],

@@ -74,6 +74,7 @@ __global__ void peer_wait_kernel(ipsb_peer_ctx c, int phase, long long budget_cl
 struct CandParams {
     const float* z_local; int64_t n_local; const int64_t* cand;
     int B, m, HT; int64_t index_base, L, slot0, cz_off, ci_off;
+    const int64_t* rows;      // row of z_local holding candidate (b, j)'s logits; null = cand (table in original order)
 };
 
 // one thread per (b, j): HT logits (<= 128 bytes) + one index to every rank
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) push_candidates_kernel(ipsb_peer_ctx c, C
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / p.m), j = (int)(i - (int64_t)b * p.m);
         const int64_t loc = p.cand[i];
-        const float* src = p.z_local + ((int64_t)b * p.n_local + loc) * p.HT;
+        const float* src = p.z_local + ((int64_t)b * p.n_local + (p.rows ? p.rows[i] : loc)) * p.HT;
         const int64_t dst_row = (int64_t)b * p.L + p.slot0 + j;
         float v[32];
 #pragma unroll 8
@@ -273,13 +274,19 @@ int ipsb_peer_status(const ipsb_peer_ctx* ctx, int* status_out, void* stream) {
 int ipsb_peer_push_candidates(const ipsb_peer_ctx* ctx, const float* z_local, int64_t n_local, const int64_t* cand,
                               int B, int m, int HT, int64_t index_base, int64_t L, int64_t slot0,
                               int64_t cz_off, int64_t ci_off, void* stream) {
+    return ipsb_peer_push_candidates_rows(ctx, z_local, n_local, cand, nullptr, B, m, HT, index_base, L, slot0, cz_off, ci_off, stream);
+}
+
+int ipsb_peer_push_candidates_rows(const ipsb_peer_ctx* ctx, const float* z_local, int64_t n_local, const int64_t* cand,
+                                   const int64_t* rows, int B, int m, int HT, int64_t index_base, int64_t L, int64_t slot0,
+                                   int64_t cz_off, int64_t ci_off, void* stream) {
     if (int rc = check_ctx(ctx)) return rc;
     IPSB_REQUIRE(z_local && cand && B > 0 && m > 0 && HT > 0 && HT <= 32, "peer_push_candidates: bad shape B=%d m=%d HT=%d", B, m, HT);
     IPSB_REQUIRE(slot0 >= 0 && slot0 + m <= L, "peer_push_candidates: slots [%lld, %lld) outside the %lld-entry list",
                  (long long)slot0, (long long)(slot0 + m), (long long)L);
     IPSB_REQUIRE(cz_off >= IPSB_PEER_HEADER_BYTES && ci_off >= IPSB_PEER_HEADER_BYTES && cz_off % 16 == 0 && ci_off % 8 == 0,
                  "peer_push_candidates: sections must lie behind the header, 16-byte aligned");
-    CandParams p{z_local, n_local, cand, B, m, HT, index_base, L, slot0, cz_off, ci_off};
+    CandParams p{z_local, n_local, cand, B, m, HT, index_base, L, slot0, cz_off, ci_off, rows};
     push_candidates_kernel<<<grid_for((int64_t)B * m, 256), 256, 0, (cudaStream_t)stream>>>(*ctx, p);
     IPSB_LAUNCH_CHECK();
     return 0;

@@ -508,6 +508,51 @@ struct ClusterScratch {
     Scratch red;
 };
 
+// ---- scan order drawn on the device (conf.scan_order_rng = 'device') ---------------------------------------------------
+// A keyed bijection of [0, N): eight rounds of (xor constant, multiply by an odd constant mod 2^k, xor-shift right) on the
+// k = ceil(log2 N) bit domain -- each step a bijection of the k-bit integers --, "cycle walking" (re-apply until the value
+// is below N) to restrict it to [0, N).  The 2 x 64-bit key comes from the CUDA generator (a device tensor: no host work,
+// capturable in a graph); round constants by splitmix64.  O(1) per element, no sort, no scratch.  The CPU restatement is
+// oracle.keyed_scan_order; statistical checks (positions uniform over keys, chunk membership) are in tests/.
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) keyed_scan_order_kernel(const int64_t* __restrict__ key, int rows, int N, int k,
+                                                               int64_t* __restrict__ perm) {
+    __shared__ uint32_t mul[8], add[8];
+    const int row = blockIdx.y;
+    if (threadIdx.x == 0) {
+        unsigned long long t = (unsigned long long)key[0] ^ splitmix64((unsigned long long)key[1] + (unsigned long long)row);
+        for (int r = 0; r < 8; ++r) {
+            t = splitmix64(t);
+            mul[r] = (uint32_t)(t >> 32) | 1u;
+            add[r] = (uint32_t)t;
+        }
+    }
+    __syncthreads();
+    const uint32_t mask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    const int h1 = (k + 1) / 2, h2 = k / 3 + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i;
+        if (N > 1) {
+            do {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    x ^= add[r] & mask;
+                    x = (x * mul[r]) & mask;
+                    x ^= x >> ((r & 1) ? h2 : h1);
+                }
+            } while (x >= (uint32_t)N);
+        }
+        perm[(int64_t)row * N + i] = (int64_t)x;
+    }
+}
+
 // zs[b, pos, :] = z[b, perm[pos], :], srcs[b, pos] = perm[pos]
 __global__ void permute_logits_kernel(const float* __restrict__ z, const int64_t* __restrict__ perm, int64_t perm_stride,
                                       int N, int HT, float* __restrict__ zs, int* __restrict__ srcs, int64_t total) {
@@ -531,7 +576,32 @@ struct ClusterArgs {
     uint32_t* m_key;      // (B, M)
     unsigned long long* m_runs;   // (B, NC * ceil(M / NC)) sorted runs of the final ordering
     int slice_cap;
+    // streamed form (ipsb_select_loop_scan): `zs` is the caller's table, already in scan order and possibly still being
+    // written by the projector kernel running next to this one; srcs == null -> table row = perm[pos] (or pos)
+    const int64_t* perm;          // (1 | B, N) scan order or null
+    int64_t perm_stride;
+    const int* tile_flags;        // [ceil(B N / tile_rows)]: != 0 once rows [t tile_rows, (t+1) tile_rows) of zs are written; or null
+    int tile_rows;
+    int* sync_words;              // [0]: set to 1 when cluster 0 is resident; [1]: != 0 if a wait ran out
 };
+
+// rows [g0, g1) of the flat (B N) scan-order table are needed: wait for their tiles (bounded: a producer that never
+// comes must not hang the device; the status word tells)
+__device__ __forceinline__ void wait_tiles(const ClusterArgs& a, int64_t g0, int64_t g1) {
+    if (a.tile_flags == nullptr || g1 <= g0) return;
+    const int t0 = (int)(g0 / a.tile_rows), t1 = (int)((g1 - 1) / a.tile_rows);
+    for (int t = t0 + (int)threadIdx.x; t <= t1; t += (int)blockDim.x) {
+        const int* f = a.tile_flags + t;
+        int v = 0;
+        for (long long spin = 0; spin < (1ll << 21); ++spin) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v != 0) break;
+            __nanosleep(64);
+        }
+        if (v == 0) atomicExch(a.sync_words + 1, 1);
+    }
+    __syncthreads();
+}
 
 template <int NC>
 __global__ void __cluster_dims__(NC, 1, 1) __launch_bounds__(512, 1)
@@ -552,7 +622,12 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
     uint32_t* allkey = reinterpret_cast<uint32_t*>(cs + 1);             // [M] final ordering
 
     const float* zs = a.zs + (int64_t)b * p.N * HT;
-    const int* srcs = a.srcs + (int64_t)b * p.N;
+    const int* srcs = a.srcs ? a.srcs + (int64_t)b * p.N : nullptr;
+    const int64_t* perm = a.perm ? a.perm + (int64_t)b * a.perm_stride : nullptr;
+    auto src_of = [&](int pos) { return srcs ? srcs[pos] : (perm ? (int)perm[pos] : pos); };
+    if (a.sync_words && blockIdx.x == 0 && tid == 0) {       // tells the host-side gate that this kernel holds its SMs
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sync_words), "r"(1) : "memory");
+    }
     float* z_buf[2] = {a.m_z + (int64_t)b * 2 * M * HT, a.m_z + (int64_t)b * 2 * M * HT + (int64_t)M * HT};
     int* pos_buf[2] = {a.m_pos + (int64_t)b * 2 * M, a.m_pos + (int64_t)b * 2 * M + M};
     int* src_buf[2] = {a.m_src + (int64_t)b * 2 * M, a.m_src + (int64_t)b * 2 * M + M};
@@ -560,8 +635,9 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
     auto csync = [&]() { if (NC == 1) __syncthreads(); else cluster.sync(); };
 
     // initial memory buffer: the first M scan positions
-    for (int i = cr * NT + tid; i < M * HT; i += NC * NT) z_buf[0][i] = zs[i];
-    for (int r = cr * NT + tid; r < M; r += NC * NT) { pos_buf[0][r] = r; src_buf[0][r] = srcs[r]; }
+    wait_tiles(a, (int64_t)b * p.N, (int64_t)b * p.N + M);
+    for (int i = cr * NT + tid; i < M * HT; i += NC * NT) z_buf[0][i] = __ldcg(zs + i);
+    for (int r = cr * NT + tid; r < M; r += NC * NT) { pos_buf[0][r] = r; src_buf[0][r] = src_of(r); }
     __threadfence();
     csync();
 
@@ -576,7 +652,10 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
         const int S = (L + NC - 1) / NC;                     // slice length
         const int l0 = cr * S;
         const int n_own = max(0, min(S, L - l0));
-        // ---- this slice's logits / positions / rows -> shared memory (coalesced 128-bit streams, 4 loads in flight)
+        // ---- this slice's logits / positions / rows -> shared memory (coalesced 128-bit streams, 4 loads in flight;
+        //      L2-coherent loads: the survivors were written by the other CTAs of the cluster one iteration ago and the
+        //      new rows possibly by the projector kernel a moment ago)
+        wait_tiles(a, (int64_t)b * p.N + lo, (int64_t)b * p.N + hi);
         {
             const int hv = HT >> 2;                              // float4 granules per row (HT is a power of two >= 4) or 0
             if (hv > 0) {
@@ -590,7 +669,7 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
                         if (e < total4) {
                             const int i = e / hv, c4 = e - i * hv, l = l0 + i;
                             const float* src_row = (l < M) ? z_buf[cur] + (int64_t)l * HT : zs + (int64_t)(lo + l - M) * HT;
-                            v4[u] = __ldg(reinterpret_cast<const float4*>(src_row) + c4);
+                            v4[u] = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
                         }
                     }
 #pragma unroll
@@ -602,14 +681,14 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
             } else {
                 for (int e = tid; e < n_own * HT; e += NT) {
                     const int i = e / HT, c = e - i * HT, l = l0 + i;
-                    zl[e] = (l < M) ? z_buf[cur][(int64_t)l * HT + c] : zs[(int64_t)(lo + l - M) * HT + c];
+                    zl[e] = __ldcg((l < M) ? z_buf[cur] + (int64_t)l * HT + c : zs + (int64_t)(lo + l - M) * HT + c);
                 }
             }
         }
         for (int i = tid; i < n_own; i += NT) {
             const int l = l0 + i;
-            if (l < M) { posl[i] = pos_buf[cur][l]; cand[i] = src_buf[cur][l]; }
-            else { posl[i] = lo + (l - M); cand[i] = srcs[lo + (l - M)]; }
+            if (l < M) { posl[i] = __ldcg(pos_buf[cur] + l); cand[i] = __ldcg(src_buf[cur] + l); }
+            else { posl[i] = lo + (l - M); cand[i] = src_of(lo + (l - M)); }
         }
         if (tid < 256) { cs->hist[0][tid] = 0; cs->hist[1][tid] = 0; cs->hist[2][tid] = 0; cs->hist[3][tid] = 0; }
         __syncthreads();
@@ -776,7 +855,7 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
         const int pad = next_pow2(Sm);
         unsigned long long* run = reinterpret_cast<unsigned long long*>(smem_raw);           // [pad] (aliases zl: free now)
         for (int r = tid; r < pad; r += NT)
-            run[r] = (r < n_mine) ? (((unsigned long long)key_buf[j0 + r] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(j0 + r))) : 0ull;
+            run[r] = (r < n_mine) ? (((unsigned long long)__ldcg(key_buf + j0 + r) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(j0 + r))) : 0ull;
         __syncthreads();
         bitonic_desc(run, pad);
         unsigned long long* g_runs = a.m_runs + (int64_t)b * NC * Sm;
@@ -808,8 +887,8 @@ select_loop_cluster_kernel(LoopParams p, ClusterArgs a) {
                 }
             }
             const int j = (int)key_pos(K);
-            p.out_pos[(int64_t)b * M + rank] = pos_buf[cur][j];
-            p.out_src[(int64_t)b * M + rank] = src_buf[cur][j];
+            p.out_pos[(int64_t)b * M + rank] = __ldcg(pos_buf[cur] + j);
+            p.out_src[(int64_t)b * M + rank] = __ldcg(src_buf[cur] + j);
             if (p.out_score) p.out_score[(int64_t)b * M + rank] = order_bits_inv((uint32_t)(K >> 32));
         }
     }
@@ -981,8 +1060,16 @@ __global__ void __launch_bounds__(NT, 1) select_loop_small_kernel(LoopParams p, 
     }
 }
 
+// table already in scan order (ipsb_select_loop_scan): no permuted copy; optional tile flags / residency word
+struct ScanArgs {
+    const int* tile_flags;
+    int tile_rows;
+    int* sync_words;
+};
+
 template <int NC>
-int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+                   const ScanArgs* scan = nullptr) {
     const int HT = p.H * p.T, M = p.M, N = p.N;
     const int cap = (Lmax + NC - 1) / NC;
     const int Sm = (M + NC - 1) / NC;
@@ -1004,12 +1091,18 @@ int launch_cluster(const LoopParams& p, int B, int Lmax, void* workspace, int64_
     a.m_key = (uint32_t*)take((size_t)B * M * 4);
     a.m_runs = (unsigned long long*)take((size_t)B * (M + 16) * 8);
     a.zs = zs; a.srcs = srcs; a.slice_cap = cap;
-    const int64_t total = (int64_t)B * N * HT;
-    int64_t g = (total + 255) / 256;
-    if (g > (int64_t)ipsb::sm_count() * 8) g = (int64_t)ipsb::sm_count() * 8;
-    permute_logits_kernel<<<(unsigned)g, 256, 0, st>>>(p.z, p.perm, p.perm_stride, N, HT, zs, srcs, total);
-    IPSB_LAUNCH_CHECK();
-    if (NC == 1 && Lmax <= 128 && getenv("IPSB_SELECT_NO_SMALL") == nullptr) {       // tiny buffers: shared-memory resident loop
+    a.perm = nullptr; a.perm_stride = 0; a.tile_flags = nullptr; a.tile_rows = 1; a.sync_words = nullptr;
+    if (scan) {
+        a.zs = p.z; a.srcs = nullptr; a.perm = p.perm; a.perm_stride = p.perm_stride;
+        a.tile_flags = scan->tile_flags; a.tile_rows = scan->tile_rows; a.sync_words = scan->sync_words;
+    } else {
+        const int64_t total = (int64_t)B * N * HT;
+        int64_t g = (total + 255) / 256;
+        if (g > (int64_t)ipsb::sm_count() * 8) g = (int64_t)ipsb::sm_count() * 8;
+        permute_logits_kernel<<<(unsigned)g, 256, 0, st>>>(p.z, p.perm, p.perm_stride, N, HT, zs, srcs, total);
+        IPSB_LAUNCH_CHECK();
+    }
+    if (NC == 1 && !scan && Lmax <= 128 && getenv("IPSB_SELECT_NO_SMALL") == nullptr) {       // tiny buffers: shared-memory resident loop
         const int Lcap = (Lmax + 3) / 4 * 4;
         const size_t sm_small = (size_t)Lcap * HT * 8 + (size_t)Lcap * 4 * 4 + ((size_t)Lcap + 4) * 4 + (size_t)Lcap * 4 +
                                 sizeof(SmallScratch) + 64;
@@ -1233,6 +1326,66 @@ int ipsb_select_loop(const float* z, const int64_t* perm, int64_t perm_batch_str
     IPSB_REQUIRE(smem <= 227 * 1024, "select_loop: %zu bytes of shared memory needed (M=%d I=%d)", smem, M, I);
     IPSB_CUDA(cudaFuncSetAttribute(select_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_loop_kernel<<<B, Lpad <= 512 ? 256 : 1024, smem, (cudaStream_t)stream>>>(p);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Streamed form of ipsb_select_loop for the feature-bag path: `zs` (B, N, H*T) is ALREADY in scan order (the projector
+// kernel gathers its rows through the same `perm`), so no permuted copy is made, and it may still be being written:
+// tile_flags[t] != 0 <=> rows [t * tile_rows, (t + 1) * tile_rows) of the flat (B N) table are complete (set by
+// ipsb_projector_logits_scan running on another stream); sync_words[0] is set when the loop's cluster is resident (gate
+// for the producer's launch: ipsb_wait_word), sync_words[1] != 0 reports a wait that ran out.  tile_flags / sync_words may
+// be null (table complete).  Returns -2 when the shape is outside the 8-CTA cluster kernel (caller uses ipsb_select_loop).
+int ipsb_select_loop_scan(const float* zs, const int64_t* perm, int64_t perm_batch_stride,
+                          int B, int N, int H, int T, int M, int I,
+                          int64_t* mem_pos, int64_t* mem_src, float* mem_score,
+                          void* workspace, int64_t workspace_bytes,
+                          const int* tile_flags, int tile_rows, int* sync_words, void* stream) {
+    IPSB_REQUIRE(B > 0 && N > 0 && M > 0 && I > 0 && H > 0 && T > 0 && M < N, "select_loop_scan: bad shape");
+    IPSB_REQUIRE(H * T <= kMaxHT, "select_loop_scan: H*T=%d exceeds %d", H * T, kMaxHT);
+    IPSB_REQUIRE(tile_flags == nullptr || tile_rows > 0, "select_loop_scan: tile_rows");
+    const int Lmax = M + (I < N - M ? I : N - M);
+    const bool ht_pow2 = ((H * T) & (H * T - 1)) == 0;
+    if (!ht_pow2 || Lmax < 2048 || workspace == nullptr) return -2;
+    LoopParams p{zs, perm, perm_batch_stride, N, H, T, M, I, mem_pos, mem_src, mem_score};
+    ScanArgs sc{tile_flags, tile_rows, sync_words};
+    const int rc = launch_cluster<8>(p, B, Lmax, workspace, workspace_bytes, (cudaStream_t)stream, &sc);
+    return rc < 0 ? -2 : rc;
+}
+
+// one thread waits (bounded) until *word != 0: orders a launch behind "the other stream's kernel is resident"
+__global__ void wait_word_kernel(const int* word) {
+    int v = 0;
+    for (long long spin = 0; spin < (1ll << 22); ++spin) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+        if (v != 0) break;
+        __nanosleep(32);
+    }
+}
+// perm (rows, N) int64: row r = the keyed bijection of [0, N) for key (key[0], key[1], r); key = two int64 on the device
+int ipsb_keyed_scan_order(const int64_t* key, int rows, int N, int64_t* perm, void* stream) {
+    IPSB_REQUIRE(key && perm && rows > 0 && N > 0, "keyed_scan_order: bad argument");
+    int k = 1;
+    while (k < 31 && (1ll << k) < (long long)N) ++k;
+    int gx = (N + 255) / 256;
+    if (gx > 4 * ipsb::sm_count()) gx = 4 * ipsb::sm_count();
+    keyed_scan_order_kernel<<<dim3((unsigned)gx, (unsigned)rows), 256, 0, (cudaStream_t)stream>>>(key, rows, N, k, perm);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// CUDA loads kernels lazily, and the first load of a function can wait for running kernels: a loop already spinning on
+// the producer's flags would then wait for a producer whose load waits for the loop.  Called once, before the first
+// streamed selection, this loads every kernel of the pair while the device is idle.
+int ipsb_streamed_preload(void) {
+    cudaFuncAttributes fa;
+    IPSB_CUDA(cudaFuncGetAttributes(&fa, wait_word_kernel));
+    IPSB_CUDA(cudaFuncGetAttributes(&fa, select_loop_cluster_kernel<8>));
+    return ipsb_projector_preload();
+}
+int ipsb_wait_word(const int* word, void* stream) {
+    IPSB_REQUIRE(word != nullptr, "wait_word: null");
+    wait_word_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(word);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

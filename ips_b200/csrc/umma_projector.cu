@@ -50,6 +50,11 @@ struct ProjParams {
     int K, N, HT, KS, halves; // KS = K / 64, halves = N / 256
     int tiles;
     float eps;
+    // scan-order form: tile row g of the flat (batches x rows_per_batch) sequence reads feature row
+    // (g / rows_per_batch) * rows_per_batch + perm[(g / rows_per_batch) * perm_stride + g % rows_per_batch]; z stays in tile order
+    const int64_t* perm;
+    int64_t perm_stride, rows_per_batch;
+    int* tile_flags;          // [tiles] set to 1 (release) once a tile's logits are in z, or null
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -176,24 +181,37 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
         // divisions in the loop): pointer to this thread's chunk of row (16 cw + sub) of the stream's tile at its k block,
         // the k block index inside the tile, and which of the thread's four rows exist (ragged last tile).
         const int esz = IN_BF16 ? 2 : 4;
-        const int64_t row_step = 4 * (int64_t)p.K * esz;         // bytes between the thread's consecutive rows (4 rows apart)
+        const int64_t row_bytes = (int64_t)p.K * esz;
+        const char* const ld_base = reinterpret_cast<const char*>(p.x) + chunk * 8 * esz;
         int ld_t = 0, ld_kb = 0;
         uint32_t ld_issued = 0;
-        const char* ld_ptr = nullptr;
-        int ld_rows = 0;                                         // number of this thread's rows (0..4) inside the tensor
+        const char* ld_ptr = ld_base;                            // ld_base + k block offset
+        int ld_row[4];                                           // feature rows of this thread's four tile rows (-1: outside)
         auto ld_enter_tile = [&]() {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)ld_t * gridDim.x;
-            const int64_t row0 = tile * TILE_M + cw * 16 + sub;
-            ld_ptr = reinterpret_cast<const char*>(p.x) + (row0 * p.K + chunk * 8) * esz;
-            const int64_t left = p.rows - row0;                  // rows row0, row0 + 4, row0 + 8, row0 + 12
-            ld_rows = left <= 0 ? 0 : (left > 12 ? 4 : (int)((left + 3) / 4));
+            const int64_t g0 = tile * TILE_M + cw * 16 + sub;    // tile rows g0, g0 + 4, g0 + 8, g0 + 12
+            ld_ptr = ld_base;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t g = g0 + 4 * j;
+                int r = -1;
+                if (g < p.rows) {
+                    if (p.perm) {
+                        const int64_t bb = g / p.rows_per_batch, s = g - bb * p.rows_per_batch;
+                        r = (int)(bb * p.rows_per_batch + __ldg(p.perm + bb * p.perm_stride + s));
+                    } else {
+                        r = (int)g;
+                    }
+                }
+                ld_row[j] = r;
+            }
         };
         ld_enter_tile();
         // quarter J of the stream's current k block: one 256-bit (fp32) / 128-bit (bf16) load
         auto load = [&](const int J, float (&buf)[8]) {
             if (ld_issued < total_q) {
-                if (J < ld_rows) {
-                    const char* src = ld_ptr + J * row_step;
+                if (ld_row[J] >= 0) {
+                    const char* src = ld_ptr + (int64_t)ld_row[J] * row_bytes;
                     if (IN_BF16) {
                         const int4 qv = ipsb::ld_stream16(src);
                         const uint32_t u[4] = {(uint32_t)qv.x, (uint32_t)qv.y, (uint32_t)qv.z, (uint32_t)qv.w};
@@ -312,6 +330,11 @@ projector_logits_kernel(const __grid_constant__ CUtensorMap tmW, const ProjParam
                             if (j < p.HT) dst[j] = r[j];
                     }
                 }
+                if (p.tile_flags) {                              // publish the tile to the selection loop running beside us
+                    __threadfence();
+                    umma::named_bar_sync(2, N_WORKERS / 2);
+                    if (erow == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_flags + tile), "r"(1) : "memory");
+                }
             }
         };
         float b0[8], b1[8], b2[8], b3[8], b4[8], b5[8], b6[8], b7[8];
@@ -355,9 +378,25 @@ EncodeTiledFn encode_fn() {
 
 extern "C" {
 
+int ipsb_projector_preload(void) {
+    cudaFuncAttributes fa;
+    IPSB_CUDA(cudaFuncGetAttributes(&fa, projector_logits_kernel<true>));
+    IPSB_CUDA(cudaFuncGetAttributes(&fa, projector_logits_kernel<false>));
+    return 0;
+}
+
 int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
                           int64_t rows, int K, int N, int HT, float eps, void* stream) {
+    return ipsb_projector_logits_scan(x, x_is_bf16, w_bf16, table, z, rows, K, N, HT, eps, nullptr, 0, rows, nullptr, 0, stream);
+}
+
+int ipsb_projector_logits_scan(const void* x, int x_is_bf16, const void* w_bf16, const float* table, float* z,
+                               int64_t rows, int K, int N, int HT, float eps,
+                               const int64_t* perm, int64_t perm_batch_stride, int64_t rows_per_batch,
+                               int* tile_flags, int max_ctas, void* stream) {
     IPSB_REQUIRE(x && w_bf16 && table && z && rows > 0, "projector_logits: null argument");
+    IPSB_REQUIRE(rows < (1ll << 31), "projector_logits: %lld rows", (long long)rows);
+    IPSB_REQUIRE(perm == nullptr || (rows_per_batch > 0 && rows % rows_per_batch == 0), "projector_logits: rows_per_batch");
     IPSB_REQUIRE(K % (2 * BK) == 0 && K >= 4 * BK, "projector_logits: K=%d must be a multiple of %d, at least %d", K, 2 * BK, 4 * BK);
     IPSB_REQUIRE(N == 256 || N == 512, "projector_logits: N=%d (256 or 512 supported: the 128 x N tile lives in TMEM)", N);
     IPSB_REQUIRE(HT >= 1 && HT <= HTP, "projector_logits: H*T=%d exceeds %d", HT, HTP);
@@ -380,10 +419,14 @@ int ipsb_projector_logits(const void* x, int x_is_bf16, const void* w_bf16, cons
     p.x = x; p.table = table; p.z = z; p.rows = rows; p.K = K; p.N = N; p.HT = HT; p.KS = K / BK; p.halves = N / 256;
     p.tiles = (int)((rows + TILE_M - 1) / TILE_M);
     p.eps = eps;
+    p.perm = perm; p.perm_stride = perm_batch_stride; p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : rows;
+    p.tile_flags = tile_flags;
     const size_t smem = 1024 + (size_t)SA * A_BYTES + (size_t)SW * W_BYTES + (size_t)N * 48 + TILE_M * 8 + 2 * TILE_M * HTP * 4 +
                         8 * (2 * SW + 2 * SA + 2) + 64;
     IPSB_REQUIRE(smem <= 227 * 1024, "projector_logits: %zu bytes of shared memory", smem);
-    const int grid = p.tiles < ipsb::sm_count() ? p.tiles : ipsb::sm_count();
+    int grid = ipsb::sm_count();
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;       // the selection loop's cluster keeps its SMs
+    if (p.tiles < grid) grid = p.tiles;
     if (x_is_bf16) {
         auto kern = projector_logits_kernel<true>;
         IPSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

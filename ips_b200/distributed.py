@@ -251,10 +251,21 @@ class ShardedIPS:
             self.z = self.ex.view(self.z_off, (self.B, self.N, self.HT), torch.float32)
         self.graph = None
         self.bytes_pushed_per_call = 0          # filled by the first call: payload bytes this rank stores into OTHER ranks
+        # conf.scan_order_rng == 'device': the scan order is drawn on the GPU inside the call (part of the captured graph).
+        # 'exact' mode needs the SAME order on every rank: a dedicated generator per rank, seeded with one broadcast seed,
+        # draws it locally -- no exchange.  'merge' shuffles each slice independently (default CUDA generator).
+        self._gen = None
+        if mode == 'exact' and net.shuffle and getattr(net, 'scan_order_rng', 'reference') == 'device':
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(net.device)
+            dist.broadcast(seed, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self._gen = torch.Generator(device=net.device)
+            self._gen.manual_seed(int(seed.item()))
 
     # ---- scan order (host side, outside any graph) ---------------------------------------------------------
     def _draw_order(self):
         net, dev = self.net, self.net.device
+        if net.shuffle and getattr(net, 'scan_order_rng', 'reference') == 'device':
+            return 'device', False                    # drawn inside _run
         if self.mode == 'merge':                      # every rank shuffles its own slice (block-wise shuffle)
             perm, per_inst = local_scan_order(net, self.B, self.hi - self.lo, torch.device('cpu'))
             return (None if perm is None else perm.to(dev, non_blocking=True).contiguous()), per_inst
@@ -265,8 +276,28 @@ class ShardedIPS:
         from . import ops
         net, ca, ctx = self.net, self.net.transf.crs_attn, self.ex.ctx
         M = self.M
-        z_local = net.patch_logits(local_patches, pos_offset=self.lo)                  # (B, n, HT), true positions
-        if self.mode == 'merge':
+        n = self.hi - self.lo
+        plan = net._get_plan()
+        if isinstance(perm, str):                     # device-side scan order (see __init__)
+            from .utils import scan_order
+            perm, per_inst = scan_order(True, net.shuffle_style, self.B, n if self.mode == 'merge' else self.N, None,
+                                        'device', net.device, self._gen)
+            perm = None if perm is None else perm.contiguous()
+        if (self.mode == 'merge' and net.streamed_select and not net.is_image and plan.get('p_table') is not None
+                and ops.streamed_select_ok(self.B, n, ca.H * ca.n_token, M, net.I)):
+            # projector and local loop side by side (ops.projector_select); the logit table stays in scan order
+            pos, cand, _, zs, _ = ops.projector_select(local_patches.reshape(self.B * n, -1), plan['p_w'], plan['p_table'],
+                                                       self.B, n, perm, per_inst, ca.H, ca.n_token, M, net.I)
+            ops.peer_push_candidates(ctx, zs, cand, self.lo, self.L, self.rank * M, self.cz_off, self.ci_off, rows=pos)
+            ops.peer_wait(ctx, 0)
+            win = ops.merge_candidates(self.cz, ca.H, ca.n_token, M)
+            ci = self.ci
+            z_local = None
+        else:
+            z_local = net.patch_logits(local_patches, pos_offset=self.lo)              # (B, n, HT), true positions
+        if z_local is None:
+            pass
+        elif self.mode == 'merge':
             cand = ops.select_loop(z_local.contiguous(), perm, per_inst, ca.H, ca.n_token, M, net.I)[1]   # local, best first
             ops.peer_push_candidates(ctx, z_local, cand, self.lo, self.L, self.rank * M, self.cz_off, self.ci_off)
             ops.peer_wait(ctx, 0)
@@ -307,7 +338,7 @@ class ShardedIPS:
             return self._result(self._run(local_patches, perm, per_inst))
         if local_patches.data_ptr() != self._g_in.data_ptr():     # (fill `static_input` in place to avoid this copy)
             self._g_in.copy_(local_patches, non_blocking=True)
-        if perm is not None:
+        if perm is not None and not isinstance(perm, str):
             self._g_perm.copy_(perm, non_blocking=True)
         self.graph.replay()
         return self._result(self._g_pos)
@@ -324,11 +355,13 @@ class ShardedIPS:
         self._check(local_patches)
         perm, per_inst = self._draw_order()
         self._g_in = local_patches.clone()
-        self._g_perm, self._g_inst = (None if perm is None else perm.clone()), per_inst
+        self._g_perm, self._g_inst = (perm if (perm is None or isinstance(perm, str)) else perm.clone()), per_inst
         self._run(self._g_in, self._g_perm, per_inst)                     # warm-up: plans, workspaces, function attributes
         torch.cuda.synchronize(self.net.device)
         dist.barrier(group=self.group)
         g = torch.cuda.CUDAGraph()
+        if self._gen is not None:
+            g.register_generator_state(self._gen)
         side = torch.cuda.Stream(device=self.net.device)
         side.wait_stream(torch.cuda.current_stream(self.net.device))
         with torch.cuda.stream(side):

@@ -167,6 +167,13 @@ class IPSNet(nn.Module):
         # 'native': one C++ call runs the whole encoder; 'python': one library call per layer (per-kernel timing)
         self.executor = os.environ.get('IPS_B200_EXECUTOR', 'native')
         self._ws_cache = {}
+        # feature bags: run the projector kernel and the selection loop side by side (ops.projector_select); False = one
+        # after the other through the original-order logit table
+        self.streamed_select = os.environ.get('IPS_B200_STREAMED_SELECT', '1') != '0' and getattr(conf, 'streamed_select', True)
+        self.last_stream_status = None
+        # 'reference': the scan order is drawn with the reference's RNG calls (CPU randperm: seeds reproduce its order);
+        # 'device': drawn on the GPU (same distribution, other stream; no host work, capturable in a CUDA graph)
+        self.scan_order_rng = os.environ.get('IPS_B200_SCAN_ORDER_RNG', getattr(conf, 'scan_order_rng', 'reference'))
         # lazy loading (`eager: False`): host inputs up to this size also keep a device copy for the final gather; larger
         # ones stream through a three-chunk ring so device memory stays O(chunk), independent of N
         self.lazy_resident_bytes = int(os.environ.get('IPS_B200_LAZY_RESIDENT_BYTES', getattr(conf, 'lazy_resident_bytes', 8 << 30)))
@@ -637,7 +644,7 @@ class IPSNet(nn.Module):
         if torch.device(device).type != 'cuda':
             raise RuntimeError('ips_b200.IPSNet.ips needs a CUDA device: there is no CPU implementation')
 
-        perm, per_inst = scan_order(self.shuffle, self.shuffle_style, B, N, patches.device)
+        perm, per_inst = scan_order(self.shuffle, self.shuffle_style, B, N, patches.device, self.scan_order_rng, device)
         if perm is not None:
             perm = perm.to(device).contiguous()
 
@@ -647,8 +654,19 @@ class IPSNet(nn.Module):
             if dev_copy is not None:
                 patches = dev_copy
         else:
-            z = self.patch_logits(patches)                        # encode + project every patch once
-        _, mem_src, _ = ops.select_loop(z, perm, per_inst, ca.H, ca.n_token, M, I)
+            z = None
+            if not self.is_image and patches.dtype in (torch.float32, torch.bfloat16) and self.streamed_select:
+                plan = self._get_plan()
+                if plan.get('p_table') is not None and ops.streamed_select_ok(B, N, ca.H * ca.n_token, M, I):
+                    # projector and selection loop side by side: the loop consumes the scan-ordered logits tile by tile
+                    _, mem_src, _, _, self.last_stream_status = ops.projector_select(
+                        patches.reshape(B * N, -1).contiguous(), plan['p_w'], plan['p_table'], B, N, perm, per_inst,
+                        ca.H, ca.n_token, M, I)
+                    z = False
+            if z is None:
+                z = self.patch_logits(patches)                    # encode + project every patch once
+        if z is not False:
+            _, mem_src, _ = ops.select_loop(z, perm, per_inst, ca.H, ca.n_token, M, I)
         self.last_mem_idx = mem_src
 
         o_patch, o_pos = self._out_views(out, row_offset, B, M)
@@ -701,7 +719,7 @@ class IPSNet(nn.Module):
                   and plan['stem']['cout'] == 64 and M < N)
         if not direct:                                            # other modes: patchify on the device, then the usual path
             return self.ips(ops.gather_patches_image(images, geo, None, (ph, pw)), out=out, row_offset=row_offset)
-        perm, per_inst = scan_order(self.shuffle, self.shuffle_style, B, N, images.device)
+        perm, per_inst = scan_order(self.shuffle, self.shuffle_style, B, N, images.device, self.scan_order_rng, self.device)
         if perm is not None:
             perm = perm.to(self.device).contiguous()
         ca = self.transf.crs_attn

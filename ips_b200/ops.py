@@ -6,6 +6,7 @@ entry points are also registered as PyTorch custom ops under ``torch.ops.ips_b20
 (see the bottom of the file).  No function here has a non-CUDA implementation.
 """
 import ctypes
+import os
 
 import torch
 
@@ -516,6 +517,91 @@ def select_loop(z, perm, per_instance, H, T, M, I):
     return mem_pos, mem_src, score
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the producer half of the streamed selection."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+def streamed_select_ok(B, N, HT, M, I):
+    """Shapes the streamed selection (`projector_select`) covers: the 8-CTA cluster loop (M + I >= 2048 entries whose
+    slices fit shared memory, H*T a power of two)."""
+    Lmax = M + min(I, N - M)
+    if M >= N or Lmax < 2048 or (HT & (HT - 1)) != 0:
+        return False
+    cap, Sm = -(-Lmax // 8), -(-M // 8)
+    front = max(cap * (HT + 3) * 4, (1 << max(Sm - 1, 0).bit_length()) * 8)
+    return front + 8 * Sm * 8 + 12 * 1024 <= 200 * 1024
+
+
+def projector_select(x, w_bf16, table, B, N, perm, per_instance, H, T, M, I, eps=1e-5, overlap=None):
+    """Feature bag (B*N, K) -> the IPS winners, projector and selection loop running SIDE BY SIDE (ips_net.py:200-241: the
+    reference embeds chunk i inside iteration i; here the projector kernel reads the rows through the scan order `perm`,
+    publishes every 128-row tile of scan-ordered logits with a flag, and the loop's cluster -- launched first, on 8 SMs per
+    bag -- consumes the chunks as they complete).  With `overlap=False` (or more than two bags: the loop's clusters would
+    take the SMs the projector needs) the two kernels run back to back on the caller's stream; either way no permuted copy
+    of the logit table is made.  Returns (mem_pos, mem_src, score, zs, status): zs (B, N, H*T) in scan order, status = the
+    loop's two sync words (status[1] != 0: a wait ran out) or None."""
+    global LAUNCHES
+    _chk(x, x.dtype, 'x'); _chk(w_bf16, torch.bfloat16, 'w'); _chk(table, torch.float32, 'table'); _chk(perm, torch.int64, 'perm')
+    HT = H * T
+    rows, K = x.shape
+    assert rows == B * N and streamed_select_ok(B, N, HT, M, I)
+    dev = x.device
+    lib = _lib.load()
+    if overlap is None:
+        overlap = B <= 2 and os.environ.get('IPSB_NO_STREAMED_OVERLAP') is None
+    if overlap and not _SIDE.get(('preloaded', dev.index)):
+        _lib.check(lib.ipsb_streamed_preload())
+        _SIDE[('preloaded', dev.index)] = True
+    zs = torch.empty((B, N, HT), dtype=torch.float32, device=dev)
+    mem_pos = torch.empty((B, M), dtype=torch.int64, device=dev)
+    mem_src = torch.empty((B, M), dtype=torch.int64, device=dev)
+    score = torch.empty((B, M), dtype=torch.float32, device=dev)
+    need = lib.ipsb_select_loop_workspace_bytes(B, N, HT, M)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    pstride = N if (perm is not None and per_instance) else 0
+    is_bf16 = int(x.dtype == torch.bfloat16)
+    Nw = w_bf16.shape[0]
+    if not overlap:
+        _call('ipsb_projector_logits_scan', _p(x), is_bf16, _p(w_bf16), _p(table), _p(zs), rows, K, Nw, HT, eps,
+              _p(perm), pstride, N, None, 0, _stream())
+        rc = lib.ipsb_select_loop_scan(_p(zs), _p(perm), pstride, B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score),
+                                       _p(ws), need, None, 128, None, _stream())
+        _lib.check(rc)
+        LAUNCHES += 1
+        return mem_pos, mem_src, score, zs, None
+    tiles = -(-rows // 128)
+    words = torch.zeros(tiles + 2, dtype=torch.int32, device=dev)          # [0:2] sync words, [2:] tile flags
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)                                                 # flags zeroed, inputs ready
+    rc = lib.ipsb_select_loop_scan(_p(zs), _p(perm), pstride, B, N, H, T, M, I, _p(mem_pos), _p(mem_src), _p(score),
+                                   _p(ws), need, words.data_ptr() + 8, 128, _p(words), _stream())
+    _lib.check(rc)
+    with torch.cuda.stream(side):
+        _call('ipsb_wait_word', _p(words), _stream())                      # the loop's cluster holds its SMs
+        _call('ipsb_projector_logits_scan', _p(x), is_bf16, _p(w_bf16), _p(table), _p(zs), rows, K, Nw, HT, eps,
+              _p(perm), pstride, N, words.data_ptr() + 8, torch.cuda.get_device_properties(dev).multi_processor_count - 8 * B, _stream())
+    main.wait_stream(side)
+    LAUNCHES += 1
+    return mem_pos, mem_src, score, zs, words[:2]
+
+
+def keyed_scan_order(key, rows, N):
+    """(rows, N) int64 scan order on the device: row r = the keyed bijection of [0, N) for (key[0], key[1], r); `key` = two
+    int64 on the device (ipsb_keyed_scan_order; oracle: ips_oracle.keyed_scan_order)."""
+    _chk(key, torch.int64, 'key')
+    perm = torch.empty((rows, N), dtype=torch.int64, device=key.device)
+    _call('ipsb_keyed_scan_order', _p(key), rows, N, _p(perm), _stream())
+    return perm
+
+
 def merge_candidates(cz, H, T, M):
     """Global re-score of a candidate list cz (B, L, H*T) and stable top-M: positions (B, M) into the list, best first,
     equal scores -> lowest position (score_and_select, ips_net.py:136-155, on the merged buffer).  Long lists run as ONE
@@ -682,11 +768,12 @@ def peer_ctx(rank, world, bases):
     return c
 
 
-def peer_push_candidates(ctx, z_local, cand, index_base, L, slot0, cz_off, ci_off):
-    _chk(z_local, torch.float32, 'z_local'); _chk(cand, torch.int64, 'cand')
+def peer_push_candidates(ctx, z_local, cand, index_base, L, slot0, cz_off, ci_off, rows=None):
+    """`rows` (B, m): rows of z_local holding the candidates' logits when the table is in scan order (default: cand)."""
+    _chk(z_local, torch.float32, 'z_local'); _chk(cand, torch.int64, 'cand'); _chk(rows, torch.int64, 'rows')
     B, n_local, HT = z_local.shape
-    _call('ipsb_peer_push_candidates', ctypes.byref(ctx), _p(z_local), n_local, _p(cand), B, cand.shape[1], HT, index_base, L, slot0,
-          cz_off, ci_off, _stream())
+    _call('ipsb_peer_push_candidates_rows', ctypes.byref(ctx), _p(z_local), n_local, _p(cand), _p(rows), B, cand.shape[1], HT,
+          index_base, L, slot0, cz_off, ci_off, _stream())
 
 
 def peer_push_logits(ctx, z_local, N, row0, z_off):

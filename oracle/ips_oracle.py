@@ -291,6 +291,51 @@ def draw_permutation(conf, B, N):
     return None  # the reference silently ignores unknown styles (ips_net.py:124-133)
 
 
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def keyed_scan_order(key0, key1, rows, N):
+    """CPU restatement of the library's DEVICE-side scan order (conf.scan_order_rng = 'device'; no counterpart in the
+    reference, whose shuffle is the host randperm of utils/utils.py:33-58): row r of the (rows, N) result is a keyed
+    bijection of [0, N): eight rounds of (xor c_r, multiply by odd m_r mod 2^k, xor-shift right by (k+1)//2 or k//3+1) on
+    k = ceil(log2 N) bits, re-applied until the value is < N (cycle walking); (m_r, c_r) from splitmix64 seeded with
+    key0 ^ splitmix64(key1 + r).  key0 / key1 are the two int64 the library draws from the CUDA generator."""
+    import numpy as np
+    out = np.zeros((rows, N), np.int64)
+    if N == 1:
+        return torch.from_numpy(out)
+    k = max(1, int(N - 1).bit_length())
+    mask = (1 << k) - 1
+    h1, h2 = (k + 1) // 2, k // 3 + 1
+    for row in range(rows):
+        t = ((key0 & _M64) ^ _splitmix64(((key1 & _M64) + row) & _M64)) & _M64
+        mul, add = [], []
+        for _ in range(8):
+            t = _splitmix64(t)
+            mul.append(((t >> 32) | 1) & 0xffffffff)
+            add.append(t & 0xffffffff)
+        x = np.arange(N, dtype=np.uint64)
+        todo = np.ones(N, bool)
+        while todo.any():
+            y = x[todo]
+            for r in range(8):
+                y ^= np.uint64(add[r] & mask)
+                y = (y * np.uint64(mul[r])) & np.uint64(mask)
+                y ^= y >> np.uint64(h1 if r % 2 == 0 else h2)
+            x[todo] = y
+            todo = x >= N
+        out[row] = x.astype(np.int64)
+    return torch.from_numpy(out)
+
+
 def ips(sd, conf, patches, perm='draw', tie='topk', trace=None):
     """The no-grad selection loop, ips_net.py:169-262.
 

@@ -433,6 +433,112 @@ def test_projector_logits_fused(dev, rows, K, N, HT, in_bf16):
     assert (z - z2).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize('B,N,M,I,shuffle,overlap', [(1, 50000, 5000, 5000, 'batch', True), (1, 50000, 5000, 5000, None, True),
+                                                      (2, 9000, 1500, 1000, 'instance', True), (3, 7000, 1024, 1024, 'batch', None),
+                                                      (1, 20011, 2000, 3000, 'batch', False), (1, 2500, 2000, 3000, 'batch', True)])
+def test_projector_select_streamed(dev, B, N, M, I, shuffle, overlap):
+    """Streamed selection (ops.projector_select: projector kernel reading the rows through the scan order + the cluster
+    loop consuming its tiles through flags, on two streams) == the sequential composition (projector in original order ->
+    ipsb_select_loop with the same perm): same logits bit for bit (scan order), same winners in the same order; shared and
+    per-instance scan orders, ragged last tile / last chunk, one chunk only, back-to-back fallback for more than two bags."""
+    from ips_b200 import ops
+    K, Nw, H, T = 512, 512, 8, 1
+    HT = H * T
+    g = torch.Generator().manual_seed(70 + N)
+    x = (torch.randn(B * N, K, generator=g) * 1.5 + 0.3).to(dev)
+    wb = (torch.randn(Nw, K, generator=g) / math.sqrt(K)).to(torch.bfloat16).to(dev)
+    scale, shift = (torch.rand(Nw, generator=g) + 0.5).to(dev), (torch.randn(Nw, generator=g) * 0.2).to(dev)
+    U = (torch.randn(Nw, HT, generator=g) * 0.5).to(dev)
+    tab = ops.projector_table(scale, shift, wb, U)
+    perm, per_inst = None, False
+    if shuffle == 'batch':
+        perm = torch.randperm(N, generator=g).unsqueeze(0).to(dev)
+    elif shuffle == 'instance':
+        perm, per_inst = torch.rand((B, N), generator=g).argsort(1).to(dev).contiguous(), True
+    assert ops.streamed_select_ok(B, N, HT, M, I)
+    z = ops.projector_logits(x, wb, tab, HT, 1e-5).view(B, N, HT)
+    pos0, src0, sc0 = ops.select_loop(z, perm, per_inst, H, T, M, I)
+    for rep in range(3):                                                # repeated: flags / sync words are per call
+        pos1, src1, sc1, zs, status = ops.projector_select(x, wb, tab, B, N, perm, per_inst, H, T, M, I, overlap=overlap)
+        torch.cuda.synchronize()
+        if status is not None:
+            assert status.tolist() == [1, 0]
+        idx = (torch.arange(N, device=dev).expand(B, N) if perm is None else perm.expand(B, N))
+        assert torch.equal(zs, torch.gather(z, 1, idx.unsqueeze(-1).expand(B, N, HT)))
+        assert torch.equal(pos0, pos1) and torch.equal(src0, src1) and torch.equal(sc0, sc1)
+
+
+@pytest.mark.parametrize('rows,N', [(1, 1), (1, 2), (3, 3), (2, 1000), (1, 50000), (4, 65536), (1, 200001)])
+def test_keyed_scan_order_matches_oracle(dev, rows, N):
+    """Device-side scan order (ipsb_keyed_scan_order) == its CPU restatement, element for element, and every row is a
+    permutation of [0, N)."""
+    from ips_b200 import ops
+    key = torch.tensor([-0x1234567890abcdef + N, 0x0fedcba987654321 - rows], dtype=torch.int64)
+    got = ops.keyed_scan_order(key.to(dev), rows, N).cpu()
+    ref = O.keyed_scan_order(int(key[0]), int(key[1]), rows, N)
+    assert torch.equal(got, ref)
+    assert torch.equal(got.sort(1).values, torch.arange(N).expand(rows, N))
+    if rows > 1 and N > 100:
+        assert not torch.equal(got[0], got[1])
+
+
+def test_streamed_select_in_ips_and_graph(dev):
+    """IPSNet.ips on a feature bag takes the streamed path and returns what the sequential path returns; the two-stream
+    call is capturable as one CUDA graph (fork / join) and the replay gives the same winners."""
+    from ips_b200 import IPSNet, Struct
+    conf = O.preset('camelyon', M=2000, I=2000, shuffle=True)
+    net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+    net.load_state_dict(O.make_state(conf, 9, q_gain=8.0))
+    net.eval()
+    x = O.make_patches(conf, 1, 12000, 31).to(dev)
+    torch.manual_seed(5)
+    a, _ = net.ips(x)
+    idx_a = net.last_mem_idx.clone()
+    assert net.last_stream_status is not None and net.last_stream_status.tolist() == [1, 0]
+    net.streamed_select = False
+    torch.manual_seed(5)
+    b, _ = net.ips(x)
+    assert torch.equal(idx_a, net.last_mem_idx) and torch.equal(a, b)
+    net.streamed_select = True
+    net.shuffle = False                                                  # (the host-side randperm cannot be captured)
+    ref, _ = net.ips(x)
+    idx_ref = net.last_mem_idx.clone()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            out, _ = net.ips(x)
+            idx_g = net.last_mem_idx
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref) and torch.equal(idx_g, idx_ref)
+    # scan order drawn on the device: part of the graph; a replay after manual_seed == the eager call on the same seed
+    net.shuffle, net.scan_order_rng = True, 'device'
+    torch.manual_seed(77)
+    ref, _ = net.ips(x)
+    idx_ref = net.last_mem_idx.clone()
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g2, stream=side):
+            out2, _ = net.ips(x)
+            idx_g2 = net.last_mem_idx
+    torch.cuda.current_stream().wait_stream(side)
+    torch.manual_seed(77)
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref) and torch.equal(idx_g2, idx_ref)
+    g2.replay()                                                           # next draw: another order, still a valid selection
+    torch.cuda.synchronize()
+    assert torch.equal(out2, x[0, idx_g2[0]].unsqueeze(0))
+
+
 @pytest.mark.parametrize('pre,precision,stem_env', [('traffic', 'bf16', None), ('mnist', 'bf16', None), ('traffic', 'fp32', None),
                                                     ('mnist', 'bf16', 'tma')])
 def test_fold_plan_one_launch(dev, pre, precision, stem_env, monkeypatch):

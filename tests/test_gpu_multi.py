@@ -139,6 +139,73 @@ def test_sharded_merge_matches_sharded_oracle(pre, B, N, over, transport, output
     assert torch.equal(ret['mem_patch1'], o_patch)
 
 
+def _worker_streamed(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    for p in (ROOT, os.path.join(ROOT, 'oracle')):
+        sys.path.insert(0, p)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        import ips_oracle as O
+        from ips_b200 import IPSNet, Struct
+        from ips_b200.distributed import ShardedIPS, shard_bounds
+        B, N = 1, 24001
+        conf = O.preset('camelyon', precision='bf16', M=2000, I=3000)
+        sd = O.make_state(conf, 3, q_gain=12.0)
+        x = O.make_patches(conf, B, N, 4).to(dev)
+        net = IPSNet(dev, Struct(**conf.__dict__)).to(dev)
+        net.load_state_dict(sd)
+        lo, hi = shard_bounds(N, world)[rank]
+        local = x[:, lo:hi].contiguous()
+        ok = {}
+        for rng in ('reference', 'device'):
+            net.scan_order_rng = rng
+            for mode in ('merge', 'exact'):
+                res = {}
+                for streamed in (True, False):
+                    net.streamed_select = streamed
+                    sh = ShardedIPS(net, B, N, x.shape[2:], mode=mode)
+                    if sh._gen is not None:
+                        sh._gen.manual_seed(11)
+                    torch.manual_seed(100 + rank if mode == 'merge' else 11)
+                    out, _ = sh(local)
+                    res[streamed] = (out.clone(), net.last_mem_idx.clone())
+                    if streamed:                              # the same call as ONE graph: replay == eager on the same seed
+                        sh.capture(local)
+                        if sh._gen is not None:
+                            sh._gen.manual_seed(11)
+                        torch.manual_seed(100 + rank if mode == 'merge' else 11)
+                        out_g, _ = sh(sh.static_input)
+                        ok['%s/%s/graph' % (rng, mode)] = (torch.equal(out_g, res[True][0]) and torch.equal(net.last_mem_idx, res[True][1])
+                                                          and sh.ex.status() == 0)
+                    del sh
+                ok['%s/%s' % (rng, mode)] = torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+                if mode == 'exact':                           # == one GPU on the same order
+                    torch.manual_seed(11)
+                    net.streamed_select = True
+                    ref, _ = net.ips(x)
+                    ok['%s/exact/single' % rng] = torch.equal(ref, res[True][0]) and torch.equal(net.last_mem_idx, res[True][1])
+        ret[rank] = {k: bool(v) for k, v in ok.items()}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_sharded_streamed_selection_and_device_scan_order():
+    """ShardedIPS on bf16 feature bags: the streamed local selection (projector and loop side by side, scan-ordered table)
+    gives the winners of the sequential path; scan order drawn with the reference's CPU calls or on the device (inside the
+    captured graph; 'exact': one seeded generator per rank, no exchange); graph replay == eager on the same seed; 'exact'
+    == IPSNet.ips on one GPU with the same seed."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_streamed, args=(2, port, ret), nprocs=2, join=True)
+    for r in range(2):
+        bad = [k for k, v in ret[r].items() if not v]
+        assert not bad, (r, bad)
+        assert len(ret[r]) == 10
+
+
 def _worker_syncbn(rank, world, port, name, ret):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):

@@ -207,3 +207,22 @@ def test_sharded_exchange_layout_is_identical_on_all_ranks():
         b = shard_bounds(N, R)
         assert b[0][0] == 0 and b[-1][1] == N and all(x[1] == y[0] for x, y in zip(b, b[1:]))
         assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def test_keyed_scan_order_oracle_is_a_uniform_looking_bijection():
+    """The device-side scan order's CPU restatement: a permutation for every N; over many keys every element lands on
+    every position equally often (chi-square on a 32 x 32 table) and a chunk's membership looks like a random sample."""
+    import numpy as np
+    for N in (1, 2, 3, 5, 64, 1000, 4097):
+        p = O.keyed_scan_order(0x1234 + N, -77, 2, N)
+        assert torch.equal(p.sort(1).values, torch.arange(N).expand(2, N))
+    N, T = 32, 6000
+    cnt = np.zeros((N, N))
+    for t in range(T):
+        p = O.keyed_scan_order(99, t, 1, N)[0].numpy()
+        cnt[np.arange(N), p] += 1
+    chi = ((cnt - T / N) ** 2 / (T / N)).sum()
+    dof = (N - 1) ** 2
+    assert abs(chi - dof) < 5 * (2 * dof) ** 0.5, chi
+    fr = [(O.keyed_scan_order(5, t, 1, 20000)[0][:2000] < 10000).double().mean().item() for t in range(30)]
+    assert abs(np.mean(fr) - 0.5) < 0.01 and np.std(fr) < 0.02
