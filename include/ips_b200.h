@@ -271,6 +271,9 @@ IPSB_API int ipsb_add_f32(const float* a, const float* b, float* y, int64_t n, v
  * (transformer.py:107,130) and the cross-attention core with a dropout mask (transformer.py:29-41,98). */
 IPSB_API int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch /* 512*cols floats */, int64_t rows, int cols,
                       void* stream);   /* biased variance, two-stage deterministic reduction */
+/* rstd = 1/sqrt(var + eps) + nn.BatchNorm's running-statistics update (unbias = rows / (rows - 1)); running_* may be NULL */
+IPSB_API int ipsb_bn_finalize_f32(const float* mean, const float* var, int cols, float momentum, float unbias, float eps, float* rstd,
+                                  float* running_mean, float* running_var, void* stream);
 IPSB_API int ipsb_bn_apply_f32(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
                       int64_t rows, int cols, int relu, void* stream);
 /* sums (2*cols) = [dbeta, dgamma]; dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*(y>0) when relu */
@@ -431,6 +434,16 @@ IPSB_API int ipsb_peer_push_logits(const ipsb_peer_ctx* ctx, const float* z_loca
  * ranks' data in rank order.  The section at sec_off holds two slots of slot_stride >= world * bytes that alternate with the
  * device-side epoch of `phase` (safe under CUDA-graph replay).  A tens-of-microseconds NCCL collective becomes two small
  * kernels (push + flag, wait + copy). */
+/* Synchronised BatchNorm over peer memory (data-parallel train step, equal rows per rank).  Forward: push this
+ * rank's [mean | var] (2 * cols floats), wait for every rank's, and in the waiting kernel combine them (mean of means,
+ * mean of var_r + (mean_r - mean)^2), write mean / rstd and update the running statistics.  Backward: push [sum g | sum g*xhat]
+ * (n floats), wait, out = the sum over the ranks in rank order.  Two launches per exchange; sections / phases as for
+ * ipsb_peer_allgather_small. */
+IPSB_API int ipsb_peer_bn_forward(const ipsb_peer_ctx* ctx, const float* mean_var, int cols, int64_t sec_off, int64_t slot_stride,
+                                  int phase, float momentum, float unbias, float eps, float* mean_out, float* rstd_out,
+                                  float* running_mean, float* running_var, void* stream);
+IPSB_API int ipsb_peer_allgather_sum(const ipsb_peer_ctx* ctx, const float* src, int n, int64_t sec_off, int64_t slot_stride, int phase,
+                                     float* out, void* stream);
 IPSB_API int ipsb_peer_allgather_small(const ipsb_peer_ctx* ctx, const void* src, int64_t bytes, int64_t sec_off, int64_t slot_stride,
                                        int phase, void* dst, void* stream);
 /* Waits until every rank has signalled `phase` for the current epoch. */

@@ -97,6 +97,7 @@ SIGNATURES = {
     'ipsb_head_activation_f32': [_ptr, _ptr, _i32, _i32, _i32, _ptr],
     'ipsb_add_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_bn_stats_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
+    'ipsb_bn_finalize_f32': [_ptr, _ptr, _i32, _f32, _f32, _f32, _ptr, _ptr, _ptr, _ptr],
     'ipsb_bn_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_bn_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_bn_backward_sums_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
@@ -128,6 +129,8 @@ SIGNATURES = {
     'ipsb_peer_push_candidates_rows': [ctypes.POINTER(PeerCtx), _ptr, _i64, _ptr, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _ptr],
     'ipsb_peer_push_candidates': [ctypes.POINTER(PeerCtx), _ptr, _i64, _ptr, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _ptr],
     'ipsb_peer_push_logits': [ctypes.POINTER(PeerCtx), _ptr, _i32, _i64, _i32, _i64, _i64, _i64, _ptr],
+    'ipsb_peer_bn_forward': [ctypes.POINTER(PeerCtx), _ptr, _i32, _i64, _i64, _i32, _f32, _f32, _f32, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'ipsb_peer_allgather_sum': [ctypes.POINTER(PeerCtx), _ptr, _i32, _i64, _i64, _i32, _ptr, _ptr],
     'ipsb_peer_allgather_small': [ctypes.POINTER(PeerCtx), _ptr, _i64, _i64, _i64, _i32, _ptr, _ptr],
     'ipsb_peer_wait': [ctypes.POINTER(PeerCtx), _i32, _ptr],
     'ipsb_peer_push_winners': [ctypes.POINTER(PeerCtx), _ptr, _i64, _i64, _ptr, _ptr, _i64, _i32, _i32, _i64, _i32, _i64, _ptr, _ptr],

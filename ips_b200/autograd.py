@@ -116,26 +116,30 @@ class BatchNormTrainFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, group=None):
         x = x.contiguous().float()
         rows, cols = x.shape
-        mean = torch.empty(cols, dtype=torch.float32, device=x.device)
-        var = torch.empty_like(mean)
+        mine = torch.empty(2 * cols, dtype=torch.float32, device=x.device)       # [mean | var] of this rank's rows
+        mean, var = mine[:cols], mine[cols:]
         scratch = torch.empty(512 * cols, dtype=torch.float32, device=x.device)
         ops._call('ipsb_bn_stats_f32', _p(x), _p(mean), _p(var), _p(scratch), rows, cols, ops._stream())
         rows_total = rows
         sync = _dist_group(group)
+        fused_tail = (running_mean is not None and running_var is not None and running_mean.is_cuda and running_mean.dtype == torch.float32 and running_mean.is_contiguous()
+                      and running_var.dtype == torch.float32 and running_var.is_contiguous())
+        rstd = None
         if sync is not None and SYNC_BN_EQUAL_SHARES:
             # every rank holds the same number of rows (fixed per-rank batch): no row counts to exchange, no host read --
             # the collectives can be captured in the train step's CUDA graph
             import torch.distributed as dist
             R = dist.get_world_size(sync)
-            mine = torch.cat([mean, var])
-            if SYNC_BN_PEER is not None and cols % 2 == 0:                 # NVLink peer-memory exchange (no NCCL call)
-                st = SYNC_BN_PEER.all_gather(mine)
+            rows_total = rows * R
+            if SYNC_BN_PEER is not None and cols % 2 == 0 and fused_tail:  # NVLink peer-memory exchange (no NCCL call):
+                # push, then ONE kernel waits, combines, writes mean / rstd and updates the running statistics
+                mean, rstd = SYNC_BN_PEER.bn_forward(mine, cols, momentum, rows_total / max(rows_total - 1, 1), eps,
+                                                     running_mean, running_var)
             else:
                 st = torch.empty((R, 2 * cols), dtype=torch.float32, device=x.device)
                 dist.all_gather_into_tensor(st, mine, group=sync)
-            rows_total = rows * R
-            mean = st[:, :cols].mean(0)
-            var = (st[:, cols:] + (st[:, :cols] - mean) ** 2).mean(0)
+                mean = st[:, :cols].mean(0)
+                var = (st[:, cols:] + (st[:, :cols] - mean) ** 2).mean(0)
         elif sync is not None:
             import torch.distributed as dist
             R = dist.get_world_size(sync)
@@ -147,10 +151,17 @@ class BatchNormTrainFn(torch.autograd.Function):
             rows_total = int(round(float(n.sum())))
             mean = (st[:, :cols] * n).sum(0) / n.sum()
             var = ((st[:, cols:2 * cols] + (st[:, :cols] - mean) ** 2) * n).sum(0) / n.sum()
-        with torch.no_grad():
-            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-            running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows_total / max(rows_total - 1, 1))
-        rstd = torch.rsqrt(var + eps)
+        if rstd is None and fused_tail:                                    # rstd + running statistics: one launch
+            mean, var = mean.contiguous(), var.contiguous()
+            rstd = torch.empty(cols, dtype=torch.float32, device=x.device)
+            with torch.no_grad():
+                ops._call('ipsb_bn_finalize_f32', _p(mean), _p(var), cols, float(momentum), rows_total / max(rows_total - 1, 1),
+                          float(eps), _p(rstd), _p(running_mean), _p(running_var), ops._stream())
+        elif rstd is None:
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var, alpha=momentum * rows_total / max(rows_total - 1, 1))
+            rstd = torch.rsqrt(var + eps)
         y = torch.empty_like(x)
         g, b = gamma.contiguous().float(), beta.contiguous().float()
         ops._call('ipsb_bn_apply_f32', _p(x), _p(mean), _p(rstd), _p(g), _p(b), _p(y), rows, cols, int(relu), ops._stream())
@@ -172,7 +183,7 @@ class BatchNormTrainFn(torch.autograd.Function):
         if ctx.sync is not None:                                           # dgamma / dbeta stay local (averaged with the other gradients)
             import torch.distributed as dist
             if SYNC_BN_PEER is not None and SYNC_BN_EQUAL_SHARES and cols % 2 == 0:
-                all_sums = SYNC_BN_PEER.all_gather(sums).sum(0)            # same order on every rank: identical results
+                all_sums = SYNC_BN_PEER.all_sum(sums)                      # rank order on every rank: identical results
             else:
                 all_sums = sums.clone()
                 dist.all_reduce(all_sums, op=dist.ReduceOp.SUM, group=ctx.sync)

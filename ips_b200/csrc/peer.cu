@@ -190,6 +190,63 @@ __global__ void __launch_bounds__(256) wait_gather_kernel(ipsb_peer_ctx c, int p
     for (int i = threadIdx.x; i < n16_total; i += blockDim.x) dst[i] = __ldcg(src + i);
 }
 
+// Synchronised BatchNorm, forward: wait for every rank's [mean | var] (cols each), then in the same kernel combine them
+// (equal row counts per rank), write mean / rstd and update the running statistics -- what were a dozen elementwise
+// launches per BatchNorm layer.  One block.
+__global__ void __launch_bounds__(256) wait_bn_forward_kernel(ipsb_peer_ctx c, int phase, long long budget_clocks, int64_t sec_off,
+                                                              int64_t slot_stride, int cols, float momentum, float unbias, float eps,
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                              float* __restrict__ running_mean, float* __restrict__ running_var) {
+    PeerHdr* me = reinterpret_cast<PeerHdr*>(c.base[c.rank]);
+    const unsigned int e = me->epoch[phase];
+    if ((int)threadIdx.x < c.world) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(&me->flags[phase][threadIdx.x]) - e) < 0) {
+            if (clock64() - t0 > budget_clocks) { me->status = 1u; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const float* st = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.base[c.rank]) + sec_off + (int64_t)((e - 1u) & 1u) * slot_stride);
+    const int R = c.world;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        float m = 0.f;
+        for (int r = 0; r < R; ++r) m += __ldcg(st + (int64_t)r * 2 * cols + j);
+        m /= (float)R;
+        float v = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float d = __ldcg(st + (int64_t)r * 2 * cols + j) - m;
+            v += __ldcg(st + (int64_t)r * 2 * cols + cols + j) + d * d;
+        }
+        v /= (float)R;
+        mean_out[j] = m;
+        rstd_out[j] = rsqrtf(v + eps);
+        running_mean[j] = running_mean[j] * (1.f - momentum) + m * momentum;
+        running_var[j] = running_var[j] * (1.f - momentum) + v * (momentum * unbias);
+    }
+}
+
+// Wait, then out[i] = sum over the ranks (in rank order: identical on every rank) of the gathered vectors.
+__global__ void __launch_bounds__(256) wait_sum_kernel(ipsb_peer_ctx c, int phase, long long budget_clocks, int64_t sec_off,
+                                                       int64_t slot_stride, int n, float* __restrict__ out) {
+    PeerHdr* me = reinterpret_cast<PeerHdr*>(c.base[c.rank]);
+    const unsigned int e = me->epoch[phase];
+    if ((int)threadIdx.x < c.world) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(&me->flags[phase][threadIdx.x]) - e) < 0) {
+            if (clock64() - t0 > budget_clocks) { me->status = 1u; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const float* st = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c.base[c.rank]) + sec_off + (int64_t)((e - 1u) & 1u) * slot_stride);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < c.world; ++r) a += __ldcg(st + (int64_t)r * n + j);
+        out[j] = a;
+    }
+}
+
 __global__ void read_status_kernel(ipsb_peer_ctx c, int* out) { *out = (int)reinterpret_cast<PeerHdr*>(c.base[c.rank])->status; }
 
 int check_ctx(const ipsb_peer_ctx* ctx) {
@@ -316,6 +373,42 @@ int ipsb_peer_allgather_small(const ipsb_peer_ctx* ctx, const void* src, int64_t
     allgather_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*ctx, (const int4*)src, n16, sec_off, slot_stride, phase);
     IPSB_LAUNCH_CHECK();
     wait_gather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*ctx, phase, 8000000000ll, sec_off, slot_stride, (int4*)dst, n16 * ctx->world);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int push_small(const ipsb_peer_ctx* ctx, const void* src, int64_t bytes, int64_t sec_off, int64_t slot_stride, int phase,
+                      void* stream, const char* who) {
+    IPSB_REQUIRE(src && bytes > 0 && bytes % 16 == 0 && ((uintptr_t)src % 16) == 0 && bytes <= (1 << 20),
+                 "%s: %lld bytes (16-byte multiples up to 1 MiB, aligned buffer)", who, (long long)bytes);
+    IPSB_REQUIRE(sec_off >= IPSB_PEER_HEADER_BYTES && sec_off % 16 == 0 && slot_stride >= bytes * ctx->world && slot_stride % 16 == 0 &&
+                 phase >= 0 && phase < 4, "%s: bad section / phase", who);
+    const int n16 = (int)(bytes / 16);
+    int grid = (n16 + 255) / 256;
+    if (grid > 8) grid = 8;
+    allgather_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*ctx, (const int4*)src, n16, sec_off, slot_stride, phase);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_peer_bn_forward(const ipsb_peer_ctx* ctx, const float* mean_var, int cols, int64_t sec_off, int64_t slot_stride, int phase,
+                         float momentum, float unbias, float eps, float* mean_out, float* rstd_out, float* running_mean,
+                         float* running_var, void* stream) {
+    if (int rc = check_ctx(ctx)) return rc;
+    IPSB_REQUIRE(cols > 0 && mean_out && rstd_out && running_mean && running_var, "peer_bn_forward: null argument");
+    if (int rc = push_small(ctx, mean_var, (int64_t)cols * 8, sec_off, slot_stride, phase, stream, "peer_bn_forward")) return rc;
+    wait_bn_forward_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*ctx, phase, 8000000000ll, sec_off, slot_stride, cols, momentum, unbias, eps,
+                                                               mean_out, rstd_out, running_mean, running_var);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_peer_allgather_sum(const ipsb_peer_ctx* ctx, const float* src, int n, int64_t sec_off, int64_t slot_stride, int phase,
+                            float* out, void* stream) {
+    if (int rc = check_ctx(ctx)) return rc;
+    IPSB_REQUIRE(n > 0 && out, "peer_allgather_sum: null argument");
+    if (int rc = push_small(ctx, src, (int64_t)n * 4, sec_off, slot_stride, phase, stream, "peer_allgather_sum")) return rc;
+    wait_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*ctx, phase, 8000000000ll, sec_off, slot_stride, n, out);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

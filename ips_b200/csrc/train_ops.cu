@@ -110,6 +110,16 @@ __global__ void col_final_kernel(const float* __restrict__ partial, float* __res
     out[i] = t * scale;
 }
 
+__global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* __restrict__ var, int cols, float momentum, float unbias,
+                                   float eps, float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const float m = mean[j], v = var[j];
+    rstd[j] = rsqrtf(v + eps);
+    if (running_mean) running_mean[j] = running_mean[j] * (1.f - momentum) + m * momentum;
+    if (running_var) running_var[j] = running_var[j] * (1.f - momentum) + v * (momentum * unbias);
+}
+
 // y = act(gamma * (x - mean) * rstd + beta)
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
@@ -403,6 +413,16 @@ int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch, i
     col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, mean, cols, kRowChunks, 1, 1.f / (float)rows);
     col_partial_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, scratch, rows, cols, 0);
     col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, var, cols, kRowChunks, 1, 1.f / (float)rows);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+/* tail of the batch statistics: rstd = 1/sqrt(var + eps) and the running-statistics update of nn.BatchNorm
+ * (running_var takes the unbiased variance: unbias = rows / (rows - 1)), one launch instead of six elementwise ones */
+int ipsb_bn_finalize_f32(const float* mean, const float* var, int cols, float momentum, float unbias, float eps, float* rstd,
+                         float* running_mean, float* running_var, void* stream) {
+    IPSB_REQUIRE(mean && var && rstd && cols > 0, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mean, var, cols, momentum, unbias, eps, rstd, running_mean, running_var);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -194,6 +194,22 @@ class PeerStatExchange:
             raise ValueError('PeerStatExchange: vector of %d floats' % v.numel())
         return ops.peer_allgather_small(self.ex.ctx, v.contiguous(), 4096, self.stride, 2, self.R)
 
+    def _check(self, v):
+        if v.numel() % 4 or v.numel() > self.max_floats or not v.is_contiguous():
+            raise ValueError('PeerStatExchange: contiguous vector of %d floats' % v.numel())
+
+    def bn_forward(self, mean_var, cols, momentum, unbias, eps, running_mean, running_var):
+        """[mean | var] of this rank -> (mean, rstd) over all ranks (equal rows per rank); running statistics updated."""
+        from . import ops
+        self._check(mean_var)
+        return ops.peer_bn_forward(self.ex.ctx, mean_var, cols, 4096, self.stride, 2, momentum, unbias, eps, running_mean, running_var)
+
+    def all_sum(self, v):
+        """Sum of `v` over the ranks, in rank order (bit-identical on every rank)."""
+        from . import ops
+        self._check(v)
+        return ops.peer_allgather_sum(self.ex.ctx, v, 4096, self.stride, 2)
+
 
 class ShardedIPS:
     """Sequence-sharded `IPSNet.ips` over NVLink peer memory for fixed shapes: this rank's slice is

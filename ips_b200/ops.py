@@ -790,6 +790,25 @@ def peer_allgather_small(ctx, src, sec_off, slot_stride, phase, world):
     return out
 
 
+def peer_bn_forward(ctx, mean_var, cols, sec_off, slot_stride, phase, momentum, unbias, eps, running_mean, running_var):
+    """Synchronised BatchNorm forward exchange: every rank's [mean | var] -> (mean, rstd) of the whole batch, running
+    statistics updated in the waiting kernel (ipsb_peer_bn_forward)."""
+    _chk(mean_var, torch.float32, 'mean_var'); _chk(running_mean, torch.float32, 'running_mean'); _chk(running_var, torch.float32, 'running_var')
+    mean = torch.empty(cols, dtype=torch.float32, device=mean_var.device)
+    rstd = torch.empty_like(mean)
+    _call('ipsb_peer_bn_forward', ctypes.byref(ctx), _p(mean_var), cols, sec_off, slot_stride, phase, float(momentum), float(unbias),
+          float(eps), _p(mean), _p(rstd), _p(running_mean), _p(running_var), _stream())
+    return mean, rstd
+
+
+def peer_allgather_sum(ctx, src, sec_off, slot_stride, phase):
+    """Sum over the ranks (rank order) of `src` (contiguous fp32, length a multiple of 4)."""
+    _chk(src, torch.float32, 'src')
+    out = torch.empty_like(src)
+    _call('ipsb_peer_allgather_sum', ctypes.byref(ctx), _p(src), src.numel(), sec_off, slot_stride, phase, _p(out), _stream())
+    return out
+
+
 def peer_wait(ctx, phase):
     _call('ipsb_peer_wait', ctypes.byref(ctx), phase, _stream())
 
