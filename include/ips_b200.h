@@ -60,6 +60,13 @@ IPSB_API int ipsb_stage_patches_padded(const float* src, const int64_t* row_idx,
  * (output (oy,ox) of patch p at row p*Sp + oy*(W/2+3) + ox, Sp = (H/2+3)*(W/2+3)); ipsb_maxpool3x3s2_pf_strided reads it. */
 IPSB_API int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows, int C, int H, int W,
                            void* dst, void* stream);
+/* The same staging through the copy engine (stage_tma.cu): one 4-D tensor-map box per band of 8 frame rows -- the zero
+ * padding on all four sides is the TMA unit's out-of-bounds fill --, fp32 -> frame pixels in shared memory, one bulk store
+ * per band.  ipsb_stage_patches_s2d dispatches here when ipsb_stage_tma_ok (16-byte aligned source, W % 4 == 0, W <= 248);
+ * IPSB_STAGE_NO_TMA=1 keeps the load/store kernel. */
+IPSB_API int ipsb_stage_tma_ok(const float* src, int C, int H, int W);
+IPSB_API int ipsb_stage_patches_s2d_tma(const float* src, const int64_t* row_idx, int64_t first_row, int64_t n_rows, int C, int H,
+                                        int W, void* dst, void* stream);
 IPSB_API int ipsb_maxpool3x3s2_pf_strided(const void* x, void* y, int64_t P, int H, int W, int C, int in_Wp, int in_Sp, void* stream);
 /* On-device patchify: the reference cuts images into patches on the CPU workers
  * (`img.unfold(1, ph, sh).unfold(2, pw, sw).permute(1, 2, 0, 3, 4).reshape(-1, C, ph, pw)`,
@@ -271,6 +278,11 @@ IPSB_API int ipsb_add_f32(const float* a, const float* b, float* y, int64_t n, v
  * (transformer.py:107,130) and the cross-attention core with a dropout mask (transformer.py:29-41,98). */
 IPSB_API int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch /* 512*cols floats */, int64_t rows, int cols,
                       void* stream);   /* biased variance, two-stage deterministic reduction */
+/* batch statistics with x read from HBM once (chunk-wise mean / M2 merged by the parallel-variance formula) and, when
+ * rstd != NULL, the tail below in the same two launches; running_* may be NULL */
+IPSB_API int ipsb_bn_stats_finalize_f32(const float* x, float* mean, float* var, float* rstd, float* running_mean, float* running_var,
+                                        float momentum, float unbias, float eps, float* scratch /* 512*cols floats */, int64_t rows,
+                                        int cols, void* stream);
 /* rstd = 1/sqrt(var + eps) + nn.BatchNorm's running-statistics update (unbias = rows / (rows - 1)); running_* may be NULL */
 IPSB_API int ipsb_bn_finalize_f32(const float* mean, const float* var, int cols, float momentum, float unbias, float eps, float* rstd,
                                   float* running_mean, float* running_var, void* stream);

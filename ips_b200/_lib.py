@@ -62,6 +62,8 @@ SIGNATURES = {
     'ipsb_stage_patches': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_stage_patches_padded': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_stage_patches_s2d': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
+    'ipsb_stage_patches_s2d_tma': [_ptr, _ptr, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
+    'ipsb_stage_tma_ok': [_ptr, _i32, _i32, _i32],
     'ipsb_stage_image_s2d': [_ptr, ctypes.POINTER(ImageGeo), _i64, _i64, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_gather_patches_image': [_ptr, ctypes.POINTER(ImageGeo), _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_im2col_bf16': [_ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _ptr],
@@ -97,6 +99,7 @@ SIGNATURES = {
     'ipsb_head_activation_f32': [_ptr, _ptr, _i32, _i32, _i32, _ptr],
     'ipsb_add_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_bn_stats_f32': [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr],
+    'ipsb_bn_stats_finalize_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _f32, _f32, _f32, _ptr, _i64, _i32, _ptr],
     'ipsb_bn_finalize_f32': [_ptr, _ptr, _i32, _f32, _f32, _f32, _ptr, _ptr, _ptr, _ptr],
     'ipsb_bn_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],
     'ipsb_bn_backward_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],

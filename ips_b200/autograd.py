@@ -119,12 +119,18 @@ class BatchNormTrainFn(torch.autograd.Function):
         mine = torch.empty(2 * cols, dtype=torch.float32, device=x.device)       # [mean | var] of this rank's rows
         mean, var = mine[:cols], mine[cols:]
         scratch = torch.empty(512 * cols, dtype=torch.float32, device=x.device)
-        ops._call('ipsb_bn_stats_f32', _p(x), _p(mean), _p(var), _p(scratch), rows, cols, ops._stream())
         rows_total = rows
         sync = _dist_group(group)
         fused_tail = (running_mean is not None and running_var is not None and running_mean.is_cuda and running_mean.dtype == torch.float32 and running_mean.is_contiguous()
                       and running_var.dtype == torch.float32 and running_var.is_contiguous())
         rstd = None
+        if sync is None and fused_tail:                                    # statistics, rstd, running statistics: two launches
+            rstd = torch.empty(cols, dtype=torch.float32, device=x.device)
+            ops._call('ipsb_bn_stats_finalize_f32', _p(x), _p(mean), _p(var), _p(rstd), _p(running_mean), _p(running_var), float(momentum),
+                      rows / max(rows - 1, 1), float(eps), _p(scratch), rows, cols, ops._stream())
+        else:
+            ops._call('ipsb_bn_stats_finalize_f32', _p(x), _p(mean), _p(var), None, None, None, 0.0, 1.0, float(eps), _p(scratch),
+                      rows, cols, ops._stream())
         if sync is not None and SYNC_BN_EQUAL_SHARES:
             # every rank holds the same number of rows (fixed per-rank batch): no row counts to exchange, no host read --
             # the collectives can be captured in the train step's CUDA graph

@@ -1,5 +1,6 @@
 // HBM-bound data movement: patch staging (NCHW fp32 -> channels-last), row gathers,
 // pooling, LayerNorm rows.  All 128-bit where alignment allows.
+#include <stdlib.h>
 #include "common.cuh"
 #include "pf.cuh"
 #include "../../include/ips_b200.h"
@@ -604,6 +605,9 @@ int ipsb_stage_patches_s2d(const float* src, const int64_t* row_idx, int64_t fir
     IPSB_REQUIRE(n_rows > 0 && C > 0 && C <= 4 && H % 2 == 0 && W % 2 == 0 && ((uintptr_t)src % 8 == 0),
                  "stage_s2d: needs C <= 4 and even H, W");
     const int Ys = H / 2 + 3, Wp = W / 2 + 3;
+    static const bool no_tma = getenv("IPSB_STAGE_NO_TMA") != nullptr;
+    if (!no_tma && ((uintptr_t)dst % 16 == 0) && ipsb_stage_tma_ok(src, C, H, W))      // copy-engine form (stage_tma.cu)
+        return ipsb_stage_patches_s2d_tma(src, row_idx, first_row, n_rows, C, H, W, dst, stream);
     const SrcGeo geo{0, (int64_t)H * W, (int64_t)W, 0, 0, 0, 0, 1};
     if (W % 4 == 0 && ((uintptr_t)src % 16 == 0))       // rows and patches start 16-byte aligned: two frame pixels per thread
         stage_s2d_kernel<true><<<grid_for(n_rows * Ys * ((Wp + 1) / 2), 256), 256, 0, (cudaStream_t)stream>>>(

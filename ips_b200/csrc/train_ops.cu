@@ -100,14 +100,117 @@ __global__ void __launch_bounds__(256) col_partial4_kernel(const float* __restri
 }
 
 
-// out[q * cols + c] = scale * sum_chunk partial[(q * R + chunk) * cols + c]
-__global__ void col_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int cols, int R, int nq, float scale) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq * cols) return;
-    const int q = i / cols, c = i - q * cols;
+// Batch statistics in ONE pass over HBM: a block sums its row chunk, derives the chunk's column means, and takes the
+// squared deviations from them in a second sweep over the same chunk (L2 / L1 hot: a chunk is rows / 256 rows);
+// partial[chunk] = column sums, partial[R + chunk] = column M2 around the chunk mean.  col_stats_final_kernel merges the
+// chunks with the parallel-variance formula  M2 = sum_k M2_k + n_k (mean_k - mean)^2  -- as accurate as the two-pass form.
+__global__ void __launch_bounds__(256) col_stats4_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t rows, int cols) {
+    __shared__ float4 p0[256];
+    __shared__ float4 cmean[256];
+    const int tpr = cols >> 2, rpi = 256 / tpr;
+    const int slot = threadIdx.x / tpr, cg = threadIdx.x - slot * tpr;
+    const int R = gridDim.x, chunk = blockIdx.x;
+    const int64_t per = (rows + R - 1) / R, r0 = chunk * per, r1 = min(rows, r0 + per);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + slot; r < r1; r += rpi) {
+        const float4 xv = reinterpret_cast<const float4*>(x)[r * tpr + cg];
+        a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
+    }
+    p0[threadIdx.x] = a;
+    __syncthreads();
+    if (slot == 0) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < rpi; ++k) { const float4 u = p0[k * tpr + cg]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        reinterpret_cast<float4*>(partial + (int64_t)chunk * cols)[cg] = t;
+        const float inv = 1.f / (float)max((int64_t)1, r1 - r0);
+        cmean[cg] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+    }
+    __syncthreads();
+    const float4 m = cmean[cg];
+    a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + slot; r < r1; r += rpi) {
+        const float4 xv = reinterpret_cast<const float4*>(x)[r * tpr + cg];
+        const float dx = xv.x - m.x, dy = xv.y - m.y, dz = xv.z - m.z, dw = xv.w - m.w;
+        a.x += dx * dx; a.y += dy * dy; a.z += dz * dz; a.w += dw * dw;
+    }
+    p0[threadIdx.x] = a;
+    __syncthreads();
+    if (slot == 0) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < rpi; ++k) { const float4 u = p0[k * tpr + cg]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        reinterpret_cast<float4*>(partial + ((int64_t)R + chunk) * cols)[cg] = t;
+    }
+}
+
+// merges the chunk statistics; optionally also rstd and the running statistics (bn_finalize) in the same launch.
+// A block owns 32 columns, 8 thread groups stride over the chunks; two sweeps (total -> mean, then the merged M2).
+__global__ void __launch_bounds__(256) col_stats_final_kernel(const float* __restrict__ partial, int64_t rows, int cols, int R,
+                                                              float* __restrict__ mean, float* __restrict__ var, float momentum,
+                                                              float unbias, float eps, float* __restrict__ rstd,
+                                                              float* __restrict__ running_mean, float* __restrict__ running_var) {
+    __shared__ float red[8][33];
+    __shared__ float mean_s[32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int64_t per = (rows + R - 1) / R;
     float t = 0.f;
-    for (int k = 0; k < R; ++k) t += partial[((int64_t)q * R + k) * cols + c];
-    out[i] = t * scale;
+    if (c < cols)
+        for (int k = g; k < R; k += 8) t += partial[(int64_t)k * cols + c];
+    red[g][lane] = t;
+    __syncthreads();
+    if (g == 0) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += red[j][lane];
+        mean_s[lane] = a / (float)rows;
+    }
+    __syncthreads();
+    const float m = mean_s[lane];
+    float m2 = 0.f;
+    if (c < cols)
+        for (int k = g; k < R; k += 8) {
+            const int64_t n_k = min(rows, (k + 1) * per) - min(rows, k * per);
+            if (n_k <= 0) continue;
+            const float d = partial[(int64_t)k * cols + c] / (float)n_k - m;
+            m2 += partial[((int64_t)R + k) * cols + c] + (float)n_k * d * d;
+        }
+    __syncthreads();
+    red[g][lane] = m2;
+    __syncthreads();
+    if (g == 0 && c < cols) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += red[j][lane];
+        const float v = a / (float)rows;
+        mean[c] = m;
+        var[c] = v;
+        if (rstd) rstd[c] = rsqrtf(v + eps);
+        if (running_mean) running_mean[c] = running_mean[c] * (1.f - momentum) + m * momentum;
+        if (running_var) running_var[c] = running_var[c] * (1.f - momentum) + v * (momentum * unbias);
+    }
+}
+
+// out[q * cols + c] = scale * sum_chunk partial[(q * R + chunk) * cols + c]
+// A block owns 32 columns of one q: 8 thread groups stride over the chunks (coalesced 128-byte rows of the partial table,
+// independent loads), the groups are summed in a fixed order (deterministic).  (One thread per column walking all R
+// chunks was a chain of R dependent L2 round trips: 20 us per launch, sixty launches per train step.)
+__global__ void __launch_bounds__(256) col_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int cols, int R, int nq,
+                                                        float scale) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int cblocks = (cols + 31) / 32;
+    const int q = blockIdx.x / cblocks, c = (blockIdx.x - q * cblocks) * 32 + lane;
+    float t = 0.f;
+    if (c < cols)
+        for (int k = g; k < R; k += 8) t += partial[((int64_t)q * R + k) * cols + c];
+    red[g][lane] = t;
+    __syncthreads();
+    if (g == 0 && c < cols) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += red[j][lane];
+        out[(int64_t)q * cols + c] = a * scale;
+    }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ mean, const float* __restrict__ var, int cols, float momentum, float unbias,
@@ -402,18 +505,40 @@ int ipsb_bn_stats_f32(const float* x, float* mean, float* var, float* scratch, i
     if (fast4(cols, x)) {                                         // float4 path: 256 row chunks
         const int R = (int)(rows < kRowChunks4 ? rows : kRowChunks4);
         col_partial4_kernel<0><<<R, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, scratch, rows, cols, 0);
-        col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, mean, cols, R, 1, 1.f / (float)rows);
+        col_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(scratch, mean, cols, R, 1, 1.f / (float)rows);
         col_partial4_kernel<1><<<R, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, scratch, rows, cols, 0);
-        col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, var, cols, R, 1, 1.f / (float)rows);
+        col_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(scratch, var, cols, R, 1, 1.f / (float)rows);
         IPSB_LAUNCH_CHECK();
         return 0;
     }
     dim3 grid((cols + 31) / 32, kRowChunks);
     col_partial_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, scratch, rows, cols, 0);
-    col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, mean, cols, kRowChunks, 1, 1.f / (float)rows);
+    col_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(scratch, mean, cols, kRowChunks, 1, 1.f / (float)rows);
     col_partial_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, scratch, rows, cols, 0);
-    col_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(scratch, var, cols, kRowChunks, 1, 1.f / (float)rows);
+    col_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(scratch, var, cols, kRowChunks, 1, 1.f / (float)rows);
     IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+/* Batch statistics + (optionally: rstd, rstd != NULL) + (optionally: running statistics) in two launches; x is read from HBM
+ * once.  scratch: 2 * 256 * cols floats.  Column counts outside the float4 form fall back to the two-pass kernels. */
+int ipsb_bn_stats_finalize_f32(const float* x, float* mean, float* var, float* rstd, float* running_mean, float* running_var,
+                               float momentum, float unbias, float eps, float* scratch, int64_t rows, int cols, void* stream) {
+    IPSB_REQUIRE(rows > 0 && cols > 0 && scratch != nullptr && mean && var, "bn_stats_finalize: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fast4(cols, x)) {
+        const int R = (int)(rows < kRowChunks4 ? rows : kRowChunks4);
+        col_stats4_kernel<<<R, 256, 0, st>>>(x, scratch, rows, cols);
+        col_stats_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(scratch, rows, cols, R, mean, var, momentum, unbias, eps, rstd,
+                                                                  running_mean, running_var);
+        IPSB_LAUNCH_CHECK();
+        return 0;
+    }
+    if (int rc = ipsb_bn_stats_f32(x, mean, var, scratch, rows, cols, stream)) return rc;
+    if (rstd || running_mean || running_var) {
+        IPSB_REQUIRE(rstd != nullptr, "bn_stats_finalize: rstd required with running statistics");
+        return ipsb_bn_finalize_f32(mean, var, cols, momentum, unbias, eps, rstd, running_mean, running_var, stream);
+    }
     return 0;
 }
 
@@ -451,11 +576,11 @@ int ipsb_bn_backward_sums_f32(const float* dy, const float* x, const float* y, c
         ((uintptr_t)rstd % 16 == 0)) {
         const int R = (int)(rows < kRowChunks4 ? rows : kRowChunks4);
         col_partial4_kernel<2><<<R, 256, 0, st>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
-        col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, st>>>(scratch, sums, cols, R, 2, 1.f);
+        col_final_kernel<<<2 * ((cols + 31) / 32), 256, 0, st>>>(scratch, sums, cols, R, 2, 1.f);
     } else {
         dim3 grid((cols + 31) / 32, kRowChunks);
         col_partial_kernel<2><<<grid, 256, 0, st>>>(x, dy, y, mean, rstd, scratch, rows, cols, relu);
-        col_final_kernel<<<(2 * cols + 255) / 256, 256, 0, st>>>(scratch, sums, cols, kRowChunks, 2, 1.f);
+        col_final_kernel<<<2 * ((cols + 31) / 32), 256, 0, st>>>(scratch, sums, cols, kRowChunks, 2, 1.f);
     }
     IPSB_LAUNCH_CHECK();
     return 0;

@@ -43,6 +43,30 @@ def test_stage_patches(dev, C, H, W, dt):
     assert torch.equal(out.cpu(), ref[6:10])
 
 
+@pytest.mark.parametrize('C,H,W,P', [(3, 100, 100, 37), (1, 52, 48, 9), (4, 20, 36, 5), (3, 100, 100, 700), (2, 6, 4, 3), (3, 160, 160, 2)])
+def test_stage_s2d_tma_equals_definition(dev, C, H, W, P, monkeypatch):
+    """Space-to-depth staging through the copy engine (stage_tma.cu: 4-D tensor-map boxes with out-of-bounds zero fill,
+    bulk stores) == the frame's definition frame(Y', X')[(dy*2+dx)*4 + c] = in(c, 2Y'+dy-4, 2X'+dx-4), bit for bit, for
+    contiguous and gathered rows; and == the load/store kernel it replaces."""
+    from ips_b200 import ops, _lib
+    x = _rand(P + 3, C, H, W, seed=7)
+    xd = x.to(dev)
+    assert _lib.load().ipsb_stage_tma_ok(xd.data_ptr(), C, H, W) == 1
+    Ys, Wp = H // 2 + 3, W // 2 + 3
+    xp = torch.zeros(P + 3, 4, 2 * Ys, 2 * Wp)
+    xp[:, :C, 4:4 + H, 4:4 + W] = x                                  # in(c, y, x) at padded (y + 4, x + 4)
+    # frame channel (dy*2+dx)*4 + c at (Y', X') = padded (2Y'+dy, 2X'+dx)
+    ref = xp.view(P + 3, 4, Ys, 2, Wp, 2).permute(0, 2, 4, 3, 5, 1).reshape(P + 3, Ys * Wp, 16).to(torch.bfloat16)
+    got = ops.stage_patches_s2d(xd, P, C, H, W, first_row=2).view(P, Ys * Wp, 16).cpu()
+    assert torch.equal(got, ref[2:2 + P])
+    idx = torch.randperm(P + 3, generator=torch.Generator().manual_seed(3))[:P]
+    got = ops.stage_patches_s2d(xd, P, C, H, W, row_idx=idx.to(dev)).view(P, Ys * Wp, 16).cpu()
+    assert torch.equal(got, ref[idx])
+    out = torch.empty((P * Ys * Wp, 16), dtype=torch.bfloat16, device=dev)
+    ops._call('ipsb_stage_patches_s2d_tma', xd.data_ptr(), 0, 1, P, C, H, W, out.data_ptr(), ops._stream())
+    assert torch.equal(out.view(P, Ys * Wp, 16).cpu(), ref[1:1 + P])
+
+
 @pytest.mark.parametrize('C,H,W', [(1, 50, 50), (3, 100, 100), (3, 8, 10)])
 def test_stage_patches_padded(dev, C, H, W):
     from ips_b200 import ops
