@@ -657,6 +657,28 @@ def run_ours(args):
             sustained['roofline'] = {'achieved': ach, 'peak': pk, 'frac': ach / pk, 'unit': 'TFLOP/s',
                                      'how': 'family share of the step (from the roofline pass) x sustained step time; peak = bf16_tflops_sustained'}
 
+    # the staging kernel alone (TMA-staged unfold): patches -> space-to-depth frame for half a step's patches,
+    # input + output larger than L2, CUDA events around 20 launches on the current stream
+    staging = None
+    if extras_ok and rank == 0 and m['conf'].is_image and 'staging' not in skip:
+        def run_staging():
+            from ips_b200 import ops
+            xs = m['x'].reshape(-1, *m['x'].shape[2:])
+            rows = xs.shape[0] // 2
+            C, H, W = xs.shape[1:]
+            if H % 2 or W % 2 or C > 4:
+                return None
+            for _ in range(3):
+                ops.stage_patches_s2d(xs, rows, C, H, W)
+            reps = 20
+            ms_st = bench.timed(lambda: ops.stage_patches_s2d(xs, rows, C, H, W, first_row=rows), reps, collective=False) / reps
+            by = rows * (C * H * W * 4 + (H // 2 + 3) * (W // 2 + 3) * 32)
+            pk = bench.peaks.get('hbm_gbs', 6545.6)
+            return {'kernel': 'stage_s2d_tma_kernel' if (W % 4 == 0 and not os.environ.get('IPSB_STAGE_NO_TMA')) else 'stage_s2d_kernel', 'rows': rows, 'ms': ms_st,
+                    'bytes': by, 'achieved': by / (ms_st / 1e3) / 1e9, 'peak': pk, 'unit': 'GB/s', 'frac': by / (ms_st / 1e3) / 1e9 / pk,
+                    'how': 'algorithmic bytes (fp32 patch read once + bf16 frame written once) / mean launch time, kernel alone'}
+        staging = guarded('staging', run_staging)
+
     train = guarded('train', lambda: bench.train(m, args.workload, max(2, min(args.steps, 5)), sync_bn=world > 1))
     train_local = None
     if world > 1 and 'train' not in skip:
@@ -746,7 +768,7 @@ def run_ours(args):
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': workload_config(args, world),
             'clocks': m['clocks'], 'e2e': m['e2e'], 'gpu_launches': m['gpu_launches'],
-            'roofline': roof, 'cpu_baseline': cpu, 'sustained': sustained, 'exact': exact, 'workloads': workloads,
+            'roofline': roof, 'staging': staging, 'cpu_baseline': cpu, 'sustained': sustained, 'exact': exact, 'workloads': workloads,
             'gpu_library_baseline': lib, 'train': train, 'seq_sharded': seq,
         }
         if train_local is not None:

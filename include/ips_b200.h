@@ -109,6 +109,11 @@ IPSB_API int ipsb_linear_f32(const float* a, const float* w, const float* scale,
                     float* y, int64_t M, int N, int K, int relu, void* stream);
 /* max_pool2d(3, stride 2, pad 1) on NHWC; dt selects fp32 / bf16 */
 IPSB_API int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, int dt, void* stream);
+/* grad-mode step, channels-last fp32: backward of max_pool2d(3, 2, 1) (gather form, torch's first-maximum rule), the
+ * BasicBlock tail y = relu(a + b) (ips_net.py:34-50 via torchvision's BasicBlock.forward) and its backward mask */
+IPSB_API int ipsb_maxpool3x3s2_bwd_f32(const float* x, const float* dy, float* dx, int64_t P, int H, int W, int C, void* stream);
+IPSB_API int ipsb_add_relu_f32(const float* a, const float* b, float* y, int64_t n, void* stream);
+IPSB_API int ipsb_relu_bwd_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream);
 /* adaptive_avg_pool2d(1): (P,HW,C) dt -> (P,C) fp32 */
 IPSB_API int ipsb_avgpool(const void* x, float* y, int64_t P, int HW, int C, int dt, void* stream);
 /* LayerNorm without affine (ips_net.py:56): y = (x-mean)/sqrt(var+eps), rows of F floats */
@@ -153,6 +158,10 @@ IPSB_API int ipsb_gemm_f32(int mode, const float* a, const float* b, const float
 IPSB_API int ipsb_colsum_f32(const float* x, const float* y, float* out, float* scratch /* 64*cols floats or NULL */, int64_t rows,
                     int cols, void* stream);   /* out[c] = sum_r x[r,c] * (y ? y[r,c] : 1) */
 IPSB_API int ipsb_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+/* grad-mode step: both bf16 operand layouts of a conv weight w (Cout, Cin, kh, kw) fp32 in one launch:
+ * w_nk (Cout, kh*kw*Cin) K-major (forward, weight gradient) and, if non-NULL, w_t (Cin, kh*kw*Cout) = flipped + transposed
+ * (input gradient as a convolution of dy). */
+IPSB_API int ipsb_conv_weight_layouts(const float* w, int Cout, int Cin, int kh, int kw, void* w_nk, void* w_t, void* stream);
 /* fp32 (rows,F) -> bf16 with optional no-affine LayerNorm fused (projector prologue) */
 IPSB_API int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);
 /* the same for features already stored as bf16 (flat bf16 feature bags halve the bytes of the CAMELYON path);

@@ -315,16 +315,19 @@ class ConvFn(torch.autograd.Function):
     def forward(ctx, x, weight, stride, pad):
         xb = ops.cast_bf16(x.contiguous().float())
         Cout, Cin, kh, kw = weight.shape
-        w_nk = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).to(torch.bfloat16).contiguous()
+        wf = weight.detach().float().contiguous()
+        w_nk = torch.empty((Cout, kh * kw * Cin), dtype=torch.bfloat16, device=x.device)
+        w_t = torch.empty((Cin, kh * kw * Cout), dtype=torch.bfloat16, device=x.device) if ctx.needs_input_grad[0] else None
+        ops._call('ipsb_conv_weight_layouts', _p(wf), Cout, Cin, kh, kw, _p(w_nk), _p(w_t), ops._stream())   # both operand layouts
         one, zero = _ones_zeros(Cout, x.device)
         y = ops.conv_bf16(xb, w_nk, one, zero, None, Cout, kh, kw, stride, pad, False, 0)
-        ctx.save_for_backward(xb, weight)
+        ctx.save_for_backward(xb, weight, w_t)
         ctx.stride, ctx.pad = stride, pad
         return y.float()
 
     @staticmethod
     def backward(ctx, dy):
-        xb, weight = ctx.saved_tensors
+        xb, weight, wt = ctx.saved_tensors
         stride, pad = ctx.stride, ctx.pad
         Cout, Cin, kh, kw = weight.shape
         P, H, W, _ = xb.shape
@@ -333,7 +336,6 @@ class ConvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             # dx = conv(dy zero-dilated to the input grid, weights flipped and transposed, pad k-1-p)
-            wt = weight.detach().float().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout).to(torch.bfloat16).contiguous()
             g = dyb
             if stride != 1:
                 g = torch.zeros((P, H, W, Cout), dtype=torch.bfloat16, device=dy.device)
@@ -380,14 +382,57 @@ def _bn2d_train(x, bn, relu, group=None):
     return y.view(x.shape)
 
 
+class MaxPoolFn(torch.autograd.Function):
+    """max_pool2d(3, 2, 1) on channels-last (P, H, W, C) fp32 maps (nn.MaxPool2d of the ResNet stem, ips_net.py:36)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        y = ops.maxpool3x3s2(x, ops.F32)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, = ctx.saved_tensors
+        P, H, W, C = x.shape
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        ops._call('ipsb_maxpool3x3s2_bwd_f32', _p(x), _p(dy), _p(dx), P, H, W, C, ops._stream())
+        return dx
+
+
+class AddReluFn(torch.autograd.Function):
+    """relu(a + b): the tail of a BasicBlock, one launch forward, one backward (both inputs get the masked gradient)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        y = torch.empty_like(a)
+        ops._call('ipsb_add_relu_f32', _p(a), _p(b), _p(y), a.numel(), ops._stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        ops._call('ipsb_relu_bwd_f32', _p(y), _p(dy), _p(dx), y.numel(), ops._stream())
+        return dx, dx
+
+
 def conv_encoder_train(encoder, patches, bn_group=None):
     """Grad-mode forward of the truncated ResNet-18 (`encoder` = the nn.Sequential of ips_net.py:34-50) on
     (P, C, H, W) patches; every convolution and BatchNorm runs forward and backward on the library's kernels.
-    Max-pool, residual add, ReLU and the average pool are PyTorch elementwise / reduction glue."""
+    Max-pool (forward and backward), residual add + ReLU and the average pool run on the library's kernels too."""
     mods = list(encoder.children())
     x = StemConvFn.apply(patches, mods[0].weight)
     x = _bn2d_train(x, mods[1], True, bn_group)
-    x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+    if x.shape[-1] % 4 == 0:
+        x = MaxPoolFn.apply(x)
+    else:
+        x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
     for layer in mods[4:-1]:
         for blk in layer:
             idt = x
@@ -395,7 +440,7 @@ def conv_encoder_train(encoder, patches, bn_group=None):
             y = _bn2d_train(ConvFn.apply(y, blk.conv2.weight, 1, 1), blk.bn2, False, bn_group)
             if blk.downsample is not None:
                 idt = _bn2d_train(ConvFn.apply(x, blk.downsample[0].weight, blk.stride, 0), blk.downsample[1], False, bn_group)
-            x = torch.relu(y + idt)
+            x = AddReluFn.apply(y, idt) if y.numel() % 4 == 0 else torch.relu(y + idt)
     return x.mean(dim=(1, 2))
 
 

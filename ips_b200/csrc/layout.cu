@@ -308,6 +308,63 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int64
     }
 }
 
+// Backward of max_pool2d(3, 2, 1), channels-last fp32, 4 channels per thread, gather form (deterministic, no atomics): an
+// input pixel receives dy of every window (at most 2 x 2) whose maximum it is.  The maximum of a window is its FIRST largest
+// element in row-major scan order (strict >), torch's rule (the forward of nn.MaxPool2d keeps that index).
+__global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t P, int H,
+                                   int W, int C, int Ho, int Wo) {
+    const int cv = C / 4;
+    const int64_t total = P * H * W * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 4;
+        int64_t t = i / cv;
+        const int ix = (int)(t % W); t /= W;
+        const int iy = (int)(t % H);
+        const int64_t p = t / H;
+        const float4 me = *reinterpret_cast<const float4*>(x + ((p * H + iy) * W + ix) * (int64_t)C + c0);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int oy0 = max(0, iy / 2), oy1 = min(Ho - 1, (iy + 1) / 2);      // windows with 2 oy - 1 <= iy <= 2 oy + 1
+        const int ox0 = max(0, ix / 2), ox1 = min(Wo - 1, (ix + 1) / 2);
+        for (int oy = oy0; oy <= oy1; ++oy)
+            for (int ox = ox0; ox <= ox1; ++ox) {
+                // is (iy, ix) the first maximum of window (oy, ox)?  per channel: nothing before it is >= it, nothing after is > it
+                bool w0 = true, w1 = true, w2 = true, w3 = true;
+                for (int r = 0; r < 3; ++r) {
+                    const int y = oy * 2 - 1 + r;
+                    if (y < 0 || y >= H) continue;
+                    for (int q = 0; q < 3; ++q) {
+                        const int xx = ox * 2 - 1 + q;
+                        if (xx < 0 || xx >= W || (y == iy && xx == ix)) continue;
+                        const float4 v = *reinterpret_cast<const float4*>(x + ((p * H + y) * W + xx) * (int64_t)C + c0);
+                        const bool before = (y < iy) || (y == iy && xx < ix);
+                        if (before) { w0 &= !(v.x >= me.x); w1 &= !(v.y >= me.y); w2 &= !(v.z >= me.z); w3 &= !(v.w >= me.w); }
+                        else { w0 &= !(v.x > me.x); w1 &= !(v.y > me.y); w2 &= !(v.z > me.z); w3 &= !(v.w > me.w); }
+                    }
+                }
+                const float4 g = *reinterpret_cast<const float4*>(dy + ((p * Ho + oy) * Wo + ox) * (int64_t)C + c0);
+                if (w0) acc.x += g.x;
+                if (w1) acc.y += g.y;
+                if (w2) acc.z += g.z;
+                if (w3) acc.w += g.w;
+            }
+        *reinterpret_cast<float4*>(dx + ((p * H + iy) * W + ix) * (int64_t)C + c0) = acc;
+    }
+}
+
+// y = relu(a + b); backward mask = y > 0 (residual tail of a BasicBlock), 4 floats per thread
+__global__ void add_relu_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 u = a[i], v = b[i];
+        y[i] = make_float4(fmaxf(u.x + v.x, 0.f), fmaxf(u.y + v.y, 0.f), fmaxf(u.z + v.z, 0.f), fmaxf(u.w + v.w, 0.f));
+    }
+}
+__global__ void relu_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ dx, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 u = y[i], g = dy[i];
+        dx[i] = make_float4(u.x > 0.f ? g.x : 0.f, u.y > 0.f ? g.y : 0.f, u.z > 0.f ? g.z : 0.f, u.w > 0.f ? g.w : 0.f);
+    }
+}
+
 template <typename T>
 __global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int64_t P, int HW, int C) {
     const int64_t total = P * C;
@@ -501,6 +558,21 @@ __global__ void colsum_kernel(const float* __restrict__ x, const float* __restri
     }
 }
 
+__global__ void conv_weight_layouts_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw, bf16* __restrict__ w_nk,
+                                           bf16* __restrict__ w_t, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        // i indexes w_nk (writes coalesced): co, r, s, ci
+        const int ci = (int)(i % Cin);
+        int64_t t = i / Cin;
+        const int sx = (int)(t % kw); t /= kw;
+        const int r = (int)(t % kh);
+        const int co = (int)(t / kh);
+        const bf16 v = __float2bfloat16_rn(w[(((int64_t)co * Cin + ci) * kh + r) * kw + sx]);
+        w_nk[i] = v;
+        if (w_t) w_t[((int64_t)ci * kh * kw + (int64_t)(kh - 1 - r) * kw + (kw - 1 - sx)) * Cout + co] = v;
+    }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -581,6 +653,31 @@ int ipsb_maxpool3x3s2(const void* x, void* y, int64_t P, int H, int W, int C, in
     } else {
         return ipsb::fail("maxpool: unknown dtype %d", dt);
     }
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_maxpool3x3s2_bwd_f32(const float* x, const float* dy, float* dx, int64_t P, int H, int W, int C, void* stream) {
+    IPSB_REQUIRE(x && dy && dx && P > 0 && C % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0),
+                 "maxpool_bwd: C=%d must be a multiple of 4, pointers 16-byte aligned", C);
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    maxpool_bwd_kernel<<<grid_for(P * H * W * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, P, H, W, C, Ho, Wo);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_add_relu_f32(const float* a, const float* b, float* y, int64_t n, void* stream) {
+    IPSB_REQUIRE(a && b && y && n > 0 && n % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)y % 16 == 0),
+                 "add_relu: n=%lld must be a multiple of 4, pointers 16-byte aligned", (long long)n);
+    add_relu_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, (float4*)y, n / 4);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_relu_bwd_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream) {
+    IPSB_REQUIRE(y && dy && dx && n > 0 && n % 4 == 0 && ((uintptr_t)y % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0),
+                 "relu_bwd: n=%lld must be a multiple of 4, pointers 16-byte aligned", (long long)n);
+    relu_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)dy, (float4*)dx, n / 4);
     IPSB_LAUNCH_CHECK();
     return 0;
 }
@@ -710,6 +807,17 @@ int ipsb_colsum_f32(const float* x, const float* y, float* out, float* scratch, 
         colsum_kernel<<<dim3((cols + 31) / 32, 64), 256, 0, (cudaStream_t)stream>>>(x, y, scratch, rows, cols);
         colsum_kernel<<<dim3((cols + 31) / 32, 1), 256, 0, (cudaStream_t)stream>>>(scratch, nullptr, out, 64, cols);
     }
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Both bf16 operand layouts of a conv weight for the grad-mode step, one launch (replaces five elementwise launches):
+//   w_nk[co, (r*kw + s)*Cin + ci]            = w[co, ci, r, s]                      forward / weight-gradient operand
+//   w_t [ci, (r*kw + s)*Cout + co]           = w[co, ci, kh-1-r, kw-1-s]            input-gradient operand (flipped, transposed)
+int ipsb_conv_weight_layouts(const float* w, int Cout, int Cin, int kh, int kw, void* w_nk, void* w_t, void* stream) {
+    IPSB_REQUIRE(w && w_nk && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "conv_weight_layouts: bad arguments");
+    const int64_t n = (int64_t)Cout * Cin * kh * kw;
+    conv_weight_layouts_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kh, kw, (bf16*)w_nk, (bf16*)w_t, n);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

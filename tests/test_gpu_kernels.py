@@ -802,6 +802,36 @@ def test_stem_pool_fused(dev, C, H, W, P):
     assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize('P,H,W,C', [(3, 50, 50, 64), (2, 7, 9, 8), (1, 2, 2, 4), (5, 25, 24, 12)])
+def test_maxpool_and_add_relu_autograd_fns(dev, P, H, W, C):
+    """MaxPoolFn / AddReluFn (grad-mode encoder glue on the library's kernels) against torch autograd, bit for bit --
+    including the tie rule of the pooling backward (post-ReLU maps are full of equal zeros: the first maximum in scan
+    order takes the gradient, like nn.MaxPool2d)."""
+    from ips_b200.autograd import MaxPoolFn, AddReluFn
+    g = torch.Generator().manual_seed(P * 100 + H)
+    x = torch.relu(torch.randn(P, H, W, C, generator=g)).to(dev)          # ~half zeros: ties in most windows
+    x[0, :, :, 0] = 1.0                                                   # a constant channel: every window is one big tie
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    ya = MaxPoolFn.apply(xa)
+    yb = torch.nn.functional.max_pool2d(xb.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(ya, yb)
+    dy = torch.randn(ya.shape, generator=g).to(dev)
+    ya.backward(dy)
+    yb.backward(dy)
+    assert torch.equal(xa.grad, xb.grad)
+    a = torch.randn(P, H, W, C, generator=g).to(dev)
+    b = torch.randn(P, H, W, C, generator=g).to(dev)
+    a1, b1, a2, b2 = (t.clone().requires_grad_(True) for t in (a, b, a, b))
+    y1 = AddReluFn.apply(a1, b1)
+    y2 = torch.relu(a2 + b2)
+    assert torch.equal(y1, y2)
+    dy = torch.randn(y1.shape, generator=g).to(dev)
+    y1.backward(dy)
+    y2.backward(dy)
+    assert torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+
+
 @pytest.mark.parametrize('case', [(64, 64, 3, 1, 1, 13, 13), (64, 128, 3, 2, 1, 13, 13), (64, 128, 1, 2, 0, 13, 13),
                                   (128, 256, 3, 2, 1, 7, 7), (256, 256, 3, 1, 1, 4, 4), (256, 512, 1, 2, 0, 7, 7),
                                   (64, 128, 3, 2, 1, 14, 14), (64, 128, 1, 2, 0, 14, 10)])      # even maps under stride 2
