@@ -550,10 +550,17 @@ class IPSNet(nn.Module):
             plan['desc'] = ops.make_resnet_desc(plan, ops.BF16 if self.precision == 'bf16' else ops.F32, self.D, HT)
         pos_idx = (torch.arange(rows, device=self.device) % N).contiguous() if self.use_pos else None
         arrived, consumed = [], []
+        # chunk boundaries; with a whole-tensor device copy and the automatic chunk size the LAST chunk is split into
+        # 1/2 + 1/4 + 1/4: only the last piece's encoder time is exposed after the final copy
+        edges = list(range(0, rows, chunk)) + [rows]
+        if resident and not self.chunk_patches and self.is_image and edges[-1] - edges[-2] >= 128:
+            a, b = edges[-2], edges[-1]
+            q = (b - a) // 4
+            edges = edges[:-1] + [a + 2 * q, a + 3 * q, b]
+        n_chunks = len(edges) - 1
 
         def issue_copy(ci):
-            lo = ci * chunk
-            n = min(chunk, rows - lo)
+            lo, n = edges[ci], edges[ci + 1] - edges[ci]
             slot = lo if resident else (ci % ring) * chunk
             with torch.cuda.stream(cs):
                 if not resident and ci >= ring:
@@ -567,8 +574,7 @@ class IPSNet(nn.Module):
         for ci in range(min(ahead, n_chunks)):
             issue_copy(ci)
         for ci in range(n_chunks):
-            lo = ci * chunk
-            n = min(chunk, rows - lo)
+            lo, n = edges[ci], edges[ci + 1] - edges[ci]
             slot = lo if resident else (ci % ring) * chunk
             main.wait_event(arrived[ci])
             if native:
