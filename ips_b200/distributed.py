@@ -282,9 +282,8 @@ class ShardedIPS:
         net, dev = self.net, self.net.device
         if net.shuffle and getattr(net, 'scan_order_rng', 'reference') == 'device':
             return 'device', False                    # drawn inside _run
-        if self.mode == 'merge':                      # every rank shuffles its own slice (block-wise shuffle)
-            perm, per_inst = local_scan_order(net, self.B, self.hi - self.lo, torch.device('cpu'))
-            return (None if perm is None else perm.to(dev, non_blocking=True).contiguous()), per_inst
+        if self.mode == 'merge':                      # every rank shuffles its own slice (block-wise shuffle, local_scan_order)
+            return net._draw_scan_order(self.B, self.hi - self.lo, torch.device('cpu'), dev)
         return _broadcast_scan_order(net, self.B, self.N, dev, self.group)
 
     # ---- the kernels of one call (capturable) -----------------------------------------------------------------
