@@ -427,7 +427,9 @@ class Bench:
         n_calls = B_train // B
         labels_t = {k: (v.repeat(n_calls, *([1] * (v.dim() - 1)))) for k, v in labels.items()}
         from ips_b200.train import GraphedTrainStep
-        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=conf.wd, capturable=True)
+        # the reference's optimizer (main.py:57: AdamW with conf.wd); `fused` = torch's multi-tensor kernel: the capturable
+        # foreach form divides by 0-dim step tensors one parameter at a time (150 tiny launches per step)
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=conf.wd, capturable=True, fused=True)
         gstep = GraphedTrainStep(net, conf, opt, B_train, data_parallel=True if self.world > 1 else None)
         for k, v in labels_t.items():
             gstep.labels[k].copy_(v)

@@ -87,7 +87,9 @@ class GraphedTrainStep:
         if self.flat_grad is not None:
             self.flat_grad.zero_()
         else:
-            self.opt.zero_grad(set_to_none=False)
+            # gradients are (re)created by backward: no zero fill and no accumulate launch per parameter; under capture they
+            # come from the graph's private pool, at the same addresses in every replay
+            self.opt.zero_grad(set_to_none=True)
         if self.fuse_loss:
             loss = fused_loss(self.conf, self.net, self.mem_patch, self.mem_pos, self.labels)
         else:
