@@ -161,6 +161,8 @@ IPSB_API int ipsb_cast_bf16(const float* x, void* y, int64_t n, void* stream);
 /* grad-mode step: both bf16 operand layouts of a conv weight w (Cout, Cin, kh, kw) fp32 in one launch:
  * w_nk (Cout, kh*kw*Cin) K-major (forward, weight gradient) and, if non-NULL, w_t (Cin, kh*kw*Cout) = flipped + transposed
  * (input gradient as a convolution of dy). */
+/* weight gradient as the TN GEMM leaves it, (K', Cout) fp32 with k = (r*kw + s)*C + ci, -> nn.Conv2d's (Cout, Cin, kh, kw) */
+IPSB_API int ipsb_wgrad_to_oihw(const float* dw_kc, int Cout, int Cin, int C, int kh, int kw, float* out, void* stream);
 IPSB_API int ipsb_conv_weight_layouts(const float* w, int Cout, int Cin, int kh, int kw, void* w_nk, void* w_t, void* stream);
 /* fp32 (rows,F) -> bf16 with optional no-affine LayerNorm fused (projector prologue) */
 IPSB_API int ipsb_rows_to_bf16(const float* x, void* y, int64_t rows, int F, int layernorm, float eps, void* stream);

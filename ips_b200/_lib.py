@@ -103,6 +103,7 @@ SIGNATURES = {
     'ipsb_maxpool3x3s2_bwd_f32': [_ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _ptr],
     'ipsb_add_relu_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
     'ipsb_relu_bwd_f32': [_ptr, _ptr, _ptr, _i64, _ptr],
+    'ipsb_wgrad_to_oihw': [_ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _ptr],
     'ipsb_conv_weight_layouts': [_ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr],
     'ipsb_bn_finalize_f32': [_ptr, _ptr, _i32, _f32, _f32, _f32, _ptr, _ptr, _ptr, _ptr],
     'ipsb_bn_apply_f32': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr],

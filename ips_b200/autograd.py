@@ -296,16 +296,19 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
-def _conv_wgrad(xb, dyb, kh, kw, stride, pad):
-    """dW[co, r, s, c] = sum_m dy[m, co] * im2col(x)[m, (r, s, c)] -> (Cout, kh, kw, C) fp32."""
+def _conv_wgrad(xb, dyb, kh, kw, stride, pad, Cin=None):
+    """dW[co, ci, r, s] = sum_m dy[m, co] * im2col(x)[m, (r, s, ci)] -> (Cout, Cin, kh, kw) fp32 (Cin <= C of xb)."""
     P, H, W, C = xb.shape
     Cout = dyb.shape[-1]
+    Cin = C if Cin is None else Cin
     K = kh * kw * C
     dy2 = dyb.reshape(-1, Cout)
     # the long side (K = kh*kw*C) goes to the GEMM's M (multiple of 128), Cout to its N: dW^T = im2col(x)^T dy
     xcol = ops.im2col_bf16(xb, kh, kw, stride, pad, _round_up(K, 128))
-    dw = ops.gemm_bf16('tn', xcol, dy2)[:K].t()                         # (Kp, Cout) -> (Cout, K)
-    return dw.reshape(Cout, kh, kw, C)
+    dw_kc = ops.gemm_bf16('tn', xcol, dy2)                               # (Kp, Cout)
+    out = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=xb.device)
+    ops._call('ipsb_wgrad_to_oihw', _p(dw_kc), Cout, Cin, C, kh, kw, _p(out), ops._stream())
+    return out
 
 
 class ConvFn(torch.autograd.Function):
@@ -343,7 +346,7 @@ class ConvFn(torch.autograd.Function):
             one, zero = _ones_zeros(Cin, dy.device)
             dx = ops.conv_bf16(g, wt, one, zero, None, Cin, kh, kw, 1, kh - 1 - pad, False, 0).float()
         if ctx.needs_input_grad[1]:
-            dw = _conv_wgrad(xb, dyb, kh, kw, stride, pad).permute(0, 3, 1, 2).contiguous()
+            dw = _conv_wgrad(xb, dyb, kh, kw, stride, pad)
         return dx, dw, None, None
 
 
@@ -369,7 +372,7 @@ class StemConvFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             dyb = ops.cast_bf16(dy.contiguous().float())
-            dw = _conv_wgrad(xb, dyb, kh, kw, 2, 3)[..., :Cin].permute(0, 3, 1, 2).contiguous()
+            dw = _conv_wgrad(xb, dyb, kh, kw, 2, 3, Cin)
         return None, dw
 
 

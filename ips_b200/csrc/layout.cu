@@ -573,6 +573,20 @@ __global__ void conv_weight_layouts_kernel(const float* __restrict__ w, int Cout
     }
 }
 
+// weight gradient from the TN GEMM (K', Cout) fp32, k = (r*kw + s)*C + ci  ->  (Cout, Cin, kh, kw) fp32 (nn.Conv2d layout),
+// ci < Cin <= C (the stem's staged input carries a zero 4th channel)
+__global__ void wgrad_to_oihw_kernel(const float* __restrict__ dw, int Cout, int Cin, int C, int kh, int kw, float* __restrict__ out,
+                                     int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int sx = (int)(i % kw);
+        int64_t t = i / kw;
+        const int r = (int)(t % kh); t /= kh;
+        const int ci = (int)(t % Cin);
+        const int co = (int)(t / Cin);
+        out[i] = dw[((int64_t)(r * kw + sx) * C + ci) * Cout + co];
+    }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -818,6 +832,14 @@ int ipsb_conv_weight_layouts(const float* w, int Cout, int Cin, int kh, int kw, 
     IPSB_REQUIRE(w && w_nk && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "conv_weight_layouts: bad arguments");
     const int64_t n = (int64_t)Cout * Cin * kh * kw;
     conv_weight_layouts_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, kh, kw, (bf16*)w_nk, (bf16*)w_t, n);
+    IPSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int ipsb_wgrad_to_oihw(const float* dw_kc, int Cout, int Cin, int C, int kh, int kw, float* out, void* stream) {
+    IPSB_REQUIRE(dw_kc && out && Cout > 0 && Cin > 0 && Cin <= C && kh > 0 && kw > 0, "wgrad_to_oihw: bad arguments");
+    const int64_t n = (int64_t)Cout * Cin * kh * kw;
+    wgrad_to_oihw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dw_kc, Cout, Cin, C, kh, kw, out, n);
     IPSB_LAUNCH_CHECK();
     return 0;
 }

@@ -85,7 +85,8 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self):
         if self.flat_grad is not None:
-            self.flat_grad.zero_()
+            for p in self._with_grad:                        # backward creates the gradients; they are packed below
+                p.grad = None
         else:
             # gradients are (re)created by backward: no zero fill and no accumulate launch per parameter; under capture they
             # come from the graph's private pool, at the same addresses in every replay
@@ -95,6 +96,12 @@ class GraphedTrainStep:
         else:
             loss = self.loss_fn(self.conf, self.net(self.mem_patch, self.mem_pos), self.labels)
         loss.backward()
+        if self.flat_grad is not None:
+            # pack: a few multi-tensor copies instead of one zero fill + one accumulate launch per parameter; from here on
+            # `p.grad` are the views of the flat buffer (what the all-reduce and the optimizer see)
+            torch._foreach_copy_(self._flat_views, [p.grad for p in self._with_grad])
+            for p, v in zip(self._with_grad, self._flat_views):
+                p.grad = v
         self.loss.copy_(loss.detach())
 
     def _sync_and_update(self):
@@ -150,9 +157,11 @@ class GraphedTrainStep:
             with_grad = [p for p in self.net.parameters() if p.grad is not None]
             self.flat_grad = torch.zeros(sum(p.numel() for p in with_grad), dtype=torch.float32, device=dev)
             off = 0
+            self._with_grad, self._flat_views = with_grad, []
             for p in with_grad:
                 n = p.numel()
-                p.grad = self.flat_grad[off:off + n].view_as(p)
+                self._flat_views.append(self.flat_grad[off:off + n].view_as(p))
+                p.grad = self._flat_views[-1]
                 off += n
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):

@@ -9,7 +9,7 @@ NG=${NG:-2}
 TAG=${TAG:-r2_n$NG}
 run() { name=$1; shift; echo "=== $name"; timeout "${TMO:-300}" "$@" > $OUT/${TAG}_$name.log 2>&1; echo "exit $?" | tee -a $OUT/${TAG}_$name.log; tail -n "${TAIL:-4}" $OUT/${TAG}_$name.log | cut -c1-600; }
 nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
-if [ -z "${NOTEST:-}" ]; then TAIL=30 TMO=600 run t_multi python -m pytest tests/test_gpu_multi.py -q -m gpu --timeout 300 -p no:cacheprovider ${PYTEST_ARGS:-}; fi
+if [ -z "${NOTEST:-}" ]; then TAIL=30 TMO=600 run t_multi python -m pytest tests/test_gpu_multi.py -q -m gpu --timeout 300 -p no:cacheprovider ${K_EXPR:+-k "$K_EXPR"}; fi
 if [ -z "${NOBENCH:-}" ]; then
   TAIL=3 TMO=${BENCH_TMO:-800} run bench python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus $NG --steps ${STEPS:-20} --warmup 5 ${BENCH_ARGS:-}
