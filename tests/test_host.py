@@ -226,3 +226,15 @@ def test_keyed_scan_order_oracle_is_a_uniform_looking_bijection():
     assert abs(chi - dof) < 5 * (2 * dof) ** 0.5, chi
     fr = [(O.keyed_scan_order(5, t, 1, 20000)[0][:2000] < 10000).double().mean().item() for t in range(30)]
     assert abs(np.mean(fr) - 0.5) < 0.01 and np.std(fr) < 0.02
+
+
+def test_streamed_select_shape_gate():
+    """ops.streamed_select_ok mirrors ipsb_select_loop_scan's -2 cases: only the 8-CTA cluster loop (M + I >= 2048, H*T a
+    power of two, slices inside shared memory) runs side by side with the projector."""
+    from ips_b200 import ops
+    assert ops.streamed_select_ok(1, 50000, 8, 5000, 5000)          # CAMELYON
+    assert ops.streamed_select_ok(16, 6250, 8, 5000, 5000)          # a rank's slice of 16 slides on 8 GPUs (one iteration)
+    assert not ops.streamed_select_ok(16, 192, 1, 10, 32)           # traffic: tiny buffers -> rank-counting kernel
+    assert not ops.streamed_select_ok(1, 5000, 8, 5000, 5000)       # M >= N: the caller's shortcut
+    assert not ops.streamed_select_ok(1, 50000, 12, 5000, 5000)     # H*T not a power of two
+    assert not ops.streamed_select_ok(1, 400000, 32, 60000, 60000)  # slices beyond shared memory
