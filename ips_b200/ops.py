@@ -551,7 +551,9 @@ def projector_select(x, w_bf16, table, B, N, perm, per_instance, H, T, M, I, eps
     _chk(x, x.dtype, 'x'); _chk(w_bf16, torch.bfloat16, 'w'); _chk(table, torch.float32, 'table'); _chk(perm, torch.int64, 'perm')
     HT = H * T
     rows, K = x.shape
-    assert rows == B * N and streamed_select_ok(B, N, HT, M, I)
+    if rows != B * N or not streamed_select_ok(B, N, HT, M, I):
+        raise RuntimeError('ips_b200: projector_select does not cover B=%d N=%d H*T=%d M=%d I=%d (see streamed_select_ok)'
+                           % (B, N, HT, M, I))
     dev = x.device
     lib = _lib.load()
     if overlap is None:
