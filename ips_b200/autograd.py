@@ -14,6 +14,8 @@ time; an operator without an entry here still runs on PyTorch autograd.
     grad input     the same kernel on dy (zero-dilated for stride 2) with flipped, transposed weights
     grad weight    im2col rows (`ipsb_im2col_bf16`) x dy as a TN GEMM (split over the pixels, deterministic)
 """
+import os
+
 import torch
 from torch import nn
 
@@ -432,7 +434,7 @@ def conv_encoder_train(encoder, patches, bn_group=None):
     mods = list(encoder.children())
     x = StemConvFn.apply(patches, mods[0].weight)
     x = _bn2d_train(x, mods[1], True, bn_group)
-    if x.shape[-1] % 4 == 0:
+    if x.shape[-1] % 4 == 0 and os.environ.get('IPS_B200_TORCH_MAXPOOL') is None:
         x = MaxPoolFn.apply(x)
     else:
         x = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
