@@ -598,7 +598,7 @@ __device__ __forceinline__ void wait_tiles(const ClusterArgs& a, int64_t g0, int
             if (v != 0) break;
             __nanosleep(64);
         }
-        if (v == 0) atomicExch(a.sync_words + 1, 1);
+        if (v == 0 && a.sync_words) atomicExch(a.sync_words + 1, 1);
     }
     __syncthreads();
 }
